@@ -1,0 +1,159 @@
+/*
+ * resselt_b200 — C ABI of the B200 (sm_100a) super-resolution forward engine.
+ *
+ * This is the drop-in boundary for the hot path of rewaifu/resselt: the `forward` of the
+ * architectures it loads.  The reference has no native layer; each entry point below replaces a
+ * group of ATen calls issued from the reference's Python `nn.Module.forward`:
+ *
+ *   rsb_plan_add_conv    <- nn.Conv2d / F.conv2d call sites
+ *                           (resselt/archs/span/arch.py:110-117,152-154,222;
+ *                            resselt/archs/spanplus/arch.py:49-56,100,141,180-184;
+ *                            resselt/archs/compact/arch.py:39,46,52;
+ *                            resselt/utilities/block.py:176-185;
+ *                            resselt/archs/plksr/rplksr.py:15,17,27,45,79,123,126)
+ *                           with the element-wise tails that follow them fused in
+ *                           (SiLU/Mish/PReLU/LeakyReLU/sigmoid: span/arch.py:169-177,
+ *                            spanplus/arch.py:119-127, compact/arch.py:41,48, utilities/block.py:25;
+ *                            SPAB gate span/arch.py:176-177; residual adds utilities/block.py:344,465;
+ *                            PixelShuffle span/arch.py:55, compact/arch.py:54-64, rplksr.py:143-147).
+ *   rsb_plan_add_groupnorm <- nn.GroupNorm + skip (resselt/archs/plksr/rplksr.py:83,91-93)
+ *   rsb_plan_forward     <- <Module>.forward (span/arch.py:231-250, spanplus/arch.py:199-201,
+ *                           compact/arch.py:56-65, esrgan/arch.py:129-138, plksr/rplksr.py:145-147)
+ *
+ * Conventions: plain C types only; every function returns 0 on success, a negative rsb_status for
+ * argument/state errors, or a positive cudaError_t value; rsb_last_error() returns a thread-local
+ * message for the last failure.  The library never allocates activation memory: the caller passes
+ * a workspace of rsb_plan_workspace_bytes() bytes.  Host weight pointers are copied during
+ * rsb_plan_add_* and may be freed afterwards.  All work is enqueued on the caller's CUDA stream.
+ */
+#ifndef RESSELT_B200_H
+#define RESSELT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSB_VERSION 100
+
+typedef struct rsb_plan rsb_plan;
+
+enum rsb_status {
+  RSB_OK = 0,
+  RSB_ERR_INVALID = -1,     /* bad argument */
+  RSB_ERR_STATE = -2,       /* call not valid in the plan's current state */
+  RSB_ERR_UNSUPPORTED = -3, /* shape / feature not implemented */
+  RSB_ERR_WORKSPACE = -4,   /* workspace too small or misaligned */
+  RSB_ERR_NO_DEVICE = -5    /* no usable sm_100 device / driver entry point */
+};
+
+enum rsb_dtype { RSB_F32 = 0, RSB_BF16 = 1, RSB_F16 = 2 };
+
+enum rsb_act {
+  RSB_ACT_NONE = 0,
+  RSB_ACT_SILU = 1,
+  RSB_ACT_MISH = 2,
+  RSB_ACT_LRELU = 3,  /* slope = act_param */
+  RSB_ACT_PRELU = 4,  /* per-channel slopes */
+  RSB_ACT_SIGMOID = 5,
+  RSB_ACT_GELU = 6    /* exact erf form */
+};
+
+/* What happens to a = act(conv + bias) before it is stored. r1/r2 are other plan buffers. */
+enum rsb_combine {
+  RSB_COMB_NONE = 0,      /* out = a                                                  */
+  RSB_COMB_SPAB_GATE = 1, /* out = (v + r1) * (sigmoid(v) - 0.5), v = conv + bias      */
+  RSB_COMB_MUL = 2,       /* out = a * r1                                              */
+  RSB_COMB_AXPY = 3       /* out = alpha * a + beta1 * r1 [+ beta2 * r2]               */
+};
+
+#define RSB_EXTERNAL_INPUT (-1)  /* src: the caller's NCHW input tensor   */
+#define RSB_EXTERNAL_OUTPUT (-2) /* dst: the caller's NCHW output tensor  */
+#define RSB_NO_BUFFER (-3)
+
+/* One convolution ('same' zero padding, stride 1) with its fused tail. */
+typedef struct rsb_conv_desc {
+  int32_t src_buf;    /* buffer id or RSB_EXTERNAL_INPUT */
+  int32_t src_ch_off; /* first input channel inside the buffer (multiple of 8) */
+  int32_t cin;
+  int32_t dst_buf;    /* buffer id or RSB_EXTERNAL_OUTPUT */
+  int32_t dst_ch_off; /* multiple of 8 */
+  int32_t cout;
+  int32_t kh, kw;           /* odd kernel extents */
+  const float* weight;      /* host, [cout][cin][kh][kw] */
+  const float* bias;        /* host, [cout] or NULL */
+  int32_t act;              /* rsb_act */
+  float act_param;          /* LeakyReLU slope */
+  const float* act_slopes;  /* host, [cout] PReLU slopes or NULL */
+  int32_t combine;          /* rsb_combine */
+  int32_t res1_buf, res1_ch_off;
+  int32_t res2_buf, res2_ch_off; /* RSB_NO_BUFFER when unused */
+  float alpha, beta1, beta2;
+  /* external input only: x' = (x - in_mean[c]) * in_scale, applied before zero padding */
+  float in_mean[4];
+  float in_scale;
+  /* external output only: PixelShuffle(ps) into NCHW [n][cout/ps^2][h*ps][w*ps];
+   * add_base: out[c][h*ps+i][w*ps+j] += x[c][h][w] (nearest-upsampled raw input);
+   * finally out = out * out_scale + out_mean[c]. */
+  int32_t ps;
+  int32_t add_base;
+  float out_scale;
+  float out_mean[4];
+  /* source sampled through a nearest-neighbour x2 upsample (src buffer lives on the half-size grid) */
+  int32_t src_upsample2;
+} rsb_conv_desc;
+
+/* GroupNorm over (channels/groups, H, W) per sample, affine, followed by "+ skip". */
+typedef struct rsb_groupnorm_desc {
+  int32_t src_buf, src_ch_off;
+  int32_t dst_buf, dst_ch_off;
+  int32_t channels, groups;
+  float eps;
+  const float* gamma; /* host [channels] */
+  const float* beta;  /* host [channels] */
+  int32_t skip_buf, skip_ch_off; /* RSB_NO_BUFFER: no skip */
+} rsb_groupnorm_desc;
+
+int rsb_version(void);
+const char* rsb_last_error(void);
+/* number of CUDA devices visible to the library (0 on a CPU-only host; never fails) */
+int rsb_device_count(void);
+
+/* compute_dtype: RSB_BF16 (tcgen05 tensor-core path, bf16 storage, fp32 accumulate)
+ *                RSB_F32  (CUDA-core FFMA path, fp32 storage) */
+int rsb_plan_create(int compute_dtype, int in_channels, int out_channels, int upscale, rsb_plan** out);
+int rsb_plan_destroy(rsb_plan* plan);
+
+/* Activation buffer on the grid (H*scale) x (W*scale); returns its id in *buf_id. */
+int rsb_plan_add_buffer(rsb_plan* plan, int channels, int scale, int* buf_id);
+int rsb_plan_add_conv(rsb_plan* plan, const rsb_conv_desc* desc);
+int rsb_plan_add_groupnorm(rsb_plan* plan, const rsb_groupnorm_desc* desc);
+
+/* Pack the weights (bf16 UMMA layout / fp32) and upload them to `device`. */
+int rsb_plan_finalize(rsb_plan* plan, int device);
+
+int rsb_plan_num_ops(const rsb_plan* plan);
+/* kernels launched by one rsb_plan_forward call (for launch accounting) */
+int rsb_plan_launches_per_forward(const rsb_plan* plan);
+/* 2 * MACs of all convolutions for an n x h x w input */
+int rsb_plan_flops(const rsb_plan* plan, int n, int h, int w, double* flops);
+
+int rsb_plan_workspace_bytes(const rsb_plan* plan, int n, int h, int w, size_t* bytes);
+
+/* x: contiguous NCHW [n][in_channels][h][w] of x_dtype on the plan's device;
+ * y: contiguous NCHW [n][out_channels][h*upscale][w*upscale] of y_dtype;
+ * workspace: 1024-byte aligned device memory of at least rsb_plan_workspace_bytes() bytes.
+ * stream: a cudaStream_t passed as void*.  force_direct != 0 runs every conv on the CUDA-core
+ * kernel (debug cross-check of the tensor-core kernel). */
+int rsb_plan_forward(rsb_plan* plan, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype,
+                     void* workspace, size_t workspace_bytes, void* stream, int force_direct);
+
+/* Copy a plan buffer (after a forward) into a dense fp32 NCHW device array, for layer-level tests. */
+int rsb_plan_read_buffer(rsb_plan* plan, int buf_id, int ch_off, int channels, float* dst_nchw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESSELT_B200_H */

@@ -1,0 +1,16 @@
+"""Architecture plugins and the module-level registry.
+
+The reference registers every ``Architecture`` subclass found by an ``os.walk`` of its ``archs``
+package (/root/reference/resselt/archs/__init__.py:7-28), i.e. in filesystem order.  Here the
+in-scope plugins are registered explicitly, in a fixed order.
+"""
+from ..registry import Registry
+from .compact import CompactArch, SRVGGNetCompact
+from .span import SPAN, SPANArch
+from .spanplus import SpanPlus, SpanPlusArch
+
+internal_registry = Registry()
+for _arch in (SPANArch, SpanPlusArch, CompactArch):
+    internal_registry.add(_arch())
+
+__all__ = ['internal_registry', 'SPAN', 'SPANArch', 'SpanPlus', 'SpanPlusArch', 'SRVGGNetCompact', 'CompactArch']

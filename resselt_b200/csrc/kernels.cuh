@@ -1,0 +1,267 @@
+// Device-side parameter blocks and the fused epilogue shared by the conv kernels.
+//
+// Activation storage ("planar-8"): a buffer with C channels on an H x W grid is stored as
+// [n][C/8][H][W][8] — planes of 8 channels, 8 channels of one pixel contiguous (16 B in bf16).
+// This makes (a) a TMA box of (W-run x rows x planes) land in shared memory directly in the
+// canonical no-swizzle K-major UMMA operand layout (8 pixels x 16 B = one core matrix),
+// (b) channel concatenation free (a concat is a range of planes), and (c) epilogue stores 16 B
+// per thread with 8 neighbouring pixels forming a full 128 B line.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/resselt_b200.h"
+
+namespace rsb {
+
+constexpr int kTileH = 16;  // output tile of the tensor-core kernel: 16 rows x 8 pixels = 128 = UMMA M
+constexpr int kTileW = 8;
+
+struct Epi {
+  const float* bias;    // [cpad] (never null; zeros when the conv has no bias)
+  const float* slopes;  // [cpad] PReLU slopes or null
+  int act;
+  float act_param;
+  int combine;
+  float alpha, beta1, beta2;
+  const void* res1;
+  int res1_planes, res1_plane0;
+  const void* res2;
+  int res2_planes, res2_plane0;
+  int dst_external;  // 0: planar buffer, 1: caller's NCHW output
+  void* dst;
+  int dst_planes, dst_plane0;
+  int cout;  // valid output channels
+  int H, W;  // conv grid
+  // external output
+  int out_dtype, ps, out_ch, add_base;
+  const void* base;  // caller's NCHW input (for add_base)
+  int base_dtype, base_ch;
+  float out_scale;
+  float out_mean[4];
+};
+
+// ------------------------------------------------------------------ scalar helpers
+__device__ __forceinline__ float ld_any(const void* p, int dtype, size_t i) {
+  if (dtype == RSB_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == RSB_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, int dtype, size_t i, float v) {
+  if (dtype == RSB_F32)
+    reinterpret_cast<float*>(p)[i] = v;
+  else if (dtype == RSB_BF16)
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&o)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&o)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0];
+  const float4 b = reinterpret_cast<const float4*>(p)[1];
+  o[0] = a.x, o[1] = a.y, o[2] = a.z, o[3] = a.w, o[4] = b.x, o[5] = b.y, o[6] = b.z, o[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+    o[2 * i] = __uint_as_float(w[i] << 16);
+    o[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(v[0], v[1]);
+  r.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[2], v[3]);
+  r.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[4], v[5]);
+  r.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[6], v[7]);
+  r.w = *reinterpret_cast<uint32_t*>(&t);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+__device__ __forceinline__ size_t planar_index(int n, int planes, int plane, int H, int W, int y, int x) {
+  return ((((size_t)n * planes + plane) * H + y) * (size_t)W + x) * 8;
+}
+
+// ------------------------------------------------------------------ activations
+// kFast = true (bf16 path): MUFU approximations, error far below bf16 resolution.
+// kFast = false (fp32 path): libdevice functions.
+template <bool kFast>
+__device__ __forceinline__ float sigmoid_f(float v) {
+  if (kFast) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+    return fmaf(0.5f, t, 0.5f);
+  }
+  return 1.0f / (1.0f + expf(-v));
+}
+template <bool kFast>
+__device__ __forceinline__ float mish_f(float v) {
+  // v * tanh(softplus(v)) == v * (e^2v + 2e^v) / (e^2v + 2e^v + 2); softplus threshold 20 as in ATen
+  if (kFast) {
+    const float e = __expf(fminf(v, 20.0f));
+    const float t = e * (e + 2.0f);
+    return v * __fdividef(t, t + 2.0f);
+  }
+  const float sp = v > 20.0f ? v : log1pf(expf(v));
+  return v * tanhf(sp);
+}
+template <bool kFast>
+__device__ __forceinline__ float activate(int act, float v, float param, float slope) {
+  switch (act) {
+    case RSB_ACT_SILU: return v * sigmoid_f<kFast>(v);
+    case RSB_ACT_MISH: return mish_f<kFast>(v);
+    case RSB_ACT_LRELU: return v >= 0.0f ? v : v * param;
+    case RSB_ACT_PRELU: return v >= 0.0f ? v : v * slope;
+    case RSB_ACT_SIGMOID: return sigmoid_f<kFast>(v);
+    case RSB_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    default: return v;
+  }
+}
+
+// ------------------------------------------------------------------ fused epilogue for 8 channels of one pixel
+// v[] holds the raw accumulators of output channels c0..c0+7 (c0 % 8 == 0) at pixel (n, y, x).
+template <typename T, bool kFast>
+__device__ __forceinline__ void epilogue8(const Epi& e, float (&v)[8], int c0, int n, int y, int x) {
+  {
+    const float4 b0 = reinterpret_cast<const float4*>(e.bias + c0)[0];
+    const float4 b1 = reinterpret_cast<const float4*>(e.bias + c0)[1];
+    v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w;
+    v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+  }
+  const int plane = c0 >> 3;
+  if (e.combine == RSB_COMB_SPAB_GATE) {
+    float r[8];
+    load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] + r[i]) * (sigmoid_f<kFast>(v[i]) - 0.5f);
+  } else {
+    if (e.act != RSB_ACT_NONE) {
+      float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (e.act == RSB_ACT_PRELU) {
+        const float4 s0 = reinterpret_cast<const float4*>(e.slopes + c0)[0];
+        const float4 s1 = reinterpret_cast<const float4*>(e.slopes + c0)[1];
+        s[0] = s0.x, s[1] = s0.y, s[2] = s0.z, s[3] = s0.w, s[4] = s1.x, s[5] = s1.y, s[6] = s1.z, s[7] = s1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = activate<kFast>(e.act, v[i], e.act_param, s[i]);
+    }
+    if (e.combine == RSB_COMB_MUL) {
+      float r[8];
+      load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= r[i];
+    } else if (e.combine == RSB_COMB_AXPY) {
+      float r[8];
+      load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(e.alpha, v[i], e.beta1 * r[i]);
+      if (e.res2 != nullptr) {
+        load8<T>(reinterpret_cast<const T*>(e.res2) + planar_index(n, e.res2_planes, e.res2_plane0 + plane, e.H, e.W, y, x), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(e.beta2, r[i], v[i]);
+      }
+    }
+  }
+  if (!e.dst_external) {
+    store8<T>(reinterpret_cast<T*>(e.dst) + planar_index(n, e.dst_planes, e.dst_plane0 + plane, e.H, e.W, y, x), v);
+    return;
+  }
+  // PixelShuffle(ps) scatter into the caller's NCHW tensor: conv channel oc -> (c, i, j) = (oc / ps^2, (oc % ps^2) / ps, oc % ps)
+  const int ps = e.ps, ps2 = ps * ps;
+  const int OH = e.H * ps, OW = e.W * ps;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int oc = c0 + i;
+    if (oc < e.cout) {
+      const int c = oc / ps2, rem = oc - c * ps2;
+      const int sy = rem / ps, sx = rem - sy * ps;
+      float o = v[i];
+      if (e.add_base) o += ld_any(e.base, e.base_dtype, (((size_t)n * e.base_ch + c) * e.H + y) * e.W + x);
+      o = fmaf(o, e.out_scale, e.out_mean[c & 3]);
+      st_any(e.dst, e.out_dtype, (((size_t)n * e.out_ch + c) * OH + (size_t)y * ps + sy) * OW + (size_t)x * ps + sx, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ kernel parameter blocks
+struct ConvTcParams {
+  int n, H, W;
+  int tiles_x, tiles_y, num_tiles;
+  int cin;   // multiple of 16
+  int npad;  // UMMA N, multiple of 16, <= 256
+  int kh, kw, pad_t, pad_l;
+  int src_plane0;
+  const void* wpack;  // bf16 [kh*kw][cin/8][npad][8]
+  uint32_t wbytes;
+  int stages;
+  uint32_t stage_bytes;  // (kTileH+kh-1) * (kTileW+kw-1) * cin * 2
+  uint32_t acc_stride;   // TMEM columns between the two accumulators
+  uint32_t tmem_cols;    // allocation (power of two >= 32)
+  int dbg_swap_lbo_sbo;  // bring-up aid (env RSB_DEBUG_DESC_SWAP): exchange the LBO/SBO descriptor fields
+  Epi epi;
+};
+
+struct ConvDirectParams {
+  int n, H, W;
+  int cin, cin_planes;  // cin_planes = ceil(cin / 8)
+  int cout, cpad;       // cpad = multiple of 32 groups actually allocated in wpack/bias
+  int kh, kw, pad_t, pad_l;
+  // source
+  int src_external;
+  const void* src;
+  int src_dtype;          // external only
+  int src_planes, src_plane0;
+  int src_upsample2;      // planar source lives on the (H/2, W/2) grid
+  float in_mean[4];
+  float in_scale;
+  const float* wpack;  // fp32 [cin_planes][kh][kw][8][cpad]
+  Epi epi;
+};
+
+struct GroupNormParams {
+  int n, H, W;
+  int channels, groups;
+  float eps;
+  const void* src;
+  int src_planes, src_plane0;
+  void* dst;
+  int dst_planes, dst_plane0;
+  const void* skip;
+  int skip_planes, skip_plane0;
+  const float* gamma;
+  const float* beta;
+  double* partial;  // [n][groups][blocks][2] (sum, sum of squares)
+  int blocks_per_group;
+};
+
+// launchers (defined in the .cu files)
+cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
+size_t conv_tc_smem_bytes(int cin, int npad, int kh, int kw, int stages);
+cudaError_t conv_tc_configure(size_t max_smem);
+cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cudaStream_t stream);
+cudaError_t launch_groupnorm(const GroupNormParams& p, bool bf16_storage, cudaStream_t stream);
+cudaError_t launch_planar_to_nchw(const void* src, bool bf16_storage, int n, int planes, int plane0, int channels,
+                                  int H, int W, float* dst, cudaStream_t stream);
+
+}  // namespace rsb

@@ -1,0 +1,582 @@
+// Host side of the C ABI (include/resselt_b200.h): a "plan" is the layer program of one model —
+// activation buffers + fused conv / GroupNorm ops — built once by the Python architecture plugin,
+// finalised (weights packed + uploaded) on one device, and replayed on the caller's stream.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+  return fail((int)e, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+#define RSB_CUDA(expr)                                   \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return fail_cuda(_e, #expr);  \
+  } while (0)
+
+constexpr size_t kWsAlign = 1024;
+constexpr size_t kMaxSmem = 227 * 1024;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+uint16_t f32_to_bf16(float f) {  // round-to-nearest-even, same as __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+struct Buffer {
+  int channels, planes, scale;
+  size_t offset = 0;  // bytes into the workspace (valid after bind)
+};
+
+struct ConvOp {
+  rsb_conv_desc d;
+  std::vector<float> w, b, slopes;
+  int scale = 1;  // grid of this conv relative to the input
+  int cin_pad16 = 0, npad = 0, cpad32 = 0, cin_planes = 0;
+  bool tc_ok = false;
+  int stages = 0;
+  void* d_wtc = nullptr;
+  uint32_t wbytes_tc = 0;
+  float* d_wdirect = nullptr;
+  float* d_bias = nullptr;
+  float* d_slopes = nullptr;
+  // bound state
+  CUtensorMap map;
+  rsb::ConvTcParams tcp;
+  rsb::ConvDirectParams dp;
+};
+
+struct GnOp {
+  rsb_groupnorm_desc d;
+  std::vector<float> gamma, beta;
+  int scale = 1;
+  float* d_gamma = nullptr;
+  float* d_beta = nullptr;
+  size_t partial_offset = 0;
+  int blocks = 0;
+  rsb::GroupNormParams gp;
+};
+
+struct Op {
+  int kind;  // 0 conv, 1 groupnorm
+  int index;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+}  // namespace
+
+struct rsb_plan {
+  int dtype, in_ch, out_ch, upscale;
+  std::vector<Buffer> bufs;
+  std::vector<ConvOp> convs;
+  std::vector<GnOp> gns;
+  std::vector<Op> ops;
+  bool finalized = false;
+  int device = -1;
+  int num_sms = 0;
+  std::mutex mu;
+  // binding
+  int bn = 0, bh = 0, bw = 0;
+  void* bws = nullptr;
+  size_t elem() const { return dtype == RSB_BF16 ? 2 : 4; }
+};
+
+namespace {
+
+size_t buffer_bytes(const rsb_plan* p, const Buffer& b, int n, int h, int w) {
+  return align_up((size_t)n * b.planes * (size_t)(h * b.scale) * (size_t)(w * b.scale) * 8 * p->elem(), kWsAlign);
+}
+
+int check_buf(const rsb_plan* p, int id, int ch_off, int channels, const char* what) {
+  if (id < 0 || id >= (int)p->bufs.size()) return fail(RSB_ERR_INVALID, "%s: unknown buffer id %d", what, id);
+  if (ch_off % 8 != 0) return fail(RSB_ERR_INVALID, "%s: channel offset %d is not a multiple of 8", what, ch_off);
+  if (ch_off + channels > p->bufs[id].planes * 8)
+    return fail(RSB_ERR_INVALID, "%s: channels [%d, %d) exceed buffer %d (%d channels)", what, ch_off, ch_off + channels, id,
+                p->bufs[id].planes * 8);
+  return 0;
+}
+
+int layout(const rsb_plan* p, int n, int h, int w, std::vector<size_t>* offsets, std::vector<size_t>* gn_offsets,
+           size_t* total) {
+  size_t off = 0;
+  if (offsets) offsets->clear();
+  for (const Buffer& b : p->bufs) {
+    if (offsets) offsets->push_back(off);
+    off += buffer_bytes(p, b, n, h, w);
+  }
+  if (gn_offsets) gn_offsets->clear();
+  for (const GnOp& g : p->gns) {
+    if (gn_offsets) gn_offsets->push_back(off);
+    off += align_up((size_t)n * g.d.groups * 1024 * 2 * sizeof(double), kWsAlign);
+  }
+  *total = off == 0 ? kWsAlign : off;
+  return 0;
+}
+
+void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi& e) {
+  const rsb_conv_desc& d = c.d;
+  memset(&e, 0, sizeof e);
+  e.bias = c.d_bias;
+  e.slopes = c.d_slopes;
+  e.act = d.act;
+  e.act_param = d.act_param;
+  e.combine = d.combine;
+  e.alpha = d.alpha, e.beta1 = d.beta1, e.beta2 = d.beta2;
+  if (d.combine != RSB_COMB_NONE) {
+    const Buffer& r = p->bufs[d.res1_buf];
+    e.res1 = ws + r.offset;
+    e.res1_planes = r.planes;
+    e.res1_plane0 = d.res1_ch_off / 8;
+    if (d.combine == RSB_COMB_AXPY && d.res2_buf >= 0) {
+      const Buffer& r2 = p->bufs[d.res2_buf];
+      e.res2 = ws + r2.offset;
+      e.res2_planes = r2.planes;
+      e.res2_plane0 = d.res2_ch_off / 8;
+    }
+  }
+  e.cout = d.cout;
+  e.H = H, e.W = W;
+  if (d.dst_buf == RSB_EXTERNAL_OUTPUT) {
+    e.dst_external = 1;
+    e.ps = d.ps;
+    e.out_ch = d.cout / (d.ps * d.ps);
+    e.add_base = d.add_base;
+    e.base_ch = p->in_ch;
+    e.out_scale = d.out_scale;
+    for (int i = 0; i < 4; ++i) e.out_mean[i] = d.out_mean[i];
+  } else {
+    const Buffer& b = p->bufs[d.dst_buf];
+    e.dst = ws + b.offset;
+    e.dst_planes = b.planes;
+    e.dst_plane0 = d.dst_ch_off / 8;
+  }
+}
+
+int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  std::vector<size_t> offs, gn_offs;
+  size_t total;
+  layout(p, n, h, w, &offs, &gn_offs, &total);
+  if (ws_bytes < total) return fail(RSB_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, total);
+  if ((uintptr_t)workspace % kWsAlign != 0) return fail(RSB_ERR_WORKSPACE, "workspace must be %zu-byte aligned", kWsAlign);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  for (size_t i = 0; i < p->bufs.size(); ++i) p->bufs[i].offset = offs[i];
+  // padded planes must hold finite values (they meet zero weights): clear once per binding
+  RSB_CUDA(cudaMemsetAsync(workspace, 0, total, stream));
+
+  for (ConvOp& c : p->convs) {
+    const rsb_conv_desc& d = c.d;
+    const int H = h * c.scale, W = w * c.scale;
+    if (c.tc_ok) {
+      EncodeTiledFn enc = get_encode_fn();
+      if (!enc) return fail(RSB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+      const Buffer& sb = p->bufs[d.src_buf];
+      const int HT = rsb::kTileH + d.kh - 1, WT = rsb::kTileW + d.kw - 1;
+      cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)sb.planes, (cuuint64_t)n};
+      cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)W * 16 * H, (cuuint64_t)W * 16 * H * sb.planes};
+      cuuint32_t box[4] = {(cuuint32_t)(8 * WT), (cuuint32_t)HT, (cuuint32_t)(c.cin_pad16 / 8), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&c.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ws + sb.offset, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(RSB_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+      rsb::ConvTcParams& t = c.tcp;
+      memset(&t, 0, sizeof t);
+      t.n = n, t.H = H, t.W = W;
+      t.tiles_x = ceil_div(W, rsb::kTileW), t.tiles_y = ceil_div(H, rsb::kTileH);
+      t.num_tiles = t.tiles_x * t.tiles_y * n;
+      t.cin = c.cin_pad16, t.npad = c.npad;
+      t.kh = d.kh, t.kw = d.kw, t.pad_t = d.kh / 2, t.pad_l = d.kw / 2;
+      t.src_plane0 = d.src_ch_off / 8;
+      t.wpack = c.d_wtc, t.wbytes = c.wbytes_tc;
+      t.stages = c.stages;
+      t.stage_bytes = (uint32_t)HT * WT * c.cin_pad16 * 2u;
+      t.acc_stride = (uint32_t)c.npad;
+      uint32_t cols = 32;
+      while (cols < 2u * c.npad) cols <<= 1;
+      t.tmem_cols = cols;
+      fill_epi(p, c, n, H, W, ws, t.epi);
+    }
+    rsb::ConvDirectParams& q = c.dp;
+    memset(&q, 0, sizeof q);
+    q.n = n, q.H = H, q.W = W;
+    q.cin = d.cin, q.cin_planes = c.cin_planes;
+    q.cout = d.cout, q.cpad = c.cpad32;
+    q.kh = d.kh, q.kw = d.kw, q.pad_t = d.kh / 2, q.pad_l = d.kw / 2;
+    if (d.src_buf == RSB_EXTERNAL_INPUT) {
+      q.src_external = 1;
+      for (int i = 0; i < 4; ++i) q.in_mean[i] = d.in_mean[i];
+      q.in_scale = d.in_scale;
+    } else {
+      const Buffer& sb = p->bufs[d.src_buf];
+      q.src = ws + sb.offset;
+      q.src_planes = sb.planes;
+      q.src_plane0 = d.src_ch_off / 8;
+      q.src_upsample2 = d.src_upsample2;
+    }
+    q.wpack = c.d_wdirect;
+    fill_epi(p, c, n, H, W, ws, q.epi);
+  }
+  for (size_t i = 0; i < p->gns.size(); ++i) {
+    GnOp& g = p->gns[i];
+    const int H = h * g.scale, W = w * g.scale;
+    rsb::GroupNormParams& q = g.gp;
+    memset(&q, 0, sizeof q);
+    q.n = n, q.H = H, q.W = W;
+    q.channels = g.d.channels, q.groups = g.d.groups, q.eps = g.d.eps;
+    const Buffer& sb = p->bufs[g.d.src_buf];
+    q.src = ws + sb.offset, q.src_planes = sb.planes, q.src_plane0 = g.d.src_ch_off / 8;
+    const Buffer& db = p->bufs[g.d.dst_buf];
+    q.dst = ws + db.offset, q.dst_planes = db.planes, q.dst_plane0 = g.d.dst_ch_off / 8;
+    if (g.d.skip_buf >= 0) {
+      const Buffer& kb = p->bufs[g.d.skip_buf];
+      q.skip = ws + kb.offset, q.skip_planes = kb.planes, q.skip_plane0 = g.d.skip_ch_off / 8;
+    }
+    q.gamma = g.d_gamma, q.beta = g.d_beta;
+    q.partial = reinterpret_cast<double*>(ws + gn_offs[i]);
+    const size_t chunks = (size_t)H * W * (g.d.channels / g.d.groups / 8);
+    q.blocks_per_group = (int)std::min<size_t>(1024, std::max<size_t>(1, chunks / 2048));
+  }
+  p->bn = n, p->bh = h, p->bw = w, p->bws = workspace;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsb_version(void) { return RSB_VERSION; }
+const char* rsb_last_error(void) { return g_last_error.c_str(); }
+
+int rsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int rsb_plan_create(int compute_dtype, int in_channels, int out_channels, int upscale, rsb_plan** out) {
+  if (!out) return fail(RSB_ERR_INVALID, "rsb_plan_create: out is NULL");
+  if (compute_dtype != RSB_F32 && compute_dtype != RSB_BF16)
+    return fail(RSB_ERR_INVALID, "rsb_plan_create: compute dtype must be RSB_F32 or RSB_BF16");
+  if (in_channels < 1 || out_channels < 1 || upscale < 1) return fail(RSB_ERR_INVALID, "rsb_plan_create: bad channel/upscale");
+  rsb_plan* p = new rsb_plan();
+  p->dtype = compute_dtype, p->in_ch = in_channels, p->out_ch = out_channels, p->upscale = upscale;
+  *out = p;
+  return 0;
+}
+
+int rsb_plan_destroy(rsb_plan* p) {
+  if (!p) return 0;
+  if (p->finalized) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(p->device);
+    for (ConvOp& c : p->convs) {
+      cudaFree(c.d_wtc), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
+    }
+    for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  delete p;
+  return 0;
+}
+
+int rsb_plan_add_buffer(rsb_plan* p, int channels, int scale, int* buf_id) {
+  if (!p || !buf_id) return fail(RSB_ERR_INVALID, "rsb_plan_add_buffer: NULL argument");
+  if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_buffer: plan already finalized");
+  if (channels < 1 || scale < 1) return fail(RSB_ERR_INVALID, "rsb_plan_add_buffer: bad channels/scale");
+  Buffer b;
+  b.channels = channels;
+  b.planes = ceil_div(channels, 16) * 2;  // whole 16-channel K steps
+  b.scale = scale;
+  p->bufs.push_back(b);
+  *buf_id = (int)p->bufs.size() - 1;
+  return 0;
+}
+
+int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
+  if (!p || !desc) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: NULL argument");
+  if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_conv: plan already finalized");
+  const rsb_conv_desc& d = *desc;
+  if (d.cin < 1 || d.cout < 1 || d.kh < 1 || d.kw < 1 || d.kh % 2 == 0 || d.kw % 2 == 0)
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: bad cin/cout/kernel (%d,%d,%dx%d)", d.cin, d.cout, d.kh, d.kw);
+  if (!d.weight) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: weight is NULL");
+  if (d.act < RSB_ACT_NONE || d.act > RSB_ACT_GELU) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: unknown activation %d", d.act);
+  if (d.act == RSB_ACT_PRELU && !d.act_slopes) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: PReLU needs act_slopes");
+  if (d.combine < RSB_COMB_NONE || d.combine > RSB_COMB_AXPY) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: unknown combine %d", d.combine);
+  ConvOp c;
+  c.d = d;
+  int scale = 1;
+  if (d.src_buf == RSB_EXTERNAL_INPUT) {
+    if (d.cin != p->in_ch) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: external input has %d channels, conv wants %d", p->in_ch, d.cin);
+    if (d.src_upsample2) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: upsampled external input");
+  } else {
+    if (int e = check_buf(p, d.src_buf, d.src_ch_off, d.cin, "rsb_plan_add_conv(src)")) return e;
+    scale = p->bufs[d.src_buf].scale * (d.src_upsample2 ? 2 : 1);
+  }
+  if (d.dst_buf == RSB_EXTERNAL_OUTPUT) {
+    if (d.ps < 1 || d.cout % (d.ps * d.ps) != 0 || d.cout / (d.ps * d.ps) != p->out_ch || scale * d.ps != p->upscale)
+      return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: external output shape mismatch (cout %d, ps %d, scale %d)", d.cout, d.ps, scale);
+    if (d.add_base && p->in_ch != p->out_ch) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: add_base needs in_ch == out_ch");
+    if (d.add_base && scale != 1) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: add_base on an upsampled grid");
+  } else {
+    if (int e = check_buf(p, d.dst_buf, d.dst_ch_off, d.cout, "rsb_plan_add_conv(dst)")) return e;
+    if (p->bufs[d.dst_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: dst buffer grid scale %d != %d", p->bufs[d.dst_buf].scale, scale);
+    if (d.dst_buf == d.src_buf && d.kh * d.kw > 1) {
+      const int a0 = d.src_ch_off, a1 = d.src_ch_off + ceil_div(d.cin, 16) * 16, b0 = d.dst_ch_off, b1 = d.dst_ch_off + d.cout;
+      if (a0 < b1 && b0 < a1) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: spatial conv cannot run in place");
+    }
+  }
+  if (d.combine != RSB_COMB_NONE) {
+    if (int e = check_buf(p, d.res1_buf, d.res1_ch_off, d.cout, "rsb_plan_add_conv(res1)")) return e;
+    if (p->bufs[d.res1_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: res1 grid mismatch");
+    if (d.combine == RSB_COMB_AXPY && d.res2_buf >= 0) {
+      if (int e = check_buf(p, d.res2_buf, d.res2_ch_off, d.cout, "rsb_plan_add_conv(res2)")) return e;
+      if (p->bufs[d.res2_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: res2 grid mismatch");
+    }
+  }
+  c.scale = scale;
+  const size_t wn = (size_t)d.cout * d.cin * d.kh * d.kw;
+  c.w.assign(d.weight, d.weight + wn);
+  if (d.bias) c.b.assign(d.bias, d.bias + d.cout);
+  if (d.act == RSB_ACT_PRELU) c.slopes.assign(d.act_slopes, d.act_slopes + d.cout);
+  c.d.weight = nullptr, c.d.bias = nullptr, c.d.act_slopes = nullptr;
+  c.cin_pad16 = ceil_div(d.cin, 16) * 16;
+  c.npad = ceil_div(d.cout, 16) * 16;
+  c.cpad32 = ceil_div(d.cout, 32) * 32;
+  c.cin_planes = ceil_div(d.cin, 8);
+  p->convs.push_back(std::move(c));
+  p->ops.push_back({0, (int)p->convs.size() - 1});
+  return 0;
+}
+
+int rsb_plan_add_groupnorm(rsb_plan* p, const rsb_groupnorm_desc* desc) {
+  if (!p || !desc) return fail(RSB_ERR_INVALID, "rsb_plan_add_groupnorm: NULL argument");
+  if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_groupnorm: plan already finalized");
+  const rsb_groupnorm_desc& d = *desc;
+  if (d.groups < 1 || d.channels < 1 || d.channels % d.groups != 0 || (d.channels / d.groups) % 8 != 0)
+    return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_groupnorm: channels per group must be a multiple of 8 (%d / %d)", d.channels, d.groups);
+  if (!d.gamma || !d.beta) return fail(RSB_ERR_INVALID, "rsb_plan_add_groupnorm: gamma/beta NULL");
+  if (int e = check_buf(p, d.src_buf, d.src_ch_off, d.channels, "rsb_plan_add_groupnorm(src)")) return e;
+  if (int e = check_buf(p, d.dst_buf, d.dst_ch_off, d.channels, "rsb_plan_add_groupnorm(dst)")) return e;
+  if (d.skip_buf >= 0)
+    if (int e = check_buf(p, d.skip_buf, d.skip_ch_off, d.channels, "rsb_plan_add_groupnorm(skip)")) return e;
+  GnOp g;
+  g.d = d;
+  g.gamma.assign(d.gamma, d.gamma + d.channels);
+  g.beta.assign(d.beta, d.beta + d.channels);
+  g.d.gamma = nullptr, g.d.beta = nullptr;
+  g.scale = p->bufs[d.src_buf].scale;
+  p->gns.push_back(std::move(g));
+  p->ops.push_back({1, (int)p->gns.size() - 1});
+  return 0;
+}
+
+int rsb_plan_finalize(rsb_plan* p, int device) {
+  if (!p) return fail(RSB_ERR_INVALID, "rsb_plan_finalize: NULL plan");
+  if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_finalize: already finalized");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return fail(RSB_ERR_NO_DEVICE, "rsb_plan_finalize: CUDA device %d not available (%d visible)", device, count);
+  }
+  cudaDeviceProp prop;
+  RSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(RSB_ERR_NO_DEVICE, "rsb_plan_finalize: device %d is sm_%d%d; this library only contains sm_100a code", device, prop.major, prop.minor);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  RSB_CUDA(cudaSetDevice(device));
+  p->device = device;
+  p->num_sms = prop.multiProcessorCount;
+  RSB_CUDA(rsb::conv_tc_configure(kMaxSmem));
+
+  for (ConvOp& c : p->convs) {
+    const rsb_conv_desc& d = c.d;
+    const int taps = d.kh * d.kw;
+    // ---- tensor-core eligibility (bf16 plan, planar source, operands fit shared memory)
+    c.tc_ok = false;
+    if (p->dtype == RSB_BF16 && d.src_buf >= 0 && !d.src_upsample2 && c.npad <= 256) {
+      const Buffer& sb = p->bufs[d.src_buf];
+      const bool planes_ok = d.src_ch_off / 8 + c.cin_pad16 / 8 <= sb.planes;
+      const int WT = rsb::kTileW + d.kw - 1, HT = rsb::kTileH + d.kh - 1;
+      int stages = 0;
+      for (int s = 4; s >= 2; --s)
+        if (rsb::conv_tc_smem_bytes(c.cin_pad16, c.npad, d.kh, d.kw, s) <= kMaxSmem) {
+          stages = s;
+          break;
+        }
+      if (planes_ok && stages >= 2 && 8 * WT <= 256 && HT <= 256 && HT * WT < 16384) {
+        c.tc_ok = true;
+        c.stages = stages;
+      }
+    }
+    const int cmax = std::max(c.npad, c.cpad32);
+    std::vector<float> bias(cmax, 0.0f), slopes(cmax, 0.0f);
+    for (int o = 0; o < d.cout; ++o) {
+      if (!c.b.empty()) bias[o] = c.b[o];
+      if (!c.slopes.empty()) slopes[o] = c.slopes[o];
+    }
+    RSB_CUDA(cudaMalloc(&c.d_bias, cmax * sizeof(float)));
+    RSB_CUDA(cudaMemcpy(c.d_bias, bias.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));
+    if (d.act == RSB_ACT_PRELU) {
+      RSB_CUDA(cudaMalloc(&c.d_slopes, cmax * sizeof(float)));
+      RSB_CUDA(cudaMemcpy(c.d_slopes, slopes.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (c.tc_ok) {
+      // [tap][cin/8][npad][8] bf16: per (tap, 8-channel slab) an N x 8 K-major panel of 128-byte core matrices
+      const int cin8 = c.cin_pad16 / 8;
+      std::vector<uint16_t> wp((size_t)taps * cin8 * c.npad * 8, 0);
+      for (int o = 0; o < d.cout; ++o)
+        for (int ci = 0; ci < d.cin; ++ci)
+          for (int t = 0; t < taps; ++t)
+            wp[(((size_t)t * cin8 + ci / 8) * c.npad + o) * 8 + (ci & 7)] = f32_to_bf16(c.w[((size_t)o * d.cin + ci) * taps + t]);
+      c.wbytes_tc = (uint32_t)(wp.size() * 2);
+      RSB_CUDA(cudaMalloc(&c.d_wtc, c.wbytes_tc));
+      RSB_CUDA(cudaMemcpy(c.d_wtc, wp.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
+    }
+    {
+      // [cin_planes][kh][kw][8][cpad32] fp32 for the CUDA-core kernel
+      std::vector<float> wp((size_t)c.cin_planes * taps * 8 * c.cpad32, 0.0f);
+      for (int o = 0; o < d.cout; ++o)
+        for (int ci = 0; ci < d.cin; ++ci)
+          for (int t = 0; t < taps; ++t)
+            wp[((((size_t)(ci / 8)) * taps + t) * 8 + (ci & 7)) * c.cpad32 + o] = c.w[((size_t)o * d.cin + ci) * taps + t];
+      RSB_CUDA(cudaMalloc(&c.d_wdirect, wp.size() * sizeof(float)));
+      RSB_CUDA(cudaMemcpy(c.d_wdirect, wp.data(), wp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    std::vector<float>().swap(c.w);
+  }
+  for (GnOp& g : p->gns) {
+    RSB_CUDA(cudaMalloc(&g.d_gamma, g.gamma.size() * sizeof(float)));
+    RSB_CUDA(cudaMalloc(&g.d_beta, g.beta.size() * sizeof(float)));
+    RSB_CUDA(cudaMemcpy(g.d_gamma, g.gamma.data(), g.gamma.size() * sizeof(float), cudaMemcpyHostToDevice));
+    RSB_CUDA(cudaMemcpy(g.d_beta, g.beta.data(), g.beta.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  p->finalized = true;
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  return 0;
+}
+
+int rsb_plan_num_ops(const rsb_plan* p) { return p ? (int)p->ops.size() : 0; }
+
+int rsb_plan_launches_per_forward(const rsb_plan* p) {
+  if (!p) return 0;
+  return (int)p->convs.size() + 2 * (int)p->gns.size();
+}
+
+int rsb_plan_flops(const rsb_plan* p, int n, int h, int w, double* flops) {
+  if (!p || !flops) return fail(RSB_ERR_INVALID, "rsb_plan_flops: NULL argument");
+  double f = 0.0;
+  for (const ConvOp& c : p->convs)
+    f += 2.0 * c.d.cout * c.d.cin * c.d.kh * c.d.kw * (double)n * (h * c.scale) * (double)(w * c.scale);
+  *flops = f;
+  return 0;
+}
+
+int rsb_plan_workspace_bytes(const rsb_plan* p, int n, int h, int w, size_t* bytes) {
+  if (!p || !bytes) return fail(RSB_ERR_INVALID, "rsb_plan_workspace_bytes: NULL argument");
+  if (n < 1 || h < 1 || w < 1) return fail(RSB_ERR_INVALID, "rsb_plan_workspace_bytes: bad shape");
+  return layout(p, n, h, w, nullptr, nullptr, bytes);
+}
+
+int rsb_plan_forward(rsb_plan* p, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype, void* workspace,
+                     size_t workspace_bytes, void* stream_, int force_direct) {
+  if (!p || !x || !y || !workspace) return fail(RSB_ERR_INVALID, "rsb_plan_forward: NULL argument");
+  if (!p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_forward: plan not finalized");
+  if (n < 1 || h < 1 || w < 1) return fail(RSB_ERR_INVALID, "rsb_plan_forward: bad shape %dx%dx%d", n, h, w);
+  if (x_dtype < RSB_F32 || x_dtype > RSB_F16 || y_dtype < RSB_F32 || y_dtype > RSB_F16)
+    return fail(RSB_ERR_INVALID, "rsb_plan_forward: bad tensor dtype");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  std::lock_guard<std::mutex> lock(p->mu);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != p->device) RSB_CUDA(cudaSetDevice(p->device));
+  int rc = 0;
+  if (p->bn != n || p->bh != h || p->bw != w || p->bws != workspace) rc = bind(p, n, h, w, workspace, workspace_bytes, stream);
+  if (rc == 0) {
+    for (const Op& op : p->ops) {
+      cudaError_t e;
+      if (op.kind == 0) {
+        ConvOp& c = p->convs[op.index];
+        if (c.tc_ok && !force_direct) {
+          rsb::ConvTcParams t = c.tcp;
+          if (t.epi.dst_external) t.epi.dst = y, t.epi.out_dtype = y_dtype;
+          t.epi.base = x, t.epi.base_dtype = x_dtype;
+          e = rsb::launch_conv_tc(c.map, t, p->num_sms, stream);
+        } else {
+          rsb::ConvDirectParams q = c.dp;
+          if (q.src_external) q.src = x, q.src_dtype = x_dtype;
+          if (q.epi.dst_external) q.epi.dst = y, q.epi.out_dtype = y_dtype;
+          q.epi.base = x, q.epi.base_dtype = x_dtype;
+          e = rsb::launch_conv_direct(q, p->dtype == RSB_BF16, stream);
+        }
+      } else {
+        e = rsb::launch_groupnorm(p->gns[op.index].gp, p->dtype == RSB_BF16, stream);
+      }
+      if (e != cudaSuccess) {
+        rc = fail_cuda(e, "kernel launch");
+        break;
+      }
+    }
+  }
+  if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
+  return rc;
+}
+
+int rsb_plan_read_buffer(rsb_plan* p, int buf_id, int ch_off, int channels, float* dst_nchw, void* stream_) {
+  if (!p || !dst_nchw) return fail(RSB_ERR_INVALID, "rsb_plan_read_buffer: NULL argument");
+  if (!p->bws) return fail(RSB_ERR_STATE, "rsb_plan_read_buffer: no forward has run yet");
+  if (int e = check_buf(p, buf_id, ch_off, channels, "rsb_plan_read_buffer")) return e;
+  const Buffer& b = p->bufs[buf_id];
+  cudaError_t e = rsb::launch_planar_to_nchw(reinterpret_cast<uint8_t*>(p->bws) + b.offset, p->dtype == RSB_BF16, p->bn, b.planes,
+                                             ch_off / 8, channels, p->bh * b.scale, p->bw * b.scale, dst_nchw,
+                                             reinterpret_cast<cudaStream_t>(stream_));
+  if (e != cudaSuccess) return fail_cuda(e, "planar_to_nchw");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""Base class of the engine-backed ``nn.Module``s the architecture plugins return.
+
+The module owns parameters/buffers under exactly the names of the reference checkpoint (so the
+registry's strict ``load_state_dict`` passes, /root/reference/resselt/registry.py:112-113) and
+lazily compiles them into a native plan per (device, compute dtype).  ``forward`` is a C-ABI call;
+there is no PyTorch-op fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .plan import Plan, PlanBuilder
+
+
+class ParamGroup(nn.Module):
+    """Name-space node of the parameter tree (mirrors the reference's sub-module names)."""
+
+
+ParamSpec = Tuple[str, Tuple[int, ...], str]  # (dotted name, shape, kind)
+# kinds: 'conv_w', 'bias:<fan_in>', 'prelu', 'ones', 'zeros', 'buffer_zeros', 'normal:<std>'
+
+
+def _init_tensor(shape, kind: str, rng: np.random.RandomState) -> torch.Tensor:
+    if kind == 'conv_w':
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
+        bound = 1.0 / math.sqrt(max(fan_in, 1))
+        a = rng.uniform(-bound, bound, size=shape)
+    elif kind.startswith('bias:'):
+        bound = 1.0 / math.sqrt(max(int(kind.split(':')[1]), 1))
+        a = rng.uniform(-bound, bound, size=shape)
+    elif kind == 'prelu':
+        a = np.full(shape, 0.25) + rng.uniform(-0.1, 0.1, size=shape)
+    elif kind == 'ones':
+        a = np.ones(shape)
+    elif kind in ('zeros', 'buffer_zeros'):
+        a = np.zeros(shape)
+    elif kind.startswith('normal:'):
+        a = rng.normal(0.0, float(kind.split(':')[1]), size=shape)
+    elif kind.startswith('affine_w'):
+        a = 1.0 + rng.uniform(-0.2, 0.2, size=shape)
+    else:
+        raise ValueError(f'unknown init kind {kind}')
+    return torch.from_numpy(np.asarray(a, dtype=np.float32).reshape(shape))
+
+
+def random_state_dict(specs: Iterable[ParamSpec], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic (numpy RandomState) weights for a parameter spec — used by tests, bench and fixtures."""
+    rng = np.random.RandomState(seed)
+    return {name: _init_tensor(shape, kind, rng) for name, shape, kind in specs}
+
+
+class EngineModule(nn.Module):
+    def __init__(self, specs: Iterable[ParamSpec], in_channels: int, out_channels: int, upscale: int, seed: int = 0):
+        super().__init__()
+        self.in_channels, self.out_channels, self.upscale = in_channels, out_channels, upscale
+        self._plans: Dict[Tuple[int, torch.dtype], Plan] = {}
+        self._plan_stamp: Dict[Tuple[int, torch.dtype], int] = {}
+        rng = np.random.RandomState(seed)
+        for name, shape, kind in specs:
+            self._register(name, _init_tensor(shape, kind, rng), is_buffer=kind.startswith('buffer'))
+
+    # ---------------------------------------------------------------- parameter tree
+    def _register(self, dotted: str, value: torch.Tensor, is_buffer: bool) -> None:
+        node: nn.Module = self
+        *path, leaf = dotted.split('.')
+        for part in path:
+            child = node._modules.get(part)
+            if child is None:
+                child = ParamGroup()
+                node.add_module(part, child)
+            node = child
+        if is_buffer:
+            node.register_buffer(leaf, value)
+        else:
+            node.register_parameter(leaf, nn.Parameter(value, requires_grad=False))
+
+    def _weights(self) -> Dict[str, torch.Tensor]:
+        """fp64 host copies of every parameter/buffer, keyed like the checkpoint."""
+        return {k: v.detach().to('cpu', torch.float64) for k, v in self.state_dict().items()}
+
+    def _stamp(self) -> int:
+        s = 0
+        for t in self.parameters():
+            s += t._version + (id(t) & 0xFFFF)
+        for t in self.buffers():
+            s += t._version + (id(t) & 0xFFFF)
+        return s
+
+    # ---------------------------------------------------------------- plan management
+    def build_plan(self, pb: PlanBuilder, w: Dict[str, torch.Tensor]) -> None:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def invalidate(self) -> None:
+        self._plans.clear()
+        self._plan_stamp.clear()
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate()
+        return super().load_state_dict(*args, **kwargs)
+
+    @staticmethod
+    def compute_dtype_for(x_dtype: torch.dtype) -> torch.dtype:
+        # bf16 tensors take the tcgen05 path; fp32 and fp16 tensors the fp32 CUDA-core path
+        return torch.bfloat16 if x_dtype == torch.bfloat16 else torch.float32
+
+    def plan_for(self, device: torch.device, x_dtype: torch.dtype) -> Plan:
+        if device.type != 'cuda':
+            raise RuntimeError(
+                'resselt_b200 modules run on CUDA sm_100 (B200) devices only; there is no CPU path. '
+                f'Got an input on {device}.'
+            )
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        cdt = self.compute_dtype_for(x_dtype)
+        key = (index, cdt)
+        stamp = self._stamp()
+        plan = self._plans.get(key)
+        if plan is None or self._plan_stamp.get(key) != stamp:
+            pb = PlanBuilder(cdt, self.in_channels, self.out_channels, self.upscale)
+            self.build_plan(pb, self._weights())
+            plan = pb.finalize(torch.device('cuda', index))
+            self._plans[key] = plan
+            self._plan_stamp[key] = stamp
+        return plan
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.plan_for(x.device, x.dtype).forward(x)

@@ -1,0 +1,140 @@
+"""ctypes binding of the C ABI declared in include/resselt_b200.h.
+
+The shared library is built in-tree (resselt_b200/csrc/libresselt_b200.so) by ``build_library`` /
+``__graft_entry__.build``.  There is no CPU implementation behind this module: if the library is
+missing or no sm_100 device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'csrc'))
+LIB_PATH = os.path.join(CSRC_DIR, 'libresselt_b200.so')
+SOURCES = ('conv_tc.cu', 'conv_direct.cu', 'plan.cu')
+HEADERS = ('kernels.cuh', 'ptx.cuh', os.path.join('..', '..', 'include', 'resselt_b200.h'))
+NVCC_FLAGS = (
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+    '-Xcompiler', '-fPIC', '-shared',
+)
+
+# enums (keep in sync with include/resselt_b200.h)
+F32, BF16, F16 = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_MISH, ACT_LRELU, ACT_PRELU, ACT_SIGMOID, ACT_GELU = range(7)
+COMB_NONE, COMB_SPAB_GATE, COMB_MUL, COMB_AXPY = range(4)
+EXTERNAL_INPUT, EXTERNAL_OUTPUT, NO_BUFFER = -1, -2, -3
+
+EXPORTED_SYMBOLS = (
+    'rsb_version', 'rsb_last_error', 'rsb_device_count', 'rsb_plan_create', 'rsb_plan_destroy',
+    'rsb_plan_add_buffer', 'rsb_plan_add_conv', 'rsb_plan_add_groupnorm', 'rsb_plan_finalize',
+    'rsb_plan_num_ops', 'rsb_plan_launches_per_forward', 'rsb_plan_flops', 'rsb_plan_workspace_bytes',
+    'rsb_plan_forward', 'rsb_plan_read_buffer',
+)
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f'resselt_b200 native error {code}: {message}')
+        self.code = code
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ('src_buf', C.c_int32), ('src_ch_off', C.c_int32), ('cin', C.c_int32),
+        ('dst_buf', C.c_int32), ('dst_ch_off', C.c_int32), ('cout', C.c_int32),
+        ('kh', C.c_int32), ('kw', C.c_int32),
+        ('weight', C.POINTER(C.c_float)), ('bias', C.POINTER(C.c_float)),
+        ('act', C.c_int32), ('act_param', C.c_float), ('act_slopes', C.POINTER(C.c_float)),
+        ('combine', C.c_int32),
+        ('res1_buf', C.c_int32), ('res1_ch_off', C.c_int32),
+        ('res2_buf', C.c_int32), ('res2_ch_off', C.c_int32),
+        ('alpha', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float),
+        ('in_mean', C.c_float * 4), ('in_scale', C.c_float),
+        ('ps', C.c_int32), ('add_base', C.c_int32), ('out_scale', C.c_float), ('out_mean', C.c_float * 4),
+        ('src_upsample2', C.c_int32),
+    ]
+
+
+class GroupNormDesc(C.Structure):
+    _fields_ = [
+        ('src_buf', C.c_int32), ('src_ch_off', C.c_int32),
+        ('dst_buf', C.c_int32), ('dst_ch_off', C.c_int32),
+        ('channels', C.c_int32), ('groups', C.c_int32), ('eps', C.c_float),
+        ('gamma', C.POINTER(C.c_float)), ('beta', C.POINTER(C.c_float)),
+        ('skip_buf', C.c_int32), ('skip_ch_off', C.c_int32),
+    ]
+
+
+def library_is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC_DIR, f) for f in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into one shared library (nvcc cross-compiles without a GPU)."""
+    if not force and not library_is_stale():
+        return LIB_PATH
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found: cannot build libresselt_b200.so')
+    cmd = [nvcc, *NVCC_FLAGS, '-o', LIB_PATH + '.tmp', *SOURCES]
+    proc = subprocess.run(cmd, cwd=CSRC_DIR, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + proc.stdout + proc.stderr)
+    os.replace(LIB_PATH + '.tmp', LIB_PATH)
+    if verbose:
+        print(proc.stdout + proc.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load the native library (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                '(resselt_b200 has no CPU or PyTorch fallback path)'
+            )
+        L = C.CDLL(LIB_PATH)
+        L.rsb_version.restype = C.c_int
+        L.rsb_last_error.restype = C.c_char_p
+        L.rsb_device_count.restype = C.c_int
+        L.rsb_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rsb_plan_destroy.argtypes = [C.c_void_p]
+        L.rsb_plan_add_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.rsb_plan_add_conv.argtypes = [C.c_void_p, C.POINTER(ConvDesc)]
+        L.rsb_plan_add_groupnorm.argtypes = [C.c_void_p, C.POINTER(GroupNormDesc)]
+        L.rsb_plan_finalize.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_plan_num_ops.argtypes = [C.c_void_p]
+        L.rsb_plan_launches_per_forward.argtypes = [C.c_void_p]
+        L.rsb_plan_flops.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.rsb_plan_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.rsb_plan_forward.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+            C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+        ]
+        L.rsb_plan_read_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        for name in EXPORTED_SYMBOLS:
+            getattr(L, name)  # AttributeError if the library does not export the declared ABI
+        _lib = L
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise NativeError(code, (lib().rsb_last_error() or b'').decode('utf-8', 'replace'))

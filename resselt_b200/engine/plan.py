@@ -1,0 +1,206 @@
+"""Python face of a native plan: the layer program an architecture plugin emits.
+
+``PlanBuilder`` records buffers and fused ops through the C ABI (include/resselt_b200.h);
+``Plan`` owns the finalised native handle and replays it on tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import native as N
+
+_TORCH_TO_RSB = {torch.float32: N.F32, torch.bfloat16: N.BF16, torch.float16: N.F16}
+
+
+def _f32(a) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        a = a.detach().to('cpu', torch.float64).numpy()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _fptr(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+class Ref:
+    """A channel range [ch_off, ch_off + channels) of a plan buffer."""
+
+    __slots__ = ('buf', 'ch_off', 'channels')
+
+    def __init__(self, buf: int, ch_off: int, channels: int):
+        self.buf, self.ch_off, self.channels = buf, ch_off, channels
+
+    def slice(self, start: int, channels: int) -> 'Ref':
+        assert start + channels <= self.channels
+        return Ref(self.buf, self.ch_off + start, channels)
+
+
+INPUT = Ref(N.EXTERNAL_INPUT, 0, 0)
+OUTPUT = Ref(N.EXTERNAL_OUTPUT, 0, 0)
+
+
+class PlanBuilder:
+    def __init__(self, compute_dtype: torch.dtype, in_channels: int, out_channels: int, upscale: int):
+        self._lib = N.lib()
+        handle = C.c_void_p()
+        N.check(self._lib.rsb_plan_create(_TORCH_TO_RSB[compute_dtype], in_channels, out_channels, upscale, C.byref(handle)))
+        self._h = handle
+        self.compute_dtype = compute_dtype
+        self.in_channels, self.out_channels, self.upscale = in_channels, out_channels, upscale
+        self.scales = {}
+
+    def buffer(self, channels: int, scale: int = 1) -> Ref:
+        bid = C.c_int()
+        N.check(self._lib.rsb_plan_add_buffer(self._h, channels, scale, C.byref(bid)))
+        self.scales[bid.value] = scale
+        return Ref(bid.value, 0, channels)
+
+    def conv(
+        self,
+        src: Ref,
+        dst: Ref,
+        weight,
+        bias=None,
+        *,
+        act: int = N.ACT_NONE,
+        act_param: float = 0.0,
+        act_slopes=None,
+        combine: int = N.COMB_NONE,
+        res1: Optional[Ref] = None,
+        res2: Optional[Ref] = None,
+        alpha: float = 1.0,
+        beta1: float = 1.0,
+        beta2: float = 1.0,
+        in_mean: Sequence[float] = (0.0, 0.0, 0.0, 0.0),
+        in_scale: float = 1.0,
+        ps: int = 1,
+        add_base: bool = False,
+        out_scale: float = 1.0,
+        out_mean: Sequence[float] = (0.0, 0.0, 0.0, 0.0),
+        src_upsample2: bool = False,
+    ) -> None:
+        w = _f32(weight)
+        assert w.ndim == 4, 'conv weight must be [cout][cin][kh][kw]'
+        cout, cin, kh, kw = w.shape
+        b = _f32(bias) if bias is not None else None
+        s = _f32(act_slopes) if act_slopes is not None else None
+        d = N.ConvDesc()
+        d.src_buf, d.src_ch_off, d.cin = src.buf, src.ch_off, cin
+        d.dst_buf, d.dst_ch_off, d.cout = dst.buf, dst.ch_off, cout
+        if src.buf >= 0:
+            assert src.channels == cin, f'conv reads {cin} channels, source range has {src.channels}'
+        if dst.buf >= 0:
+            assert dst.channels == cout, f'conv writes {cout} channels, destination range has {dst.channels}'
+        d.kh, d.kw = kh, kw
+        d.weight, d.bias = _fptr(w), _fptr(b)
+        d.act, d.act_param, d.act_slopes = act, float(act_param), _fptr(s)
+        d.combine = combine
+        d.res1_buf, d.res1_ch_off = (res1.buf, res1.ch_off) if res1 is not None else (N.NO_BUFFER, 0)
+        d.res2_buf, d.res2_ch_off = (res2.buf, res2.ch_off) if res2 is not None else (N.NO_BUFFER, 0)
+        d.alpha, d.beta1, d.beta2 = float(alpha), float(beta1), float(beta2)
+        mean4 = (list(in_mean) + [0.0] * 4)[:4]
+        d.in_mean = (C.c_float * 4)(*mean4)
+        d.in_scale = float(in_scale)
+        d.ps, d.add_base, d.out_scale = int(ps), int(bool(add_base)), float(out_scale)
+        omean4 = (list(out_mean) + [0.0] * 4)[:4]
+        d.out_mean = (C.c_float * 4)(*omean4)
+        d.src_upsample2 = int(bool(src_upsample2))
+        N.check(self._lib.rsb_plan_add_conv(self._h, C.byref(d)))
+
+    def groupnorm(self, src: Ref, dst: Ref, groups: int, gamma, beta, eps: float = 1e-5, skip: Optional[Ref] = None) -> None:
+        g, b = _f32(gamma), _f32(beta)
+        d = N.GroupNormDesc()
+        d.src_buf, d.src_ch_off = src.buf, src.ch_off
+        d.dst_buf, d.dst_ch_off = dst.buf, dst.ch_off
+        d.channels, d.groups, d.eps = src.channels, groups, float(eps)
+        d.gamma, d.beta = _fptr(g), _fptr(b)
+        d.skip_buf, d.skip_ch_off = (skip.buf, skip.ch_off) if skip is not None else (N.NO_BUFFER, 0)
+        N.check(self._lib.rsb_plan_add_groupnorm(self._h, C.byref(d)))
+
+    def finalize(self, device: torch.device) -> 'Plan':
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        N.check(self._lib.rsb_plan_finalize(self._h, index))
+        handle, self._h = self._h, None
+        return Plan(handle, self, torch.device('cuda', index))
+
+    def __del__(self):
+        if getattr(self, '_h', None):
+            self._lib.rsb_plan_destroy(self._h)
+
+
+class Plan:
+    """Finalised native plan bound to one CUDA device."""
+
+    def __init__(self, handle, builder: PlanBuilder, device: torch.device):
+        self._lib = builder._lib
+        self._h = handle
+        self.device = device
+        self.compute_dtype = builder.compute_dtype
+        self.in_channels, self.out_channels, self.upscale = builder.in_channels, builder.out_channels, builder.upscale
+        self._workspace: Optional[torch.Tensor] = None
+        self._ws_shape = None
+        self.force_direct = False
+        self._scale_of = dict(builder.scales)
+        weakref.finalize(self, self._lib.rsb_plan_destroy, handle)
+
+    @property
+    def launches_per_forward(self) -> int:
+        return int(self._lib.rsb_plan_launches_per_forward(self._h))
+
+    def flops(self, n: int, h: int, w: int) -> float:
+        out = C.c_double()
+        N.check(self._lib.rsb_plan_flops(self._h, n, h, w, C.byref(out)))
+        return out.value
+
+    def workspace_bytes(self, n: int, h: int, w: int) -> int:
+        out = C.c_size_t()
+        N.check(self._lib.rsb_plan_workspace_bytes(self._h, n, h, w, C.byref(out)))
+        return int(out.value)
+
+    def _workspace_for(self, n: int, h: int, w: int) -> torch.Tensor:
+        if self._ws_shape != (n, h, w):
+            self._workspace = None  # release before allocating the next one
+            nbytes = self.workspace_bytes(n, h, w)
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            shift = (-raw.data_ptr()) % 1024
+            self._workspace = raw[shift:shift + nbytes]
+            self._ws_shape = (n, h, w)
+        return self._workspace
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x.device != self.device:
+            raise RuntimeError(f'plan lives on {self.device}, input is on {x.device}')
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise RuntimeError(f'expected NCHW input with {self.in_channels} channels, got {tuple(x.shape)}')
+        if x.dtype not in _TORCH_TO_RSB:
+            raise RuntimeError(f'unsupported input dtype {x.dtype}')
+        x = x.contiguous()
+        n, _, h, w = x.shape
+        shape = (n, self.out_channels, h * self.upscale, w * self.upscale)
+        if out is None:
+            out = torch.empty(shape, dtype=x.dtype, device=x.device)
+        elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in _TORCH_TO_RSB:
+            raise RuntimeError('out tensor has the wrong shape/layout')
+        ws = self._workspace_for(n, h, w)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(
+            self._lib.rsb_plan_forward(
+                self._h, x.data_ptr(), _TORCH_TO_RSB[x.dtype], n, h, w, out.data_ptr(), _TORCH_TO_RSB[out.dtype],
+                ws.data_ptr(), ws.numel(), stream, int(self.force_direct),
+            )
+        )
+        return out
+
+    def read_buffer(self, ref: Ref) -> torch.Tensor:
+        """Debug/test helper: fp32 NCHW copy of a buffer range after the last forward."""
+        n, h, w = self._ws_shape
+        scale = self._scale_of[ref.buf]
+        dst = torch.empty((n, ref.channels, h * scale, w * scale), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(self._lib.rsb_plan_read_buffer(self._h, ref.buf, ref.ch_off, ref.channels, dst.data_ptr(), stream))
+        return dst
