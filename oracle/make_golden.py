@@ -1,0 +1,70 @@
+"""Generate tests/golden/*.npz from the LIVE reference (run in the build container only).
+
+    python oracle/make_golden.py
+
+For every case: weights come from the engine's deterministic ``random_state_dict`` (numpy
+RandomState, so tests can regenerate them anywhere from the recorded seed), are loaded through the
+*reference's own* ``resselt.load_from_state_dict`` (strict), and the reference's fp32 CPU forward
+output is stored together with the input.  The reference is imported from /root/reference; it does
+not travel to the GPU box — the fixtures do.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+def cases():
+    """name -> (engine class path, constructor kwargs, weight seed, input shape, input seed)."""
+    return {
+        'span_x2_f48': ('SPAN', dict(num_in_ch=3, num_out_ch=3, feature_channels=48, upscale=2), 11, (1, 3, 20, 28), 101),
+        'span_x4_f32_nonorm': ('SPAN', dict(num_in_ch=3, num_out_ch=3, feature_channels=32, upscale=4, norm=False), 12, (1, 3, 16, 16), 102),
+        'spanplus_x2_b4': ('SPANPlus', dict(num_in_ch=3, num_out_ch=3, blocks=[4], feature_channels=48, upscale=2, upsampler='ps'), 13, (1, 3, 24, 20), 103),
+        'spanplus_x2_b2_3': ('SPANPlus', dict(num_in_ch=3, num_out_ch=3, blocks=[2, 3], feature_channels=32, upscale=2, upsampler='ps'), 14, (2, 3, 16, 18), 104),
+        'compact_x4_nf64_nc16': ('Compact', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_conv=16, upscale=4), 15, (1, 3, 18, 22), 105),
+        'compact_x2_nf24_nc8': ('Compact', dict(num_in_ch=3, num_out_ch=3, num_feat=24, num_conv=8, upscale=2), 16, (2, 3, 16, 12), 106),
+    }
+
+
+def engine_model(kind: str, kwargs: dict, seed: int):
+    from resselt_b200 import archs
+
+    cls = {'SPAN': archs.SPAN, 'SPANPlus': archs.SpanPlus, 'Compact': archs.SRVGGNetCompact}
+    extra = {k: getattr(archs, k) for k in ('RRDBNet', 'RealPLKSR') if hasattr(archs, k)}
+    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR')})
+    return cls[kind](seed=seed, **kwargs)
+
+
+def main():
+    import resselt as reference  # the unmodified reference package
+
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    index = {}
+    for name, (kind, kwargs, wseed, xshape, xseed) in cases().items():
+        sd = {k: v.clone() for k, v in engine_model(kind, kwargs, wseed).state_dict().items()}
+        ref_model = reference.load_from_state_dict(dict(sd)).eval()
+        x = torch.from_numpy(np.random.RandomState(xseed).rand(*xshape).astype(np.float32))
+        with torch.inference_mode():
+            y = ref_model(x)
+        info = ref_model.parameters_info
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + '.npz'), x=x.numpy(), y=y.numpy().astype(np.float32))
+        index[name] = dict(kind=kind, kwargs=kwargs, weight_seed=wseed, x_shape=list(xshape), x_seed=xseed,
+                           meta=dict(name=info.name, in_channels=info.in_channels, out_channels=info.out_channels, upscale=info.upscale),
+                           y_min=float(y.min()), y_max=float(y.max()))
+        print(f'{name}: y {tuple(y.shape)} range [{float(y.min()):.4f}, {float(y.max()):.4f}]')
+    with open(os.path.join(GOLDEN_DIR, 'index.json'), 'w') as f:
+        json.dump(dict(reference='rewaifu/resselt v1.4.1 @ /root/reference', torch=torch.__version__, cases=index), f, indent=1, sort_keys=True)
+
+
+if __name__ == '__main__':
+    main()

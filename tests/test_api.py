@@ -1,0 +1,146 @@
+"""Drop-in behaviour of the loading API (reference: resselt/__init__.py, registry.py, factory/, utilities/state_dict.py)."""
+import collections
+import os
+import pickle
+
+import pytest
+import torch
+
+import resselt_b200
+from resselt_b200.archs import SPAN, SpanPlus, SRVGGNetCompact, internal_registry
+from resselt_b200.factory import Architecture, KeyCondition
+from resselt_b200.factory.arch import ModelMetadata
+from resselt_b200.registry import ArchitectureNotFound, Registry
+from resselt_b200.utilities.state_dict import canonicalize_state_dict, get_seq_len, pixelshuffle_scale
+
+
+def _sd(model):
+    return {k: v.clone() for k, v in model.state_dict().items()}
+
+
+def test_public_surface():
+    assert resselt_b200.__all__ == ['add', 'get', 'load_from_file', 'load_from_state_dict']
+    assert {'SPAN', 'spanplus', 'Compact'} <= set(internal_registry.store)
+    assert resselt_b200.get('SPAN').id == 'SPAN'
+    with pytest.raises(KeyError):  # same as the reference's dict lookup (registry.py:74)
+        resselt_b200.get('nope')
+
+
+def test_metadata_field_order():
+    m = ModelMetadata(3, 4, 2, 'x')
+    assert (m.in_channels, m.out_channels, m.upscale, m.name) == (3, 4, 2, 'x')
+
+
+@pytest.mark.parametrize(
+    'model,meta',
+    [
+        (SPAN(feature_channels=48, upscale=2), ('SPAN', 3, 3, 2)),
+        (SPAN(feature_channels=32, upscale=4, norm=False), ('SPAN', 3, 3, 4)),
+        (SPAN(num_in_ch=1, num_out_ch=1, feature_channels=56, upscale=2, norm=False), ('SPAN', 1, 1, 2)),
+        (SpanPlus(blocks=[4], upscale=2), ('SPANPlus', 3, 3, 2)),
+        (SpanPlus(blocks=[2, 3], feature_channels=32, upscale=4), ('SPANPlus', 3, 3, 4)),
+        (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4), ('Compact', 3, 3, 4)),
+        (SRVGGNetCompact(num_feat=24, num_conv=8, upscale=2), ('Compact', 3, 3, 2)),
+        (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=1), ('Compact', 3, 3, 1)),
+    ],
+)
+def test_detect_and_hyperparameter_inference(model, meta):
+    sd = _sd(model)
+    loaded = resselt_b200.load_from_state_dict(dict(sd))
+    info = loaded.parameters_info
+    assert (info.name, info.in_channels, info.out_channels, info.upscale) == meta
+    assert type(loaded) is type(model)
+    assert list(loaded.state_dict()) == list(sd)  # same names, same order -> strict load passed
+    for k, v in loaded.state_dict().items():
+        assert torch.equal(v, sd[k])
+    if isinstance(model, SpanPlus):
+        assert loaded.blocks == model.blocks
+    if isinstance(model, SPAN):
+        assert loaded.norm == model.norm
+
+
+def test_wrapped_and_prefixed_checkpoints():
+    sd = _sd(SRVGGNetCompact(num_feat=16, num_conv=2, upscale=2))
+    wrapped = {'params_ema': {'module.' + k: v for k, v in sd.items()}}
+    assert resselt_b200.load_from_state_dict(wrapped).parameters_info.name == 'Compact'
+    assert list(canonicalize_state_dict({'state_dict': {'netG.a': 1, 'netG.b': 2}})) == ['a', 'b']
+    assert list(canonicalize_state_dict({'module.a': 1, 'b': 2})) == ['module.a', 'b']  # prefix only if on every key
+
+
+def test_no_norm_marker_is_normalised_in_callers_dict():
+    sd = _sd(SPAN(feature_channels=16, upscale=2, norm=False))
+    sd['no_norm'] = torch.ones(1) * 5
+    resselt_b200.load_from_state_dict(sd)
+    assert torch.equal(sd['no_norm'], torch.zeros(1))  # reference mutates the dict the same way (span/__init__.py:41-43)
+
+
+def test_unknown_state_dict_and_strict_mismatch():
+    with pytest.raises(ArchitectureNotFound):
+        resselt_b200.load_from_state_dict({'foo.weight': torch.zeros(1)})
+    sd = _sd(SRVGGNetCompact(num_feat=16, num_conv=2, upscale=2))
+    sd['body.0.extra'] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        resselt_b200.load_from_state_dict(sd)
+
+
+def test_load_from_file_formats(tmp_path):
+    import safetensors.torch
+
+    sd = _sd(SRVGGNetCompact(num_feat=16, num_conv=2, upscale=2))
+    p_pth, p_ckpt, p_st, p_pt = (str(tmp_path / n) for n in ('m.pth', 'm.CKPT', 'm.safetensors', 'm.pt'))
+    torch.save(collections.OrderedDict(sd), p_pth)
+    torch.save({'params': sd}, p_ckpt)
+    safetensors.torch.save_file(sd, p_st)
+    torch.save(sd, p_pt)  # not TorchScript -> pickle fallback (registry.py:81-93)
+    for p in (p_pth, p_ckpt, p_st, p_pt):
+        assert resselt_b200.load_from_file(p).parameters_info.name == 'Compact'
+    with pytest.raises(ValueError, match='Unsupported model file extension'):
+        resselt_b200.load_from_file(str(tmp_path / 'm.onnx'))
+
+
+def test_restricted_unpickler_blocks_code_execution(tmp_path):
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ('echo pwned',))
+
+    p = str(tmp_path / 'evil.pth')
+    torch.save({'body.0.weight': Evil()}, p)
+    with pytest.raises(pickle.UnpicklingError):
+        resselt_b200.load_from_file(p)
+
+
+def test_plugin_contract_custom_architecture():
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.only = torch.nn.Conv2d(1, 1, 1)
+
+    class TinyArch(Architecture[Tiny]):
+        def __init__(self):
+            super().__init__(uid='tiny', detect=KeyCondition.has_all('only.weight', KeyCondition.has_any('only.bias', 'zzz')))
+
+        def load(self, state_dict):
+            return self._enhance_model(model=Tiny(), in_channels=1, out_channels=1, upscale=1, name='Tiny')
+
+    reg = Registry()
+    reg.add(TinyArch())
+    assert 'tiny' in reg and len(list(reg)) == 1
+    m = reg.load_from_state_dict(Tiny().state_dict())
+    assert m.parameters_info == ModelMetadata(1, 1, 1, 'Tiny')
+    with pytest.raises(TypeError):
+        Architecture('x', KeyCondition.has_all())  # abstract
+
+
+def test_state_dict_helpers():
+    sd = {'body.0.w': 0, 'body.10.w': 0, 'body.3.x.y': 0, 'bodyguard.99.w': 0}
+    assert get_seq_len(sd, 'body') == 11 and get_seq_len(sd, 'nothing') == 0
+    assert pixelshuffle_scale(48, 3) == 4 and pixelshuffle_scale(12, 3) == 2
+
+
+def test_spanplus_dysample_checkpoint_is_refused_explicitly():
+    sd = _sd(SpanPlus(blocks=[1], feature_channels=16, upscale=2))
+    del sd['upsampler.0.weight'], sd['upsampler.0.bias']
+    sd['upsampler.end_conv.weight'] = torch.zeros(3, 16, 1, 1)
+    sd['upsampler.offset.weight'] = torch.zeros(32, 16, 1, 1)
+    with pytest.raises(NotImplementedError):
+        resselt_b200.load_from_state_dict(sd)

@@ -1,0 +1,62 @@
+"""The CPU oracle against outputs of the reference itself (tests/golden, made by oracle/make_golden.py),
+plus the semantic known-answer checks SURVEY.md §8c lists."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle.sr_forward import conv3xc_merged
+from conftest import golden_case, golden_index, norm_err
+
+
+@pytest.mark.parametrize('name', sorted(golden_index()))
+def test_oracle_matches_reference_fixture(name):
+    kind, sd, x, y_ref, meta = golden_case(name)
+    y32 = oracle.forward_by_name(kind, sd, x, torch.float32)
+    y64 = oracle.forward_by_name(kind, sd, x, torch.float64)
+    assert y32.shape == y_ref.shape
+    # fp32 re-association noise only (the reference forward itself is fp32)
+    assert norm_err(y32, y_ref) <= 2e-6
+    assert norm_err(y64, y_ref) <= 2e-6
+    assert y_ref.shape[1] == meta['out_channels'] and y_ref.shape[2] == x.shape[2] * meta['upscale']
+
+
+def test_dead_eval_conv_tensors_do_not_matter():
+    # the reference overwrites eval_conv.* on every forward (span/arch.py:152-154): randomising them changes nothing
+    kind, sd, x, y_ref, _ = golden_case('span_x2_f48')
+    g = torch.Generator().manual_seed(0)
+    sd2 = {k: (torch.randn(v.shape, generator=g) if '.eval_conv.' in k else v) for k, v in sd.items()}
+    assert torch.equal(oracle.forward_by_name(kind, sd, x), oracle.forward_by_name(kind, sd2, x))
+
+
+def test_conv3xc_closed_form_equals_sequential_composition():
+    # interior pixels of conv1x1 -> conv3x3 -> conv1x1 (+ 1x1 skip) equal one merged 3x3 conv
+    _, sd, _, _, _ = golden_case('span_x2_f48')
+    x = torch.randn(1, 48, 12, 12, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    p = 'block_2.c2_r'
+    g = lambda k: sd[f'{p}.{k}'].double()
+    seq = F.conv2d(F.conv2d(F.conv2d(x, g('conv.0.weight'), g('conv.0.bias')), g('conv.1.weight'), g('conv.1.bias')),
+                   g('conv.2.weight'), g('conv.2.bias')) + F.conv2d(x, g('sk.weight'), g('sk.bias'))[:, :, 1:-1, 1:-1]
+    k, b = conv3xc_merged(sd, p, torch.float64)
+    merged = F.conv2d(x, k, b)
+    assert (seq - merged).abs().max() < 1e-12
+
+
+def test_engine_weight_merge_matches_oracle_merge():
+    from resselt_b200.archs._common import merge_conv3xc
+
+    _, sd, _, _, _ = golden_case('spanplus_x2_b4')
+    w = {k: v.double() for k, v in sd.items()}
+    for p in ('feats.0', 'feats.1.block_1.c1_r', 'feats.1.conv_2'):
+        k1, b1 = merge_conv3xc(w, p)
+        k2, b2 = conv3xc_merged(sd, p, torch.float64)
+        assert (k1 - k2).abs().max() < 1e-13 and (b1 - b2).abs().max() < 1e-13
+
+
+def test_spab_second_output_is_activated():
+    from oracle.sr_forward import _conv3xc, _spab
+
+    _, sd, _, _, _ = golden_case('span_x2_f48')
+    x = torch.randn(1, 48, 8, 8, generator=torch.Generator().manual_seed(5))
+    _, o1 = _spab(sd, 'block_6', x, F.silu)
+    assert torch.allclose(o1, F.silu(_conv3xc(sd, 'block_6.c1_r', x)))
