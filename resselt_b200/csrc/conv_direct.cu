@@ -5,6 +5,8 @@
 // Thread = one output pixel x 32 output channels; block = 32 x 8 pixel tile; weights streamed through shared
 // memory one (input-plane, kernel-row) slab at a time so any Cin / kernel size fits.
 // Also here: GroupNorm (+affine +skip) and the planar-8 -> NCHW debug read-back.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace rsb {
@@ -83,8 +85,37 @@ __global__ void __launch_bounds__(kDThreads) conv_direct_kernel(const __grid_con
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = acc[j8 * 8 + i];
-      epilogue8<T, kFast>(p.epi, v, c0, n, y, x);
+      epilogue8<T, kFast>(p.epi, p.epi.bias, p.epi.slopes, v, c0, n, y, x);
     }
+  }
+}
+
+// ---------------------------------------------------------------- im2col pack of the external input
+__global__ void __launch_bounds__(256) pack_input_kernel(const __grid_constant__ PackParams p) {
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t total = (size_t)p.n * p.kplanes * hw;
+  const int kreal = p.cin * p.kh * p.kw;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.W);
+    const int y = (int)((i / p.W) % p.H);
+    const int plane = (int)((i / hw) % p.kplanes);
+    const int n = (int)(i / (hw * p.kplanes));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = plane * 8 + j;
+      float val = 0.0f;
+      if (k < kreal) {
+        const int ci = k / (p.kh * p.kw), t = k - ci * p.kh * p.kw;
+        const int ky = t / p.kw, kx = t - ky * p.kw;
+        const int sy = y + ky - p.pad_t, sx = x + kx - p.pad_l;
+        if (sy >= 0 && sy < p.H && sx >= 0 && sx < p.W)
+          val = (ld_any(p.src, p.src_dtype, (((size_t)n * p.cin + ci) * p.H + sy) * p.W + sx) - p.in_mean[ci & 3]) * p.in_scale;
+      }
+      v[j] = val;
+    }
+    store8<__nv_bfloat16>(dst + i * 8, v);
   }
 }
 
@@ -190,6 +221,13 @@ cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cud
     conv_direct_kernel<__nv_bfloat16, true><<<grid, kDThreads, smem, stream>>>(p);
   else
     conv_direct_kernel<float, false><<<grid, kDThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_input(const PackParams& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.n * p.kplanes * p.H * p.W;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  pack_input_kernel<<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -10,13 +10,14 @@
 //              8 consecutive pixels x 16 B are exactly one canonical no-swizzle K-major core matrix. A tap is then
 //              just a different start address inside the same halo tile (+ (dy*WT + dx) * 16 B): the 9 taps of a 3x3
 //              re-use one shared-memory copy, no im2col, no per-tap reload.
-//   warp 1   : single-thread tcgen05.mma issuer; accumulators live in TMEM (two buffers, so tile i+1's MMAs overlap
-//              tile i's epilogue).
+//   warp 1   : single-thread tcgen05.mma issuer; accumulators live in TMEM, num_acc (<= 4) buffers deep.
 //   warp 2   : TMEM allocation / release.
-//   warps 4-7: epilogue. tcgen05.ld (32 lanes x 16 columns) -> bias / activation / gate / residual / PixelShuffle
-//              (kernels.cuh::epilogue8) -> 16-byte stores, 8 neighbouring pixels filling one 128-byte line.
-// The packed weights of the layer ([tap][cin/8][npad][8] bf16, also canonical K-major) stay resident in shared
-// memory for the CTA's lifetime (one cp.async.bulk).
+//   warps 4+ : num_acc epilogue warpgroups; warpgroup g drains accumulator g (tiles g, g+A, g+2A, ...), so up to four
+//              tile epilogues are in flight per SM and hide each other's TMEM / global-load / MUFU latencies while
+//              the MMA warp runs ahead.  tcgen05.ld (32 lanes x 16 columns) -> bias / activation / gate / residual /
+//              PixelShuffle (kernels.cuh::epilogue8) -> 16-byte stores, 8 neighbouring pixels filling a 128-byte line.
+// The packed weights of the layer ([tap][cin/8][npad][8] bf16, also canonical K-major), its bias and PReLU slopes
+// stay resident in shared memory for the CTA's lifetime.
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -26,47 +27,56 @@ namespace rsb {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kMaxAcc = 4;
+constexpr int kMaxThreads = 128 + 128 * kMaxAcc;
 constexpr uint32_t kAlign = 1024;
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-template <typename T, bool kFast>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int ACT, int COMB>
+__global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using namespace ptx;
+  using T = __nv_bfloat16;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = p.stages;
+  const int A = p.num_acc;
 
   const uint32_t w_al = align_up(p.wbytes, kAlign);
   const uint32_t st_al = align_up(p.stage_bytes, kAlign);
   uint8_t* const wsm = smem;
   uint8_t* const stage0 = smem + w_al;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)S * st_al);
+  float* const bias_sm = reinterpret_cast<float*>(stage0 + (size_t)S * st_al);
+  float* const slope_sm = bias_sm + p.npad;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(slope_sm + p.npad);
   uint64_t* const full = bars;
   uint64_t* const empty = bars + S;
   uint64_t* const tfull = bars + 2 * S;
-  uint64_t* const tempty = bars + 2 * S + 2;
-  uint64_t* const wbar = bars + 2 * S + 4;
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+  uint64_t* const tempty = tfull + kMaxAcc;
+  uint64_t* const wbar = tempty + kMaxAcc;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(&tfull[0], 1);
-    mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4);
-    mbar_init(&tempty[1], 4);
+    for (int a = 0; a < kMaxAcc; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
+    bias_sm[i] = p.epi.bias[i];
+    slope_sm[i] = p.epi.slopes != nullptr ? p.epi.slopes[i] : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -85,10 +95,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const uint32_t len = min(32768u, p.wbytes - off);
         bulk_load_1d(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, len, wbar);
       }
-      int i = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
-        const int s = i % S;
-        const uint32_t ph = (i / S) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], p.stage_bytes);
         const int n = tile / tiles_per_img;
@@ -96,6 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         tma_load_4d(stage0 + (size_t)s * st_al, &src_map, &full[s], 8 * (tx * kTileW - p.pad_l),
                     ty * kTileH - p.pad_t, p.src_plane0, n);
+        if (++s == S) s = 0, ph ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -111,12 +121,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       const int ksteps = p.cin >> 4;
       const int cin8 = p.cin >> 3;
       const int taps = p.kh * p.kw;
-      int i = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
-        const int s = i % S;
-        const uint32_t ph = (i / S) & 1;
-        const int acc = i & 1;
-        const uint32_t aph = (i >> 1) & 1;
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], aph ^ 1);
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -136,42 +143,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         }
         umma_commit(&empty[s]);    // shared-memory stage may be refilled once these MMAs have read it
         umma_commit(&tfull[acc]);  // accumulator complete
+        if (++s == S) s = 0, ph ^= 1;
+        if (++acc == A) acc = 0, aph ^= 1;
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;
-    const int ry = row >> 3, rx = row & 7;
-    const int cstore = (p.epi.cout + 7) & ~7;
-    int i = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
-      const int acc = i & 1;
-      const uint32_t aph = (i >> 1) & 1;
-      mbar_wait(&tfull[acc], aph);
-      tc_fence_after();
-      const int n = tile / tiles_per_img;
-      const int rem = tile - n * tiles_per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int y = ty * kTileH + ry, x = tx * kTileW + rx;
-      const bool valid = (y < p.H) && (x < p.W);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * p.acc_stride;
-      for (int c = 0; c < p.npad; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        if (valid) {
-          float v[8];
+    const int g = (warp - 4) >> 2;  // epilogue warpgroup == accumulator buffer it drains
+    if (g < A) {
+      const int q = warp & 3;  // TMEM lane quarter this warp may read
+      const int row = q * 32 + lane;
+      const int ry = row >> 3, rx = row & 7;
+      const int cstore = (p.epi.cout + 7) & ~7;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * p.acc_stride;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x + g * gridDim.x; tile < p.num_tiles; tile += A * gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int y = ty * kTileH + ry, x = tx * kTileW + rx;
+        const bool valid = (y < p.H) && (x < p.W);
+        mbar_wait(&tfull[g], aph);
+        tc_fence_after();
+        for (int c = 0; c < p.npad; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)c, r);
+          tmem_ld_wait();
+          if (valid) {
+            float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-          if (c < cstore) epilogue8<T, kFast>(p.epi, v, c, n, y, x);
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+            if (c < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c, n, y, x);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
-          if (c + 8 < cstore) epilogue8<T, kFast>(p.epi, v, c + 8, n, y, x);
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
+            if (c + 8 < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x);
+          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[g]);
+        aph ^= 1;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
   }
 
@@ -180,30 +191,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+typedef void (*KernelFn)(const CUtensorMap, const ConvTcParams);
+
+struct Variant {
+  int act, comb;
+  KernelFn fn;
+};
+
+// specialised (branch-free) epilogues for the combinations the in-scope architectures emit; anything else takes the
+// runtime-dispatch instantiation
+const Variant kVariants[] = {
+    {RSB_ACT_NONE, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_NONE, RSB_COMB_NONE>},
+    {RSB_ACT_SILU, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_SILU, RSB_COMB_NONE>},
+    {RSB_ACT_MISH, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_MISH, RSB_COMB_NONE>},
+    {RSB_ACT_LRELU, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_LRELU, RSB_COMB_NONE>},
+    {RSB_ACT_PRELU, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_PRELU, RSB_COMB_NONE>},
+    {RSB_ACT_NONE, RSB_COMB_SPAB_GATE, conv_tc_kernel<RSB_ACT_NONE, RSB_COMB_SPAB_GATE>},
+    {RSB_ACT_SIGMOID, RSB_COMB_MUL, conv_tc_kernel<RSB_ACT_SIGMOID, RSB_COMB_MUL>},
+    {RSB_ACT_NONE, RSB_COMB_AXPY, conv_tc_kernel<RSB_ACT_NONE, RSB_COMB_AXPY>},
+    {kRuntime, kRuntime, conv_tc_kernel<kRuntime, kRuntime>},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+KernelFn pick(int act, int comb) {
+  // the gate ignores `act`; normalise so it hits its specialisation
+  if (comb == RSB_COMB_SPAB_GATE) act = RSB_ACT_NONE;
+  for (int i = 0; i < kNumVariants - 1; ++i)
+    if (kVariants[i].act == act && kVariants[i].comb == comb) return kVariants[i].fn;
+  return kVariants[kNumVariants - 1].fn;
+}
+
 }  // namespace
 
 size_t conv_tc_smem_bytes(int cin, int npad, int kh, int kw, int stages) {
   const uint32_t wbytes = (uint32_t)kh * kw * cin * npad * 2u;
   const uint32_t stage = (uint32_t)(kTileH + kh - 1) * (kTileW + kw - 1) * cin * 2u;
-  return (size_t)align_up(wbytes, kAlign) + (size_t)stages * align_up(stage, kAlign) + (2 * stages + 5) * 8 + 16;
+  return (size_t)align_up(wbytes, kAlign) + (size_t)stages * align_up(stage, kAlign) + 2 * npad * sizeof(float) +
+         (2 * stages + 2 * kMaxAcc + 1) * 8 + 16;
+}
+
+int conv_tc_num_acc(int npad) {
+  int a = 512 / npad;
+  return a > kMaxAcc ? kMaxAcc : (a < 1 ? 1 : a);
 }
 
 cudaError_t conv_tc_configure(size_t max_smem) {
-  return cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)max_smem);
+  for (int i = 0; i < kNumVariants; ++i) {
+    cudaError_t e = cudaFuncSetAttribute(kVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_tc_smem_bytes(p.cin, p.npad, p.kh, p.kw, p.stages);
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const int threads = 128 + 128 * p.num_acc;
+  KernelFn fn = pick(p.epi.act, p.epi.combine);
   static const bool swap_fields = getenv("RSB_DEBUG_DESC_SWAP") != nullptr;
   if (swap_fields) {
     ConvTcParams q = p;
     q.dbg_swap_lbo_sbo = 1;
-    conv_tc_kernel<__nv_bfloat16, true><<<grid, kThreads, smem, stream>>>(src_map, q);
+    fn<<<grid, threads, smem, stream>>>(src_map, q);
     return cudaGetLastError();
   }
-  conv_tc_kernel<__nv_bfloat16, true><<<grid, kThreads, smem, stream>>>(src_map, p);
+  fn<<<grid, threads, smem, stream>>>(src_map, p);
   return cudaGetLastError();
 }
 

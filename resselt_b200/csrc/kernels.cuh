@@ -126,8 +126,11 @@ __device__ __forceinline__ float mish_f(float v) {
   const float sp = v > 20.0f ? v : log1pf(expf(v));
   return v * tanhf(sp);
 }
-template <bool kFast>
-__device__ __forceinline__ float activate(int act, float v, float param, float slope) {
+constexpr int kRuntime = -1;  // template value meaning "read act / combine from the parameter block"
+
+template <bool kFast, int ACT>
+__device__ __forceinline__ float activate(int act_rt, float v, float param, float slope) {
+  const int act = ACT == kRuntime ? act_rt : ACT;  // folds to a constant for specialised kernels
   switch (act) {
     case RSB_ACT_SILU: return v * sigmoid_f<kFast>(v);
     case RSB_ACT_MISH: return mish_f<kFast>(v);
@@ -141,37 +144,51 @@ __device__ __forceinline__ float activate(int act, float v, float param, float s
 
 // ------------------------------------------------------------------ fused epilogue for 8 channels of one pixel
 // v[] holds the raw accumulators of output channels c0..c0+7 (c0 % 8 == 0) at pixel (n, y, x).
-template <typename T, bool kFast>
-__device__ __forceinline__ void epilogue8(const Epi& e, float (&v)[8], int c0, int n, int y, int x) {
+// bias / slopes may point to shared or global memory.  `res1v` optionally carries the already-loaded 16-byte
+// residual chunk (tensor-core kernel prefetches it before the accumulator is ready).
+template <typename T, bool kFast, int ACT = kRuntime, int COMB = kRuntime>
+__device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const float* slopes, float (&v)[8], int c0, int n,
+                                          int y, int x) {
+  const int act = ACT == kRuntime ? e.act : ACT;
+  const int comb = COMB == kRuntime ? e.combine : COMB;
   {
-    const float4 b0 = reinterpret_cast<const float4*>(e.bias + c0)[0];
-    const float4 b1 = reinterpret_cast<const float4*>(e.bias + c0)[1];
+    const float4 b0 = reinterpret_cast<const float4*>(bias + c0)[0];
+    const float4 b1 = reinterpret_cast<const float4*>(bias + c0)[1];
     v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w;
     v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
   }
   const int plane = c0 >> 3;
-  if (e.combine == RSB_COMB_SPAB_GATE) {
+  if (comb == RSB_COMB_SPAB_GATE) {
     float r[8];
     load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+    if (kFast) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (v[i] + r[i]) * (sigmoid_f<kFast>(v[i]) - 0.5f);
+      for (int i = 0; i < 8; ++i) {  // sigmoid(v) - 0.5 == 0.5 * tanh(v / 2): one MUFU op
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v[i]));
+        v[i] = (v[i] + r[i]) * (0.5f * t);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (v[i] + r[i]) * (sigmoid_f<false>(v[i]) - 0.5f);
+    }
   } else {
-    if (e.act != RSB_ACT_NONE) {
+    if (act != RSB_ACT_NONE) {
       float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (e.act == RSB_ACT_PRELU) {
-        const float4 s0 = reinterpret_cast<const float4*>(e.slopes + c0)[0];
-        const float4 s1 = reinterpret_cast<const float4*>(e.slopes + c0)[1];
+      if (act == RSB_ACT_PRELU) {
+        const float4 s0 = reinterpret_cast<const float4*>(slopes + c0)[0];
+        const float4 s1 = reinterpret_cast<const float4*>(slopes + c0)[1];
         s[0] = s0.x, s[1] = s0.y, s[2] = s0.z, s[3] = s0.w, s[4] = s1.x, s[5] = s1.y, s[6] = s1.z, s[7] = s1.w;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = activate<kFast>(e.act, v[i], e.act_param, s[i]);
+      for (int i = 0; i < 8; ++i) v[i] = activate<kFast, ACT>(e.act, v[i], e.act_param, s[i]);
     }
-    if (e.combine == RSB_COMB_MUL) {
+    if (comb == RSB_COMB_MUL) {
       float r[8];
       load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= r[i];
-    } else if (e.combine == RSB_COMB_AXPY) {
+    } else if (comb == RSB_COMB_AXPY) {
       float r[8];
       load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
 #pragma unroll
@@ -216,7 +233,8 @@ struct ConvTcParams {
   uint32_t wbytes;
   int stages;
   uint32_t stage_bytes;  // (kTileH+kh-1) * (kTileW+kw-1) * cin * 2
-  uint32_t acc_stride;   // TMEM columns between the two accumulators
+  int num_acc;           // accumulator buffers in TMEM == epilogue warpgroups (1..4)
+  uint32_t acc_stride;   // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;    // allocation (power of two >= 32)
   int dbg_swap_lbo_sbo;  // bring-up aid (env RSB_DEBUG_DESC_SWAP): exchange the LBO/SBO descriptor fields
   Epi epi;
@@ -239,6 +257,19 @@ struct ConvDirectParams {
   Epi epi;
 };
 
+// im2col of the caller's NCHW tensor into a planar-8 bf16 buffer: channel k = (ci*kh + ky)*kw + kx holds
+// (x[ci][y+ky-pad][x+kx-pad] - mean[ci]) * scale, zero outside the image (== zero padding of the normalised input)
+struct PackParams {
+  int n, H, W;
+  int cin, kh, kw, pad_t, pad_l;
+  int kplanes;
+  const void* src;
+  int src_dtype;
+  float in_mean[4];
+  float in_scale;
+  void* dst;
+};
+
 struct GroupNormParams {
   int n, H, W;
   int channels, groups;
@@ -258,8 +289,10 @@ struct GroupNormParams {
 // launchers (defined in the .cu files)
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
 size_t conv_tc_smem_bytes(int cin, int npad, int kh, int kw, int stages);
+int conv_tc_num_acc(int npad);
 cudaError_t conv_tc_configure(size_t max_smem);
 cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cudaStream_t stream);
+cudaError_t launch_pack_input(const PackParams& p, cudaStream_t stream);
 cudaError_t launch_groupnorm(const GroupNormParams& p, bool bf16_storage, cudaStream_t stream);
 cudaError_t launch_planar_to_nchw(const void* src, bool bf16_storage, int n, int planes, int plane0, int channels,
                                   int H, int W, float* dst, cudaStream_t stream);

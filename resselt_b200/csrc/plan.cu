@@ -60,6 +60,12 @@ struct ConvOp {
   int cin_pad16 = 0, npad = 0, cpad32 = 0, cin_planes = 0;
   bool tc_ok = false;
   int stages = 0;
+  // bf16 plans lower a small-Cin conv on the caller's NCHW tensor to [im2col pack -> 1x1 tensor-core conv]:
+  // pack_buf is a hidden planar buffer with pack_k = pad16(cin*kh*kw) channels
+  int pack_buf = -1, pack_k = 0;
+  // geometry the tensor-core kernel sees (differs from d.* only for packed convs)
+  int tc_src_buf = -1, tc_src_ch_off = 0, tc_cin = 0, tc_kh = 0, tc_kw = 0;
+  rsb::PackParams pk;
   void* d_wtc = nullptr;
   uint32_t wbytes_tc = 0;
   float* d_wdirect = nullptr;
@@ -210,11 +216,11 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     if (c.tc_ok) {
       EncodeTiledFn enc = get_encode_fn();
       if (!enc) return fail(RSB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
-      const Buffer& sb = p->bufs[d.src_buf];
-      const int HT = rsb::kTileH + d.kh - 1, WT = rsb::kTileW + d.kw - 1;
+      const Buffer& sb = p->bufs[c.tc_src_buf];
+      const int HT = rsb::kTileH + c.tc_kh - 1, WT = rsb::kTileW + c.tc_kw - 1;
       cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)sb.planes, (cuuint64_t)n};
       cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)W * 16 * H, (cuuint64_t)W * 16 * H * sb.planes};
-      cuuint32_t box[4] = {(cuuint32_t)(8 * WT), (cuuint32_t)HT, (cuuint32_t)(c.cin_pad16 / 8), 1};
+      cuuint32_t box[4] = {(cuuint32_t)(8 * WT), (cuuint32_t)HT, (cuuint32_t)(c.tc_cin / 8), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(&c.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ws + sb.offset, dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -225,17 +231,27 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.n = n, t.H = H, t.W = W;
       t.tiles_x = ceil_div(W, rsb::kTileW), t.tiles_y = ceil_div(H, rsb::kTileH);
       t.num_tiles = t.tiles_x * t.tiles_y * n;
-      t.cin = c.cin_pad16, t.npad = c.npad;
-      t.kh = d.kh, t.kw = d.kw, t.pad_t = d.kh / 2, t.pad_l = d.kw / 2;
-      t.src_plane0 = d.src_ch_off / 8;
+      t.cin = c.tc_cin, t.npad = c.npad;
+      t.kh = c.tc_kh, t.kw = c.tc_kw, t.pad_t = c.tc_kh / 2, t.pad_l = c.tc_kw / 2;
+      t.src_plane0 = c.tc_src_ch_off / 8;
       t.wpack = c.d_wtc, t.wbytes = c.wbytes_tc;
       t.stages = c.stages;
-      t.stage_bytes = (uint32_t)HT * WT * c.cin_pad16 * 2u;
+      t.stage_bytes = (uint32_t)HT * WT * c.tc_cin * 2u;
+      t.num_acc = rsb::conv_tc_num_acc(c.npad);
       t.acc_stride = (uint32_t)c.npad;
       uint32_t cols = 32;
-      while (cols < 2u * c.npad) cols <<= 1;
+      while (cols < (uint32_t)t.num_acc * c.npad) cols <<= 1;
       t.tmem_cols = cols;
       fill_epi(p, c, n, H, W, ws, t.epi);
+      if (c.pack_buf >= 0) {
+        rsb::PackParams& k = c.pk;
+        memset(&k, 0, sizeof k);
+        k.n = n, k.H = H, k.W = W, k.cin = d.cin, k.kh = d.kh, k.kw = d.kw, k.pad_t = d.kh / 2, k.pad_l = d.kw / 2;
+        k.kplanes = c.pack_k / 8;
+        for (int i = 0; i < 4; ++i) k.in_mean[i] = d.in_mean[i];
+        k.in_scale = d.in_scale;
+        k.dst = ws + sb.offset;
+      }
     }
     rsb::ConvDirectParams& q = c.dp;
     memset(&q, 0, sizeof q);
@@ -388,6 +404,15 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
   c.npad = ceil_div(d.cout, 16) * 16;
   c.cpad32 = ceil_div(d.cout, 32) * 32;
   c.cin_planes = ceil_div(d.cin, 8);
+  c.tc_src_buf = d.src_buf, c.tc_src_ch_off = d.src_ch_off, c.tc_cin = c.cin_pad16, c.tc_kh = d.kh, c.tc_kw = d.kw;
+  if (p->dtype == RSB_BF16 && d.src_buf == RSB_EXTERNAL_INPUT && d.cin * d.kh * d.kw <= 256) {
+    Buffer hb;
+    c.pack_k = ceil_div(d.cin * d.kh * d.kw, 16) * 16;
+    hb.channels = c.pack_k, hb.planes = c.pack_k / 8, hb.scale = 1;
+    p->bufs.push_back(hb);
+    c.pack_buf = (int)p->bufs.size() - 1;
+    c.tc_src_buf = c.pack_buf, c.tc_src_ch_off = 0, c.tc_cin = c.pack_k, c.tc_kh = 1, c.tc_kw = 1;
+  }
   p->convs.push_back(std::move(c));
   p->ops.push_back({0, (int)p->convs.size() - 1});
   return 0;
@@ -439,13 +464,13 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
     const int taps = d.kh * d.kw;
     // ---- tensor-core eligibility (bf16 plan, planar source, operands fit shared memory)
     c.tc_ok = false;
-    if (p->dtype == RSB_BF16 && d.src_buf >= 0 && !d.src_upsample2 && c.npad <= 256) {
-      const Buffer& sb = p->bufs[d.src_buf];
-      const bool planes_ok = d.src_ch_off / 8 + c.cin_pad16 / 8 <= sb.planes;
-      const int WT = rsb::kTileW + d.kw - 1, HT = rsb::kTileH + d.kh - 1;
+    if (p->dtype == RSB_BF16 && c.tc_src_buf >= 0 && !d.src_upsample2 && c.npad <= 256) {
+      const Buffer& sb = p->bufs[c.tc_src_buf];
+      const bool planes_ok = c.tc_src_ch_off / 8 + c.tc_cin / 8 <= sb.planes;
+      const int WT = rsb::kTileW + c.tc_kw - 1, HT = rsb::kTileH + c.tc_kh - 1;
       int stages = 0;
       for (int s = 4; s >= 2; --s)
-        if (rsb::conv_tc_smem_bytes(c.cin_pad16, c.npad, d.kh, d.kw, s) <= kMaxSmem) {
+        if (rsb::conv_tc_smem_bytes(c.tc_cin, c.npad, c.tc_kh, c.tc_kw, s) <= kMaxSmem) {
           stages = s;
           break;
         }
@@ -466,7 +491,16 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       RSB_CUDA(cudaMalloc(&c.d_slopes, cmax * sizeof(float)));
       RSB_CUDA(cudaMemcpy(c.d_slopes, slopes.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (c.tc_ok) {
+    if (c.tc_ok && c.pack_buf >= 0) {
+      // packed conv == 1x1 conv over k = (ci*kh + ky)*kw + kx, which is the OIHW flattening of the weight
+      const int k8 = c.pack_k / 8, kreal = d.cin * taps;
+      std::vector<uint16_t> wp((size_t)k8 * c.npad * 8, 0);
+      for (int o = 0; o < d.cout; ++o)
+        for (int k = 0; k < kreal; ++k) wp[((size_t)(k / 8) * c.npad + o) * 8 + (k & 7)] = f32_to_bf16(c.w[(size_t)o * kreal + k]);
+      c.wbytes_tc = (uint32_t)(wp.size() * 2);
+      RSB_CUDA(cudaMalloc(&c.d_wtc, c.wbytes_tc));
+      RSB_CUDA(cudaMemcpy(c.d_wtc, wp.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
+    } else if (c.tc_ok) {
       // [tap][cin/8][npad][8] bf16: per (tap, 8-channel slab) an N x 8 K-major panel of 128-byte core matrices
       const int cin8 = c.cin_pad16 / 8;
       std::vector<uint16_t> wp((size_t)taps * cin8 * c.npad * 8, 0);
@@ -505,7 +539,9 @@ int rsb_plan_num_ops(const rsb_plan* p) { return p ? (int)p->ops.size() : 0; }
 
 int rsb_plan_launches_per_forward(const rsb_plan* p) {
   if (!p) return 0;
-  return (int)p->convs.size() + 2 * (int)p->gns.size();
+  int packed = 0;
+  for (const ConvOp& c : p->convs) packed += (c.pack_buf >= 0 && c.tc_ok) ? 1 : 0;
+  return (int)p->convs.size() + packed + 2 * (int)p->gns.size();
 }
 
 int rsb_plan_flops(const rsb_plan* p, int n, int h, int w, double* flops) {
@@ -543,6 +579,15 @@ int rsb_plan_forward(rsb_plan* p, const void* x, int x_dtype, int n, int h, int 
       if (op.kind == 0) {
         ConvOp& c = p->convs[op.index];
         if (c.tc_ok && !force_direct) {
+          if (c.pack_buf >= 0) {
+            rsb::PackParams k = c.pk;
+            k.src = x, k.src_dtype = x_dtype;
+            e = rsb::launch_pack_input(k, stream);
+            if (e != cudaSuccess) {
+              rc = fail_cuda(e, "kernel launch");
+              break;
+            }
+          }
           rsb::ConvTcParams t = c.tcp;
           if (t.epi.dst_external) t.epi.dst = y, t.epi.out_dtype = y_dtype;
           t.epi.base = x, t.epi.base_dtype = x_dtype;
