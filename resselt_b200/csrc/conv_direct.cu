@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kDThreads) conv_direct_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------- im2col pack of the external input
+// generic version: one thread per (pixel, 8-channel plane)
 __global__ void __launch_bounds__(256) pack_input_kernel(const __grid_constant__ PackParams p) {
   const size_t hw = (size_t)p.H * p.W;
   const size_t total = (size_t)p.n * p.kplanes * hw;
@@ -116,6 +117,47 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const __grid_constant__
       v[j] = val;
     }
     store8<__nv_bfloat16>(dst + i * 8, v);
+  }
+}
+
+// compile-time geometry (the RGB 3x3 stem every in-scope model starts with): one thread per pixel gathers its whole
+// receptive field into registers (all indices static) and writes every plane
+template <typename TIn, int CIN, int KH, int KW>
+__global__ void __launch_bounds__(256) pack_input_fixed_kernel(const __grid_constant__ PackParams p) {
+  constexpr int KREAL = CIN * KH * KW, KPLANES = (KREAL + 15) / 16 * 2;
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t total = (size_t)p.n * hw;
+  const TIn* src = reinterpret_cast<const TIn*>(p.src);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.W);
+    const int y = (int)((i / p.W) % p.H);
+    const int n = (int)(i / hw);
+    float v[KPLANES * 8];
+#pragma unroll
+    for (int k = 0; k < KPLANES * 8; ++k) v[k] = 0.0f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const TIn* plane = src + ((size_t)n * CIN + ci) * hw;
+      const float mean = p.in_mean[ci & 3];
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+        const int sy = y + ky - KH / 2;
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx) {
+          const int sx = x + kx - KW / 2;
+          if (sy >= 0 && sy < p.H && sx >= 0 && sx < p.W)
+            v[(ci * KH + ky) * KW + kx] = ((float)plane[(size_t)sy * p.W + sx] - mean) * p.in_scale;
+        }
+      }
+    }
+#pragma unroll
+    for (int pl = 0; pl < KPLANES; ++pl) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v[pl * 8 + j];
+      store8<__nv_bfloat16>(dst + (((size_t)n * KPLANES + pl) * hw + (size_t)y * p.W + x) * 8, o);
+    }
   }
 }
 
@@ -226,6 +268,17 @@ cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cud
 
 cudaError_t launch_pack_input(const PackParams& p, cudaStream_t stream) {
   const size_t total = (size_t)p.n * p.kplanes * p.H * p.W;
+  if (p.cin == 3 && p.kh == 3 && p.kw == 3) {
+    const size_t pixels = (size_t)p.n * p.H * p.W;
+    const int g = (int)std::min<size_t>((pixels + 255) / 256, 148 * 32);
+    if (p.src_dtype == RSB_BF16)
+      pack_input_fixed_kernel<__nv_bfloat16, 3, 3, 3><<<g, 256, 0, stream>>>(p);
+    else if (p.src_dtype == RSB_F16)
+      pack_input_fixed_kernel<__half, 3, 3, 3><<<g, 256, 0, stream>>>(p);
+    else
+      pack_input_fixed_kernel<float, 3, 3, 3><<<g, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
   pack_input_kernel<<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();

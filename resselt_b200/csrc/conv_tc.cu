@@ -78,13 +78,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     bias_sm[i] = p.epi.bias[i];
     slope_sm[i] = p.epi.slopes != nullptr ? p.epi.slopes[i] : 0.0f;
   }
+  const int HT = kTileH + p.kh - 1;
+  const int WT = kTileW + p.kw - 1;
+  const int ksteps = p.cin >> 4;
+  const uint32_t a_lbo = (uint32_t)(HT * WT) * 16u;  // next 8-channel plane
+  const uint32_t a_sbo = (uint32_t)WT * 16u;         // next tile row (8 pixels = one core matrix)
+  const uint32_t b_lbo = (uint32_t)p.npad * 16u;     // next 8-input-channel slab
+  const uint32_t b_sbo = 128u;                       // next 8 output channels
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int HT = kTileH + p.kh - 1;
-  const int WT = kTileW + p.kw - 1;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
@@ -109,44 +114,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(wbar, 0);
-      const uint32_t idesc = make_idesc_bf16(128, p.npad);
-      const uint32_t w_base = smem_u32(wsm);
-      const uint32_t a_lbo = (uint32_t)(HT * WT) * 16u;  // next 8-channel plane
-      const uint32_t a_sbo = (uint32_t)WT * 16u;         // next tile row (8 pixels = one core matrix)
-      const uint32_t b_lbo = (uint32_t)p.npad * 16u;     // next 8-input-channel slab
-      const uint32_t b_sbo = 128u;                       // next 8 output channels
-      const bool swp = p.dbg_swap_lbo_sbo != 0;
-      const int ksteps = p.cin >> 4;
-      const int cin8 = p.cin >> 3;
-      const int taps = p.kh * p.kw;
-      int s = 0, acc = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], aph ^ 1);
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(stage0 + (size_t)s * st_al);
-        const uint32_t d = tmem_base + (uint32_t)acc * p.acc_stride;
-        uint32_t accum = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.kw, dx = tap - dy * p.kw;
-          const uint32_t a_tap = a_base + (uint32_t)(dy * WT + dx) * 16u;
-          const uint32_t b_tap = w_base + (uint32_t)(tap * cin8) * b_lbo;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t da = make_smem_desc(a_tap + (uint32_t)(2 * kk) * a_lbo, swp ? a_sbo : a_lbo, swp ? a_lbo : a_sbo);
-            const uint64_t db = make_smem_desc(b_tap + (uint32_t)(2 * kk) * b_lbo, swp ? b_sbo : b_lbo, swp ? b_lbo : b_sbo);
-            umma_bf16(d, da, db, idesc, accum);
-            accum = 1;
+    // The whole warp walks the loop (so every operand stays in uniform registers); one elected lane issues.
+    const bool leader = elect_one();
+    mbar_wait(wbar, 0);
+    const uint32_t idesc = make_idesc_bf16(128, p.npad);
+    const uint32_t a_hi = (uint32_t)(make_smem_desc(0, a_lbo, a_sbo) >> 32);
+    const uint32_t b_hi = (uint32_t)(make_smem_desc(0, b_lbo, b_sbo) >> 32);
+    const uint32_t a_lo_const = (uint32_t)make_smem_desc(0, a_lbo, a_sbo);  // LBO field of the low word
+    const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(wsm), b_lbo, b_sbo);
+    const uint32_t a_kstep = 2u * (a_lbo >> 4);  // descriptor address units (16 B) per 16-channel K step
+    const uint32_t b_kstep = 2u * (b_lbo >> 4);
+    int s = 0, acc = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], aph ^ 1);
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t a_lo0 = a_lo_const + (smem_u32(stage0 + (size_t)s * st_al) >> 4);
+      const uint32_t d = tmem_base + (uint32_t)acc * p.acc_stride;
+      uint32_t b_lo = b_lo0;
+      // first MMA overwrites the accumulator, all others accumulate; weights are laid out [tap][k-step] so the
+      // B descriptor simply advances by one K step per MMA
+      if (leader) umma_bf16_lohi<false>(d, a_lo0, a_hi, b_lo, b_hi, idesc);
+      b_lo += b_kstep;
+      for (int dy = 0; dy < p.kh; ++dy) {
+        for (int dx = 0; dx < p.kw; ++dx) {
+          const int kk0 = (dy | dx) == 0 ? 1 : 0;
+          uint32_t a_lo = a_lo0 + (uint32_t)(dy * WT + dx) + (uint32_t)kk0 * a_kstep;
+          for (int kk = kk0; kk < ksteps; ++kk) {
+            if (leader) umma_bf16_lohi<true>(d, a_lo, a_hi, b_lo, b_hi, idesc);
+            a_lo += a_kstep;
+            b_lo += b_kstep;
           }
         }
+      }
+      if (leader) {
         umma_commit(&empty[s]);    // shared-memory stage may be refilled once these MMAs have read it
         umma_commit(&tfull[acc]);  // accumulator complete
-        if (++s == S) s = 0, ph ^= 1;
-        if (++acc == A) acc = 0, aph ^= 1;
       }
+      if (++s == S) s = 0, ph ^= 1;
+      if (++acc == A) acc = 0, aph ^= 1;
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const int g = (warp - 4) >> 2;  // epilogue warpgroup == accumulator buffer it drains
     if (g < A) {
