@@ -33,7 +33,9 @@ constexpr uint32_t kAlign = 1024;
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-template <int ACT, int COMB>
+// KH/KW/KSTEPS > 0: geometry known at compile time -> the MMA issue loop is straight-line code (one UIADD3.64 + one
+// UTCHMMA per MMA); KH == 0: geometry read from the parameter block (nested runtime loops).
+template <int KH, int KW, int KSTEPS, int ACT, int COMB>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -130,21 +132,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       mbar_wait(&tempty[acc], aph ^ 1);
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      const uint32_t a_lo0 = a_lo_const + (smem_u32(stage0 + (size_t)s * st_al) >> 4);
       const uint32_t d = tmem_base + (uint32_t)acc * p.acc_stride;
-      uint32_t b_lo = b_lo0;
-      // first MMA overwrites the accumulator, all others accumulate; weights are laid out [tap][k-step] so the
-      // B descriptor simply advances by one K step per MMA
-      if (leader) umma_bf16_lohi<false>(d, a_lo0, a_hi, b_lo, b_hi, idesc);
-      b_lo += b_kstep;
-      for (int dy = 0; dy < p.kh; ++dy) {
-        for (int dx = 0; dx < p.kw; ++dx) {
-          const int kk0 = (dy | dx) == 0 ? 1 : 0;
-          uint32_t a_lo = a_lo0 + (uint32_t)(dy * WT + dx) + (uint32_t)kk0 * a_kstep;
-          for (int kk = kk0; kk < ksteps; ++kk) {
-            if (leader) umma_bf16_lohi<true>(d, a_lo, a_hi, b_lo, b_hi, idesc);
-            a_lo += a_kstep;
-            b_lo += b_kstep;
+      if constexpr (KH > 0) {
+        constexpr uint32_t kPlane = (uint32_t)((kTileH + KH - 1) * (kTileW + KW - 1));  // 16-byte units per 8-ch plane
+        const uint64_t da = make_smem_desc(smem_u32(stage0 + (size_t)s * st_al), kPlane * 16u, (uint32_t)(kTileW + KW - 1) * 16u);
+        const uint64_t db = make_smem_desc(smem_u32(wsm), b_lbo, b_sbo);
+        if (leader) {
+#pragma unroll
+          for (int dy = 0; dy < KH; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < KW; ++dx)
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint64_t a = da + (uint64_t)((uint32_t)(dy * (kTileW + KW - 1) + dx) + 2u * kk * kPlane);
+                const uint64_t b = db + (uint64_t)((uint32_t)((dy * KW + dx) * KSTEPS + kk) * b_kstep);
+                umma_bf16(d, a, b, idesc, (dy | dx | kk) != 0 ? 1u : 0u);
+              }
+        }
+      } else {
+        const uint32_t a_lo0 = a_lo_const + (smem_u32(stage0 + (size_t)s * st_al) >> 4);
+        uint32_t b_lo = b_lo0;
+        // first MMA overwrites the accumulator, all others accumulate; weights are laid out [tap][k-step] so the
+        // B descriptor simply advances by one K step per MMA
+        if (leader) umma_bf16_lohi<false>(d, a_lo0, a_hi, b_lo, b_hi, idesc);
+        b_lo += b_kstep;
+        for (int dy = 0; dy < p.kh; ++dy) {
+          for (int dx = 0; dx < p.kw; ++dx) {
+            const int kk0 = (dy | dx) == 0 ? 1 : 0;
+            uint32_t a_lo = a_lo0 + (uint32_t)(dy * WT + dx) + (uint32_t)kk0 * a_kstep;
+            for (int kk = kk0; kk < ksteps; ++kk) {
+              if (leader) umma_bf16_lohi<true>(d, a_lo, a_hi, b_lo, b_hi, idesc);
+              a_lo += a_kstep;
+              b_lo += b_kstep;
+            }
           }
         }
       }
@@ -203,30 +223,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 typedef void (*KernelFn)(const CUtensorMap, const ConvTcParams);
 
 struct Variant {
-  int act, comb;
+  int kh, kw, ksteps, act, comb;
   KernelFn fn;
 };
 
-// specialised (branch-free) epilogues for the combinations the in-scope architectures emit; anything else takes the
-// runtime-dispatch instantiation
+#define RSB_V(KH, KW, KS, ACT, COMB) {KH, KW, KS, ACT, COMB, conv_tc_kernel<KH, KW, KS, ACT, COMB>}
+// Specialisations for the (geometry, epilogue) pairs the in-scope architectures emit.  Lookup order: exact match,
+// then runtime geometry with the specialised epilogue, then the fully runtime kernel.
 const Variant kVariants[] = {
-    {RSB_ACT_NONE, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_NONE, RSB_COMB_NONE>},
-    {RSB_ACT_SILU, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_SILU, RSB_COMB_NONE>},
-    {RSB_ACT_MISH, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_MISH, RSB_COMB_NONE>},
-    {RSB_ACT_LRELU, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_LRELU, RSB_COMB_NONE>},
-    {RSB_ACT_PRELU, RSB_COMB_NONE, conv_tc_kernel<RSB_ACT_PRELU, RSB_COMB_NONE>},
-    {RSB_ACT_NONE, RSB_COMB_SPAB_GATE, conv_tc_kernel<RSB_ACT_NONE, RSB_COMB_SPAB_GATE>},
-    {RSB_ACT_SIGMOID, RSB_COMB_MUL, conv_tc_kernel<RSB_ACT_SIGMOID, RSB_COMB_MUL>},
-    {RSB_ACT_NONE, RSB_COMB_AXPY, conv_tc_kernel<RSB_ACT_NONE, RSB_COMB_AXPY>},
-    {kRuntime, kRuntime, conv_tc_kernel<kRuntime, kRuntime>},
+    // SPAN / SPANPlus (48 channels): stem 1x1 over the im2col buffer, SPAB convs, conv_cat, upsampler
+    RSB_V(1, 1, 2, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(3, 3, 3, RSB_ACT_SILU, RSB_COMB_NONE),
+    RSB_V(3, 3, 3, RSB_ACT_MISH, RSB_COMB_NONE),
+    RSB_V(3, 3, 3, RSB_ACT_NONE, RSB_COMB_SPAB_GATE),
+    RSB_V(3, 3, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(1, 1, 12, RSB_ACT_NONE, RSB_COMB_NONE),
+    // Compact (64 channels, PReLU)
+    RSB_V(1, 1, 2, RSB_ACT_PRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, RSB_ACT_PRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, RSB_ACT_NONE, RSB_COMB_NONE),
+    // ESRGAN dense blocks (64 + 32k input channels) and RealPLKSR
+    RSB_V(3, 3, 4, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 6, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 8, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 10, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, RSB_ACT_MISH, RSB_COMB_NONE),
+    RSB_V(3, 3, 8, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, RSB_ACT_SIGMOID, RSB_COMB_MUL),
+    RSB_V(1, 1, 4, RSB_ACT_NONE, RSB_COMB_NONE),
+    // runtime geometry, specialised epilogue
+    RSB_V(0, 0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(0, 0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(0, 0, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
+    // fully runtime
+    RSB_V(0, 0, 0, kRuntime, kRuntime),
 };
+#undef RSB_V
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-KernelFn pick(int act, int comb) {
-  // the gate ignores `act`; normalise so it hits its specialisation
-  if (comb == RSB_COMB_SPAB_GATE) act = RSB_ACT_NONE;
-  for (int i = 0; i < kNumVariants - 1; ++i)
-    if (kVariants[i].act == act && kVariants[i].comb == comb) return kVariants[i].fn;
+KernelFn pick(const ConvTcParams& p) {
+  int act = p.epi.act;
+  const int comb = p.epi.combine;
+  if (comb == RSB_COMB_SPAB_GATE) act = RSB_ACT_NONE;  // the gate ignores `act`
+  const int ks = p.cin >> 4;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < kNumVariants; ++i) {
+      const Variant& v = kVariants[i];
+      const bool geo = pass == 0 ? (v.kh == p.kh && v.kw == p.kw && v.ksteps == ks) : v.kh == 0;
+      if (geo && v.act == act && v.comb == comb) return v.fn;
+    }
   return kVariants[kNumVariants - 1].fn;
 }
 
@@ -256,14 +301,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, in
   const size_t smem = conv_tc_smem_bytes(p.cin, p.npad, p.kh, p.kw, p.stages);
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   const int threads = 128 + 128 * p.num_acc;
-  KernelFn fn = pick(p.epi.act, p.epi.combine);
-  static const bool swap_fields = getenv("RSB_DEBUG_DESC_SWAP") != nullptr;
-  if (swap_fields) {
-    ConvTcParams q = p;
-    q.dbg_swap_lbo_sbo = 1;
-    fn<<<grid, threads, smem, stream>>>(src_map, q);
-    return cudaGetLastError();
-  }
+  KernelFn fn = pick(p);
   fn<<<grid, threads, smem, stream>>>(src_map, p);
   return cudaGetLastError();
 }

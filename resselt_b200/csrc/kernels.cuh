@@ -236,7 +236,6 @@ struct ConvTcParams {
   int num_acc;           // accumulator buffers in TMEM == epilogue warpgroups (1..4)
   uint32_t acc_stride;   // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;    // allocation (power of two >= 32)
-  int dbg_swap_lbo_sbo;  // bring-up aid (env RSB_DEBUG_DESC_SWAP): exchange the LBO/SBO descriptor fields
   Epi epi;
 };
 
