@@ -150,6 +150,13 @@ int rsb_plan_workspace_bytes(const rsb_plan* plan, int n, int h, int w, size_t* 
 int rsb_plan_forward(rsb_plan* plan, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype,
                      void* workspace, size_t workspace_bytes, void* stream, int force_direct);
 
+/* Same as rsb_plan_forward but only runs ops [op_begin, op_end) of the plan (ops are numbered in the order they were
+ * added; a conv lowered to im2col-pack + 1x1 counts as one op).  For per-layer timing and profiling; the buffers
+ * keep whatever the previous calls left in them. */
+int rsb_plan_forward_ops(rsb_plan* plan, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype,
+                         void* workspace, size_t workspace_bytes, void* stream, int force_direct, int op_begin,
+                         int op_end);
+
 /* Copy a plan buffer (after a forward) into a dense fp32 NCHW device array, for layer-level tests. */
 int rsb_plan_read_buffer(rsb_plan* plan, int buf_id, int ch_off, int channels, float* dst_nchw, void* stream);
 

@@ -29,6 +29,10 @@ class SRVGGNetCompact(EngineModule):
         if num_in_ch != num_out_ch:
             raise ValueError('the nearest-upsampled input residual needs num_in_ch == num_out_ch (compact/arch.py:63-64)')
 
+    @property
+    def receptive_radius(self) -> int:
+        return self.num_conv + 2  # every body conv is a 3x3
+
     def build_plan(self, pb: PlanBuilder, w) -> None:
         ping = [pb.buffer(self.num_feat), pb.buffer(self.num_feat)]
         src = INPUT

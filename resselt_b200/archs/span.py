@@ -56,6 +56,11 @@ class SPAN(EngineModule):
         if f % 8 != 0:
             raise ValueError('feature_channels must be a multiple of 8 for the planar-8 activation layout')
 
+    @property
+    def receptive_radius(self) -> int:
+        # conv_1 (1) + 6 SPABs x 3 convs + conv_2 (1) + upsampler conv (1); conv_cat is 1x1
+        return 1 + 6 * 3 + 1 + 1
+
     def build_plan(self, pb: PlanBuilder, w) -> None:
         f = self.feature_channels
         cat = pb.buffer(4 * f)  # [conv_1 out | conv_2 out | block_1 out | act(block_6.c1_r)] == the reference's torch.cat

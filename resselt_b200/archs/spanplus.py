@@ -51,6 +51,11 @@ class SpanPlus(EngineModule):
         if f % 8 != 0:
             raise ValueError('feature_channels must be a multiple of 8 for the planar-8 activation layout')
 
+    @property
+    def receptive_radius(self) -> int:
+        # stem (1) + per group: (n + 2) SPABs x 3 convs + conv_2 (1); + upsampler conv (1)
+        return 1 + sum(3 * (n + 2) + 1 for n in self.blocks) + 1
+
     def build_plan(self, pb: PlanBuilder, w) -> None:
         f = self.feature_channels
         t1, t2, p0, p1 = (pb.buffer(f) for _ in range(4))

@@ -35,7 +35,9 @@ __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v
 
 // KH/KW/KSTEPS > 0: geometry known at compile time -> the MMA issue loop is straight-line code (one UIADD3.64 + one
 // UTCHMMA per MMA); KH == 0: geometry read from the parameter block (nested runtime loops).
-template <int KH, int KW, int KSTEPS, int ACT, int COMB>
+// NCH > 0: the accumulator is NCH 16-column chunks wide (npad == 16 * NCH) -> unrolled epilogue with the residual
+// operand prefetched before the accumulator-ready wait.
+template <int KH, int KW, int KSTEPS, int NCH, int ACT, int COMB>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -191,20 +193,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y = ty * kTileH + ry, x = tx * kTileW + rx;
         const bool valid = (y < p.H) && (x < p.W);
-        mbar_wait(&tfull[g], aph);
-        tc_fence_after();
-        for (int c = 0; c < p.npad; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)c, r);
-          tmem_ld_wait();
-          if (valid) {
-            float v[8];
+        if constexpr (NCH > 0) {
+          constexpr bool kUsesRes = COMB == RSB_COMB_SPAB_GATE || COMB == RSB_COMB_MUL || COMB == RSB_COMB_AXPY;
+          uint4 pre[kUsesRes ? 2 * NCH : 1];
+          if constexpr (kUsesRes) {
+            // the residual does not depend on this tile's MMAs: fetch it while they are still running
+            if (valid) {
+              const T* rp = reinterpret_cast<const T*>(p.epi.res1) + planar_index(n, p.epi.res1_planes, p.epi.res1_plane0, p.H, p.W, y, x);
+              const size_t plane_stride = (size_t)p.H * p.W * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-            if (c < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c, n, y, x);
+              for (int j = 0; j < 2 * NCH; ++j)
+                if (j * 8 < cstore) pre[j] = *reinterpret_cast<const uint4*>(rp + j * plane_stride);
+            }
+          }
+          mbar_wait(&tfull[g], aph);
+          tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
-            if (c + 8 < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x);
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int c = ci * 16;
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)c, r);
+            tmem_ld_wait();
+            if (valid) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+              if (c < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
+              if (c + 8 < cstore)
+                epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr);
+            }
+          }
+        } else {
+          mbar_wait(&tfull[g], aph);
+          tc_fence_after();
+          for (int c = 0; c < p.npad; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)c, r);
+            tmem_ld_wait();
+            if (valid) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+              if (c < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c, n, y, x);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
+              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x);
+            }
           }
         }
         tc_fence_before();
@@ -223,40 +259,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 typedef void (*KernelFn)(const CUtensorMap, const ConvTcParams);
 
 struct Variant {
-  int kh, kw, ksteps, act, comb;
+  int kh, kw, ksteps, nch, act, comb;
   KernelFn fn;
 };
 
-#define RSB_V(KH, KW, KS, ACT, COMB) {KH, KW, KS, ACT, COMB, conv_tc_kernel<KH, KW, KS, ACT, COMB>}
+#define RSB_V(KH, KW, KS, NCH, ACT, COMB) {KH, KW, KS, NCH, ACT, COMB, conv_tc_kernel<KH, KW, KS, NCH, ACT, COMB>}
 // Specialisations for the (geometry, epilogue) pairs the in-scope architectures emit.  Lookup order: exact match,
 // then runtime geometry with the specialised epilogue, then the fully runtime kernel.
 const Variant kVariants[] = {
     // SPAN / SPANPlus (48 channels): stem 1x1 over the im2col buffer, SPAB convs, conv_cat, upsampler
-    RSB_V(1, 1, 2, RSB_ACT_NONE, RSB_COMB_NONE),
-    RSB_V(3, 3, 3, RSB_ACT_SILU, RSB_COMB_NONE),
-    RSB_V(3, 3, 3, RSB_ACT_MISH, RSB_COMB_NONE),
-    RSB_V(3, 3, 3, RSB_ACT_NONE, RSB_COMB_SPAB_GATE),
-    RSB_V(3, 3, 3, RSB_ACT_NONE, RSB_COMB_NONE),
-    RSB_V(1, 1, 12, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(1, 1, 2, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(3, 3, 3, 3, RSB_ACT_SILU, RSB_COMB_NONE),
+    RSB_V(3, 3, 3, 3, RSB_ACT_MISH, RSB_COMB_NONE),
+    RSB_V(3, 3, 3, 3, RSB_ACT_NONE, RSB_COMB_SPAB_GATE),
+    RSB_V(3, 3, 3, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(1, 1, 12, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(3, 3, 3, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     // Compact (64 channels, PReLU)
-    RSB_V(1, 1, 2, RSB_ACT_PRELU, RSB_COMB_NONE),
-    RSB_V(3, 3, 4, RSB_ACT_PRELU, RSB_COMB_NONE),
-    RSB_V(3, 3, 4, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(1, 1, 2, 0, RSB_ACT_PRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, 0, RSB_ACT_PRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     // ESRGAN dense blocks (64 + 32k input channels) and RealPLKSR
-    RSB_V(3, 3, 4, RSB_ACT_LRELU, RSB_COMB_NONE),
-    RSB_V(3, 3, 6, RSB_ACT_LRELU, RSB_COMB_NONE),
-    RSB_V(3, 3, 8, RSB_ACT_LRELU, RSB_COMB_NONE),
-    RSB_V(3, 3, 10, RSB_ACT_LRELU, RSB_COMB_NONE),
-    RSB_V(3, 3, 4, RSB_ACT_MISH, RSB_COMB_NONE),
-    RSB_V(3, 3, 8, RSB_ACT_NONE, RSB_COMB_NONE),
-    RSB_V(3, 3, 4, RSB_ACT_SIGMOID, RSB_COMB_MUL),
-    RSB_V(1, 1, 4, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 6, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 8, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 10, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, 0, RSB_ACT_MISH, RSB_COMB_NONE),
+    RSB_V(3, 3, 8, 0, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(3, 3, 4, 0, RSB_ACT_SIGMOID, RSB_COMB_MUL),
+    RSB_V(1, 1, 4, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     // runtime geometry, specialised epilogue
-    RSB_V(0, 0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
-    RSB_V(0, 0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
-    RSB_V(0, 0, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
+    RSB_V(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(0, 0, 0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
     // fully runtime
-    RSB_V(0, 0, 0, kRuntime, kRuntime),
+    RSB_V(0, 0, 0, 0, kRuntime, kRuntime),
 };
 #undef RSB_V
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -270,7 +307,8 @@ KernelFn pick(const ConvTcParams& p) {
     for (int i = 0; i < kNumVariants; ++i) {
       const Variant& v = kVariants[i];
       const bool geo = pass == 0 ? (v.kh == p.kh && v.kw == p.kw && v.ksteps == ks) : v.kh == 0;
-      if (geo && v.act == act && v.comb == comb) return v.fn;
+      const bool width = v.nch == 0 || v.nch * 16 == p.npad;
+      if (geo && width && v.act == act && v.comb == comb) return v.fn;
     }
   return kVariants[kNumVariants - 1].fn;
 }

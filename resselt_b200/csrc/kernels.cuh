@@ -146,9 +146,21 @@ __device__ __forceinline__ float activate(int act_rt, float v, float param, floa
 // v[] holds the raw accumulators of output channels c0..c0+7 (c0 % 8 == 0) at pixel (n, y, x).
 // bias / slopes may point to shared or global memory.  `res1v` optionally carries the already-loaded 16-byte
 // residual chunk (tensor-core kernel prefetches it before the accumulator is ready).
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& q, float (&o)[8]);
+template <>
+__device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& q, float (&o)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = __uint_as_float(w[i] << 16);
+    o[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
 template <typename T, bool kFast, int ACT = kRuntime, int COMB = kRuntime>
 __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const float* slopes, float (&v)[8], int c0, int n,
-                                          int y, int x) {
+                                          int y, int x, const uint4* res1_pre = nullptr) {
   const int act = ACT == kRuntime ? e.act : ACT;
   const int comb = COMB == kRuntime ? e.combine : COMB;
   {
@@ -160,7 +172,11 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
   const int plane = c0 >> 3;
   if (comb == RSB_COMB_SPAB_GATE) {
     float r[8];
-    load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+    if (res1_pre != nullptr) {
+      if constexpr (sizeof(T) == 2) unpack8<__nv_bfloat16>(*res1_pre, r);
+    } else {
+      load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+    }
     if (kFast) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {  // sigmoid(v) - 0.5 == 0.5 * tanh(v / 2): one MUFU op
@@ -185,12 +201,20 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
     }
     if (comb == RSB_COMB_MUL) {
       float r[8];
-      load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+      if (res1_pre != nullptr) {
+        if constexpr (sizeof(T) == 2) unpack8<__nv_bfloat16>(*res1_pre, r);
+      } else {
+        load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= r[i];
     } else if (comb == RSB_COMB_AXPY) {
       float r[8];
-      load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+      if (res1_pre != nullptr) {
+        if constexpr (sizeof(T) == 2) unpack8<__nv_bfloat16>(*res1_pre, r);
+      } else {
+        load8<T>(reinterpret_cast<const T*>(e.res1) + planar_index(n, e.res1_planes, e.res1_plane0 + plane, e.H, e.W, y, x), r);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = fmaf(e.alpha, v[i], e.beta1 * r[i]);
       if (e.res2 != nullptr) {

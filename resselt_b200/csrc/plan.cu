@@ -561,7 +561,15 @@ int rsb_plan_workspace_bytes(const rsb_plan* p, int n, int h, int w, size_t* byt
 
 int rsb_plan_forward(rsb_plan* p, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype, void* workspace,
                      size_t workspace_bytes, void* stream_, int force_direct) {
+  return rsb_plan_forward_ops(p, x, x_dtype, n, h, w, y, y_dtype, workspace, workspace_bytes, stream_, force_direct, 0,
+                              p ? (int)p->ops.size() : 0);
+}
+
+int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype, void* workspace,
+                         size_t workspace_bytes, void* stream_, int force_direct, int op_begin, int op_end) {
   if (!p || !x || !y || !workspace) return fail(RSB_ERR_INVALID, "rsb_plan_forward: NULL argument");
+  if (op_begin < 0 || op_end > (int)p->ops.size() || op_begin > op_end)
+    return fail(RSB_ERR_INVALID, "rsb_plan_forward_ops: op range [%d, %d) outside [0, %zu)", op_begin, op_end, p->ops.size());
   if (!p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_forward: plan not finalized");
   if (n < 1 || h < 1 || w < 1) return fail(RSB_ERR_INVALID, "rsb_plan_forward: bad shape %dx%dx%d", n, h, w);
   if (x_dtype < RSB_F32 || x_dtype > RSB_F16 || y_dtype < RSB_F32 || y_dtype > RSB_F16)
@@ -574,7 +582,8 @@ int rsb_plan_forward(rsb_plan* p, const void* x, int x_dtype, int n, int h, int 
   int rc = 0;
   if (p->bn != n || p->bh != h || p->bw != w || p->bws != workspace) rc = bind(p, n, h, w, workspace, workspace_bytes, stream);
   if (rc == 0) {
-    for (const Op& op : p->ops) {
+    for (int oi = op_begin; oi < op_end; ++oi) {
+      const Op& op = p->ops[oi];
       cudaError_t e;
       if (op.kind == 0) {
         ConvOp& c = p->convs[op.index];

@@ -133,3 +133,12 @@ class EngineModule(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.plan_for(x.device, x.dtype).forward(x)
+
+    def forward_into(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Forward writing into a caller-owned NCHW tensor (streaming runners reuse their output slots)."""
+        return self.plan_for(x.device, x.dtype).forward(x, out=out)
+
+    @property
+    def receptive_radius(self) -> int:
+        """Input pixels beyond a tile edge that influence the tile's output (exact halo for tiled_forward)."""
+        raise NotImplementedError

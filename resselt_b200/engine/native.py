@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     'rsb_version', 'rsb_last_error', 'rsb_device_count', 'rsb_plan_create', 'rsb_plan_destroy',
     'rsb_plan_add_buffer', 'rsb_plan_add_conv', 'rsb_plan_add_groupnorm', 'rsb_plan_finalize',
     'rsb_plan_num_ops', 'rsb_plan_launches_per_forward', 'rsb_plan_flops', 'rsb_plan_workspace_bytes',
-    'rsb_plan_forward', 'rsb_plan_read_buffer',
+    'rsb_plan_forward', 'rsb_plan_forward_ops', 'rsb_plan_read_buffer',
 )
 
 
@@ -127,6 +127,10 @@ def lib() -> C.CDLL:
         L.rsb_plan_forward.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
             C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+        ]
+        L.rsb_plan_forward_ops.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+            C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int,
         ]
         L.rsb_plan_read_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         for name in EXPORTED_SYMBOLS:

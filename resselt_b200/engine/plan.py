@@ -172,7 +172,12 @@ class Plan:
             self._ws_shape = (n, h, w)
         return self._workspace
 
-    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    @property
+    def num_ops(self) -> int:
+        return int(self._lib.rsb_plan_num_ops(self._h))
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, ops: Optional[tuple] = None) -> torch.Tensor:
+        """Run the plan (or only ops[0]..ops[1]-1 of it, for per-layer timing) on the current stream."""
         if x.device != self.device:
             raise RuntimeError(f'plan lives on {self.device}, input is on {x.device}')
         if x.dim() != 4 or x.shape[1] != self.in_channels:
@@ -188,10 +193,11 @@ class Plan:
             raise RuntimeError('out tensor has the wrong shape/layout')
         ws = self._workspace_for(n, h, w)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        begin, end = ops if ops is not None else (0, self.num_ops)
         N.check(
-            self._lib.rsb_plan_forward(
+            self._lib.rsb_plan_forward_ops(
                 self._h, x.data_ptr(), _TORCH_TO_RSB[x.dtype], n, h, w, out.data_ptr(), _TORCH_TO_RSB[out.dtype],
-                ws.data_ptr(), ws.numel(), stream, int(self.force_direct),
+                ws.data_ptr(), ws.numel(), stream, int(self.force_direct), begin, end,
             )
         )
         return out
