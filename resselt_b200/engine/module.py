@@ -84,11 +84,12 @@ class EngineModule(nn.Module):
         return {k: v.detach().to('cpu', torch.float64) for k, v in self.state_dict().items()}
 
     def _stamp(self) -> int:
+        """Cheap fingerprint of the weights: changes when a tensor is replaced or written in place."""
         s = 0
-        for t in self.parameters():
-            s += t._version + (id(t) & 0xFFFF)
-        for t in self.buffers():
-            s += t._version + (id(t) & 0xFFFF)
+        for group in (self.parameters(), self.buffers()):
+            for t in group:
+                # tensors created under inference_mode carry no version counter; their storage address still moves
+                s += (0 if t.is_inference() else t._version) + (t.data_ptr() & 0xFFFFFFF)
         return s
 
     # ---------------------------------------------------------------- plan management

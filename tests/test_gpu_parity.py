@@ -155,7 +155,7 @@ def test_full_size_1080p_properties():
         crop = m(x[:, :, y0 - r:y0 + hh + r, x0 - r:x0 + ww + r].contiguous())
         assert torch.equal(crop[:, :, 2 * r:2 * (r + hh), 2 * r:2 * (r + ww)], y1[:, :, 2 * y0:2 * (y0 + hh), 2 * x0:2 * (x0 + ww)])
         # and a 256x256 corner of the full frame against the CPU oracle computed on the padded neighbourhood
-        sd = {k: v.float() for k, v in m.state_dict().items()}
+        sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
         ref = oracle.forward_by_name('SPAN', sd, x[:, :, :256 + r, :256 + r].float().cpu(), torch.float32)[:, :, :512, :512]
         assert psnr(y1[:, :, :512, :512].float().cpu(), ref) >= BF16_PSNR_DB
 
