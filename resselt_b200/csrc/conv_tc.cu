@@ -37,7 +37,7 @@ __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v
 // UTCHMMA per MMA); KH == 0: geometry read from the parameter block (nested runtime loops).
 // NCH > 0: the accumulator is NCH 16-column chunks wide (npad == 16 * NCH) -> unrolled epilogue with the residual
 // operand prefetched before the accumulator-ready wait.
-template <int KH, int KW, int KSTEPS, int NCH, int ACT, int COMB>
+template <int KH, int KW, int KSTEPS, int NCH, int ACT, int COMB, int EXT>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -117,8 +117,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         if (++s == S) s = 0, ph ^= 1;
       }
     }
-  } else if (warp == 1) {
-    // The whole warp walks the loop (so every operand stays in uniform registers); one elected lane issues.
+  } else if (warp == 1 || warp == 3) {
+    // Two issuing warps (warp 1: even tiles, warp 3: odd tiles): a single thread cannot generate descriptors fast
+    // enough to keep the tensor pipe full with N = 48 MMAs (~24 math cycles each).  Each tile's MMAs stay in order
+    // inside one warp, so the accumulation order per output pixel is fixed.  The whole warp walks the loop (so every
+    // operand stays in uniform registers); one elected lane issues.
+    const int first = warp == 1 ? 0 : 1;
     const bool leader = elect_one();
     mbar_wait(wbar, 0);
     const uint32_t idesc = make_idesc_bf16(128, p.npad);
@@ -128,9 +132,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(wsm), b_lbo, b_sbo);
     const uint32_t a_kstep = 2u * (a_lbo >> 4);  // descriptor address units (16 B) per 16-channel K step
     const uint32_t b_kstep = 2u * (b_lbo >> 4);
-    int s = 0, acc = 0;
-    uint32_t ph = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int i = first;
+    for (int tile = blockIdx.x + first * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, i += 2) {
+      const int s = i % S, acc = i % A;
+      const uint32_t ph = (uint32_t)(i / S) & 1u, aph = (uint32_t)(i / A) & 1u;
       mbar_wait(&tempty[acc], aph ^ 1);
       mbar_wait(&full[s], ph);
       tc_fence_after();
@@ -174,8 +179,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         umma_commit(&empty[s]);    // shared-memory stage may be refilled once these MMAs have read it
         umma_commit(&tfull[acc]);  // accumulator complete
       }
-      if (++s == S) s = 0, ph ^= 1;
-      if (++acc == A) acc = 0, aph ^= 1;
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -208,21 +211,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           }
           mbar_wait(&tfull[g], aph);
           tc_fence_after();
+          // software-pipelined accumulator reads: chunk ci+1 is in flight while chunk ci goes through the epilogue
+          uint32_t r[2][16];
+          tmem_ld16(taddr, r[0]);
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             const int c = ci * 16;
-            uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t)c, r);
             tmem_ld_wait();
+            if (ci + 1 < NCH) tmem_ld16(taddr + (uint32_t)(c + 16), r[(ci + 1) & 1]);
             if (valid) {
               float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-              if (c < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr);
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ci & 1][j]);
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ci & 1][8 + j]);
               if (c + 8 < cstore)
-                epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr);
+                epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr);
             }
           }
         } else {
@@ -236,10 +241,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-              if (c < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c, n, y, x);
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
-              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x);
+              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x);
             }
           }
         }
@@ -259,11 +264,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 typedef void (*KernelFn)(const CUtensorMap, const ConvTcParams);
 
 struct Variant {
-  int kh, kw, ksteps, nch, act, comb;
+  int kh, kw, ksteps, nch, act, comb, ext;
   KernelFn fn;
 };
 
-#define RSB_V(KH, KW, KS, NCH, ACT, COMB) {KH, KW, KS, NCH, ACT, COMB, conv_tc_kernel<KH, KW, KS, NCH, ACT, COMB>}
+#define RSB_V(KH, KW, KS, NCH, ACT, COMB) {KH, KW, KS, NCH, ACT, COMB, 0, conv_tc_kernel<KH, KW, KS, NCH, ACT, COMB, 0>}
+#define RSB_X(KH, KW, KS, NCH, ACT, COMB) {KH, KW, KS, NCH, ACT, COMB, kRuntime, conv_tc_kernel<KH, KW, KS, NCH, ACT, COMB, kRuntime>}
 // Specialisations for the (geometry, epilogue) pairs the in-scope architectures emit.  Lookup order: exact match,
 // then runtime geometry with the specialised epilogue, then the fully runtime kernel.
 const Variant kVariants[] = {
@@ -274,11 +280,12 @@ const Variant kVariants[] = {
     RSB_V(3, 3, 3, 3, RSB_ACT_NONE, RSB_COMB_SPAB_GATE),
     RSB_V(3, 3, 3, 3, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_V(1, 1, 12, 3, RSB_ACT_NONE, RSB_COMB_NONE),
-    RSB_V(3, 3, 3, 0, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_X(3, 3, 3, 0, RSB_ACT_NONE, RSB_COMB_NONE),  // upsampler conv -> PixelShuffle store into the caller's tensor
     // Compact (64 channels, PReLU)
     RSB_V(1, 1, 2, 0, RSB_ACT_PRELU, RSB_COMB_NONE),
     RSB_V(3, 3, 4, 0, RSB_ACT_PRELU, RSB_COMB_NONE),
     RSB_V(3, 3, 4, 0, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_X(3, 3, 4, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     // ESRGAN dense blocks (64 + 32k input channels) and RealPLKSR
     RSB_V(3, 3, 4, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_V(3, 3, 6, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
@@ -293,9 +300,11 @@ const Variant kVariants[] = {
     RSB_V(0, 0, 0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_V(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
     // fully runtime
-    RSB_V(0, 0, 0, 0, kRuntime, kRuntime),
+    RSB_X(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_X(0, 0, 0, 0, kRuntime, kRuntime),
 };
 #undef RSB_V
+#undef RSB_X
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 KernelFn pick(const ConvTcParams& p) {
@@ -308,7 +317,8 @@ KernelFn pick(const ConvTcParams& p) {
       const Variant& v = kVariants[i];
       const bool geo = pass == 0 ? (v.kh == p.kh && v.kw == p.kw && v.ksteps == ks) : v.kh == 0;
       const bool width = v.nch == 0 || v.nch * 16 == p.npad;
-      if (geo && width && v.act == act && v.comb == comb) return v.fn;
+      const bool ext = p.epi.dst_external ? v.ext == kRuntime : v.ext == 0;
+      if (geo && width && ext && v.act == act && v.comb == comb) return v.fn;
     }
   return kVariants[kNumVariants - 1].fn;
 }

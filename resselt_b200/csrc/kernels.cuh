@@ -158,7 +158,8 @@ __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& q, float (&o
   }
 }
 
-template <typename T, bool kFast, int ACT = kRuntime, int COMB = kRuntime>
+// EXT = 0: destination is known to be a planar buffer (the NCHW scatter code is compiled out); kRuntime: check e.dst_external.
+template <typename T, bool kFast, int ACT = kRuntime, int COMB = kRuntime, int EXT = kRuntime>
 __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const float* slopes, float (&v)[8], int c0, int n,
                                           int y, int x, const uint4* res1_pre = nullptr) {
   const int act = ACT == kRuntime ? e.act : ACT;
@@ -224,7 +225,7 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
       }
     }
   }
-  if (!e.dst_external) {
+  if (EXT == 0 || !e.dst_external) {
     store8<T>(reinterpret_cast<T*>(e.dst) + planar_index(n, e.dst_planes, e.dst_plane0 + plane, e.H, e.W, y, x), v);
     return;
   }
