@@ -81,7 +81,7 @@ typedef struct rsb_conv_desc {
   int32_t dst_buf;    /* buffer id or RSB_EXTERNAL_OUTPUT */
   int32_t dst_ch_off; /* multiple of 8 */
   int32_t cout;
-  int32_t kh, kw;           /* odd kernel extents */
+  int32_t kh, kw;           /* kernel extents (odd unless pad_t/pad_l are given) */
   const float* weight;      /* host, [cout][cin][kh][kw] */
   const float* bias;        /* host, [cout] or NULL */
   int32_t act;              /* rsb_act */
@@ -103,6 +103,19 @@ typedef struct rsb_conv_desc {
   float out_mean[4];
   /* source sampled through a nearest-neighbour x2 upsample (src buffer lives on the half-size grid) */
   int32_t src_upsample2;
+  /* buffer destinations only.
+   * dst_ps > 1: sub-pixel convolution — cout = dst_ps^2 * C, channel blocks are phase-major
+   *   (channel (a*dst_ps + b)*C + c is output channel c of pixel (y*dst_ps + a, x*dst_ps + b)); dst_buf lives on the
+   *   dst_ps-times finer grid and receives C channels.
+   * dst2_buf != RSB_NO_BUFFER: output channels >= split_ch are written to dst2_buf starting at dst2_ch_off
+   *   (split_ch multiple of 8); channels < split_ch go to dst_buf as usual. */
+  int32_t dst_ps;
+  int32_t dst2_buf, dst2_ch_off, split_ch;
+  /* dst_phase >= 0 (with dst_ps > 1): this conv produces only phase dst_phase = a*dst_ps + b (cout = C). */
+  int32_t dst_phase;
+  /* explicit top/left zero padding; -1 selects the 'same' default kh/2, kw/2.  With explicit pads the kernel
+   * extents may be even (used for the 2x2 phase kernels of a nearest-upsample + 3x3 conv). Output size == input size. */
+  int32_t pad_t, pad_l;
 } rsb_conv_desc;
 
 /* GroupNorm over (channels/groups, H, W) per sample, affine, followed by "+ skip". */

@@ -16,7 +16,9 @@ pinned against outputs of the reference itself, generated in the build container
 """
 from .sr_forward import (  # noqa: F401
     compact_forward,
+    esrgan_forward,
     forward_by_name,
+    realplksr_forward,
     span_forward,
     spanplus_forward,
 )

@@ -33,6 +33,13 @@ def cases():
         'spanplus_x2_b2_3': ('SPANPlus', dict(num_in_ch=3, num_out_ch=3, blocks=[2, 3], feature_channels=32, upscale=2, upsampler='ps'), 14, (2, 3, 16, 18), 104),
         'compact_x4_nf64_nc16': ('Compact', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_conv=16, upscale=4), 15, (1, 3, 18, 22), 105),
         'compact_x2_nf24_nc8': ('Compact', dict(num_in_ch=3, num_out_ch=3, num_feat=24, num_conv=8, upscale=2), 16, (2, 3, 16, 12), 106),
+        'esrgan_x4_nb2': ('ESRGAN', dict(in_nc=3, out_nc=3, num_filters=64, num_blocks=2, scale=4), 17, (1, 3, 20, 24), 107),
+        'esrgan_plus_x2_nb1': ('ESRGAN', dict(in_nc=3, out_nc=3, num_filters=64, num_blocks=1, scale=2, plus=True), 18, (2, 3, 12, 16), 108),
+        'realesrgan_x2_unshuffle_nb1': ('ESRGAN', dict(in_nc=12, out_nc=3, num_filters=64, num_blocks=1, scale=4, shuffle_factor=2), 19, (1, 3, 21, 17), 109),
+        'realplksr_x4_nb2': ('RealPLKSR', dict(in_ch=3, dim=64, n_blocks=2, upscaling_factor=4, kernel_size=17, split_ratio=0.25,
+                                               use_ea=True, norm_groups=4, dysample=False), 20, (1, 3, 24, 20), 110),
+        'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
+                                                    use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
     }
 
 

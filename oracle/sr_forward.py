@@ -109,7 +109,93 @@ def compact_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tenso
     return F.pixel_shuffle(out, r) + F.interpolate(x, scale_factor=r, mode='nearest')
 
 
+def _esrgan_keys(sd: SD):
+    if 'model.0.weight' in sd:
+        nb = _seq_len(sd, 'model.1.sub') - 1
+        n_up = (_seq_len(sd, 'model') - 5) // 3
+        return dict(first='model.0', rdb=lambda i, j, k: f'model.1.sub.{i}.RDB{j}.conv{k}.0', one=lambda i, j: f'model.1.sub.{i}.RDB{j}.conv1x1',
+                    trunk=f'model.1.sub.{nb}', up=lambda u: f'model.{3 * u}', hr=f'model.{3 * n_up + 2}', last=f'model.{3 * n_up + 4}'), nb, n_up
+    new = 'conv_body.weight' in sd
+    body = 'body' if new else 'RRDB_trunk'
+    nb = _seq_len(sd, body)
+    up = 'conv_up' if new else 'upconv'
+    n_up = sum(1 for u in range(1, 6) if f'{up}{u}.weight' in sd)
+    rdb = (lambda i, j, k: f'body.{i}.rdb{j}.conv{k}') if new else (lambda i, j, k: f'RRDB_trunk.{i}.RDB{j}.conv{k}')
+    return dict(first='conv_first', rdb=rdb, one=None, trunk='conv_body' if new else 'trunk_conv', up=lambda u: f'{up}{u}',
+                hr='conv_hr' if new else 'HRconv', last='conv_last'), nb, n_up
+
+
+def esrgan_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """RRDBNet.forward (/root/reference/resselt/archs/esrgan/arch.py:129-138) over the flattened Sequential of
+    :72-127; RRDB / ResidualDenseBlock_5C per /root/reference/resselt/utilities/block.py:340-344, :454-465 (incl. the
+    ESRGAN+ conv1x1 paths :457-463); upconv_block = nearest x2 -> conv -> LeakyReLU(0.2) (:510-537)."""
+    x = x.to(dtype)
+    K, nb, n_up = _esrgan_keys(sd)
+    lrelu = lambda t: F.leaky_relu(t, 0.2)
+    in_nc, out_nc = sd[K['first'] + '.weight'].shape[1], sd[K['last'] + '.weight'].shape[0]
+    factor = int(math.sqrt(in_nc / out_nc)) if in_nc in (out_nc * 4, out_nc * 16) else None
+    h, w = x.shape[-2:]
+    if factor:  # Real-ESRGAN x2/x1: reflect-pad, pixel-unshuffle (:130-134)
+        x = F.pad(x, (0, (factor - w % factor) % factor, 0, (factor - h % factor) % factor), 'reflect')
+        x = F.pixel_unshuffle(x, factor)
+    plus = any('.conv1x1.' in k for k in sd)
+    fea = _conv(sd, K['first'], x, 1)
+    t = fea
+    for i in range(nb):
+        rrdb_in = t
+        for j in (1, 2, 3):
+            c = lambda k, inp: _conv(sd, K['rdb'](i, j, k), inp, 1)
+            x0 = t
+            x1 = lrelu(c(1, x0))
+            x2 = lrelu(c(2, torch.cat((x0, x1), 1)))
+            if plus:
+                x2 = x2 + F.conv2d(x0, sd[K['one'](i, j) + '.weight'].to(dtype))
+            x3 = lrelu(c(3, torch.cat((x0, x1, x2), 1)))
+            x4 = lrelu(c(4, torch.cat((x0, x1, x2, x3), 1)))
+            if plus:
+                x4 = x4 + x2
+            x5 = c(5, torch.cat((x0, x1, x2, x3, x4), 1))
+            t = x5 * 0.2 + x0
+        t = t * 0.2 + rrdb_in
+    t = fea + _conv(sd, K['trunk'], t, 1)
+    for u in range(1, n_up + 1):
+        t = lrelu(_conv(sd, K['up'](u), F.interpolate(t, scale_factor=2, mode='nearest'), 1))
+    t = lrelu(_conv(sd, K['hr'], t, 1))
+    y = _conv(sd, K['last'], t, 1)
+    if factor:
+        s = (2 ** n_up) // factor
+        y = y[:, :, : h * s, : w * s]
+    return y
+
+
+def realplksr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, norm_groups: int = 4) -> torch.Tensor:
+    """realplksr.forward, eval mode, PixelShuffle head (/root/reference/resselt/archs/plksr/rplksr.py:145-147);
+    PLKBlock.forward :85-93 = DCCM (:10-19) -> in-place 17x17 conv on the first pdim channels (:36-37) ->
+    EA x*sigmoid(conv(x)) (:48-49) -> 1x1 refine -> GroupNorm(4) -> + skip.  norm_groups is fixed to 4 by the loader
+    (/root/reference/resselt/archs/plksr/__init__.py:116)."""
+    x = x.to(dtype)
+    total = _seq_len(sd, 'feats')
+    t = _conv(sd, 'feats.0', x, 1)
+    for i in range(1, total - 2):
+        p = f'feats.{i}'
+        skip = t
+        t = _conv(sd, f'{p}.channel_mixer.2', F.mish(_conv(sd, f'{p}.channel_mixer.0', t, 1)), 1)
+        lk_w = sd[f'{p}.lk.conv.weight']
+        pdim, k = lk_w.shape[0], lk_w.shape[2]
+        t = torch.cat([_conv(sd, f'{p}.lk.conv', t[:, :pdim], k // 2), t[:, pdim:]], 1)
+        if f'{p}.attn.f.0.weight' in sd:
+            t = t * torch.sigmoid(_conv(sd, f'{p}.attn.f.0', t, 1))
+        t = _conv(sd, f'{p}.refine', t, 0)
+        t = F.group_norm(t, norm_groups, sd[f'{p}.norm.weight'].to(dtype), sd[f'{p}.norm.bias'].to(dtype), 1e-5)
+        t = t + skip
+    t = _conv(sd, f'feats.{total - 1}', t, 1)
+    r2 = t.shape[1] // x.shape[1]
+    return F.pixel_shuffle(t + torch.repeat_interleave(x, r2, dim=1), math.isqrt(r2))
+
+
 _FORWARDS: Dict[str, Callable] = {
+    'RealPLKSR': realplksr_forward,
+    'ESRGAN': esrgan_forward,
     'SPAN': span_forward,
     'SPANPlus': spanplus_forward,
     'Compact': compact_forward,

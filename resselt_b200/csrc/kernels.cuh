@@ -34,6 +34,12 @@ struct Epi {
   int dst_external;  // 0: planar buffer, 1: caller's NCHW output
   void* dst;
   int dst_planes, dst_plane0;
+  // buffer destinations only: channels >= split_ch go to a second buffer range (dst2); dst_ps > 1 scatters the
+  // phase-major channel blocks (phase = c / phase_ch) of a sub-pixel conv onto the (H*dst_ps) x (W*dst_ps) grid
+  int split_ch;
+  void* dst2;
+  int dst2_planes, dst2_plane0;
+  int dst_ps, phase_ch, phase0;
   int cout;  // valid output channels
   int H, W;  // conv grid
   // external output
@@ -57,6 +63,35 @@ __device__ __forceinline__ void st_any(void* p, int dtype, size_t i, float v) {
     reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
   else
     reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+
+// R consecutive elements (R = 2 or 4) at element index i (i % R == 0) of the caller's tensor
+template <int R>
+__device__ __forceinline__ void st_any_vec(void* p, int dtype, size_t i, const float* v) {
+  if (dtype == RSB_F32) {
+    if (R == 2)
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(p) + i) = make_float2(v[0], v[1]);
+    else
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if (dtype == RSB_BF16) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    if (R == 2) {
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = a;
+    } else {
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 q = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = q;
+    }
+  } else {
+    __half2 a = __floats2half2_rn(v[0], v[1]);
+    if (R == 2) {
+      *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p) + i) = a;
+    } else {
+      __half2 b = __floats2half2_rn(v[2], v[3]);
+      uint2 q = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p) + i) = q;
+    }
+  }
 }
 
 template <typename T>
@@ -226,12 +261,54 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
     }
   }
   if (EXT == 0 || !e.dst_external) {
-    store8<T>(reinterpret_cast<T*>(e.dst) + planar_index(n, e.dst_planes, e.dst_plane0 + plane, e.H, e.W, y, x), v);
+    if (e.dst_ps > 1) {
+      // sub-pixel conv: this 8-channel block belongs to phase (a, b) of the upsampled grid
+      const int pidx = c0 / e.phase_ch, cc = c0 - pidx * e.phase_ch;
+      const int phase = e.phase0 + pidx;
+      const int a = phase / e.dst_ps, b = phase - a * e.dst_ps;
+      store8<T>(reinterpret_cast<T*>(e.dst) + planar_index(n, e.dst_planes, e.dst_plane0 + (cc >> 3), e.H * e.dst_ps, e.W * e.dst_ps,
+                                                           y * e.dst_ps + a, x * e.dst_ps + b), v);
+    } else if (e.dst2 != nullptr && c0 >= e.split_ch) {
+      store8<T>(reinterpret_cast<T*>(e.dst2) + planar_index(n, e.dst2_planes, e.dst2_plane0 + ((c0 - e.split_ch) >> 3), e.H, e.W, y, x), v);
+    } else {
+      store8<T>(reinterpret_cast<T*>(e.dst) + planar_index(n, e.dst_planes, e.dst_plane0 + plane, e.H, e.W, y, x), v);
+    }
     return;
   }
   // PixelShuffle(ps) scatter into the caller's NCHW tensor: conv channel oc -> (c, i, j) = (oc / ps^2, (oc % ps^2) / ps, oc % ps)
   const int ps = e.ps, ps2 = ps * ps;
   const int OH = e.H * ps, OW = e.W * ps;
+  if (ps == 2 || ps == 4) {
+    // the ps sub-pixels of one output row segment are adjacent in memory: vector stores
+#pragma unroll
+    for (int i = 0; i < 8; i += 4) {
+      if (ps == 4) {
+        const int oc = c0 + i;
+        if (oc < e.cout) {
+          const int c = oc >> 4, sy = (oc >> 2) & 3;
+          const float base = e.add_base ? ld_any(e.base, e.base_dtype, (((size_t)n * e.base_ch + c) * e.H + y) * e.W + x) : 0.0f;
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fmaf(v[i + j] + base, e.out_scale, e.out_mean[c & 3]);
+          st_any_vec<4>(e.dst, e.out_dtype, (((size_t)n * e.out_ch + c) * OH + (size_t)y * 4 + sy) * OW + (size_t)x * 4, o);
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 4; h += 2) {
+          const int oc = c0 + i + h;
+          if (oc < e.cout) {
+            const int c = oc >> 2, sy = (oc >> 1) & 1;
+            const float base = e.add_base ? ld_any(e.base, e.base_dtype, (((size_t)n * e.base_ch + c) * e.H + y) * e.W + x) : 0.0f;
+            float o[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) o[j] = fmaf(v[i + h + j] + base, e.out_scale, e.out_mean[c & 3]);
+            st_any_vec<2>(e.dst, e.out_dtype, (((size_t)n * e.out_ch + c) * OH + (size_t)y * 2 + sy) * OW + (size_t)x * 2, o);
+          }
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int oc = c0 + i;

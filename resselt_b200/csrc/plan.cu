@@ -196,6 +196,16 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
     e.dst = ws + b.offset;
     e.dst_planes = b.planes;
     e.dst_plane0 = d.dst_ch_off / 8;
+    e.dst_ps = d.dst_ps > 1 ? d.dst_ps : 1;
+    e.phase_ch = (e.dst_ps > 1 && d.dst_phase < 0) ? d.cout / (e.dst_ps * e.dst_ps) : d.cout;
+    e.phase0 = (e.dst_ps > 1 && d.dst_phase >= 0) ? d.dst_phase : 0;
+    if (e.dst_ps == 1 && d.dst2_buf >= 0) {
+      const Buffer& b2 = p->bufs[d.dst2_buf];
+      e.dst2 = ws + b2.offset;
+      e.dst2_planes = b2.planes;
+      e.dst2_plane0 = d.dst2_ch_off / 8;
+      e.split_ch = d.split_ch;
+    }
   }
 }
 
@@ -232,7 +242,8 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.tiles_x = ceil_div(W, rsb::kTileW), t.tiles_y = ceil_div(H, rsb::kTileH);
       t.num_tiles = t.tiles_x * t.tiles_y * n;
       t.cin = c.tc_cin, t.npad = c.npad;
-      t.kh = c.tc_kh, t.kw = c.tc_kw, t.pad_t = c.tc_kh / 2, t.pad_l = c.tc_kw / 2;
+      t.kh = c.tc_kh, t.kw = c.tc_kw;
+      t.pad_t = c.pack_buf >= 0 ? 0 : d.pad_t, t.pad_l = c.pack_buf >= 0 ? 0 : d.pad_l;
       t.src_plane0 = c.tc_src_ch_off / 8;
       t.wpack = c.d_wtc, t.wbytes = c.wbytes_tc;
       t.stages = c.stages;
@@ -246,7 +257,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       if (c.pack_buf >= 0) {
         rsb::PackParams& k = c.pk;
         memset(&k, 0, sizeof k);
-        k.n = n, k.H = H, k.W = W, k.cin = d.cin, k.kh = d.kh, k.kw = d.kw, k.pad_t = d.kh / 2, k.pad_l = d.kw / 2;
+        k.n = n, k.H = H, k.W = W, k.cin = d.cin, k.kh = d.kh, k.kw = d.kw, k.pad_t = d.pad_t, k.pad_l = d.pad_l;
         k.kplanes = c.pack_k / 8;
         for (int i = 0; i < 4; ++i) k.in_mean[i] = d.in_mean[i];
         k.in_scale = d.in_scale;
@@ -258,7 +269,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     q.n = n, q.H = H, q.W = W;
     q.cin = d.cin, q.cin_planes = c.cin_planes;
     q.cout = d.cout, q.cpad = c.cpad32;
-    q.kh = d.kh, q.kw = d.kw, q.pad_t = d.kh / 2, q.pad_l = d.kw / 2;
+    q.kh = d.kh, q.kw = d.kw, q.pad_t = d.pad_t, q.pad_l = d.pad_l;
     if (d.src_buf == RSB_EXTERNAL_INPUT) {
       q.src_external = 1;
       for (int i = 0; i < 4; ++i) q.in_mean[i] = d.in_mean[i];
@@ -357,7 +368,9 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
   if (!p || !desc) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: NULL argument");
   if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_conv: plan already finalized");
   const rsb_conv_desc& d = *desc;
-  if (d.cin < 1 || d.cout < 1 || d.kh < 1 || d.kw < 1 || d.kh % 2 == 0 || d.kw % 2 == 0)
+  const bool default_pad = d.pad_t < 0 || d.pad_l < 0;
+  if (d.cin < 1 || d.cout < 1 || d.kh < 1 || d.kw < 1 || (default_pad && (d.kh % 2 == 0 || d.kw % 2 == 0)) ||
+      (!default_pad && (d.pad_t >= d.kh || d.pad_l >= d.kw)))
     return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: bad cin/cout/kernel (%d,%d,%dx%d)", d.cin, d.cout, d.kh, d.kw);
   if (!d.weight) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: weight is NULL");
   if (d.act < RSB_ACT_NONE || d.act > RSB_ACT_GELU) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: unknown activation %d", d.act);
@@ -365,6 +378,7 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
   if (d.combine < RSB_COMB_NONE || d.combine > RSB_COMB_AXPY) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: unknown combine %d", d.combine);
   ConvOp c;
   c.d = d;
+  if (default_pad) c.d.pad_t = d.kh / 2, c.d.pad_l = d.kw / 2;
   int scale = 1;
   if (d.src_buf == RSB_EXTERNAL_INPUT) {
     if (d.cin != p->in_ch) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: external input has %d channels, conv wants %d", p->in_ch, d.cin);
@@ -379,8 +393,24 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
     if (d.add_base && p->in_ch != p->out_ch) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: add_base needs in_ch == out_ch");
     if (d.add_base && scale != 1) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: add_base on an upsampled grid");
   } else {
-    if (int e = check_buf(p, d.dst_buf, d.dst_ch_off, d.cout, "rsb_plan_add_conv(dst)")) return e;
-    if (p->bufs[d.dst_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: dst buffer grid scale %d != %d", p->bufs[d.dst_buf].scale, scale);
+    const int dps = d.dst_ps > 1 ? d.dst_ps : 1;
+    int main_ch = d.cout;
+    if (dps > 1 && d.dst_phase >= 0) {
+      if (d.dst_phase >= dps * dps || d.cout % 8 != 0 || d.dst2_buf >= 0)
+        return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: bad single-phase sub-pixel destination");
+    } else if (dps > 1) {
+      if (d.cout % (dps * dps) != 0 || (d.cout / (dps * dps)) % 8 != 0 || d.dst2_buf >= 0)
+        return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: sub-pixel destination needs cout = %d * 8k channels and no dst2", dps * dps);
+      main_ch = d.cout / (dps * dps);
+    } else if (d.dst2_buf >= 0) {
+      if (d.split_ch <= 0 || d.split_ch >= d.cout || d.split_ch % 8 != 0)
+        return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: split_ch %d must be a multiple of 8 inside (0, cout)", d.split_ch);
+      if (int e = check_buf(p, d.dst2_buf, d.dst2_ch_off, d.cout - d.split_ch, "rsb_plan_add_conv(dst2)")) return e;
+      if (p->bufs[d.dst2_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: dst2 grid mismatch");
+      main_ch = d.split_ch;
+    }
+    if (int e = check_buf(p, d.dst_buf, d.dst_ch_off, main_ch, "rsb_plan_add_conv(dst)")) return e;
+    if (p->bufs[d.dst_buf].scale != scale * dps) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: dst buffer grid scale %d != %d", p->bufs[d.dst_buf].scale, scale * dps);
     if (d.dst_buf == d.src_buf && d.kh * d.kw > 1) {
       const int a0 = d.src_ch_off, a1 = d.src_ch_off + ceil_div(d.cin, 16) * 16, b0 = d.dst_ch_off, b1 = d.dst_ch_off + d.cout;
       if (a0 < b1 && b0 < a1) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: spatial conv cannot run in place");

@@ -55,9 +55,13 @@ def random_state_dict(specs: Iterable[ParamSpec], seed: int = 0) -> Dict[str, to
 
 
 class EngineModule(nn.Module):
-    def __init__(self, specs: Iterable[ParamSpec], in_channels: int, out_channels: int, upscale: int, seed: int = 0):
+    def __init__(self, specs: Iterable[ParamSpec], in_channels: int, out_channels: int, upscale: int, seed: int = 0,
+                 plan_io: Optional[Tuple[int, int, int]] = None):
         super().__init__()
+        # what the caller sees ...
         self.in_channels, self.out_channels, self.upscale = in_channels, out_channels, upscale
+        # ... and what the native plan is built for (differs only when host-side glue reshapes the input first)
+        self._plan_io = plan_io if plan_io is not None else (in_channels, out_channels, upscale)
         self._plans: Dict[Tuple[int, torch.dtype], Plan] = {}
         self._plan_stamp: Dict[Tuple[int, torch.dtype], int] = {}
         rng = np.random.RandomState(seed)
@@ -125,7 +129,7 @@ class EngineModule(nn.Module):
         stamp = self._stamp()
         plan = self._plans.get(key)
         if plan is None or self._plan_stamp.get(key) != stamp:
-            pb = PlanBuilder(cdt, self.in_channels, self.out_channels, self.upscale)
+            pb = PlanBuilder(cdt, *self._plan_io)
             self.build_plan(pb, self._weights())
             plan = pb.finalize(torch.device('cuda', index))
             self._plans[key] = plan

@@ -55,6 +55,8 @@ class ConvDesc(C.Structure):
         ('in_mean', C.c_float * 4), ('in_scale', C.c_float),
         ('ps', C.c_int32), ('add_base', C.c_int32), ('out_scale', C.c_float), ('out_mean', C.c_float * 4),
         ('src_upsample2', C.c_int32),
+        ('dst_ps', C.c_int32), ('dst2_buf', C.c_int32), ('dst2_ch_off', C.c_int32), ('split_ch', C.c_int32),
+        ('dst_phase', C.c_int32), ('pad_t', C.c_int32), ('pad_l', C.c_int32),
     ]
 
 

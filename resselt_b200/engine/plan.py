@@ -83,6 +83,10 @@ class PlanBuilder:
         out_scale: float = 1.0,
         out_mean: Sequence[float] = (0.0, 0.0, 0.0, 0.0),
         src_upsample2: bool = False,
+        dst_ps: int = 1,
+        dst_phase: int = -1,
+        dst2: Optional[Ref] = None,
+        pad: Optional[tuple] = None,
     ) -> None:
         w = _f32(weight)
         assert w.ndim == 4, 'conv weight must be [cout][cin][kh][kw]'
@@ -94,8 +98,9 @@ class PlanBuilder:
         d.dst_buf, d.dst_ch_off, d.cout = dst.buf, dst.ch_off, cout
         if src.buf >= 0:
             assert src.channels == cin, f'conv reads {cin} channels, source range has {src.channels}'
+        main_ch = cout // (dst_ps * dst_ps) if (dst_ps > 1 and dst_phase < 0) else (cout - dst2.channels if dst2 is not None else cout)
         if dst.buf >= 0:
-            assert dst.channels == cout, f'conv writes {cout} channels, destination range has {dst.channels}'
+            assert dst.channels == main_ch, f'conv writes {main_ch} channels, destination range has {dst.channels}'
         d.kh, d.kw = kh, kw
         d.weight, d.bias = _fptr(w), _fptr(b)
         d.act, d.act_param, d.act_slopes = act, float(act_param), _fptr(s)
@@ -110,6 +115,11 @@ class PlanBuilder:
         omean4 = (list(out_mean) + [0.0] * 4)[:4]
         d.out_mean = (C.c_float * 4)(*omean4)
         d.src_upsample2 = int(bool(src_upsample2))
+        d.dst_ps = int(dst_ps)
+        d.dst_phase = int(dst_phase)
+        d.pad_t, d.pad_l = (int(pad[0]), int(pad[1])) if pad is not None else (-1, -1)
+        d.dst2_buf, d.dst2_ch_off = (dst2.buf, dst2.ch_off) if dst2 is not None else (N.NO_BUFFER, 0)
+        d.split_ch = main_ch if dst2 is not None else 0
         N.check(self._lib.rsb_plan_add_conv(self._h, C.byref(d)))
 
     def groupnorm(self, src: Ref, dst: Ref, groups: int, gamma, beta, eps: float = 1e-5, skip: Optional[Ref] = None) -> None:

@@ -84,7 +84,7 @@ def stage_models():
     import torch
     import oracle
     import resselt_b200
-    from resselt_b200.archs import SPAN, SpanPlus, SRVGGNetCompact
+    from resselt_b200.archs import SPAN, SpanPlus, SRVGGNetCompact, RRDBNet, RealPLKSR
 
     dev = 'cuda:0'
     ok_all = True
@@ -94,11 +94,15 @@ def stage_models():
         ('SPAN', SPAN(feature_channels=48, upscale=2, seed=3)),
         ('SPANPlus', SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=4)),
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=5)),
+        ('ESRGAN', RRDBNet(num_blocks=3, scale=4, seed=6)),
+        ('ESRGAN', RRDBNet(num_blocks=1, scale=2, plus=True, seed=7)),
+        ('RealPLKSR', RealPLKSR(n_blocks=3, upscaling_factor=4, seed=8)),
     ]
     for name, proto in models:
         sd = {k: v.clone() for k, v in proto.state_dict().items()}
         ref = oracle.forward_by_name(name, sd, x, torch.float32)
-        span = max(1.0, float(ref.max() - ref.min()))
+        rng = float(ref.max() - ref.min())
+        span = max(1.0, rng)
         m = resselt_b200.load_from_state_dict(dict(sd)).eval().to(dev)
         with torch.inference_mode():
             y32 = m(x.to(dev)).float().cpu()
@@ -110,7 +114,7 @@ def stage_models():
             y16d = m16(xb).float().cpu()
             plan.force_direct = False
         e32 = float((y32 - ref).abs().max()) / span
-        psnr = lambda y: float(10 * torch.log10(torch.tensor(span * span) / ((y - ref) ** 2).mean().clamp_min(1e-30)))
+        psnr = lambda y: float(10 * torch.log10(torch.tensor(rng * rng) / ((y - ref) ** 2).mean().clamp_min(1e-30)))
         rec = dict(stage='model', name=name, err_fp32=e32, psnr_bf16_tc=psnr(y16), psnr_bf16_direct=psnr(y16d),
                    tc_vs_direct=float((y16 - y16d).abs().max()) / span)
         rec['ok'] = e32 <= 1e-4 and rec['psnr_bf16_tc'] >= 50.0
