@@ -10,7 +10,7 @@ import torch.nn.functional as F
 import oracle
 import resselt_b200
 from conftest import golden_case, golden_index, norm_err, psnr
-from resselt_b200.archs import SPAN, SpanPlus, SRVGGNetCompact
+from resselt_b200.archs import SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact
 from resselt_b200.engine import INPUT, OUTPUT, PlanBuilder
 from resselt_b200.engine import native as N
 from resselt_b200.runner import FramePipeline, tiled_forward
@@ -53,6 +53,12 @@ def test_golden_fixtures_fp32_and_bf16(name):
         ('SPANPlus', SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=23), (1, 3, 70, 50)),
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=24), (3, 3, 45, 61)),
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=1, seed=25), (1, 3, 40, 40)),
+        ('ESRGAN', RRDBNet(num_blocks=23, scale=4, seed=26), (1, 3, 48, 40)),           # full depth: 69 dense blocks
+        ('ESRGAN', RRDBNet(num_blocks=2, scale=8, seed=27), (1, 3, 19, 23)),
+        ('ESRGAN', RRDBNet(num_blocks=2, scale=4, key_style='new', seed=28), (2, 3, 24, 17)),  # Real-ESRGAN key names
+        ('ESRGAN', RRDBNet(in_nc=12, out_nc=3, num_blocks=2, scale=4, shuffle_factor=2, seed=29), (1, 3, 33, 27)),
+        ('RealPLKSR', RealPLKSR(n_blocks=28, upscaling_factor=4, seed=30), (1, 3, 48, 56)),  # full depth
+        ('RealPLKSR', RealPLKSR(dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, use_ea=False, seed=31), (2, 3, 21, 30)),
     ],
 )
 def test_against_oracle_on_seeded_inputs(kind, model, shape):
@@ -124,6 +130,7 @@ def test_single_conv_layer_tensor_core_vs_fp64(cin, cout, k, n, H, W, act):
         (SPAN(feature_channels=48, upscale=2, seed=31), (90, 120), (40, 56)),
         (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=32), (70, 64), (32, 32)),
         (SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=33), (64, 100), (30, 64)),
+        (RRDBNet(num_blocks=1, scale=4, seed=34), (60, 72), (24, 40)),
     ],
 )
 def test_tile_seams_bit_identical(model, hw, tile, dtype):
@@ -135,6 +142,36 @@ def test_tile_seams_bit_identical(model, hw, tile, dtype):
         short = tiled_forward(m, x, m.upscale, tile, halo=2)
     assert torch.equal(full, tiled), 'exact-halo tiling must reproduce the untiled output bit for bit'
     assert not torch.equal(full, short), 'a too-small halo must be visible (guards against a vacuous test)'
+
+
+def test_subpixel_and_dual_destination_epilogues():
+    """The two buffer-destination modes ESRGAN / RealPLKSR rely on, in isolation, tensor-core vs CUDA-core vs fp64."""
+    from resselt_b200.archs.esrgan import upconv_phase_kernels
+
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(1, 64, 21, 19, generator=g)
+    wt = torch.randn(64, 64, 3, 3, generator=g) / 24
+    bias = torch.randn(64, generator=g)
+    w2 = torch.randn(64, 64, 3, 3, generator=g) / 24
+    pb = PlanBuilder(torch.bfloat16, 64, 64, 2)
+    a, up, side, rest = pb.buffer(64), pb.buffer(64, scale=2), pb.buffer(16), pb.buffer(64)
+    pb.conv(INPUT, a, torch.eye(64).view(64, 64, 1, 1))
+    for phase, wk, pad in upconv_phase_kernels(wt.double()):
+        pb.conv(a, up, wk, bias, dst_ps=2, dst_phase=phase, pad=pad, act=N.ACT_LRELU, act_param=0.2)
+    pb.conv(a, side, w2, None, dst2=rest.slice(16, 48))          # channels 0..15 -> side, 16..63 -> rest[16:]
+    pb.conv(up, OUTPUT, torch.eye(64).view(64, 64, 1, 1), ps=1)
+    plan = pb.finalize(torch.device(DEV))
+    q = lambda t: t.to(torch.bfloat16).double()
+    ref_up = F.leaky_relu(F.conv2d(F.interpolate(q(x), scale_factor=2, mode='nearest'), wt.double(), bias.double(), padding=1), 0.2)
+    ref_split = F.conv2d(q(x), q(w2), None, padding=1)
+    for direct in (False, True):
+        plan.force_direct = direct
+        y = plan.forward(x.to(DEV, torch.bfloat16)).double().cpu()
+        assert float((y - ref_up).abs().max()) / float(ref_up.abs().max()) < 1.2e-2   # pre-summed taps are rounded to bf16 once
+        got_side, got_rest = plan.read_buffer(side).double().cpu(), plan.read_buffer(rest.slice(16, 48)).double().cpu()
+        scale = float(ref_split.abs().max())
+        assert float((got_side - ref_split[:, :16]).abs().max()) / scale < 8e-3
+        assert float((got_rest - ref_split[:, 16:]).abs().max()) / scale < 8e-3
 
 
 def test_full_size_1080p_properties():
