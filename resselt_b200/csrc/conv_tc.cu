@@ -84,7 +84,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   }
   const int HT = kTileH + p.kh - 1;
   const int WT = kTileW + p.kw - 1;
-  const int ksteps = p.cin >> 4;
   const uint32_t a_lbo = (uint32_t)(HT * WT) * 16u;  // next 8-channel plane
   const uint32_t a_sbo = (uint32_t)WT * 16u;         // next tile row (8 pixels = one core matrix)
   const uint32_t b_lbo = (uint32_t)p.npad * 16u;     // next 8-input-channel slab
@@ -106,15 +105,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       }
       int s = 0;
       uint32_t ph = 0;
+      const int cp8 = p.kchunk >> 3;  // planes per K chunk (one shared-memory stage holds one chunk of one tile)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], p.stage_bytes);
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        tma_load_4d(stage0 + (size_t)s * st_al, &src_map, &full[s], 8 * (tx * kTileW - p.pad_l),
-                    ty * kTileH - p.pad_t, p.src_plane0, n);
-        if (++s == S) s = 0, ph ^= 1;
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], p.stage_bytes);
+          tma_load_4d(stage0 + (size_t)s * st_al, &src_map, &full[s], 8 * (tx * kTileW - p.pad_l),
+                      ty * kTileH - p.pad_t, p.src_plane0 + c * cp8, n);
+          if (++s == S) s = 0, ph ^= 1;
+        }
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -134,13 +136,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const uint32_t b_kstep = 2u * (b_lbo >> 4);
     int i = first;
     for (int tile = blockIdx.x + first * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, i += 2) {
-      const int s = i % S, acc = i % A;
-      const uint32_t ph = (uint32_t)(i / S) & 1u, aph = (uint32_t)(i / A) & 1u;
+      const int acc = i % A;
+      const uint32_t aph = (uint32_t)(i / A) & 1u;
       mbar_wait(&tempty[acc], aph ^ 1);
-      mbar_wait(&full[s], ph);
-      tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)acc * p.acc_stride;
       if constexpr (KH > 0) {
+        const int s = i % S;  // static geometry: one chunk per tile
+        mbar_wait(&full[s], (uint32_t)(i / S) & 1u);
+        tc_fence_after();
         constexpr uint32_t kPlane = (uint32_t)((kTileH + KH - 1) * (kTileW + KW - 1));  // 16-byte units per 8-ch plane
         const uint64_t da = make_smem_desc(smem_u32(stage0 + (size_t)s * st_al), kPlane * 16u, (uint32_t)(kTileW + KW - 1) * 16u);
         const uint64_t db = make_smem_desc(smem_u32(wsm), b_lbo, b_sbo);
@@ -156,29 +159,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 umma_bf16(d, a, b, idesc, (dy | dx | kk) != 0 ? 1u : 0u);
               }
         }
+        if (leader) umma_commit(&empty[s]);  // shared-memory stage may be refilled once these MMAs have read it
       } else {
-        const uint32_t a_lo0 = a_lo_const + (smem_u32(stage0 + (size_t)s * st_al) >> 4);
-        uint32_t b_lo = b_lo0;
-        // first MMA overwrites the accumulator, all others accumulate; weights are laid out [tap][k-step] so the
-        // B descriptor simply advances by one K step per MMA
-        if (leader) umma_bf16_lohi<false>(d, a_lo0, a_hi, b_lo, b_hi, idesc);
-        b_lo += b_kstep;
-        for (int dy = 0; dy < p.kh; ++dy) {
-          for (int dx = 0; dx < p.kw; ++dx) {
-            const int kk0 = (dy | dx) == 0 ? 1 : 0;
-            uint32_t a_lo = a_lo0 + (uint32_t)(dy * WT + dx) + (uint32_t)kk0 * a_kstep;
-            for (int kk = kk0; kk < ksteps; ++kk) {
-              if (leader) umma_bf16_lohi<true>(d, a_lo, a_hi, b_lo, b_hi, idesc);
-              a_lo += a_kstep;
-              b_lo += b_kstep;
+        // runtime geometry, K-chunked: chunk c of this tile sits in stage (i * nchunks + c) % S
+        const int kc_steps = p.kchunk >> 4;
+        const uint32_t cin8_units = (uint32_t)(p.cin >> 3) * (b_lbo >> 4);  // B descriptor units per tap
+        uint32_t accum = 0;
+        for (int c = 0; c < p.nchunks; ++c) {
+          const int j = i * p.nchunks + c;
+          const int s = j % S;
+          mbar_wait(&full[s], (uint32_t)(j / S) & 1u);
+          tc_fence_after();
+          const uint32_t a_lo0 = a_lo_const + (smem_u32(stage0 + (size_t)s * st_al) >> 4);
+          uint32_t b_tap = b_lo0 + (uint32_t)(c * (p.kchunk >> 3)) * (b_lbo >> 4);
+          for (int dy = 0; dy < p.kh; ++dy) {
+            for (int dx = 0; dx < p.kw; ++dx) {
+              uint32_t a_lo = a_lo0 + (uint32_t)(dy * WT + dx);
+              uint32_t b_lo = b_tap;
+              for (int kk = 0; kk < kc_steps; ++kk) {
+                if (leader) umma_bf16_lohi_rt(d, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+                accum = 1;
+                a_lo += a_kstep;
+                b_lo += b_kstep;
+              }
+              b_tap += cin8_units;
             }
           }
+          if (leader) umma_commit(&empty[s]);
         }
       }
-      if (leader) {
-        umma_commit(&empty[s]);    // shared-memory stage may be refilled once these MMAs have read it
-        umma_commit(&tfull[acc]);  // accumulator complete
-      }
+      if (leader) umma_commit(&tfull[acc]);  // accumulator complete
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -315,7 +325,7 @@ KernelFn pick(const ConvTcParams& p) {
   for (int pass = 0; pass < 2; ++pass)
     for (int i = 0; i < kNumVariants; ++i) {
       const Variant& v = kVariants[i];
-      const bool geo = pass == 0 ? (v.kh == p.kh && v.kw == p.kw && v.ksteps == ks) : v.kh == 0;
+      const bool geo = pass == 0 ? (v.kh == p.kh && v.kw == p.kw && v.ksteps == ks && p.nchunks == 1) : v.kh == 0;
       const bool width = v.nch == 0 || v.nch * 16 == p.npad;
       const bool ext = p.epi.dst_external ? v.ext == kRuntime : v.ext == 0;
       if (geo && width && ext && v.act == act && v.comb == comb) return v.fn;
@@ -325,9 +335,9 @@ KernelFn pick(const ConvTcParams& p) {
 
 }  // namespace
 
-size_t conv_tc_smem_bytes(int cin, int npad, int kh, int kw, int stages) {
+size_t conv_tc_smem_bytes(int cin, int kchunk, int npad, int kh, int kw, int stages) {
   const uint32_t wbytes = (uint32_t)kh * kw * cin * npad * 2u;
-  const uint32_t stage = (uint32_t)(kTileH + kh - 1) * (kTileW + kw - 1) * cin * 2u;
+  const uint32_t stage = (uint32_t)(kTileH + kh - 1) * (kTileW + kw - 1) * kchunk * 2u;
   return (size_t)align_up(wbytes, kAlign) + (size_t)stages * align_up(stage, kAlign) + 2 * npad * sizeof(float) +
          (2 * stages + 2 * kMaxAcc + 1) * 8 + 16;
 }
@@ -346,7 +356,7 @@ cudaError_t conv_tc_configure(size_t max_smem) {
 }
 
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
-  const size_t smem = conv_tc_smem_bytes(p.cin, p.npad, p.kh, p.kw, p.stages);
+  const size_t smem = conv_tc_smem_bytes(p.cin, p.kchunk, p.npad, p.kh, p.kw, p.stages);
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   const int threads = 128 + 128 * p.num_acc;
   KernelFn fn = pick(p);

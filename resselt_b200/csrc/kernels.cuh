@@ -328,13 +328,14 @@ struct ConvTcParams {
   int n, H, W;
   int tiles_x, tiles_y, num_tiles;
   int cin;   // multiple of 16
+  int kchunk, nchunks;  // K chunking of the shared-memory stages: cin == kchunk * nchunks, kchunk % 16 == 0
   int npad;  // UMMA N, multiple of 16, <= 256
   int kh, kw, pad_t, pad_l;
   int src_plane0;
   const void* wpack;  // bf16 [kh*kw][cin/8][npad][8]
   uint32_t wbytes;
   int stages;
-  uint32_t stage_bytes;  // (kTileH+kh-1) * (kTileW+kw-1) * cin * 2
+  uint32_t stage_bytes;  // (kTileH+kh-1) * (kTileW+kw-1) * kchunk * 2
   int num_acc;           // accumulator buffers in TMEM == epilogue warpgroups (1..4)
   uint32_t acc_stride;   // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;    // allocation (power of two >= 32)
@@ -389,7 +390,7 @@ struct GroupNormParams {
 
 // launchers (defined in the .cu files)
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
-size_t conv_tc_smem_bytes(int cin, int npad, int kh, int kw, int stages);
+size_t conv_tc_smem_bytes(int cin, int kchunk, int npad, int kh, int kw, int stages);
 int conv_tc_num_acc(int npad);
 cudaError_t conv_tc_configure(size_t max_smem);
 cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cudaStream_t stream);

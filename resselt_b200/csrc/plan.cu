@@ -59,7 +59,7 @@ struct ConvOp {
   int scale = 1;  // grid of this conv relative to the input
   int cin_pad16 = 0, npad = 0, cpad32 = 0, cin_planes = 0;
   bool tc_ok = false;
-  int stages = 0;
+  int stages = 0, kchunk = 0;
   // bf16 plans lower a small-Cin conv on the caller's NCHW tensor to [im2col pack -> 1x1 tensor-core conv]:
   // pack_buf is a hidden planar buffer with pack_k = pad16(cin*kh*kw) channels
   int pack_buf = -1, pack_k = 0;
@@ -230,7 +230,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       const int HT = rsb::kTileH + c.tc_kh - 1, WT = rsb::kTileW + c.tc_kw - 1;
       cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)sb.planes, (cuuint64_t)n};
       cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)W * 16 * H, (cuuint64_t)W * 16 * H * sb.planes};
-      cuuint32_t box[4] = {(cuuint32_t)(8 * WT), (cuuint32_t)HT, (cuuint32_t)(c.tc_cin / 8), 1};
+      cuuint32_t box[4] = {(cuuint32_t)(8 * WT), (cuuint32_t)HT, (cuuint32_t)(c.kchunk / 8), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(&c.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ws + sb.offset, dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -242,12 +242,13 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.tiles_x = ceil_div(W, rsb::kTileW), t.tiles_y = ceil_div(H, rsb::kTileH);
       t.num_tiles = t.tiles_x * t.tiles_y * n;
       t.cin = c.tc_cin, t.npad = c.npad;
+      t.kchunk = c.kchunk, t.nchunks = c.tc_cin / c.kchunk;
       t.kh = c.tc_kh, t.kw = c.tc_kw;
       t.pad_t = c.pack_buf >= 0 ? 0 : d.pad_t, t.pad_l = c.pack_buf >= 0 ? 0 : d.pad_l;
       t.src_plane0 = c.tc_src_ch_off / 8;
       t.wpack = c.d_wtc, t.wbytes = c.wbytes_tc;
       t.stages = c.stages;
-      t.stage_bytes = (uint32_t)HT * WT * c.tc_cin * 2u;
+      t.stage_bytes = (uint32_t)HT * WT * c.kchunk * 2u;
       t.num_acc = rsb::conv_tc_num_acc(c.npad);
       t.acc_stride = (uint32_t)c.npad;
       uint32_t cols = 32;
@@ -498,15 +499,23 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       const Buffer& sb = p->bufs[c.tc_src_buf];
       const bool planes_ok = c.tc_src_ch_off / 8 + c.tc_cin / 8 <= sb.planes;
       const int WT = rsb::kTileW + c.tc_kw - 1, HT = rsb::kTileH + c.tc_kh - 1;
-      int stages = 0;
-      for (int s = 4; s >= 2; --s)
-        if (rsb::conv_tc_smem_bytes(c.tc_cin, c.npad, c.tc_kh, c.tc_kw, s) <= kMaxSmem) {
-          stages = s;
-          break;
-        }
+      // prefer the whole Cin per stage (static-geometry kernels); otherwise stage K chunks of 64/48/32/16 channels
+      int stages = 0, kchunk = 0;
+      const int cands[5] = {c.tc_cin, 64, 48, 32, 16};
+      for (int ci = 0; ci < 5 && stages == 0; ++ci) {
+        const int kc = cands[ci];
+        if (kc > c.tc_cin || c.tc_cin % kc != 0) continue;
+        const int min_stages = ci == 0 ? 2 : 3;
+        for (int s = 4; s >= min_stages; --s)
+          if (rsb::conv_tc_smem_bytes(c.tc_cin, kc, c.npad, c.tc_kh, c.tc_kw, s) <= kMaxSmem) {
+            stages = s, kchunk = kc;
+            break;
+          }
+      }
       if (planes_ok && stages >= 2 && 8 * WT <= 256 && HT <= 256 && HT * WT < 16384) {
         c.tc_ok = true;
         c.stages = stages;
+        c.kchunk = kchunk;
       }
     }
     const int cmax = std::max(c.npad, c.cpad32);
