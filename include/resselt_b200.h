@@ -129,6 +129,37 @@ typedef struct rsb_groupnorm_desc {
   int32_t skip_buf, skip_ch_off; /* RSB_NO_BUFFER: no skip */
 } rsb_groupnorm_desc;
 
+/* Token-wise / attention ops of the transformer architectures (DAT).  A token is a pixel of a planar buffer.
+ * Call sites replaced: /root/reference/resselt/archs/dat/arch.py:48,636,672,897,924 (LayerNorm), :49,345,547
+ * (depthwise conv), :224-267 + :456-482 (shifted-window attention), :565-589 (channel attention), :492-508 and
+ * :594-607 (adaptive interaction module). */
+enum rsb_op_kind {
+  RSB_OP_LAYERNORM = 1, /* dst = LN_channels(src) * w[0] + w[1];  f[0] = eps                                         */
+  RSB_OP_DWCONV3 = 2,   /* dst = act(dwconv3x3(src; w[0] = [C][9], w[1] = bias[C])) [* src2];  i[0] = rsb_act          */
+  RSB_OP_WINATTN = 3,   /* src = [q | k | v]; i[0] heads, i[1] split_h, i[2] split_w, i[3] shifted, i[4] channel stride
+                           between q, k and v (0: channels);
+                           f[0] = qk scale; w[0] / w[1] = position-bias tables of the two branches                    */
+  RSB_OP_CHANATTN = 4,  /* src = [q | k | v]; i[0] heads, i[1] q/k/v channel stride (0: channels); w[0] = temperature[heads] */
+  RSB_OP_AIM = 5        /* src = attention output, src2 = conv branch, dst = gated sum; i[0] mode (0 window block,
+                           1 channel block), i[1] / i[2] hidden widths of the channel / spatial MLPs;
+                           w[0..3] = channel MLP (W1 [h1][C], b1, W2 [C][h1], b2), w[4..7] = spatial MLP
+                           (W1 [h2][C], b1, w2 [h2], b2 [1]); BatchNorm folded by the caller                           */
+};
+
+typedef struct rsb_op_desc {
+  int32_t kind;
+  int32_t src_buf, src_ch_off;
+  int32_t src2_buf, src2_ch_off; /* RSB_NO_BUFFER when unused */
+  int32_t dst_buf, dst_ch_off;
+  int32_t channels;
+  int32_t i[8];
+  float f[4];
+  const float* w[8]; /* host arrays, copied */
+  int64_t wn[8];     /* their element counts */
+} rsb_op_desc;
+
+int rsb_plan_add_op(rsb_plan* plan, const rsb_op_desc* desc);
+
 int rsb_version(void);
 const char* rsb_last_error(void);
 /* number of CUDA devices visible to the library (0 on a CPU-only host; never fails) */

@@ -16,6 +16,7 @@ pinned against outputs of the reference itself, generated in the build container
 """
 from .sr_forward import (  # noqa: F401
     compact_forward,
+    dat_forward,
     esrgan_forward,
     forward_by_name,
     realplksr_forward,

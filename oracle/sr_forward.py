@@ -193,7 +193,171 @@ def realplksr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, norm_groups:
     return F.pixel_shuffle(t + torch.repeat_interleave(x, r2, dim=1), math.isqrt(r2))
 
 
+# ---------------------------------------------------------------------------------------------- DAT
+def _lin(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    b = sd.get(name + '.bias')
+    return F.linear(x, sd[name + '.weight'].to(x.dtype), None if b is None else b.to(x.dtype))
+
+
+def _ln(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    return F.layer_norm(x, (x.shape[-1],), sd[name + '.weight'].to(x.dtype), sd[name + '.bias'].to(x.dtype), 1e-5)
+
+
+def _bn(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    g = lambda k: sd[f'{name}.{k}'].to(x.dtype)
+    return F.batch_norm(x, g('running_mean'), g('running_var'), g('weight'), g('bias'), False, 0.0, 1e-5)
+
+
+def _dat_pos_table(sd: SD, p: str, dtype) -> torch.Tensor:
+    """DynamicPosBias.forward with residual=False (/root/reference/resselt/archs/dat/arch.py:135-143): a 4-layer MLP
+    over the (2Hs-1)(2Ws-1) relative offsets stored in rpe_biases -> [offsets][heads]."""
+    t = _lin(sd, f'{p}.pos.pos_proj', sd[f'{p}.rpe_biases'].to(dtype))
+    for blk in ('pos1', 'pos2', 'pos3'):
+        t = _lin(sd, f'{p}.pos.{blk}.2', F.relu(_ln(sd, f'{p}.pos.{blk}.0', t)))
+    return t
+
+
+def _dat_shift_mask(Hp, Wp, Hs, Ws, sh, sw, dtype):
+    """calculate_mask (/root/reference/resselt/archs/dat/arch.py:363-428) for one branch: region labels of the rolled
+    image, -100 between tokens of different regions inside a window."""
+    img = torch.zeros(Hp, Wp, dtype=dtype)
+    cnt = 0
+    for hs in (slice(0, -Hs), slice(-Hs, -sh), slice(-sh, None)):
+        for ws in (slice(0, -Ws), slice(-Ws, -sw), slice(-sw, None)):
+            img[hs, ws] = cnt
+            cnt += 1
+    win = img.view(Hp // Hs, Hs, Wp // Ws, Ws).permute(0, 2, 1, 3).reshape(-1, Hs * Ws)
+    diff = win.unsqueeze(1) - win.unsqueeze(2)
+    return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
+
+
+def _dat_window_attention(sd: SD, p: str, q, k, v, Hp, Wp, Hs, Ws, heads, scale, mask):
+    """Spatial_Attention.forward (/root/reference/resselt/archs/dat/arch.py:224-267); q,k,v: [B, Hp, Wp, C]."""
+    B, _, _, C = q.shape
+
+    def win(t):  # im2win (:217-222): -> [B*nW, heads, N, C/heads]
+        t = t.view(B, Hp // Hs, Hs, Wp // Ws, Ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, Hs * Ws, heads, C // heads)
+        return t.permute(0, 2, 1, 3)
+
+    qw, kw, vw = win(q) * scale, win(k), win(v)
+    attn = qw @ kw.transpose(-2, -1)
+    table = _dat_pos_table(sd, p, q.dtype)
+    idx = sd[f'{p}.relative_position_index'].long().view(-1)
+    attn = attn + table[idx].view(Hs * Ws, Hs * Ws, -1).permute(2, 0, 1).unsqueeze(0)
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = (attn.view(B, nW, heads, Hs * Ws, Hs * Ws) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, Hs * Ws, Hs * Ws)
+    out = (attn.softmax(-1) @ vw).transpose(1, 2).reshape(-1, Hs * Ws, C)
+    return out.view(B, Hp // Hs, Wp // Ws, Hs, Ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)  # windows2img (:28-37)
+
+
+def _dat_aim_convs(sd: SD, p: str, v_img):
+    conv_x = F.gelu(_bn(sd, f'{p}.dwconv.1', F.conv2d(v_img, sd[f'{p}.dwconv.0.weight'].to(v_img.dtype), sd[f'{p}.dwconv.0.bias'].to(v_img.dtype),
+                                                       padding=1, groups=v_img.shape[1])))
+    def channel_interaction(t):
+        t = F.adaptive_avg_pool2d(t, 1)
+        t = F.gelu(_bn(sd, f'{p}.channel_interaction.2', _conv(sd, f'{p}.channel_interaction.1', t, 0)))
+        return _conv(sd, f'{p}.channel_interaction.4', t, 0)
+    def spatial_interaction(t):
+        t = F.gelu(_bn(sd, f'{p}.spatial_interaction.1', _conv(sd, f'{p}.spatial_interaction.0', t, 0)))
+        return _conv(sd, f'{p}.spatial_interaction.3', t, 0)
+    return conv_x, channel_interaction, spatial_interaction
+
+
+def _dat_spatial_block(sd: SD, p: str, x, H, W, split, shifted, heads):
+    """Adaptive_Spatial_Attention.forward (/root/reference/resselt/archs/dat/arch.py:430-513)."""
+    B, L, C = x.shape
+    qkv = _lin(sd, f'{p}.qkv', x).reshape(B, L, 3, C).permute(2, 0, 1, 3)
+    v_img = qkv[2].transpose(-2, -1).reshape(B, C, H, W)
+    m = max(split)
+    Hp, Wp = H + (m - H % m) % m, W + (m - W % m) % m
+    qkv = F.pad(qkv.reshape(3 * B, H, W, C).permute(0, 3, 1, 2), (0, Wp - W, 0, Hp - H)).permute(0, 2, 3, 1).reshape(3, B, Hp, Wp, C)
+    scale = (C // 2 // (heads // 2)) ** -0.5
+    outs = []
+    for br in (0, 1):
+        Hs, Ws = (split[0], split[1]) if br == 0 else (split[1], split[0])
+        sh, sw = Hs // 2, Ws // 2
+        t = qkv[..., br * (C // 2):(br + 1) * (C // 2)]
+        mask = None
+        if shifted:
+            t = torch.roll(t, shifts=(-sh, -sw), dims=(2, 3))
+            mask = _dat_shift_mask(Hp, Wp, Hs, Ws, sh, sw, x.dtype)
+        o = _dat_window_attention(sd, f'{p}.attns.{br}', t[0], t[1], t[2], Hp, Wp, Hs, Ws, heads // 2, scale, mask)
+        if shifted:
+            o = torch.roll(o, shifts=(sh, sw), dims=(1, 2))
+        outs.append(o[:, :H, :W].reshape(B, L, C // 2))
+    att = torch.cat(outs, 2)
+    conv_x, channel_interaction, spatial_interaction = _dat_aim_convs(sd, p, v_img)
+    cmap = channel_interaction(conv_x).permute(0, 2, 3, 1).reshape(B, 1, C)
+    smap = spatial_interaction(att.transpose(-2, -1).reshape(B, C, H, W))
+    att = att * torch.sigmoid(cmap)
+    conv_x = (torch.sigmoid(smap) * conv_x).permute(0, 2, 3, 1).reshape(B, L, C)
+    return _lin(sd, f'{p}.proj', att + conv_x)
+
+
+def _dat_channel_block(sd: SD, p: str, x, H, W, heads):
+    """Adaptive_Channel_Attention.forward (/root/reference/resselt/archs/dat/arch.py:565-612)."""
+    B, N, C = x.shape
+    qkv = _lin(sd, f'{p}.qkv', x).reshape(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = (t.transpose(-2, -1) for t in (qkv[0], qkv[1], qkv[2]))  # [B, heads, d, N]
+    v_img = v.reshape(B, C, N).view(B, C, H, W)
+    attn = (F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)) * sd[f'{p}.temperature'].to(x.dtype)
+    att = (attn.softmax(-1) @ v).permute(0, 3, 1, 2).reshape(B, N, C)
+    conv_x, channel_interaction, spatial_interaction = _dat_aim_convs(sd, p, v_img)
+    cmap = channel_interaction(att.transpose(-2, -1).reshape(B, C, H, W))
+    smap = spatial_interaction(conv_x).permute(0, 2, 3, 1).reshape(B, N, 1)
+    att = att * torch.sigmoid(smap)
+    conv_x = (conv_x * torch.sigmoid(cmap)).permute(0, 2, 3, 1).reshape(B, N, C)
+    return _lin(sd, f'{p}.proj', att + conv_x)
+
+
+def _dat_sgfn(sd: SD, p: str, x, H, W):
+    """SGFN / SpatialGate (/root/reference/resselt/archs/dat/arch.py:40-101)."""
+    B, N, _ = x.shape
+    t = F.gelu(_lin(sd, f'{p}.fc1', x))
+    x1, x2 = t.chunk(2, dim=-1)
+    c = x2.shape[-1]
+    x2 = _ln(sd, f'{p}.sg.norm', x2).transpose(1, 2).reshape(B, c, H, W)
+    x2 = F.conv2d(x2, sd[f'{p}.sg.conv.weight'].to(x.dtype), sd[f'{p}.sg.conv.bias'].to(x.dtype), padding=1, groups=c)
+    return _lin(sd, f'{p}.fc2', x1 * x2.flatten(2).transpose(-1, -2))
+
+
+def dat_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, img_range: float = 1.0) -> torch.Tensor:
+    """DAT.forward, 'pixelshuffle' head and '1conv' residual connection (/root/reference/resselt/archs/dat/arch.py:970-990,
+    forward_features :959-968, ResidualGroup.forward :763-780, DATB.forward :674-683).  Which blocks shift follows
+    :335 / :456: (rg even and b in {2, 6, ..}) or (rg odd and b % 4 == 0)."""
+    x = x.to(dtype)
+    in_ch = x.shape[1]
+    mean = torch.tensor((0.4488, 0.4371, 0.4040), dtype=dtype).view(1, 3, 1, 1) if in_ch == 3 else torch.zeros(1, 1, 1, 1, dtype=dtype)
+    x = (x - mean) * img_range
+    B, _, H, W = x.shape
+    split = [int(v) + 1 for v in sd['layers.0.blocks.0.attn.attns.0.rpe_biases'][-1]]
+    feat = _conv(sd, 'conv_first', x, 1)
+    t = _ln(sd, 'before_RG.1', feat.flatten(2).transpose(1, 2))
+    for rg in range(_seq_len(sd, 'layers')):
+        res = t
+        for b in range(_seq_len(sd, f'layers.{rg}.blocks')):
+            p = f'layers.{rg}.blocks.{b}'
+            n1 = _ln(sd, f'{p}.norm1', t)
+            if b % 2 == 0:
+                heads = 2 * sd[f'{p}.attn.attns.0.pos.pos3.2.weight'].shape[0]
+                shifted = (rg % 2 == 0 and b > 0 and (b - 2) % 4 == 0) or (rg % 2 != 0 and b % 4 == 0)
+                t = t + _dat_spatial_block(sd, f'{p}.attn', n1, H, W, split, shifted, heads)
+            else:
+                t = t + _dat_channel_block(sd, f'{p}.attn', n1, H, W, sd[f'{p}.attn.temperature'].shape[0])
+            t = t + _dat_sgfn(sd, f'{p}.ffn', _ln(sd, f'{p}.norm2', t), H, W)
+        img = t.transpose(1, 2).reshape(B, -1, H, W)
+        t = res + _conv(sd, f'layers.{rg}.conv', img, 1).flatten(2).transpose(1, 2)
+    t = _ln(sd, 'norm', t).transpose(1, 2).reshape(B, -1, H, W)
+    t = _conv(sd, 'conv_after_body', t, 1) + feat
+    t = F.leaky_relu(_conv(sd, 'conv_before_upsample.0', t, 1), 0.01)
+    for i in range(0, _seq_len(sd, 'upsample'), 2):
+        t = F.pixel_shuffle(_conv(sd, f'upsample.{i}', t, 1), 2)
+    return _conv(sd, 'conv_last', t, 1) / img_range + mean
+
+
 _FORWARDS: Dict[str, Callable] = {
+    'DAT': dat_forward,
     'RealPLKSR': realplksr_forward,
     'ESRGAN': esrgan_forward,
     'SPAN': span_forward,

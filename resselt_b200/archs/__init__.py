@@ -6,13 +6,14 @@ in-scope plugins are registered explicitly, in a fixed order.
 """
 from ..registry import Registry
 from .compact import CompactArch, SRVGGNetCompact
+from .dat import DAT, DatArch
 from .esrgan import ESRGANArch, RRDBNet
 from .plksr import PLKSRArch, RealPLKSR
 from .span import SPAN, SPANArch
 from .spanplus import SpanPlus, SpanPlusArch
 
 internal_registry = Registry()
-for _arch in (SPANArch, SpanPlusArch, CompactArch, ESRGANArch, PLKSRArch):
+for _arch in (SPANArch, SpanPlusArch, CompactArch, ESRGANArch, PLKSRArch, DatArch):
     internal_registry.add(_arch())
 
-__all__ = ['internal_registry', 'SPAN', 'SPANArch', 'SpanPlus', 'SpanPlusArch', 'SRVGGNetCompact', 'CompactArch', 'RRDBNet', 'ESRGANArch', 'RealPLKSR', 'PLKSRArch']
+__all__ = ['internal_registry', 'SPAN', 'SPANArch', 'SpanPlus', 'SpanPlusArch', 'SRVGGNetCompact', 'CompactArch', 'RRDBNet', 'ESRGANArch', 'RealPLKSR', 'PLKSRArch', 'DAT', 'DatArch']

@@ -1,0 +1,530 @@
+// Token-wise and attention kernels for DAT (Dual Aggregation Transformer) on planar-8 activations (token == pixel).
+//
+//   layernorm_kernel      LayerNorm over the channel dimension of every pixel (nn.LayerNorm call sites of
+//                         /root/reference/resselt/archs/dat/arch.py:48,636,672,897,924)
+//   dwconv3_kernel        depthwise 3x3 conv (+ folded BatchNorm + GELU, or * gate operand)   (arch.py:49,345,547)
+//   winattn_kernel        fused shifted-window attention: one CTA per (window, head): K/V of the window in shared
+//                         memory, one query per thread, QK^T + dynamic position bias + shift mask -> online softmax
+//                         -> PV in registers; roll / pad / window (un)partition are pure addressing  (arch.py:224-267,456-482)
+//   chanattn_*            channel attention: split-N Gram + norms reduction (deterministic two-stage), 30x30 softmax,
+//                         per-token apply                                                        (arch.py:565-589)
+//   aim_*                 adaptive interaction module: global average pool -> MLP -> channel map, per-pixel MLP ->
+//                         spatial map, and the gated sum                                          (arch.py:492-508,594-607)
+// All arithmetic is fp32 regardless of the storage type T (bf16 or fp32), so one set of kernels serves both plans.
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace rsb {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ld_ch(const T* base, int n, int planes, int plane0, int H, int W, int y, int x, int c) {
+  return (float)base[planar_index(n, planes, plane0 + (c >> 3), H, W, y, x) + (c & 7)];
+}
+template <typename T>
+__device__ __forceinline__ void st_ch(T* base, int n, int planes, int plane0, int H, int W, int y, int x, int c, float v) {
+  base[planar_index(n, planes, plane0 + (c >> 3), H, W, y, x) + (c & 7)] = (T)v;
+}
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float sigm_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ TokenOpParams p) {
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t total = (size_t)p.n * hw;
+  const int C = p.channels, planes = (C + 7) >> 3;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / hw);
+    const size_t pix = i - (size_t)n * hw;
+    const T* s = src + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8 + pix * 8;
+    float sum = 0.0f;
+    for (int pl = 0; pl < planes; ++pl) {
+      float v[8];
+      load8<T>(s + (size_t)pl * hw * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (pl * 8 + k < C) sum += v[k];
+    }
+    const float mean = sum / C;
+    float sq = 0.0f;
+    for (int pl = 0; pl < planes; ++pl) {
+      float v[8];
+      load8<T>(s + (size_t)pl * hw * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (pl * 8 + k < C) sq += (v[k] - mean) * (v[k] - mean);
+    }
+    const float rstd = rsqrtf(sq / C + p.f0);
+    T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
+    for (int pl = 0; pl < planes; ++pl) {
+      float v[8];
+      load8<T>(s + (size_t)pl * hw * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = pl * 8 + k;
+        v[k] = c < C ? (v[k] - mean) * rstd * p.w0[c] + p.w1[c] : 0.0f;
+      }
+      store8<T>(d + (size_t)pl * hw * 8, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise 3x3
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3_kernel(const __grid_constant__ TokenOpParams p) {
+  const size_t hw = (size_t)p.H * p.W;
+  const int C = p.channels, planes = (C + 7) >> 3;
+  const size_t total = (size_t)p.n * planes * hw;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  const T* mul = reinterpret_cast<const T*>(p.src2);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.W);
+    const int y = (int)((i / p.W) % p.H);
+    const int pl = (int)((i / hw) % planes);
+    const int n = (int)(i / (hw * planes));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = pl * 8 + k < C ? p.w1[pl * 8 + k] : 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = y + ky - 1;
+      if (sy < 0 || sy >= p.H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = x + kx - 1;
+        if (sx < 0 || sx >= p.W) continue;
+        float v[8];
+        load8<T>(src + planar_index(n, p.src_planes, p.src_plane0 + pl, p.H, p.W, sy, sx), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (pl * 8 + k < C) acc[k] = fmaf(v[k], p.w0[(pl * 8 + k) * 9 + ky * 3 + kx], acc[k]);
+      }
+    }
+    if (p.i0 == RSB_ACT_GELU) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = gelu_f(acc[k]);
+    }
+    if (mul != nullptr) {
+      float g[8];
+      load8<T>(mul + planar_index(n, p.src2_planes, p.src2_plane0 + pl, p.H, p.W, y, x), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] *= g[k];
+    }
+    store8<T>(dst + planar_index(n, p.dst_planes, p.dst_plane0 + pl, p.H, p.W, y, x), acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ window attention
+constexpr int kHD = 32;  // head_dim padded (<= 32 supported)
+
+template <typename T>
+__global__ void __launch_bounds__(256) winattn_kernel(const __grid_constant__ WinAttnParams p) {
+  extern __shared__ float sm[];
+  const int br = blockIdx.z, h = blockIdx.y;
+  const int Hs = br == 0 ? p.split_h : p.split_w, Ws = br == 0 ? p.split_w : p.split_h;
+  const int N = Hs * Ws;
+  const int sh = p.shifted ? Hs / 2 : 0, sw = p.shifted ? Ws / 2 : 0;
+  const int nWx = p.Wp / Ws, nWy = p.Hp / Hs;
+  const int win = blockIdx.x % (nWx * nWy), n = blockIdx.x / (nWx * nWy);
+  const int wy = win / nWx, wx = win - wy * nWx;
+  const int d = p.head_dim;
+  const int tab_w = 2 * Ws - 1, tab_n = (2 * Hs - 1) * tab_w;
+  float* Ks = sm;                       // [N][kHD]
+  float* Vs = Ks + (size_t)N * kHD;     // [N][kHD]
+  float* tab = Vs + (size_t)N * kHD;    // [tab_n] bias of this head
+  int* labs = reinterpret_cast<int*>(tab + tab_n);  // [N]
+  const float* table = br == 0 ? p.table0 : p.table1;
+  const int hpb = p.heads / 2;  // heads per branch
+  for (int i = threadIdx.x; i < tab_n; i += blockDim.x) tab[i] = table[(size_t)i * hpb + h];
+
+  const int t = threadIdx.x;
+  const bool active = t < N;
+  const int ty = active ? t / Ws : 0, tx = active ? t - ty * Ws : 0;
+  const int yr = wy * Hs + ty, xr = wx * Ws + tx;       // coordinates in the rolled, padded image
+  const int yo = (yr + sh) % p.Hp, xo = (xr + sw) % p.Wp;  // where that token lives in the un-rolled image
+  const bool inb = active && yo < p.H && xo < p.W;      // padded tokens have q = k = v = 0
+  const T* src = reinterpret_cast<const T*>(p.src);
+  const int half = p.dim / 2;
+  const int cq = p.src_ch_off + br * half + h * d;
+  float q[kHD];
+#pragma unroll
+  for (int c = 0; c < kHD; ++c) {
+    float qv = 0.0f, kv = 0.0f, vv = 0.0f;
+    if (inb && c < d) {
+      qv = ld_ch<T>(src, n, p.src_planes, 0, p.H, p.W, yo, xo, cq + c);
+      kv = ld_ch<T>(src, n, p.src_planes, 0, p.H, p.W, yo, xo, cq + p.qkv_stride + c);
+      vv = ld_ch<T>(src, n, p.src_planes, 0, p.H, p.W, yo, xo, cq + 2 * p.qkv_stride + c);
+    }
+    q[c] = qv * p.scale;
+    if (active) Ks[t * kHD + c] = kv, Vs[t * kHD + c] = vv;
+  }
+  if (active) {
+    int lab = 0;
+    if (p.shifted) {
+      const int ry = yr < p.Hp - Hs ? 0 : (yr < p.Hp - sh ? 1 : 2);
+      const int rx = xr < p.Wp - Ws ? 0 : (xr < p.Wp - sw ? 1 : 2);
+      lab = 3 * ry + rx;
+    }
+    labs[t] = lab;
+  }
+  __syncthreads();
+  if (!active) return;
+  const int my_lab = labs[t];
+  float m = -INFINITY, l = 0.0f;
+  float o[kHD];
+#pragma unroll
+  for (int c = 0; c < kHD; ++c) o[c] = 0.0f;
+  int jy = 0, jx = 0;
+  for (int j = 0; j < N; ++j) {
+    const float4* k4 = reinterpret_cast<const float4*>(Ks + j * kHD);
+    float s = 0.0f;
+#pragma unroll
+    for (int c4 = 0; c4 < kHD / 4; ++c4) {
+      const float4 kk = k4[c4];
+      s = fmaf(q[4 * c4 + 0], kk.x, s);
+      s = fmaf(q[4 * c4 + 1], kk.y, s);
+      s = fmaf(q[4 * c4 + 2], kk.z, s);
+      s = fmaf(q[4 * c4 + 3], kk.w, s);
+    }
+    s += tab[(ty - jy + Hs - 1) * tab_w + (tx - jx + Ws - 1)];
+    if (p.shifted && labs[j] != my_lab) s += -100.0f;
+    if (s > m) {  // rescale the running sums to the new maximum
+      const float corr = __expf(m - s);
+      l *= corr;
+#pragma unroll
+      for (int c = 0; c < kHD; ++c) o[c] *= corr;
+      m = s;
+    }
+    const float pj = __expf(s - m);
+    l += pj;
+    const float4* v4 = reinterpret_cast<const float4*>(Vs + j * kHD);
+#pragma unroll
+    for (int c4 = 0; c4 < kHD / 4; ++c4) {
+      const float4 vv = v4[c4];
+      o[4 * c4 + 0] = fmaf(pj, vv.x, o[4 * c4 + 0]);
+      o[4 * c4 + 1] = fmaf(pj, vv.y, o[4 * c4 + 1]);
+      o[4 * c4 + 2] = fmaf(pj, vv.z, o[4 * c4 + 2]);
+      o[4 * c4 + 3] = fmaf(pj, vv.w, o[4 * c4 + 3]);
+    }
+    if (++jx == Ws) jx = 0, ++jy;
+  }
+  if (inb) {
+    const float inv = 1.0f / l;
+    T* dst = reinterpret_cast<T*>(p.dst);
+    const int co = p.dst_ch_off + br * half + h * d;
+#pragma unroll
+    for (int c = 0; c < kHD; ++c)
+      if (c < d) st_ch<T>(dst, n, p.dst_planes, 0, p.H, p.W, yo, xo, co + c, o[c] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ channel attention
+constexpr int kTok = 32;  // tokens per shared-memory tile of the Gram reduction
+
+// partial[n][head][block][d*d + 2d]: Gram q^T k and squared column norms of q and k over this block's token range
+template <typename T>
+__global__ void __launch_bounds__(256) chanattn_reduce_kernel(const __grid_constant__ ChanAttnParams p) {
+  __shared__ float qs[kTok][kHD + 1], ks[kTok][kHD + 1];
+  const int h = blockIdx.y, n = blockIdx.z, d = p.head_dim;
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t chunk = (hw + gridDim.x - 1) / gridDim.x;
+  const size_t t0 = (size_t)blockIdx.x * chunk, t1 = min(hw, t0 + chunk);
+  const T* src = reinterpret_cast<const T*>(p.src);
+  const int cq = p.src_ch_off + h * d, ck = cq + p.qkv_stride;
+  float acc[4] = {0, 0, 0, 0};
+  float nrm = 0.0f;
+  for (size_t base = t0; base < t1; base += kTok) {
+    for (int e = threadIdx.x; e < kTok * d * 2; e += blockDim.x) {
+      const int which = e / (kTok * d), r = e - which * kTok * d;
+      const int tt = r / d, c = r - tt * d;
+      const size_t tok = base + tt;
+      float v = 0.0f;
+      if (tok < t1) {
+        const int ch = (which ? ck : cq) + c;
+        v = (float)src[(((size_t)n * p.src_planes + (ch >> 3)) * hw + tok) * 8 + (ch & 7)];
+      }
+      (which ? ks : qs)[tt][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = threadIdx.x + r * 256;
+      if (e < d * d) {
+        const int i = e / d, j = e - i * d;
+        float a = acc[r];
+#pragma unroll 8
+        for (int tt = 0; tt < kTok; ++tt) a = fmaf(qs[tt][i], ks[tt][j], a);
+        acc[r] = a;
+      }
+    }
+    if (threadIdx.x < 2 * d) {
+      const int c = threadIdx.x < d ? threadIdx.x : threadIdx.x - d;
+      for (int tt = 0; tt < kTok; ++tt) {
+        const float v = threadIdx.x < d ? qs[tt][c] : ks[tt][c];
+        nrm = fmaf(v, v, nrm);
+      }
+    }
+    __syncthreads();
+  }
+  float* out = p.partial + (((size_t)n * p.heads + h) * gridDim.x + blockIdx.x) * (d * d + 2 * d);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = threadIdx.x + r * 256;
+    if (e < d * d) out[e] = acc[r];
+  }
+  if (threadIdx.x < 2 * d) out[d * d + threadIdx.x] = nrm;
+}
+
+// attn[n][head][i][j] = softmax_j( G[i][j] / (max(|q_i|, eps) max(|k_j|, eps)) * temperature[head] )
+__global__ void __launch_bounds__(256) chanattn_finalize_kernel(const __grid_constant__ ChanAttnParams p) {
+  __shared__ float g[kHD * kHD + 2 * kHD];
+  const int h = blockIdx.x, n = blockIdx.y, d = p.head_dim;
+  const int len = d * d + 2 * d;
+  const float* in = p.partial + ((size_t)n * p.heads + h) * p.blocks * len;
+  for (int e = threadIdx.x; e < len; e += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < p.blocks; ++b) s += in[(size_t)b * len + e];  // fixed order: run-to-run deterministic
+    g[e] = (float)s;
+  }
+  __syncthreads();
+  if (threadIdx.x < d) {
+    const int i = threadIdx.x;
+    const float qn = fmaxf(sqrtf(g[d * d + i]), 1e-12f);
+    const float temp = p.temperature[h];
+    float row[kHD];
+    float mx = -INFINITY;
+    for (int j = 0; j < d; ++j) {
+      const float kn = fmaxf(sqrtf(g[d * d + d + j]), 1e-12f);
+      row[j] = g[i * d + j] / (qn * kn) * temp;
+      mx = fmaxf(mx, row[j]);
+    }
+    float sum = 0.0f;
+    for (int j = 0; j < d; ++j) {
+      row[j] = expf(row[j] - mx);
+      sum += row[j];
+    }
+    float* out = p.attn + (((size_t)n * p.heads + h) * d + i) * d;
+    for (int j = 0; j < d; ++j) out[j] = row[j] / sum;
+  }
+}
+
+// out[token][head*d + i] = sum_j attn[head][i][j] * v[token][head*d + j]
+template <typename T>
+__global__ void __launch_bounds__(256) chanattn_apply_kernel(const __grid_constant__ ChanAttnParams p) {
+  __shared__ float a[kHD * kHD];
+  const int h = blockIdx.y, n = blockIdx.z, d = p.head_dim;
+  const size_t hw = (size_t)p.H * p.W;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) a[e] = p.attn[((size_t)n * p.heads + h) * d * d + e];
+  __syncthreads();
+  const size_t tok = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= hw) return;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  const int cv = p.src_ch_off + 2 * p.qkv_stride + h * d;
+  float v[kHD];
+#pragma unroll
+  for (int c = 0; c < kHD; ++c) {
+    const int ch = cv + c;
+    v[c] = c < d ? (float)src[(((size_t)n * p.src_planes + (ch >> 3)) * hw + tok) * 8 + (ch & 7)] : 0.0f;
+  }
+  const int co = p.dst_ch_off + h * d;
+  for (int i = 0; i < d; ++i) {
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kHD; ++j)
+      if (j < d) s = fmaf(a[i * d + j], v[j], s);
+    const int ch = co + i;
+    dst[(((size_t)n * p.dst_planes + (ch >> 3)) * hw + tok) * 8 + (ch & 7)] = (T)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ AIM
+// pool partial sums: partial[n][block][plane*8 + k]
+template <typename T>
+__global__ void __launch_bounds__(256) aim_pool_kernel(const __grid_constant__ AimParams p) {
+  __shared__ float red[256][8];
+  const int pl = blockIdx.y, n = blockIdx.z;
+  const size_t hw = (size_t)p.H * p.W;
+  const T* base = reinterpret_cast<const T*>(p.pool_src) + ((size_t)n * p.pool_planes + p.pool_plane0 + pl) * hw * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8<T>(base + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[threadIdx.x][k] += red[threadIdx.x + o][k];
+    __syncthreads();
+  }
+  if (threadIdx.x < 8) p.partial[((size_t)n * gridDim.x + blockIdx.x) * p.cpad + pl * 8 + threadIdx.x] = red[0][threadIdx.x];
+}
+
+// cmap[n][c] = sigmoid( W2 . gelu(W1 . mean + b1) + b2 )     (BatchNorm already folded into W1/b1)
+__global__ void __launch_bounds__(256) aim_cmap_kernel(const __grid_constant__ AimParams p) {
+  __shared__ float mean[512], hid[64];
+  const int n = blockIdx.x, C = p.channels;
+  const float inv = 1.0f / ((float)p.H * (float)p.W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < p.blocks; ++b) s += p.partial[((size_t)n * p.blocks + b) * p.cpad + c];
+    mean[c] = (float)s * inv;
+  }
+  __syncthreads();
+  if (threadIdx.x < p.ci_hidden) {
+    float s = p.ci_b1[threadIdx.x];
+    for (int c = 0; c < C; ++c) s = fmaf(p.ci_w1[threadIdx.x * C + c], mean[c], s);
+    hid[threadIdx.x] = gelu_f(s);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = p.ci_b2[c];
+    for (int k = 0; k < p.ci_hidden; ++k) s = fmaf(p.ci_w2[c * p.ci_hidden + k], hid[k], s);
+    p.cmap[(size_t)n * p.cpad + c] = sigm_f(s);
+  }
+}
+
+// per pixel: smap = sigmoid(w2 . gelu(W1 . s + b1) + b2) on the spatial-map source, then the gated sum
+//   mode 0 (window-attention block): Y = ATT * cmap[c] + smap * CONVX      (arch.py:503-508)
+//   mode 1 (channel-attention block): Y = ATT * smap + CONVX * cmap[c]     (arch.py:602-607)
+template <typename T>
+__global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant__ AimParams p) {
+  extern __shared__ float sm[];
+  const int C = p.channels, planes = (C + 7) >> 3, hidn = p.si_hidden;
+  float* w1 = sm;                 // [hidn][cpad]
+  float* cm = w1 + hidn * p.cpad; // [cpad]
+  const int n = blockIdx.y;
+  for (int e = threadIdx.x; e < hidn * p.cpad; e += blockDim.x) {
+    const int k = e / p.cpad, c = e - k * p.cpad;
+    w1[e] = c < C ? p.si_w1[k * C + c] : 0.0f;
+  }
+  for (int c = threadIdx.x; c < p.cpad; c += blockDim.x) cm[c] = c < C ? p.cmap[(size_t)n * p.cpad + c] : 0.0f;
+  __syncthreads();
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  const T* att = reinterpret_cast<const T*>(p.att) + ((size_t)n * p.att_planes + p.att_plane0) * hw * 8 + pix * 8;
+  const T* cvx = reinterpret_cast<const T*>(p.convx) + ((size_t)n * p.convx_planes + p.convx_plane0) * hw * 8 + pix * 8;
+  const T* ssrc = p.mode == 0 ? att : cvx;
+  float hid[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) hid[k] = k < hidn ? p.si_b1[k] : 0.0f;
+  for (int pl = 0; pl < planes; ++pl) {
+    float v[8];
+    load8<T>(ssrc + (size_t)pl * hw * 8, v);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < hidn) {
+        const float* wr = w1 + k * p.cpad + pl * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) hid[k] = fmaf(wr[c], v[c], hid[k]);
+      }
+  }
+  float s = p.si_b2;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k < hidn) s = fmaf(p.si_w2[k], gelu_f(hid[k]), s);
+  const float smap = sigm_f(s);
+  T* dst = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
+  for (int pl = 0; pl < planes; ++pl) {
+    float a[8], b[8], o[8];
+    load8<T>(att + (size_t)pl * hw * 8, a);
+    load8<T>(cvx + (size_t)pl * hw * 8, b);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float cmv = cm[pl * 8 + c];
+      o[c] = p.mode == 0 ? fmaf(a[c], cmv, smap * b[c]) : fmaf(a[c], smap, b[c] * cmv);
+    }
+    store8<T>(dst + (size_t)pl * hw * 8, o);
+  }
+}
+
+inline int grid_for(size_t total, int threads = 256, int cap = 148 * 32) {
+  return (int)std::max<size_t>(1, std::min<size_t>((total + threads - 1) / threads, (size_t)cap));
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s) {
+  const int g = grid_for((size_t)p.n * p.H * p.W);
+  if (bf16)
+    layernorm_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    layernorm_kernel<float><<<g, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s) {
+  const int g = grid_for((size_t)p.n * ((p.channels + 7) / 8) * p.H * p.W);
+  if (bf16)
+    dwconv3_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    dwconv3_kernel<float><<<g, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+size_t winattn_smem_bytes(int split_h, int split_w) {
+  const int N = split_h * split_w;
+  return (size_t)N * kHD * 4 * 2 + (size_t)(2 * split_h - 1) * (2 * split_w - 1) * 4 + (size_t)N * 4;
+}
+
+cudaError_t winattn_configure() {
+  cudaError_t e = cudaFuncSetAttribute(winattn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(winattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+}
+
+cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
+  const int windows = (p.Hp / p.split_h) * (p.Wp / p.split_w);
+  const dim3 grid(windows * p.n, p.heads / 2, 2);
+  const size_t smem = winattn_smem_bytes(p.split_h, p.split_w);
+  if (bf16)
+    winattn_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
+  else
+    winattn_kernel<float><<<grid, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, cudaStream_t s) {
+  const size_t hw = (size_t)p.H * p.W;
+  const dim3 g1(p.blocks, p.heads, p.n), g2(p.heads, p.n), g3((unsigned)((hw + 255) / 256), p.heads, p.n);
+  if (bf16)
+    chanattn_reduce_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>(p);
+  else
+    chanattn_reduce_kernel<float><<<g1, 256, 0, s>>>(p);
+  chanattn_finalize_kernel<<<g2, 256, 0, s>>>(p);
+  if (bf16)
+    chanattn_apply_kernel<__nv_bfloat16><<<g3, 256, 0, s>>>(p);
+  else
+    chanattn_apply_kernel<float><<<g3, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s) {
+  const size_t hw = (size_t)p.H * p.W;
+  const int planes = (p.channels + 7) / 8;
+  const dim3 g1(p.blocks, planes, p.n), g3((unsigned)((hw + 255) / 256), p.n);
+  const size_t smem = ((size_t)p.si_hidden * p.cpad + p.cpad) * sizeof(float);
+  if (bf16)
+    aim_pool_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>(p);
+  else
+    aim_pool_kernel<float><<<g1, 256, 0, s>>>(p);
+  aim_cmap_kernel<<<p.n, 256, 0, s>>>(p);
+  if (bf16)
+    aim_combine_kernel<__nv_bfloat16><<<g3, 256, smem, s>>>(p);
+  else
+    aim_combine_kernel<float><<<g3, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace rsb

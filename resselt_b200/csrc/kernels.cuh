@@ -388,6 +388,69 @@ struct GroupNormParams {
   int blocks_per_group;
 };
 
+// ---- DAT token / attention ops (dat_ops.cu)
+struct TokenOpParams {  // LayerNorm and depthwise 3x3
+  int n, H, W, channels;
+  const void* src;
+  int src_planes, src_plane0;
+  const void* src2;  // dwconv: optional multiplicative gate
+  int src2_planes, src2_plane0;
+  void* dst;
+  int dst_planes, dst_plane0;
+  const float* w0;  // LayerNorm gamma | dwconv weight [C][9]
+  const float* w1;  // LayerNorm beta  | dwconv bias [C]
+  float f0;         // LayerNorm eps
+  int i0;           // dwconv activation (RSB_ACT_NONE / RSB_ACT_GELU)
+};
+
+struct WinAttnParams {
+  int n, H, W, Hp, Wp;  // Hp/Wp: padded to a multiple of max(split)
+  int dim, heads, head_dim, split_h, split_w, shifted;
+  float scale;
+  const void* src;  // q at channel src_ch_off, k at + qkv_stride, v at + 2 qkv_stride
+  int src_planes, src_ch_off, qkv_stride;
+  void* dst;
+  int dst_planes, dst_ch_off;
+  const float* table0;  // [(2 split_h - 1)(2 split_w - 1)][heads / 2]
+  const float* table1;  // [(2 split_w - 1)(2 split_h - 1)][heads / 2]
+};
+
+struct ChanAttnParams {
+  int n, H, W;
+  int dim, heads, head_dim, blocks;
+  const void* src;
+  int src_planes, src_ch_off, qkv_stride;
+  void* dst;
+  int dst_planes, dst_ch_off;
+  const float* temperature;
+  float* partial;  // [n][heads][blocks][d*d + 2d]
+  float* attn;     // [n][heads][d][d]
+};
+
+struct AimParams {
+  int n, H, W, channels, cpad, mode, ci_hidden, si_hidden, blocks;
+  const void* att;
+  int att_planes, att_plane0;
+  const void* convx;
+  int convx_planes, convx_plane0;
+  const void* pool_src;
+  int pool_planes, pool_plane0;
+  void* dst;
+  int dst_planes, dst_plane0;
+  const float *ci_w1, *ci_b1, *ci_w2, *ci_b2, *si_w1, *si_b1, *si_w2;
+  float si_b2;
+  float* partial;  // [n][blocks][cpad]
+  float* cmap;     // [n][cpad]
+};
+
+cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s);
+cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s);
+size_t winattn_smem_bytes(int split_h, int split_w);
+cudaError_t winattn_configure();
+cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s);
+cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, cudaStream_t s);
+cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s);
+
 // launchers (defined in the .cu files)
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
 size_t conv_tc_smem_bytes(int cin, int kchunk, int npad, int kh, int kw, int stages);

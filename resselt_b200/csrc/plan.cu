@@ -88,8 +88,19 @@ struct GnOp {
   rsb::GroupNormParams gp;
 };
 
+struct AuxOp {
+  rsb_op_desc d;
+  std::vector<float> w[8];
+  float* dw[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int scale = 1;
+  rsb::TokenOpParams tok;
+  rsb::WinAttnParams win;
+  rsb::ChanAttnParams chan;
+  rsb::AimParams aim;
+};
+
 struct Op {
-  int kind;  // 0 conv, 1 groupnorm
+  int kind;  // 0 conv, 1 groupnorm, 2 aux (rsb_op_desc)
   int index;
 };
 
@@ -117,6 +128,7 @@ struct rsb_plan {
   std::vector<Buffer> bufs;
   std::vector<ConvOp> convs;
   std::vector<GnOp> gns;
+  std::vector<AuxOp> auxs;
   std::vector<Op> ops;
   bool finalized = false;
   int device = -1;
@@ -143,8 +155,23 @@ int check_buf(const rsb_plan* p, int id, int ch_off, int channels, const char* w
   return 0;
 }
 
+constexpr int kAuxBlocks = 128;  // partial-sum blocks of the global reductions (channel attention Gram, AIM pooling)
+
+size_t aux_scratch_bytes(const AuxOp& a, int n) {
+  const rsb_op_desc& d = a.d;
+  if (d.kind == RSB_OP_CHANATTN) {
+    const int heads = d.i[0], hd = d.channels / heads;
+    return ((size_t)n * heads * kAuxBlocks * (hd * hd + 2 * hd) + (size_t)n * heads * hd * hd) * sizeof(float);
+  }
+  if (d.kind == RSB_OP_AIM) {
+    const int cpad = ceil_div(d.channels, 8) * 8;
+    return ((size_t)n * kAuxBlocks * cpad + (size_t)n * cpad) * sizeof(float);
+  }
+  return 0;
+}
+
 int layout(const rsb_plan* p, int n, int h, int w, std::vector<size_t>* offsets, std::vector<size_t>* gn_offsets,
-           size_t* total) {
+           size_t* total, size_t* aux_offset = nullptr) {
   size_t off = 0;
   if (offsets) offsets->clear();
   for (const Buffer& b : p->bufs) {
@@ -156,6 +183,11 @@ int layout(const rsb_plan* p, int n, int h, int w, std::vector<size_t>* offsets,
     if (gn_offsets) gn_offsets->push_back(off);
     off += align_up((size_t)n * g.d.groups * 1024 * 2 * sizeof(double), kWsAlign);
   }
+  // one scratch region shared by all aux ops (they run one after another on the stream)
+  size_t aux = 0;
+  for (const AuxOp& a : p->auxs) aux = std::max(aux, aux_scratch_bytes(a, n));
+  if (aux_offset) *aux_offset = off;
+  off += align_up(aux, kWsAlign);
   *total = off == 0 ? kWsAlign : off;
   return 0;
 }
@@ -211,8 +243,8 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
 
 int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   std::vector<size_t> offs, gn_offs;
-  size_t total;
-  layout(p, n, h, w, &offs, &gn_offs, &total);
+  size_t total, aux_off = 0;
+  layout(p, n, h, w, &offs, &gn_offs, &total, &aux_off);
   if (ws_bytes < total) return fail(RSB_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, total);
   if ((uintptr_t)workspace % kWsAlign != 0) return fail(RSB_ERR_WORKSPACE, "workspace must be %zu-byte aligned", kWsAlign);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
@@ -305,6 +337,65 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     const size_t chunks = (size_t)H * W * (g.d.channels / g.d.groups / 8);
     q.blocks_per_group = (int)std::min<size_t>(1024, std::max<size_t>(1, chunks / 2048));
   }
+  for (AuxOp& a : p->auxs) {
+    const rsb_op_desc& d = a.d;
+    const int H = h * a.scale, W = w * a.scale;
+    const Buffer& sb = p->bufs[d.src_buf];
+    const Buffer& db = p->bufs[d.dst_buf];
+    uint8_t* scratch = ws + aux_off;
+    if (d.kind == RSB_OP_LAYERNORM || d.kind == RSB_OP_DWCONV3) {
+      rsb::TokenOpParams& t = a.tok;
+      memset(&t, 0, sizeof t);
+      t.n = n, t.H = H, t.W = W, t.channels = d.channels;
+      t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_plane0 = d.src_ch_off / 8;
+      t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_plane0 = d.dst_ch_off / 8;
+      if (d.src2_buf >= 0) {
+        const Buffer& s2 = p->bufs[d.src2_buf];
+        t.src2 = ws + s2.offset, t.src2_planes = s2.planes, t.src2_plane0 = d.src2_ch_off / 8;
+      }
+      t.w0 = a.dw[0], t.w1 = a.dw[1], t.f0 = d.f[0], t.i0 = d.i[0];
+    } else if (d.kind == RSB_OP_WINATTN) {
+      rsb::WinAttnParams& t = a.win;
+      memset(&t, 0, sizeof t);
+      const int m = std::max(d.i[1], d.i[2]);
+      t.n = n, t.H = H, t.W = W, t.Hp = ceil_div(H, m) * m, t.Wp = ceil_div(W, m) * m;
+      t.dim = d.channels, t.heads = d.i[0], t.head_dim = d.channels / d.i[0];
+      t.split_h = d.i[1], t.split_w = d.i[2], t.shifted = d.i[3], t.scale = d.f[0];
+      t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_ch_off = d.src_ch_off;
+      t.qkv_stride = d.i[4] > 0 ? d.i[4] : d.channels;
+      t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_ch_off = d.dst_ch_off;
+      t.table0 = a.dw[0], t.table1 = a.dw[1];
+    } else if (d.kind == RSB_OP_CHANATTN) {
+      rsb::ChanAttnParams& t = a.chan;
+      memset(&t, 0, sizeof t);
+      t.n = n, t.H = H, t.W = W, t.dim = d.channels, t.heads = d.i[0], t.head_dim = d.channels / d.i[0];
+      t.blocks = (int)std::min<size_t>(kAuxBlocks, std::max<size_t>(1, ((size_t)H * W + 255) / 256));
+      t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_ch_off = d.src_ch_off;
+      t.qkv_stride = d.i[1] > 0 ? d.i[1] : d.channels;
+      t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_ch_off = d.dst_ch_off;
+      t.temperature = a.dw[0];
+      t.partial = reinterpret_cast<float*>(scratch);
+      t.attn = t.partial + (size_t)n * t.heads * kAuxBlocks * (t.head_dim * t.head_dim + 2 * t.head_dim);
+    } else if (d.kind == RSB_OP_AIM) {
+      rsb::AimParams& t = a.aim;
+      memset(&t, 0, sizeof t);
+      const Buffer& cb = p->bufs[d.src2_buf];
+      t.n = n, t.H = H, t.W = W, t.channels = d.channels, t.cpad = ceil_div(d.channels, 8) * 8;
+      t.mode = d.i[0], t.ci_hidden = d.i[1], t.si_hidden = d.i[2];
+      t.blocks = (int)std::min<size_t>(kAuxBlocks, std::max<size_t>(1, ((size_t)H * W + 1023) / 1024));
+      t.att = ws + sb.offset, t.att_planes = sb.planes, t.att_plane0 = d.src_ch_off / 8;
+      t.convx = ws + cb.offset, t.convx_planes = cb.planes, t.convx_plane0 = d.src2_ch_off / 8;
+      if (t.mode == 0)
+        t.pool_src = t.convx, t.pool_planes = t.convx_planes, t.pool_plane0 = t.convx_plane0;
+      else
+        t.pool_src = t.att, t.pool_planes = t.att_planes, t.pool_plane0 = t.att_plane0;
+      t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_plane0 = d.dst_ch_off / 8;
+      t.ci_w1 = a.dw[0], t.ci_b1 = a.dw[1], t.ci_w2 = a.dw[2], t.ci_b2 = a.dw[3];
+      t.si_w1 = a.dw[4], t.si_b1 = a.dw[5], t.si_w2 = a.dw[6], t.si_b2 = a.w[7].empty() ? 0.0f : a.w[7][0];
+      t.partial = reinterpret_cast<float*>(scratch);
+      t.cmap = t.partial + (size_t)n * kAuxBlocks * t.cpad;
+    }
+  }
   p->bn = n, p->bh = h, p->bw = w, p->bws = workspace;
   return 0;
 }
@@ -346,6 +437,8 @@ int rsb_plan_destroy(rsb_plan* p) {
       cudaFree(c.d_wtc), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
+    for (AuxOp& a : p->auxs)
+      for (int k = 0; k < 8; ++k) cudaFree(a.dw[k]);
     if (prev >= 0) cudaSetDevice(prev);
   }
   delete p;
@@ -471,6 +564,53 @@ int rsb_plan_add_groupnorm(rsb_plan* p, const rsb_groupnorm_desc* desc) {
   return 0;
 }
 
+int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
+  if (!p || !desc) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: NULL argument");
+  if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_op: plan already finalized");
+  const rsb_op_desc& d = *desc;
+  if (d.kind < RSB_OP_LAYERNORM || d.kind > RSB_OP_AIM) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown kind %d", d.kind);
+  if (d.channels < 1) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: bad channel count");
+  const bool qkv = d.kind == RSB_OP_WINATTN || d.kind == RSB_OP_CHANATTN;
+  if (d.src_buf < 0 || d.src_buf >= (int)p->bufs.size() || d.dst_buf < 0 || d.dst_buf >= (int)p->bufs.size())
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown buffer");
+  const int stride = d.kind == RSB_OP_WINATTN ? d.i[4] : (d.kind == RSB_OP_CHANATTN ? d.i[1] : 0);
+  const int src_need = d.src_ch_off + (qkv ? 2 * (stride > 0 ? stride : d.channels) : 0) + d.channels;
+  if (src_need > p->bufs[d.src_buf].planes * 8 || d.dst_ch_off + d.channels > p->bufs[d.dst_buf].planes * 8)
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel range exceeds buffer");
+  if (!qkv && (d.src_ch_off % 8 != 0 || d.dst_ch_off % 8 != 0))
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel offsets must be multiples of 8");
+  if (p->bufs[d.src_buf].scale != p->bufs[d.dst_buf].scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: grid mismatch");
+  if (d.src2_buf >= 0) {
+    if (int e = check_buf(p, d.src2_buf, d.src2_ch_off, d.channels, "rsb_plan_add_op(src2)")) return e;
+  } else if (d.kind == RSB_OP_AIM) {
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_op: AIM needs src2 (the conv branch)");
+  }
+  if (qkv) {
+    const int heads = d.i[0];
+    if (heads < 1 || d.channels % heads != 0 || d.channels / heads > 32)
+      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: attention needs head_dim <= 32 (dim %d, heads %d)", d.channels, heads);
+    if (d.kind == RSB_OP_WINATTN) {
+      if (heads % 2 != 0 || d.i[1] < 1 || d.i[2] < 1 || d.i[1] * d.i[2] > 256)
+        return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: window attention needs even heads and <= 256 tokens per window");
+      const int64_t tab = (int64_t)(2 * d.i[1] - 1) * (2 * d.i[2] - 1) * (heads / 2);
+      if (!d.w[0] || !d.w[1] || d.wn[0] != tab || d.wn[1] != tab)
+        return fail(RSB_ERR_INVALID, "rsb_plan_add_op: position-bias tables must hold %lld entries", (long long)tab);
+    }
+  }
+  if (d.kind == RSB_OP_AIM && (d.i[1] < 1 || d.i[1] > 64 || d.i[2] < 1 || d.i[2] > 16 || d.channels > 512))
+    return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: AIM hidden widths out of range");
+  AuxOp a;
+  a.d = d;
+  for (int k = 0; k < 8; ++k) {
+    if (d.w[k] && d.wn[k] > 0) a.w[k].assign(d.w[k], d.w[k] + d.wn[k]);
+    a.d.w[k] = nullptr;
+  }
+  a.scale = p->bufs[d.src_buf].scale;
+  p->auxs.push_back(std::move(a));
+  p->ops.push_back({2, (int)p->auxs.size() - 1});
+  return 0;
+}
+
 int rsb_plan_finalize(rsb_plan* p, int device) {
   if (!p) return fail(RSB_ERR_INVALID, "rsb_plan_finalize: NULL plan");
   if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_finalize: already finalized");
@@ -569,6 +709,13 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
     RSB_CUDA(cudaMemcpy(g.d_gamma, g.gamma.data(), g.gamma.size() * sizeof(float), cudaMemcpyHostToDevice));
     RSB_CUDA(cudaMemcpy(g.d_beta, g.beta.data(), g.beta.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
+  RSB_CUDA(rsb::winattn_configure());
+  for (AuxOp& a : p->auxs)
+    for (int k = 0; k < 8; ++k)
+      if (!a.w[k].empty()) {
+        RSB_CUDA(cudaMalloc(&a.dw[k], a.w[k].size() * sizeof(float)));
+        RSB_CUDA(cudaMemcpy(a.dw[k], a.w[k].data(), a.w[k].size() * sizeof(float), cudaMemcpyHostToDevice));
+      }
   p->finalized = true;
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   return 0;
@@ -580,7 +727,9 @@ int rsb_plan_launches_per_forward(const rsb_plan* p) {
   if (!p) return 0;
   int packed = 0;
   for (const ConvOp& c : p->convs) packed += (c.pack_buf >= 0 && c.tc_ok) ? 1 : 0;
-  return (int)p->convs.size() + packed + 2 * (int)p->gns.size();
+  int aux = 0;
+  for (const AuxOp& a : p->auxs) aux += (a.d.kind == RSB_OP_CHANATTN || a.d.kind == RSB_OP_AIM) ? 3 : 1;
+  return (int)p->convs.size() + packed + 2 * (int)p->gns.size() + aux;
 }
 
 int rsb_plan_flops(const rsb_plan* p, int n, int h, int w, double* flops) {
@@ -647,8 +796,18 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           q.epi.base = x, q.epi.base_dtype = x_dtype;
           e = rsb::launch_conv_direct(q, p->dtype == RSB_BF16, stream);
         }
-      } else {
+      } else if (op.kind == 1) {
         e = rsb::launch_groupnorm(p->gns[op.index].gp, p->dtype == RSB_BF16, stream);
+      } else {
+        AuxOp& a = p->auxs[op.index];
+        const bool bf = p->dtype == RSB_BF16;
+        switch (a.d.kind) {
+          case RSB_OP_LAYERNORM: e = rsb::launch_layernorm(a.tok, bf, stream); break;
+          case RSB_OP_DWCONV3: e = rsb::launch_dwconv3(a.tok, bf, stream); break;
+          case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, stream); break;
+          case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, stream); break;
+          default: e = rsb::launch_aim(a.aim, bf, stream); break;
+        }
       }
       if (e != cudaSuccess) {
         rc = fail_cuda(e, "kernel launch");

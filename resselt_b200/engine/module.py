@@ -26,6 +26,14 @@ ParamSpec = Tuple[str, Tuple[int, ...], str]  # (dotted name, shape, kind)
 
 
 def _init_tensor(shape, kind: str, rng: np.random.RandomState) -> torch.Tensor:
+    if kind == 'buffer_tensor':  # the "shape" slot carries the (deterministic) value itself
+        return shape.clone()
+    if kind == 'buffer_long':
+        return torch.zeros(shape, dtype=torch.int64)
+    if kind == 'buffer_var':
+        return torch.from_numpy(rng.uniform(0.5, 1.5, size=shape).astype(np.float32))
+    if kind.startswith('buffer_normal:'):
+        return torch.from_numpy(np.asarray(rng.normal(0.0, float(kind.split(':')[1]), size=shape), dtype=np.float32))
     if kind == 'conv_w':
         fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
         bound = 1.0 / math.sqrt(max(fan_in, 1))

@@ -14,7 +14,7 @@ import threading
 
 CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'csrc'))
 LIB_PATH = os.path.join(CSRC_DIR, 'libresselt_b200.so')
-SOURCES = ('conv_tc.cu', 'conv_direct.cu', 'plan.cu')
+SOURCES = ('conv_tc.cu', 'conv_direct.cu', 'dat_ops.cu', 'plan.cu')
 HEADERS = ('kernels.cuh', 'ptx.cuh', os.path.join('..', '..', 'include', 'resselt_b200.h'))
 NVCC_FLAGS = (
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -26,10 +26,11 @@ F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_MISH, ACT_LRELU, ACT_PRELU, ACT_SIGMOID, ACT_GELU = range(7)
 COMB_NONE, COMB_SPAB_GATE, COMB_MUL, COMB_AXPY = range(4)
 EXTERNAL_INPUT, EXTERNAL_OUTPUT, NO_BUFFER = -1, -2, -3
+OP_LAYERNORM, OP_DWCONV3, OP_WINATTN, OP_CHANATTN, OP_AIM = 1, 2, 3, 4, 5
 
 EXPORTED_SYMBOLS = (
     'rsb_version', 'rsb_last_error', 'rsb_device_count', 'rsb_plan_create', 'rsb_plan_destroy',
-    'rsb_plan_add_buffer', 'rsb_plan_add_conv', 'rsb_plan_add_groupnorm', 'rsb_plan_finalize',
+    'rsb_plan_add_buffer', 'rsb_plan_add_conv', 'rsb_plan_add_groupnorm', 'rsb_plan_add_op', 'rsb_plan_finalize',
     'rsb_plan_num_ops', 'rsb_plan_launches_per_forward', 'rsb_plan_flops', 'rsb_plan_workspace_bytes',
     'rsb_plan_forward', 'rsb_plan_forward_ops', 'rsb_plan_read_buffer',
 )
@@ -67,6 +68,18 @@ class GroupNormDesc(C.Structure):
         ('channels', C.c_int32), ('groups', C.c_int32), ('eps', C.c_float),
         ('gamma', C.POINTER(C.c_float)), ('beta', C.POINTER(C.c_float)),
         ('skip_buf', C.c_int32), ('skip_ch_off', C.c_int32),
+    ]
+
+
+class OpDesc(C.Structure):
+    _fields_ = [
+        ('kind', C.c_int32),
+        ('src_buf', C.c_int32), ('src_ch_off', C.c_int32),
+        ('src2_buf', C.c_int32), ('src2_ch_off', C.c_int32),
+        ('dst_buf', C.c_int32), ('dst_ch_off', C.c_int32),
+        ('channels', C.c_int32),
+        ('i', C.c_int32 * 8), ('f', C.c_float * 4),
+        ('w', C.POINTER(C.c_float) * 8), ('wn', C.c_int64 * 8),
     ]
 
 
@@ -121,6 +134,7 @@ def lib() -> C.CDLL:
         L.rsb_plan_add_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.rsb_plan_add_conv.argtypes = [C.c_void_p, C.POINTER(ConvDesc)]
         L.rsb_plan_add_groupnorm.argtypes = [C.c_void_p, C.POINTER(GroupNormDesc)]
+        L.rsb_plan_add_op.argtypes = [C.c_void_p, C.POINTER(OpDesc)]
         L.rsb_plan_finalize.argtypes = [C.c_void_p, C.c_int]
         L.rsb_plan_num_ops.argtypes = [C.c_void_p]
         L.rsb_plan_launches_per_forward.argtypes = [C.c_void_p]

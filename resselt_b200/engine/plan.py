@@ -132,6 +132,33 @@ class PlanBuilder:
         d.skip_buf, d.skip_ch_off = (skip.buf, skip.ch_off) if skip is not None else (N.NO_BUFFER, 0)
         N.check(self._lib.rsb_plan_add_groupnorm(self._h, C.byref(d)))
 
+    def op(self, kind: int, src: Ref, dst: Ref, channels: int, *, src2: Optional[Ref] = None, ints: Sequence[int] = (),
+           floats: Sequence[float] = (), weights: Sequence = ()) -> None:
+        """Token-wise / attention op (rsb_op_desc): LayerNorm, depthwise 3x3, window / channel attention, AIM."""
+        d = N.OpDesc()
+        d.kind = kind
+        d.src_buf, d.src_ch_off = src.buf, src.ch_off
+        d.src2_buf, d.src2_ch_off = (src2.buf, src2.ch_off) if src2 is not None else (N.NO_BUFFER, 0)
+        d.dst_buf, d.dst_ch_off = dst.buf, dst.ch_off
+        d.channels = channels
+        for k, v in enumerate(ints):
+            d.i[k] = int(v)
+        for k, v in enumerate(floats):
+            d.f[k] = float(v)
+        keep = []
+        for k, arr in enumerate(weights):
+            a = _f32(arr).reshape(-1)
+            keep.append(a)
+            d.w[k] = _fptr(a)
+            d.wn[k] = a.size
+        N.check(self._lib.rsb_plan_add_op(self._h, C.byref(d)))
+
+    def layernorm(self, src: Ref, dst: Ref, gamma, beta, eps: float = 1e-5) -> None:
+        self.op(N.OP_LAYERNORM, src, dst, src.channels, floats=(eps,), weights=(gamma, beta))
+
+    def dwconv3(self, src: Ref, dst: Ref, weight, bias, act: int = N.ACT_NONE, gate: Optional[Ref] = None) -> None:
+        self.op(N.OP_DWCONV3, src, dst, src.channels, src2=gate, ints=(act,), weights=(weight, bias))
+
     def finalize(self, device: torch.device) -> 'Plan':
         index = device.index if device.index is not None else torch.cuda.current_device()
         N.check(self._lib.rsb_plan_finalize(self._h, index))

@@ -84,12 +84,13 @@ def stage_models():
     import torch
     import oracle
     import resselt_b200
-    from resselt_b200.archs import SPAN, SpanPlus, SRVGGNetCompact, RRDBNet, RealPLKSR
+    from resselt_b200.archs import DAT, SPAN, SpanPlus, SRVGGNetCompact, RRDBNet, RealPLKSR
 
     dev = 'cuda:0'
     ok_all = True
     torch.manual_seed(1)
     x = torch.rand(1, 3, 64, 96)
+    only = os.environ.get('RSB_CHECK_ONLY')
     models = [
         ('SPAN', SPAN(feature_channels=48, upscale=2, seed=3)),
         ('SPANPlus', SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=4)),
@@ -97,8 +98,11 @@ def stage_models():
         ('ESRGAN', RRDBNet(num_blocks=3, scale=4, seed=6)),
         ('ESRGAN', RRDBNet(num_blocks=1, scale=2, plus=True, seed=7)),
         ('RealPLKSR', RealPLKSR(n_blocks=3, upscaling_factor=4, seed=8)),
+        ('DAT', DAT(depth=[3, 3], num_heads=[6, 6], upscale=4, seed=9)),
     ]
     for name, proto in models:
+        if only and name != only:
+            continue
         sd = {k: v.clone() for k, v in proto.state_dict().items()}
         ref = oracle.forward_by_name(name, sd, x, torch.float32)
         rng = float(ref.max() - ref.min())
