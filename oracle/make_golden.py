@@ -40,7 +40,7 @@ def cases():
                                                use_ea=True, norm_groups=4, dysample=False), 20, (1, 3, 24, 20), 110),
         'dat_x4_d3_3': ('DAT', dict(img_size=64, in_chans=3, embed_dim=180, split_size=[8, 32], depth=[3, 3], num_heads=[6, 6],
                                    expansion_factor=2.0, upscale=4), 22, (1, 3, 40, 56), 112),
-        'dat_x2_d2_s4_8': ('DAT', dict(img_size=32, in_chans=3, embed_dim=60, split_size=[4, 8], depth=[2, 3], num_heads=[2, 2],
+        'dat_x2_d3_2_s4_8': ('DAT', dict(img_size=32, in_chans=3, embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2],
                                       expansion_factor=2.0, upscale=2), 23, (2, 3, 19, 27), 113),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import resselt_b200
-from resselt_b200.archs import SPAN, SpanPlus, SRVGGNetCompact, internal_registry
+from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, internal_registry
 from resselt_b200.factory import Architecture, KeyCondition
 from resselt_b200.factory.arch import ModelMetadata
 from resselt_b200.registry import ArchitectureNotFound, Registry
@@ -20,7 +20,7 @@ def _sd(model):
 
 def test_public_surface():
     assert resselt_b200.__all__ == ['add', 'get', 'load_from_file', 'load_from_state_dict']
-    assert {'SPAN', 'spanplus', 'Compact'} <= set(internal_registry.store)
+    assert {'SPAN', 'spanplus', 'Compact', 'ESRGAN', 'PLKSR', 'dat'} <= set(internal_registry.store)
     assert resselt_b200.get('SPAN').id == 'SPAN'
     with pytest.raises(KeyError):  # same as the reference's dict lookup (registry.py:74)
         resselt_b200.get('nope')
@@ -42,6 +42,16 @@ def test_metadata_field_order():
         (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4), ('Compact', 3, 3, 4)),
         (SRVGGNetCompact(num_feat=24, num_conv=8, upscale=2), ('Compact', 3, 3, 2)),
         (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=1), ('Compact', 3, 3, 1)),
+        (RRDBNet(num_blocks=2, scale=4), ('ESRGAN', 3, 3, 4)),
+        (RRDBNet(num_blocks=1, scale=2, plus=True), ('ESRGAN', 3, 3, 2)),
+        (RRDBNet(num_blocks=1, scale=8), ('ESRGAN', 3, 3, 8)),
+        (RRDBNet(in_nc=12, out_nc=3, num_blocks=1, scale=4, shuffle_factor=2), ('ESRGAN', 3, 3, 2)),
+        (RRDBNet(num_blocks=1, scale=4, key_style='new'), ('ESRGAN', 3, 3, 4)),
+        (RRDBNet(num_blocks=1, scale=2, key_style='bsrgan'), ('ESRGAN', 3, 3, 2)),
+        (RealPLKSR(n_blocks=2, upscaling_factor=4), ('RealPLKSR', 3, 3, 4)),
+        (RealPLKSR(dim=32, n_blocks=2, upscaling_factor=2, kernel_size=13, use_ea=False), ('RealPLKSR', 3, 3, 2)),
+        (DAT(depth=[3, 2], num_heads=[6, 6], upscale=4), ('DAT', 3, 3, 4)),
+        (DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=2, img_size=32), ('DAT', 3, 3, 2)),
     ],
 )
 def test_detect_and_hyperparameter_inference(model, meta):
@@ -57,6 +67,13 @@ def test_detect_and_hyperparameter_inference(model, meta):
         assert loaded.blocks == model.blocks
     if isinstance(model, SPAN):
         assert loaded.norm == model.norm
+    if isinstance(model, RRDBNet):
+        assert (loaded.num_blocks, loaded.plus, loaded.shuffle_factor, loaded._keys.style) == (
+            model.num_blocks, model.plus, model.shuffle_factor, model._keys.style)
+    if isinstance(model, RealPLKSR):
+        assert (loaded.dim, loaded.n_blocks, loaded.kernel_size, loaded.use_ea) == (model.dim, model.n_blocks, model.kernel_size, model.use_ea)
+    if isinstance(model, DAT):
+        assert (loaded.depth, loaded.heads, loaded.split, loaded.img_size) == (model.depth, model.heads, model.split, model.img_size)
 
 
 def test_wrapped_and_prefixed_checkpoints():
