@@ -69,7 +69,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     }
     for (int a = 0; a < kMaxAcc; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 4 * (kMaxAcc / A));  // every epilogue warp that reads accumulator a arrives once
     }
     mbar_init(wbar, 1);
     fence_mbar_init();
@@ -192,8 +192,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int g = (warp - 4) >> 2;  // epilogue warpgroup == accumulator buffer it drains
-    if (g < A) {
+    // four epilogue warpgroups share the A accumulator buffers: warpgroup wg drains accumulator wg % A and, when
+    // A < 4 (wide N), only every (4/A)-th 16-column chunk of it, so wide layers still get four warpgroups of epilogue
+    const int wg = (warp - 4) >> 2;
+    const int g = wg % A, part = wg / A, parts = kMaxAcc / A;
+    {
       const int q = warp & 3;  // TMEM lane quarter this warp may read
       const int row = q * 32 + lane;
       const int ry = row >> 3, rx = row & 7;
@@ -243,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         } else {
           mbar_wait(&tfull[g], aph);
           tc_fence_after();
-          for (int c = 0; c < p.npad; c += 16) {
+          for (int c = part * 16; c < p.npad; c += 16 * parts) {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)c, r);
             tmem_ld_wait();
@@ -301,6 +304,9 @@ const Variant kVariants[] = {
     RSB_V(3, 3, 6, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_V(3, 3, 8, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_V(3, 3, 10, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
+    RSB_V(3, 3, 6, 0, RSB_ACT_NONE, RSB_COMB_AXPY),  // the two halves of the K-split 192->64 conv
+    RSB_V(3, 3, 4, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
+    RSB_V(2, 2, 4, 0, RSB_ACT_LRELU, RSB_COMB_NONE),  // 2x2 phase kernels of the nearest-x2 upconv
     RSB_V(3, 3, 4, 0, RSB_ACT_MISH, RSB_COMB_NONE),
     RSB_V(3, 3, 8, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_V(3, 3, 4, 0, RSB_ACT_SIGMOID, RSB_COMB_MUL),
@@ -309,6 +315,10 @@ const Variant kVariants[] = {
     RSB_V(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_V(0, 0, 0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_V(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
+    RSB_V(0, 0, 0, 0, RSB_ACT_GELU, RSB_COMB_NONE),
+    RSB_V(1, 1, 12, 0, RSB_ACT_NONE, RSB_COMB_NONE),  // DAT token linears: 192 -> 180
+    RSB_V(1, 1, 12, 0, RSB_ACT_GELU, RSB_COMB_NONE),
+    RSB_V(1, 1, 12, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
     // fully runtime
     RSB_X(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_X(0, 0, 0, 0, kRuntime, kRuntime),
@@ -343,8 +353,8 @@ size_t conv_tc_smem_bytes(int cin, int kchunk, int npad, int kh, int kw, int sta
 }
 
 int conv_tc_num_acc(int npad) {
-  int a = 512 / npad;
-  return a > kMaxAcc ? kMaxAcc : (a < 1 ? 1 : a);
+  const int a = 512 / npad;
+  return a >= 4 ? 4 : (a >= 2 ? 2 : 1);
 }
 
 cudaError_t conv_tc_configure(size_t max_smem) {
@@ -358,7 +368,7 @@ cudaError_t conv_tc_configure(size_t max_smem) {
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_tc_smem_bytes(p.cin, p.kchunk, p.npad, p.kh, p.kw, p.stages);
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  const int threads = 128 + 128 * p.num_acc;
+  const int threads = kMaxThreads;
   KernelFn fn = pick(p);
   fn<<<grid, threads, smem, stream>>>(src_map, p);
   return cudaGetLastError();

@@ -172,7 +172,16 @@ __device__ __forceinline__ float activate(int act_rt, float v, float param, floa
     case RSB_ACT_LRELU: return v >= 0.0f ? v : v * param;
     case RSB_ACT_PRELU: return v >= 0.0f ? v : v * slope;
     case RSB_ACT_SIGMOID: return sigmoid_f<kFast>(v);
-    case RSB_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    case RSB_ACT_GELU:
+      if (kFast) {
+        // erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 resolution): one ex2 + one rcp
+        const float z = fabsf(v) * 0.70710678118654752f;
+        const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+        const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+        const float erf_abs = 1.0f - poly * __expf(-z * z);
+        return 0.5f * v * (1.0f + copysignf(erf_abs, v));
+      }
+      return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default: return v;
   }
 }

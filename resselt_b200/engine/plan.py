@@ -60,7 +60,33 @@ class PlanBuilder:
         self.scales[bid.value] = scale
         return Ref(bid.value, 0, channels)
 
-    def conv(
+    def conv(self, src: Ref, dst: Ref, weight, bias=None, **kw) -> None:
+        """Add a conv op.  On the bf16 (tensor-core) plan a conv whose packed kernel would not fit shared memory next
+        to the activation stages is split over its output channels into several ops (each re-reads the input; every
+        op keeps its slice of bias / PReLU slopes / residual / destination)."""
+        w = _f32(weight)
+        cout, cin, kh, kw_ = w.shape
+        cin16 = (cin + 15) // 16 * 16
+        budget = 150 * 1024
+        splittable = (self.compute_dtype == torch.bfloat16 and src.buf >= 0 and dst.buf >= 0 and kw.get('dst_ps', 1) == 1
+                      and kw.get('dst2') is None and not kw.get('src_upsample2', False))
+        npad = (cout + 15) // 16 * 16
+        if not splittable or (kh * kw_ * cin16 * npad * 2 <= budget and npad <= 256):
+            return self._conv_one(src, dst, w, bias, **kw)
+        per = max(16, min(256, budget // (kh * kw_ * cin16 * 2) // 16 * 16))
+        b = _f32(bias) if bias is not None else None
+        slopes = _f32(kw['act_slopes']) if kw.get('act_slopes') is not None else None
+        for c0 in range(0, cout, per):
+            n = min(per, cout - c0)
+            sub = dict(kw)
+            if slopes is not None:
+                sub['act_slopes'] = slopes[c0:c0 + n]
+            for key in ('res1', 'res2'):
+                if sub.get(key) is not None:
+                    sub[key] = sub[key].slice(c0, n)
+            self._conv_one(src, dst.slice(c0, n), w[c0:c0 + n], None if b is None else b[c0:c0 + n], **sub)
+
+    def _conv_one(
         self,
         src: Ref,
         dst: Ref,
