@@ -342,12 +342,14 @@ struct ConvTcParams {
   int kh, kw, pad_t, pad_l;
   int src_plane0;
   const void* wpack;  // bf16 [kh*kw][cin/8][npad][8]
+  const void* wpack2; // bf16 [2][kh*kw][cin/8][npad/2][8]: per-CTA halves for the cta_group::2 kernel (or null)
   uint32_t wbytes;
   int stages;
   uint32_t stage_bytes;  // (kTileH+kh-1) * (kTileW+kw-1) * kchunk * 2
   int num_acc;           // accumulator buffers in TMEM == epilogue warpgroups (1..4)
   uint32_t acc_stride;   // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;    // allocation (power of two >= 32)
+  int dbg;               // bring-up switches of the CTA-pair kernel (env RSB_TC2_DBG)
   Epi epi;
 };
 
@@ -465,6 +467,9 @@ cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, in
 size_t conv_tc_smem_bytes(int cin, int kchunk, int npad, int kh, int kw, int stages);
 int conv_tc_num_acc(int npad);
 cudaError_t conv_tc_configure(size_t max_smem);
+bool conv_tc2_supported(const ConvTcParams& p);
+cudaError_t conv_tc2_configure(size_t max_smem);
+cudaError_t launch_conv_tc2(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cudaStream_t stream);
 cudaError_t launch_pack_input(const PackParams& p, cudaStream_t stream);
 cudaError_t launch_groupnorm(const GroupNormParams& p, bool bf16_storage, cudaStream_t stream);

@@ -67,6 +67,7 @@ struct ConvOp {
   int tc_src_buf = -1, tc_src_ch_off = 0, tc_cin = 0, tc_kh = 0, tc_kw = 0;
   rsb::PackParams pk;
   void* d_wtc = nullptr;
+  void* d_wtc2 = nullptr;  // per-CTA halves for the CTA-pair kernel
   uint32_t wbytes_tc = 0;
   float* d_wdirect = nullptr;
   float* d_bias = nullptr;
@@ -279,6 +280,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.pad_t = c.pack_buf >= 0 ? 0 : d.pad_t, t.pad_l = c.pack_buf >= 0 ? 0 : d.pad_l;
       t.src_plane0 = c.tc_src_ch_off / 8;
       t.wpack = c.d_wtc, t.wbytes = c.wbytes_tc;
+      t.wpack2 = c.d_wtc2;
       t.stages = c.stages;
       t.stage_bytes = (uint32_t)HT * WT * c.kchunk * 2u;
       t.num_acc = rsb::conv_tc_num_acc(c.npad);
@@ -434,7 +436,7 @@ int rsb_plan_destroy(rsb_plan* p) {
     cudaGetDevice(&prev);
     cudaSetDevice(p->device);
     for (ConvOp& c : p->convs) {
-      cudaFree(c.d_wtc), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
+      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
     for (AuxOp& a : p->auxs)
@@ -629,6 +631,7 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
   p->device = device;
   p->num_sms = prop.multiProcessorCount;
   RSB_CUDA(rsb::conv_tc_configure(kMaxSmem));
+  RSB_CUDA(rsb::conv_tc2_configure(kMaxSmem));
 
   for (ConvOp& c : p->convs) {
     const rsb_conv_desc& d = c.d;
@@ -690,6 +693,19 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       c.wbytes_tc = (uint32_t)(wp.size() * 2);
       RSB_CUDA(cudaMalloc(&c.d_wtc, c.wbytes_tc));
       RSB_CUDA(cudaMemcpy(c.d_wtc, wp.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
+      if (c.npad % 16 == 0 && c.kchunk == c.tc_cin) {
+        // CTA-pair layout: CTA r of a pair holds output channels [r*N/2, (r+1)*N/2)
+        const int nh = c.npad / 2;
+        std::vector<uint16_t> w2(wp.size(), 0);
+        for (int r = 0; r < 2; ++r)
+          for (int t = 0; t < taps; ++t)
+            for (int g = 0; g < cin8; ++g)
+              for (int j = 0; j < nh; ++j)
+                for (int e = 0; e < 8; ++e)
+                  w2[((((size_t)r * taps + t) * cin8 + g) * nh + j) * 8 + e] = wp[(((size_t)t * cin8 + g) * c.npad + r * nh + j) * 8 + e];
+        RSB_CUDA(cudaMalloc(&c.d_wtc2, c.wbytes_tc));
+        RSB_CUDA(cudaMemcpy(c.d_wtc2, w2.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
+      }
     }
     {
       // [cin_planes][kh][kw][8][cpad32] fp32 for the CUDA-core kernel
@@ -788,7 +804,11 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           rsb::ConvTcParams t = c.tcp;
           if (t.epi.dst_external) t.epi.dst = y, t.epi.out_dtype = y_dtype;
           t.epi.base = x, t.epi.base_dtype = x_dtype;
-          e = rsb::launch_conv_tc(c.map, t, p->num_sms, stream);
+          static const bool pair_kernel = getenv("RSB_TC2") != nullptr;
+          if (pair_kernel && rsb::conv_tc2_supported(t))
+            e = rsb::launch_conv_tc2(c.map, t, p->num_sms, stream);
+          else
+            e = rsb::launch_conv_tc(c.map, t, p->num_sms, stream);
         } else {
           rsb::ConvDirectParams q = c.dp;
           if (q.src_external) q.src = x, q.src_dtype = x_dtype;
