@@ -353,6 +353,23 @@ struct ConvTcParams {
   Epi epi;
 };
 
+// Row-streaming 3x3 kernel (conv_rs.cu): units are (image, 128-pixel column strip, row)
+struct ConvRsParams {
+  int n, H, W;
+  int cols;   // ceil(W / 128)
+  int units;  // n * cols * H
+  int cin;    // multiple of 16
+  int np;     // UMMA N per kernel row (cout padded to 16); 3 * np <= 256
+  int nslots; // output-row accumulators in the TMEM ring: 512 / np
+  int src_plane0;
+  const void* wpack;  // bf16 [3 kw][cin/8][3 kh * np][8]
+  uint32_t wbytes;
+  int stages;
+  uint32_t stage_bytes;  // cin/8 planes x 18 groups x 128 B
+  int dbg;               // bring-up switches (env RSB_RS_DBG): 1 no epilogue work, 2 no TMA loads, 4 no MMAs
+  Epi epi;
+};
+
 struct ConvDirectParams {
   int n, H, W;
   int cin, cin_planes;  // cin_planes = ceil(cin / 8)
@@ -470,6 +487,10 @@ cudaError_t conv_tc_configure(size_t max_smem);
 bool conv_tc2_supported(const ConvTcParams& p);
 cudaError_t conv_tc2_configure(size_t max_smem);
 cudaError_t launch_conv_tc2(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
+size_t conv_rs_smem_bytes(int cin, int np, int stages);
+uint32_t conv_rs_stage_bytes(int cin);
+cudaError_t conv_rs_configure(size_t max_smem);
+cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cudaStream_t stream);
 cudaError_t launch_pack_input(const PackParams& p, cudaStream_t stream);
 cudaError_t launch_groupnorm(const GroupNormParams& p, bool bf16_storage, cudaStream_t stream);

@@ -72,9 +72,15 @@ struct ConvOp {
   float* d_wdirect = nullptr;
   float* d_bias = nullptr;
   float* d_slopes = nullptr;
+  // row-streaming 3x3 kernel (conv_rs.cu): eligibility is decided at finalize, use at bind (needs W % 8 == 0)
+  bool rs_elig = false, use_rs = false;
+  int rs_stages = 0;
+  void* d_wrs = nullptr;
+  uint32_t wbytes_rs = 0;
   // bound state
-  CUtensorMap map;
+  CUtensorMap map, map_rs;
   rsb::ConvTcParams tcp;
+  rsb::ConvRsParams rsp;
   rsb::ConvDirectParams dp;
 };
 
@@ -289,6 +295,30 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       while (cols < (uint32_t)t.num_acc * c.npad) cols <<= 1;
       t.tmem_cols = cols;
       fill_epi(p, c, n, H, W, ws, t.epi);
+      c.use_rs = c.rs_elig && W % 8 == 0;
+      if (c.use_rs) {
+        // the same tensor viewed as [n][plane][H][W/8][8 px x 8 ch]: a box of 18 pixel groups of one row lands as
+        // [plane][18][128 B], i.e. 144 consecutive pixels per plane
+        cuuint64_t dims5[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)H, (cuuint64_t)sb.planes, (cuuint64_t)n};
+        cuuint64_t strides5[4] = {128, (cuuint64_t)W * 16, (cuuint64_t)W * 16 * H, (cuuint64_t)W * 16 * H * sb.planes};
+        cuuint32_t box5[5] = {64, 18, 1, (cuuint32_t)(c.tc_cin / 8), 1};
+        cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+        CUresult r5 = enc(&c.map_rs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ws + sb.offset, dims5, strides5, box5, estr5,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r5 != CUDA_SUCCESS) return fail(RSB_ERR_INVALID, "cuTensorMapEncodeTiled (5-D) failed with CUresult %d", (int)r5);
+        rsb::ConvRsParams& q = c.rsp;
+        memset(&q, 0, sizeof q);
+        q.n = n, q.H = H, q.W = W;
+        q.cols = ceil_div(W, 128);
+        q.units = n * q.cols * H;
+        q.cin = c.tc_cin, q.np = c.npad, q.nslots = std::min(32, 512 / c.npad);
+        q.src_plane0 = c.tc_src_ch_off / 8;
+        q.wpack = c.d_wrs, q.wbytes = c.wbytes_rs;
+        q.stages = c.rs_stages;
+        q.stage_bytes = rsb::conv_rs_stage_bytes(c.tc_cin);
+        q.epi = t.epi;
+      }
       if (c.pack_buf >= 0) {
         rsb::PackParams& k = c.pk;
         memset(&k, 0, sizeof k);
@@ -436,7 +466,7 @@ int rsb_plan_destroy(rsb_plan* p) {
     cudaGetDevice(&prev);
     cudaSetDevice(p->device);
     for (ConvOp& c : p->convs) {
-      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
+      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wrs), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
     for (AuxOp& a : p->auxs)
@@ -632,6 +662,8 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
   p->num_sms = prop.multiProcessorCount;
   RSB_CUDA(rsb::conv_tc_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_tc2_configure(kMaxSmem));
+  RSB_CUDA(rsb::conv_rs_configure(kMaxSmem));
+  static const bool no_rs = getenv("RSB_NO_RS") != nullptr;
 
   for (ConvOp& c : p->convs) {
     const rsb_conv_desc& d = c.d;
@@ -693,6 +725,25 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       c.wbytes_tc = (uint32_t)(wp.size() * 2);
       RSB_CUDA(cudaMalloc(&c.d_wtc, c.wbytes_tc));
       RSB_CUDA(cudaMemcpy(c.d_wtc, wp.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
+      if (!no_rs && d.kh == 3 && d.kw == 3 && d.pad_t == 1 && d.pad_l == 1 && 3 * c.npad <= 256 && 512 / c.npad >= 5) {
+        // row-streaming kernel: [kw][cin/8][kh * npad + o][8] — the three kernel rows side by side on the N axis
+        for (int s = 8; s >= 3 && c.rs_stages == 0; --s)
+          if (rsb::conv_rs_smem_bytes(c.tc_cin, c.npad, s) <= kMaxSmem) c.rs_stages = s;
+        if (c.rs_stages > 0) {
+          const int n3 = 3 * c.npad;
+          std::vector<uint16_t> wr((size_t)3 * cin8 * n3 * 8, 0);
+          for (int o = 0; o < d.cout; ++o)
+            for (int ci = 0; ci < d.cin; ++ci)
+              for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx)
+                  wr[(((size_t)kx * cin8 + ci / 8) * n3 + ky * c.npad + o) * 8 + (ci & 7)] =
+                      f32_to_bf16(c.w[((size_t)o * d.cin + ci) * 9 + ky * 3 + kx]);
+          c.wbytes_rs = (uint32_t)(wr.size() * 2);
+          RSB_CUDA(cudaMalloc(&c.d_wrs, c.wbytes_rs));
+          RSB_CUDA(cudaMemcpy(c.d_wrs, wr.data(), c.wbytes_rs, cudaMemcpyHostToDevice));
+          c.rs_elig = true;
+        }
+      }
       if (c.npad % 16 == 0 && c.kchunk == c.tc_cin) {
         // CTA-pair layout: CTA r of a pair holds output channels [r*N/2, (r+1)*N/2)
         const int nh = c.npad / 2;
@@ -791,7 +842,7 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
       cudaError_t e;
       if (op.kind == 0) {
         ConvOp& c = p->convs[op.index];
-        if (c.tc_ok && !force_direct) {
+        if (c.tc_ok && force_direct != 1) {
           if (c.pack_buf >= 0) {
             rsb::PackParams k = c.pk;
             k.src = x, k.src_dtype = x_dtype;
@@ -805,7 +856,11 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           if (t.epi.dst_external) t.epi.dst = y, t.epi.out_dtype = y_dtype;
           t.epi.base = x, t.epi.base_dtype = x_dtype;
           static const bool pair_kernel = getenv("RSB_TC2") != nullptr;
-          if (pair_kernel && rsb::conv_tc2_supported(t))
+          if (c.use_rs && force_direct != 2) {
+            rsb::ConvRsParams q = c.rsp;
+            q.epi = t.epi;
+            e = rsb::launch_conv_rs(c.map_rs, q, p->num_sms, stream);
+          } else if (pair_kernel && rsb::conv_tc2_supported(t))
             e = rsb::launch_conv_tc2(c.map, t, p->num_sms, stream);
           else
             e = rsb::launch_conv_tc(c.map, t, p->num_sms, stream);
