@@ -27,6 +27,7 @@
 //                 (tcgen05.ld -> kernels.cuh::epilogue8 -> 16-byte stores).
 // Accumulation order per output pixel: input rows y-1, y, y+1, each over (dx, 16-channel step) — identical to
 // conv_tc's (dy, dx, k) order and independent of the strip partition, so results do not depend on tile origin.
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -112,10 +113,27 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 4 && warp < 8) {
+    // all accumulator slots start out zero (afterwards the epilogue clears each slot it has read)
+    const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c = 0; c < NS * NP; c += 16) tmem_st16_zero(tz + (uint32_t)c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   const int u0 = (int)((long long)p.units * blockIdx.x / gridDim.x);
   const int u1 = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
 
+  // Hand-shakes (the tcgen05.mma issuing thread is the scarce resource — ~48 cycles per MMA issue, ~40 per barrier
+  // poll, ~68 per tcgen05.commit against 72 cycles of math per N = 144 MMA — so it only polls `full` and commits
+  // `tfull`):
+  //   full[st]     producer -> MMA     TMA bytes of an input row have landed AND the accumulator slot that row writes
+  //                                    first has been drained + cleared (the producer checks tempty before loading)
+  //   tfull[slot]  MMA -> epilogue     tcgen05.commit: every contribution to an output row has completed
+  //   tempty[slot] epilogue -> producer  slot read out and zeroed
+  //   empty[st]    epilogue -> producer  the MMAs that read a stage have completed (implied by the tfull the epilogue saw)
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&src_map);
@@ -124,13 +142,19 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const uint32_t len = min(32768u, p.wbytes - off);
         bulk_load_1d(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, len, wbar);
       }
-      int st = 0, u = u0;
+      int st = 0, qbase = 0, u = u0;
       uint32_t st_par = 1;
       Strip s;
       while (next_strip(p, u, u1, s)) {
         const int ya = max(s.y0 - 1, 0), yb = min(s.y1, p.H - 1);
         for (int yi = ya; yi <= yb; ++yi) {
           mbar_wait(&empty[st], st_par);
+          // output rows that receive their first contribution from this input row: yi + 1, and row 0 at yi == 0
+          for (int r = (yi == 0 ? 0 : yi + 1); r <= yi + 1; ++r)
+            if (r >= s.y0 && r < s.y1) {
+              const int q = qbase + (r - s.y0);
+              mbar_wait(&tempty[q % NS], (((uint32_t)(q / NS)) & 1u) ^ 1u);
+            }
           if (p.dbg & 2) {
             mbar_arrive(&full[st]);
           } else {
@@ -139,6 +163,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           }
           if (++st == S) st = 0, st_par ^= 1u;
         }
+        qbase += s.y1 - s.y0;
       }
     }
   } else if (warp == 1) {
@@ -153,7 +178,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const uint32_t st_units = st_al >> 4;
     const int ksteps = KS > 0 ? KS : (p.cin >> 4);
     const int cin8 = 2 * ksteps;
-    int st = 0, qbase = 0, u = u0;
+    const uint32_t tfull_s = smem_u32(tfull);
+    int st = 0, qbase = 0, u = u0, trow = 0;
     uint32_t st_par = 0;
     Strip s;
     while (next_strip(p, u, u1, s)) {
@@ -161,86 +187,77 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       for (int yi = ya; yi <= yb; ++yi) {
         const uint32_t a_lo = a_lo0 + (uint32_t)st * st_units;
         const int qn = qbase + (yi + 1 - s.y0);  // CTA-local index of output row yi + 1
-        const int use_n = qn / NS, slot_n = qn - use_n * NS;
-        if (KS > 0 && NCH > 0 && yi >= 1 && yi - 1 >= s.y0 && yi + 1 < s.y1 && slot_n >= 2) {
-          // steady state: rows yi+1 (first write), yi, yi-1 sit in three consecutive slots -> straight-line issue
+        const int slot_n = qn % NS;
+        long long* const tr = (p.trace != nullptr && blockIdx.x == 0 && leader && trow < 160) ? p.trace + 8 * trow : nullptr;
+        ++trow;
+        if (tr) {
+          tr[0] = clock64();
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          tr[1] = (long long)gt;
+        }
+        mbar_wait(&full[st], st_par);
+        tc_fence_after();
+        if (tr) tr[2] = clock64();
+        // every accumulator slot is zero when it is handed over (the epilogue clears it after reading): all MMAs accumulate
+        if (KS > 0 && NCH > 0 && yi - 1 >= s.y0 && yi + 1 < s.y1 && slot_n >= 2) {
+          // steady state: rows yi+1, yi, yi-1 sit in three consecutive slots -> one N = 3 * npad MMA per (dx, k step)
           constexpr uint32_t kN = 16u * (NCH > 0 ? NCH : 1);
-          constexpr uint32_t kI1 = make_idesc_bf16(128, (int)kN), kI2 = make_idesc_bf16(128, (int)(2 * kN)), kI3 = make_idesc_bf16(128, (int)(3 * kN));
-          mbar_wait(&tempty[slot_n], ((uint32_t)use_n & 1u) ^ 1u);
-          mbar_wait(&full[st], st_par);
-          tc_fence_after();
+          constexpr uint32_t kI3 = make_idesc_bf16(128, (int)(3 * kN));
           const uint32_t d0 = tmem_base + (uint32_t)(NS - 1 - slot_n) * kN;
-          if (leader && !(p.dbg & 4)) {
-            umma_bf16_lohi<false>(d0, a_lo, a_hi, b_lo0, b_hi, kI1);
-            umma_bf16_lohi<true>(d0 + kN, a_lo, a_hi, b_lo0 + kN, b_hi, kI2);
+          if (leader) {
+            if (!(p.dbg & 4)) {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
+              for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-              for (int kk = 0; kk < (KS > 0 ? KS : 1); ++kk)
-                if (dx | kk)
+                for (int kk = 0; kk < (KS > 0 ? KS : 1); ++kk)
                   umma_bf16_lohi<true>(d0, a_lo + (uint32_t)(dx + kk * 2 * (int)(kRsPlaneBytes >> 4)), a_hi,
                                        b_lo0 + (uint32_t)((dx * 2 * KS + 2 * kk) * 3 * (int)kN), b_hi, kI3);
-          }
-          if (leader) {
-            umma_commit(&empty[st]);
-            umma_commit(&tfull[slot_n - 2]);  // output row yi - 1 is complete
+            }
+            umma_commit_addr(tfull_s + 8u * (uint32_t)(slot_n - 2));  // output row yi - 1 is complete
           }
         } else {
           // strip / image borders and ring wrap: N block g (kernel row kh = g) feeds output row r = yi + 1 - g
-          bool v[3], fr[3];
+          bool v[3];
           uint32_t col[3];
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
             const int r = yi + 1 - g;
             v[g] = r >= s.y0 && r < s.y1;
-            const int q = qn - g;
-            const int slot = v[g] ? q % NS : 0;
+            const int slot = v[g] ? (qn - g) % NS : 0;
             col[g] = (uint32_t)((NS - 1 - slot) * NP);
-            fr[g] = v[g] && (yi == max(r - 1, 0));  // first contribution: the slot must have been drained
-            if (fr[g]) mbar_wait(&tempty[slot], (((uint32_t)(q / NS)) & 1u) ^ 1u);
           }
-          mbar_wait(&full[st], st_par);
-          tc_fence_after();
-          // merge neighbouring blocks into one MMA when their slots are contiguous and they agree on accumulate;
-          // phase 0 = the first MMA of the row (fresh slots are overwritten), phase 1 = the other MMAs
-          uint32_t idg[2][3];
-#pragma unroll
-          for (int ph = 0; ph < 2; ++ph) {
-            const bool a0 = ph || !fr[0], a1 = ph || !fr[1], a2 = ph || !fr[2];
-            const bool m01 = v[0] && v[1] && col[1] == col[0] + (uint32_t)NP && a0 == a1;
-            const bool m12 = v[1] && v[2] && col[2] == col[1] + (uint32_t)NP && a1 == a2;
-            const int n0 = v[0] ? 1 + (m01 ? 1 + (m12 ? 1 : 0) : 0) : 0;
-            const int n1 = (v[1] && !m01) ? 1 + (m12 ? 1 : 0) : 0;
-            const int n2 = (v[2] && !m12) ? 1 : 0;
-            idg[ph][0] = n0 ? idesc0 | ((uint32_t)((n0 * NP) >> 3) << 17) : 0u;
-            idg[ph][1] = n1 ? idesc0 | ((uint32_t)((n1 * NP) >> 3) << 17) : 0u;
-            idg[ph][2] = n2 ? idesc0 | ((uint32_t)((n2 * NP) >> 3) << 17) : 0u;
-          }
-          if (leader && !(p.dbg & 4)) {
-            uint32_t b_dx = b_lo0;
-            for (int dx = 0; dx < 3; ++dx) {
-              uint32_t a = a_lo + (uint32_t)dx, b = b_dx;
-              for (int kk = 0; kk < ksteps; ++kk) {
-                const int ph = (dx | kk) != 0 ? 1 : 0;
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                  const uint32_t id = ph ? idg[1][g] : idg[0][g];
-                  if (id != 0u)
-                    umma_bf16_lohi_rt(tmem_base + col[g], a, a_hi, b + (uint32_t)(g * NP), b_hi, id, (ph || !fr[g]) ? 1u : 0u);
-                }
-                a += 2u * (kRsPlaneBytes >> 4);
-                b += 2u * (uint32_t)(3 * NP);
-              }
-              b_dx += (uint32_t)(cin8 * 3 * NP);
-            }
-          }
+          // neighbouring blocks whose slots are contiguous go out as one MMA
+          const bool m01 = v[0] && v[1] && col[1] == col[0] + (uint32_t)NP;
+          const bool m12 = v[1] && v[2] && col[2] == col[1] + (uint32_t)NP;
+          const int n0 = v[0] ? 1 + (m01 ? 1 + (m12 ? 1 : 0) : 0) : 0;
+          const int n1 = (v[1] && !m01) ? 1 + (m12 ? 1 : 0) : 0;
+          const int n2 = (v[2] && !m12) ? 1 : 0;
+          uint32_t idg[3];
+          idg[0] = n0 ? idesc0 | ((uint32_t)((n0 * NP) >> 3) << 17) : 0u;
+          idg[1] = n1 ? idesc0 | ((uint32_t)((n1 * NP) >> 3) << 17) : 0u;
+          idg[2] = n2 ? idesc0 | ((uint32_t)((n2 * NP) >> 3) << 17) : 0u;
           if (leader) {
-            umma_commit(&empty[st]);  // the stage may be refilled once these MMAs have read it
+            if (!(p.dbg & 4)) {
+              uint32_t b_dx = b_lo0;
+              for (int dx = 0; dx < 3; ++dx) {
+                uint32_t a = a_lo + (uint32_t)dx, b = b_dx;
+                for (int kk = 0; kk < ksteps; ++kk) {
+#pragma unroll
+                  for (int g = 0; g < 3; ++g)
+                    if (idg[g] != 0u) umma_bf16_lohi<true>(tmem_base + col[g], a, a_hi, b + (uint32_t)(g * NP), b_hi, idg[g]);
+                  a += 2u * (kRsPlaneBytes >> 4);
+                  b += 2u * (uint32_t)(3 * NP);
+                }
+                b_dx += (uint32_t)(cin8 * 3 * NP);
+              }
+            }
             // output rows whose last contribution this was: r = yi - 1 always, r = yi on the image's last row
-            if (v[2]) umma_commit(&tfull[(qn - 2) % NS]);
-            if (v[1] && yi == p.H - 1) umma_commit(&tfull[(qn - 1) % NS]);
+            if (v[2]) umma_commit_addr(tfull_s + 8u * (uint32_t)((qn - 2) % NS));
+            if (v[1] && yi == p.H - 1) umma_commit_addr(tfull_s + 8u * (uint32_t)((qn - 1) % NS));
           }
         }
+        if (tr) tr[3] = clock64();
         if (++st == S) st = 0, st_par ^= 1u;
       }
       qbase += s.y1 - s.y0;
@@ -250,20 +267,21 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const int wg = (warp - 4) >> 2;
     const int qd = warp & 3;  // TMEM lane quarter this warp may read
     const int cstore = (p.epi.cout + 7) & ~7;
-    const int nrows = u1 - u0;
-    for (int q = wg; q < nrows; q += kRsWG) {
-      const int uu = u0 + q;
-      const int t = uu / p.H;
-      const int y = uu - t * p.H;
-      const int n = t / p.cols;
-      const int cx = t - n * p.cols;
-      const int x = cx * 128 + qd * 32 + lane;
+    int qbase = 0, jbase = 0, u = u0;
+    Strip s;
+    while (next_strip(p, u, u1, s)) {
+      const int ya = max(s.y0 - 1, 0), yb = min(s.y1, p.H - 1);
+      const int n = s.n;
+      const int x = s.cx * 128 + qd * 32 + lane;
       const bool valid = x < p.W && !(p.dbg & 1);
-      const int slot = q % NS;
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((NS - 1 - slot) * NP);
-      const uint32_t par = ((uint32_t)(q / NS)) & 1u;
-      if constexpr (NCH > 0) {
-        constexpr bool kUsesRes = COMB == RSB_COMB_SPAB_GATE || COMB == RSB_COMB_MUL || COMB == RSB_COMB_AXPY;
+      for (int y = s.y0 + ((wg - qbase) & (kRsWG - 1)); y < s.y1; y += kRsWG) {
+        const int q = qbase + (y - s.y0);  // q % kRsWG == wg
+        const int slot = q % NS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((NS - 1 - slot) * NP);
+        const uint32_t par = ((uint32_t)(q / NS)) & 1u;
+        long long* const te = (p.trace != nullptr && blockIdx.x == 0 && qd == 0 && lane == 0 && q < 160) ? p.trace + 8 * 160 + 4 * q : nullptr;
+        if (te) te[0] = clock64();
+        constexpr bool kUsesRes = NCH > 0 && (COMB == RSB_COMB_SPAB_GATE || COMB == RSB_COMB_MUL || COMB == RSB_COMB_AXPY);
         uint4 pre[kUsesRes ? 2 * NCH : 1];
         if constexpr (kUsesRes) {
           // the residual does not depend on this row's MMAs: fetch it while they are still running
@@ -277,45 +295,66 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         }
         mbar_wait(&tfull[slot], par);
         tc_fence_after();
-        uint32_t r[2][16];
-        tmem_ld16(taddr, r[0]);
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          const int c = ci * 16;
-          tmem_ld_wait();
-          if (ci + 1 < NCH) tmem_ld16(taddr + (uint32_t)(c + 16), r[(ci + 1) & 1]);
-          if (valid) {
-            float vv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[ci & 1][k]);
-            if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[ci & 1][8 + k]);
-            if (c + 8 < cstore)
-              epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr);
-          }
+        if (te) te[1] = clock64();
+        if (qd == 0 && lane == 0) {
+          // every MMA up to input row min(y + 1, H - 1) has completed: hand those rows' stages back to the producer
+          // (row y + 1 by its predecessor's epilogue; the strip's first output row also covers the rows before it)
+          const int lo = y == s.y0 ? ya : y + 1;
+          const int hi = min(y + 1, yb);
+          for (int yi = lo; yi <= hi; ++yi) mbar_arrive(&empty[(jbase + (yi - ya)) % S]);
         }
-      } else {
-        mbar_wait(&tfull[slot], par);
-        tc_fence_after();
-        for (int c = 0; c < NP; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)c, r);
-          tmem_ld_wait();
-          if (valid) {
-            float vv[8];
+        if constexpr (NCH > 0) {
+          uint32_t r[2][16];
+          tmem_ld16(taddr, r[0]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[k]);
-            if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c, n, y, x);
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int c = ci * 16;
+            tmem_ld_wait();
+            if (ci + 1 < NCH) tmem_ld16(taddr + (uint32_t)(c + 16), r[(ci + 1) & 1]);
+            tmem_st16_zero(taddr + (uint32_t)c);  // chunk c is in registers: hand the slot back cleared
+            if (ci + 1 == NCH) {
+              // the accumulator is free as soon as it has been read and cleared — before this row's math and stores
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[slot]);
+            }
+            if (valid) {
+              float vv[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[8 + k]);
-            if (c + 8 < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c + 8, n, y, x);
+              for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[ci & 1][k]);
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[ci & 1][8 + k]);
+              if (c + 8 < cstore)
+                epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr);
+            }
           }
+        } else {
+          for (int c = 0; c < NP; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)c, r);
+            tmem_ld_wait();
+            tmem_st16_zero(taddr + (uint32_t)c);
+            if (valid) {
+              float vv[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[k]);
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c, n, y, x);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[8 + k]);
+              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, vv, c + 8, n, y, x);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[slot]);
         }
+        if (te) te[2] = clock64();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[slot]);
+      qbase += s.y1 - s.y0;
+      jbase += yb - ya + 1;
     }
   }
 
@@ -405,10 +444,33 @@ cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, in
   const int grid = p.units < num_sms ? p.units : num_sms;
   RsKernelFn fn = rs_pick(p);
   const char* dbg = getenv("RSB_RS_DBG");
-  if (dbg != nullptr) {
+  const char* trace = getenv("RSB_RS_TRACE");
+  if (dbg != nullptr || trace != nullptr) {
     ConvRsParams q = p;
-    q.dbg = atoi(dbg);
+    q.dbg = dbg != nullptr ? atoi(dbg) : 0;
+    static long long* d_trace = nullptr;
+    const size_t tbytes = (8 * 160 + 4 * 160) * sizeof(long long);
+    if (trace != nullptr) {
+      if (d_trace == nullptr) cudaMalloc(&d_trace, tbytes);
+      cudaMemsetAsync(d_trace, 0, tbytes, stream);
+      q.trace = d_trace;
+    }
     fn<<<grid, kRsThreads, smem, stream>>>(src_map, q);
+    if (trace != nullptr) {
+      static long long h[8 * 160 + 4 * 160];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, d_trace, tbytes, cudaMemcpyDeviceToHost);
+      FILE* f = fopen(trace, "w");
+      if (f != nullptr) {
+        for (int r = 0; r < 160; ++r) {
+          fprintf(f, "%d", r);
+          for (int k = 0; k < 5; ++k) fprintf(f, " %lld", h[8 * r + k]);
+          for (int k = 0; k < 3; ++k) fprintf(f, " %lld", h[8 * 160 + 4 * r + k]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
     return cudaGetLastError();
   }
   fn<<<grid, kRsThreads, smem, stream>>>(src_map, p);

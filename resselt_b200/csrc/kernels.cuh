@@ -366,7 +366,8 @@ struct ConvRsParams {
   uint32_t wbytes;
   int stages;
   uint32_t stage_bytes;  // cin/8 planes x 18 groups x 128 B
-  int dbg;               // bring-up switches (env RSB_RS_DBG): 1 no epilogue work, 2 no TMA loads, 4 no MMAs
+  long long* trace;      // bring-up: per-row clock stamps of CTA 0 (env RSB_RS_TRACE=<file>)
+  int dbg;               // bring-up switches (env RSB_RS_DBG): 1 no epilogue work, 2 no TMA loads, 4 no MMAs, 8 no tcgen05.ld, 16 no tcgen05.st
   Epi epi;
 };
 
