@@ -306,6 +306,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         if constexpr (NCH > 0) {
           uint32_t r[2][16];
           tmem_ld16(taddr, r[0]);
+          const bool lean = EXT == 0 && p.epi.simple;
+          T* const drow = reinterpret_cast<T*>(p.epi.dst) + planar_index(n, p.epi.dst_planes, p.epi.dst_plane0, p.H, p.W, y, x);
+          const size_t dstride = (size_t)p.H * p.W * 8;
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             const int c = ci * 16;
@@ -319,7 +322,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[slot]);
             }
-            if (valid) {
+            if (lean) {
+              if (valid) epilogue16_planar<ACT, COMB>(p.epi, bias_sm, slope_sm, r[ci & 1], c, cstore, drow, dstride, kUsesRes ? &pre[2 * ci] : nullptr);
+            } else if (valid) {
               float vv[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(r[ci & 1][k]);

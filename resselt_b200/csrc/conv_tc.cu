@@ -227,12 +227,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           // software-pipelined accumulator reads: chunk ci+1 is in flight while chunk ci goes through the epilogue
           uint32_t r[2][16];
           tmem_ld16(taddr, r[0]);
+          const bool lean = EXT == 0 && p.epi.simple;
+          T* const drow = reinterpret_cast<T*>(p.epi.dst) + planar_index(n, p.epi.dst_planes, p.epi.dst_plane0, p.H, p.W, y, x);
+          const size_t dstride = (size_t)p.H * p.W * 8;
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             const int c = ci * 16;
             tmem_ld_wait();
             if (ci + 1 < NCH) tmem_ld16(taddr + (uint32_t)(c + 16), r[(ci + 1) & 1]);
-            if (valid) {
+            if (lean) {
+              if (valid) epilogue16_planar<ACT, COMB>(p.epi, bias_sm, slope_sm, r[ci & 1], c, cstore, drow, dstride, kUsesRes ? &pre[2 * ci] : nullptr);
+            } else if (valid) {
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ci & 1][j]);

@@ -32,6 +32,7 @@ struct Epi {
   const void* res2;
   int res2_planes, res2_plane0;
   int dst_external;  // 0: planar buffer, 1: caller's NCHW output
+  int simple;        // planar destination without sub-pixel scatter / split / second residual: the lean epilogue applies
   void* dst;
   int dst_planes, dst_plane0;
   // buffer destinations only: channels >= split_ch go to a second buffer range (dst2); dst_ps > 1 scatters the
@@ -161,13 +162,27 @@ __device__ __forceinline__ float mish_f(float v) {
   const float sp = v > 20.0f ? v : log1pf(expf(v));
   return v * tanhf(sp);
 }
+// (v + r) * (sigmoid(v) - 0.5) == (v/2 + r/2) * tanh(v/2): one MUFU op
+__device__ __forceinline__ float spab_gate_fast(float v, float r) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(0.5f, r, h) * t;
+}
 constexpr int kRuntime = -1;  // template value meaning "read act / combine from the parameter block"
 
 template <bool kFast, int ACT>
 __device__ __forceinline__ float activate(int act_rt, float v, float param, float slope) {
   const int act = ACT == kRuntime ? act_rt : ACT;  // folds to a constant for specialised kernels
   switch (act) {
-    case RSB_ACT_SILU: return v * sigmoid_f<kFast>(v);
+    case RSB_ACT_SILU:
+      if (kFast) {  // v * sigmoid(v) == h + h * tanh(h), h = v / 2: one MUFU op, two FMA-pipe ops
+        const float h = 0.5f * v;
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        return fmaf(h, t, h);
+      }
+      return v * sigmoid_f<kFast>(v);
     case RSB_ACT_MISH: return mish_f<kFast>(v);
     case RSB_ACT_LRELU: return v >= 0.0f ? v : v * param;
     case RSB_ACT_PRELU: return v >= 0.0f ? v : v * slope;
@@ -224,11 +239,7 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
     }
     if (kFast) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {  // sigmoid(v) - 0.5 == 0.5 * tanh(v / 2): one MUFU op
-        float t;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v[i]));
-        v[i] = (v[i] + r[i]) * (0.5f * t);
-      }
+      for (int i = 0; i < 8; ++i) v[i] = spab_gate_fast(v[i], r[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (v[i] + r[i]) * (sigmoid_f<false>(v[i]) - 0.5f);
@@ -328,6 +339,56 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
       if (e.add_base) o += ld_any(e.base, e.base_dtype, (((size_t)n * e.base_ch + c) * e.H + y) * e.W + x);
       o = fmaf(o, e.out_scale, e.out_mean[c & 3]);
       st_any(e.dst, e.out_dtype, (((size_t)n * e.out_ch + c) * OH + (size_t)y * ps + sy) * OW + (size_t)x * ps + sx, o);
+    }
+  }
+}
+
+// Lean epilogue of the tensor-core kernels for the common destination (Epi::simple): 16 accumulator columns c..c+15 of
+// one pixel -> bias / activation / combine (same arithmetic as epilogue8) -> two 16-byte stores at drow + plane * stride.
+// `pre` holds the prefetched residual chunks of this pixel (COMB != NONE).
+template <int ACT, int COMB>
+__device__ __forceinline__ void epilogue16_planar(const Epi& e, const float* bias, const float* slopes, const uint32_t (&acc)[16], int c,
+                                                  int cstore, __nv_bfloat16* drow, size_t plane_stride, const uint4* pre) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int c0 = c + 8 * half;
+    if (c0 < cstore) {
+      float v[8];
+      const float4 b0 = reinterpret_cast<const float4*>(bias + c0)[0];
+      const float4 b1 = reinterpret_cast<const float4*>(bias + c0)[1];
+      v[0] = __uint_as_float(acc[8 * half + 0]) + b0.x, v[1] = __uint_as_float(acc[8 * half + 1]) + b0.y;
+      v[2] = __uint_as_float(acc[8 * half + 2]) + b0.z, v[3] = __uint_as_float(acc[8 * half + 3]) + b0.w;
+      v[4] = __uint_as_float(acc[8 * half + 4]) + b1.x, v[5] = __uint_as_float(acc[8 * half + 5]) + b1.y;
+      v[6] = __uint_as_float(acc[8 * half + 6]) + b1.z, v[7] = __uint_as_float(acc[8 * half + 7]) + b1.w;
+      if (COMB == RSB_COMB_SPAB_GATE) {
+        float r[8];
+        unpack8<__nv_bfloat16>(pre[half], r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = spab_gate_fast(v[i], r[i]);
+      } else {
+        if (ACT != RSB_ACT_NONE) {
+          float sl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          if (ACT == RSB_ACT_PRELU) {
+            const float4 s0 = reinterpret_cast<const float4*>(slopes + c0)[0];
+            const float4 s1 = reinterpret_cast<const float4*>(slopes + c0)[1];
+            sl[0] = s0.x, sl[1] = s0.y, sl[2] = s0.z, sl[3] = s0.w, sl[4] = s1.x, sl[5] = s1.y, sl[6] = s1.z, sl[7] = s1.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = activate<true, ACT>(ACT, v[i], e.act_param, sl[i]);
+        }
+        if (COMB == RSB_COMB_MUL) {
+          float r[8];
+          unpack8<__nv_bfloat16>(pre[half], r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= r[i];
+        } else if (COMB == RSB_COMB_AXPY) {
+          float r[8];
+          unpack8<__nv_bfloat16>(pre[half], r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaf(e.alpha, v[i], e.beta1 * r[i]);
+        }
+      }
+      store8<__nv_bfloat16>(drow + (size_t)(c0 >> 3) * plane_stride, v);
     }
   }
 }

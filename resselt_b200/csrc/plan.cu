@@ -245,6 +245,7 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
       e.dst2_plane0 = d.dst2_ch_off / 8;
       e.split_ch = d.split_ch;
     }
+    e.simple = (e.dst_ps == 1 && e.dst2 == nullptr && e.res2 == nullptr) ? 1 : 0;
   }
 }
 
