@@ -71,6 +71,18 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   using T = __nv_bfloat16;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (p.timeline != nullptr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    atomicMin(&p.timeline[0], gt);
+  }
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[8 * 159 + 0] = clock64();
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 160) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[2000 + 2 * blockIdx.x] = (long long)gt;
+  }
   const int S = p.stages;
   const int NS = NCH > 0 ? (512 / (16 * (NCH > 0 ? NCH : 1)) > kRsMaxSlots ? kRsMaxSlots : 512 / (16 * (NCH > 0 ? NCH : 1))) : p.nslots;
   const int NP = NCH > 0 ? 16 * NCH : p.np;
@@ -100,6 +112,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     }
     mbar_init(wbar, 1);
     fence_mbar_init();
+    // the packed weights are not produced by the previous kernel: fetch them before the grid-dependency wait
+    prefetch_tmap(&src_map);
+    mbar_expect_tx(wbar, p.wbytes);
+    for (uint32_t off = 0; off < p.wbytes; off += 32768u) {
+      const uint32_t len = min(32768u, p.wbytes - off);
+      bulk_load_1d(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, len, wbar);
+    }
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
@@ -123,6 +142,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   __syncthreads();
   tc_fence_after();
 
+  pdl_wait();  // everything below reads or writes activation buffers
+  if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.timeline[2] = gt;
+  }
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[8 * 159 + 1] = clock64();
   const int u0 = (int)((long long)p.units * blockIdx.x / gridDim.x);
   const int u1 = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
 
@@ -136,12 +162,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   //   empty[st]    epilogue -> producer  the MMAs that read a stage have completed (implied by the tfull the epilogue saw)
   if (warp == 0) {
     if (lane == 0) {
-      prefetch_tmap(&src_map);
-      mbar_expect_tx(wbar, p.wbytes);
-      for (uint32_t off = 0; off < p.wbytes; off += 32768u) {
-        const uint32_t len = min(32768u, p.wbytes - off);
-        bulk_load_1d(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, len, wbar);
-      }
       int st = 0, qbase = 0, u = u0;
       uint32_t st_par = 1;
       Strip s;
@@ -199,6 +219,11 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         mbar_wait(&full[st], st_par);
         tc_fence_after();
         if (tr) tr[2] = clock64();
+        if (p.timeline != nullptr && trow == 1 && blockIdx.x == 0 && leader) {
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          p.timeline[3] = gt;
+        }
         // every accumulator slot is zero when it is handed over (the epilogue clears it after reading): all MMAs accumulate
         if (KS > 0 && NCH > 0 && yi - 1 >= s.y0 && yi + 1 < s.y1 && slot_n >= 2) {
           // steady state: rows yi+1, yi, yi-1 sit in three consecutive slots -> one N = 3 * npad MMA per (dx, k step)
@@ -365,6 +390,17 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.timeline != nullptr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    atomicMax(&p.timeline[1], gt);
+  }
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[8 * 159 + 2] = clock64();
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 160) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[2000 + 2 * blockIdx.x + 1] = (long long)gt;
+  }
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -448,21 +484,53 @@ cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, in
   if (smem < 120 * 1024) smem = 120 * 1024;
   const int grid = p.units < num_sms ? p.units : num_sms;
   RsKernelFn fn = rs_pick(p);
+  static const char* tl_file = getenv("RSB_RS_TIMELINE");
+  if (tl_file != nullptr) {
+    // bring-up: globaltimer stamps of the first 64 launches, dumped after the 64th
+    static unsigned long long* d_tl = nullptr;
+    static int count = 0;
+    if (d_tl == nullptr) {
+      cudaMalloc(&d_tl, 64 * 4 * sizeof(unsigned long long));
+      static unsigned long long init[64 * 4];
+      for (int i = 0; i < 64; ++i) init[4 * i] = ~0ull, init[4 * i + 1] = 0, init[4 * i + 2] = 0, init[4 * i + 3] = 0;
+      cudaMemcpy(d_tl, init, sizeof init, cudaMemcpyHostToDevice);
+    }
+    if (count < 64) {
+      ConvRsParams q = p;
+      q.timeline = d_tl + 4 * count;
+      ++count;
+      cudaError_t e = launch_pdl(fn, dim3(grid), dim3(kRsThreads), smem, stream, src_map, q);
+      if (count == 64) {
+        static unsigned long long h[64 * 4];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, d_tl, sizeof h, cudaMemcpyDeviceToHost);
+        FILE* f = fopen(tl_file, "w");
+        if (f != nullptr) {
+          for (int i = 0; i < 64; ++i)
+            fprintf(f, "%d start %llu end %llu dur %llu gap_from_prev_end %lld wait_done+%lld first_mma+%lld\n", i, h[4 * i] - h[0], h[4 * i + 1] - h[0],
+                    h[4 * i + 1] - h[4 * i], i ? (long long)(h[4 * i] - h[4 * i - 3]) : 0ll, (long long)(h[4 * i + 2] - h[4 * i]),
+                    (long long)(h[4 * i + 3] - h[4 * i]));
+          fclose(f);
+        }
+      }
+      return e;
+    }
+  }
   const char* dbg = getenv("RSB_RS_DBG");
   const char* trace = getenv("RSB_RS_TRACE");
   if (dbg != nullptr || trace != nullptr) {
     ConvRsParams q = p;
     q.dbg = dbg != nullptr ? atoi(dbg) : 0;
     static long long* d_trace = nullptr;
-    const size_t tbytes = (8 * 160 + 4 * 160) * sizeof(long long);
+    const size_t tbytes = (2000 + 2 * 160) * sizeof(long long);
     if (trace != nullptr) {
       if (d_trace == nullptr) cudaMalloc(&d_trace, tbytes);
       cudaMemsetAsync(d_trace, 0, tbytes, stream);
       q.trace = d_trace;
     }
-    fn<<<grid, kRsThreads, smem, stream>>>(src_map, q);
+    launch_pdl(fn, dim3(grid), dim3(kRsThreads), smem, stream, src_map, q);
     if (trace != nullptr) {
-      static long long h[8 * 160 + 4 * 160];
+      static long long h[2000 + 2 * 160];
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, d_trace, tbytes, cudaMemcpyDeviceToHost);
       FILE* f = fopen(trace, "w");
@@ -471,6 +539,7 @@ cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, in
           fprintf(f, "%d", r);
           for (int k = 0; k < 5; ++k) fprintf(f, " %lld", h[8 * r + k]);
           for (int k = 0; k < 3; ++k) fprintf(f, " %lld", h[8 * 160 + 4 * r + k]);
+          fprintf(f, " %lld %lld", h[2000 + 2 * r], h[2000 + 2 * r + 1]);
           fprintf(f, "\n");
         }
         fclose(f);
@@ -478,8 +547,7 @@ cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, in
     }
     return cudaGetLastError();
   }
-  fn<<<grid, kRsThreads, smem, stream>>>(src_map, p);
-  return cudaGetLastError();
+  return launch_pdl(fn, dim3(grid), dim3(kRsThreads), smem, stream, src_map, p);
 }
 
 }  // namespace rsb

@@ -47,6 +47,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int S = p.stages;
   const int A = p.num_acc;
+  pdl_launch_dependents();
 
   const uint32_t w_al = align_up(p.wbytes, kAlign);
   const uint32_t st_al = align_up(p.stage_bytes, kAlign);
@@ -92,6 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything below reads or writes activation buffers
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
@@ -375,8 +377,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, in
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   const int threads = kMaxThreads;
   KernelFn fn = pick(p);
-  fn<<<grid, threads, smem, stream>>>(src_map, p);
-  return cudaGetLastError();
+  return launch_pdl(fn, dim3(grid), dim3(threads), smem, stream, src_map, p);
 }
 
 }  // namespace rsb

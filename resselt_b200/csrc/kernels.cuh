@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/resselt_b200.h"
 
@@ -428,6 +429,7 @@ struct ConvRsParams {
   int stages;
   uint32_t stage_bytes;  // cin/8 planes x 18 groups x 128 B
   long long* trace;      // bring-up: per-row clock stamps of CTA 0 (env RSB_RS_TRACE=<file>)
+  unsigned long long* timeline;  // bring-up: [4] = min CTA start, max CTA end, CTA 0 after grid-dependency wait, CTA 0 first MMA (globaltimer ns)
   int dbg;               // bring-up switches (env RSB_RS_DBG): 1 no epilogue work, 2 no TMA loads, 4 no MMAs, 8 no tcgen05.ld, 16 no tcgen05.st
   Epi epi;
 };
@@ -540,6 +542,20 @@ cudaError_t winattn_configure();
 cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s);
 cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, cudaStream_t s);
 cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s);
+
+// Launch with programmatic stream serialization: the kernel may be scheduled while the previous kernel of the stream
+// drains; it must call ptx::pdl_wait() before touching activation memory.  RSB_NO_PDL=1 restores plain launches.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool no_pdl = getenv("RSB_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...);
+}
 
 // launchers (defined in the .cu files)
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
