@@ -191,7 +191,8 @@ int rsb_plan_workspace_bytes(const rsb_plan* plan, int n, int h, int w, size_t* 
  * workspace: 1024-byte aligned device memory of at least rsb_plan_workspace_bytes() bytes.
  * stream: a cudaStream_t passed as void*.  force_direct selects the conv kernels: 0 = fastest available,
  * 1 = every conv on the CUDA-core kernel (debug cross-check of the tensor-core kernels), 2 = tensor-core tile
- * kernel only (no row-streaming 3x3 kernel; cross-check of the two tensor-core formulations). */
+ * kernel only (no row-streaming 3x3 kernel; cross-check of the two tensor-core formulations), 3 = row-streaming
+ * kernel for every eligible 3x3 conv even where the tile kernel would be preferred (small images). */
 int rsb_plan_forward(rsb_plan* plan, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype,
                      void* workspace, size_t workspace_bytes, void* stream, int force_direct);
 

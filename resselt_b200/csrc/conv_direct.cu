@@ -279,6 +279,17 @@ cudaError_t launch_pack_input(const PackParams& p, cudaStream_t stream) {
       pack_input_fixed_kernel<float, 3, 3, 3><<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
   }
+  if (p.cin == 3 && p.kh == 1 && p.kw == 1 && p.kplanes == 2) {  // NCHW RGB -> planar-8 with 16 channels (13 of them zero)
+    const size_t pixels = (size_t)p.n * p.H * p.W;
+    const int g = (int)std::min<size_t>((pixels + 255) / 256, 148 * 32);
+    if (p.src_dtype == RSB_BF16)
+      pack_input_fixed_kernel<__nv_bfloat16, 3, 1, 1><<<g, 256, 0, stream>>>(p);
+    else if (p.src_dtype == RSB_F16)
+      pack_input_fixed_kernel<__half, 3, 1, 1><<<g, 256, 0, stream>>>(p);
+    else
+      pack_input_fixed_kernel<float, 3, 1, 1><<<g, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
   pack_input_kernel<<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();

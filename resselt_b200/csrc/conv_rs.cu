@@ -419,6 +419,10 @@ const RsVariant kRsVariants[] = {
     RSB_V(3, 3, RSB_ACT_MISH, RSB_COMB_NONE),
     RSB_V(3, 3, RSB_ACT_NONE, RSB_COMB_SPAB_GATE),
     RSB_V(3, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    // first layers on the 16-channel planar copy of the caller's input (3 real channels)
+    RSB_V(1, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(1, 4, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(1, 4, RSB_ACT_PRELU, RSB_COMB_NONE),
     // Compact (64 -> 64, PReLU)
     RSB_V(4, 4, RSB_ACT_PRELU, RSB_COMB_NONE),
     // ESRGAN dense blocks (64 + 32k -> 32), trunk / HR convs (64 -> 64), RealPLKSR

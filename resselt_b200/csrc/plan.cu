@@ -63,6 +63,9 @@ struct ConvOp {
   // bf16 plans lower a small-Cin conv on the caller's NCHW tensor to [im2col pack -> 1x1 tensor-core conv]:
   // pack_buf is a hidden planar buffer with pack_k = pad16(cin*kh*kw) channels
   int pack_buf = -1, pack_k = 0;
+  // pack_planar: the hidden buffer holds the normalised input itself (channels padded to 16) and the conv keeps its
+  // kernel extents, so a 3x3 stem runs on the row-streaming kernel; otherwise the buffer is the im2col matrix
+  bool pack_planar = false;
   // geometry the tensor-core kernel sees (differs from d.* only for packed convs)
   int tc_src_buf = -1, tc_src_ch_off = 0, tc_cin = 0, tc_kh = 0, tc_kw = 0;
   rsb::PackParams pk;
@@ -73,7 +76,7 @@ struct ConvOp {
   float* d_bias = nullptr;
   float* d_slopes = nullptr;
   // row-streaming 3x3 kernel (conv_rs.cu): eligibility is decided at finalize, use at bind (needs W % 8 == 0)
-  bool rs_elig = false, use_rs = false;
+  bool rs_elig = false, rs_ready = false, rs_pref = false;
   int rs_stages = 0;
   void* d_wrs = nullptr;
   uint32_t wbytes_rs = 0;
@@ -284,7 +287,8 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.cin = c.tc_cin, t.npad = c.npad;
       t.kchunk = c.kchunk, t.nchunks = c.tc_cin / c.kchunk;
       t.kh = c.tc_kh, t.kw = c.tc_kw;
-      t.pad_t = c.pack_buf >= 0 ? 0 : d.pad_t, t.pad_l = c.pack_buf >= 0 ? 0 : d.pad_l;
+      const bool im2col = c.pack_buf >= 0 && !c.pack_planar;
+      t.pad_t = im2col ? 0 : d.pad_t, t.pad_l = im2col ? 0 : d.pad_l;
       t.src_plane0 = c.tc_src_ch_off / 8;
       t.wpack = c.d_wtc, t.wbytes = c.wbytes_tc;
       t.wpack2 = c.d_wtc2;
@@ -296,8 +300,10 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       while (cols < (uint32_t)t.num_acc * c.npad) cols <<= 1;
       t.tmem_cols = cols;
       fill_epi(p, c, n, H, W, ws, t.epi);
-      c.use_rs = c.rs_elig && W % 8 == 0;
-      if (c.use_rs) {
+      // each CTA streams a contiguous run of rows and pays ~2 halo rows per run: worth it from ~8 rows per CTA
+      c.rs_ready = c.rs_elig && W % 8 == 0;
+      c.rs_pref = (long long)n * ceil_div(W, 128) * H >= 8ll * p->num_sms;
+      if (c.rs_ready) {
         // the same tensor viewed as [n][plane][H][W/8][8 px x 8 ch]: a box of 18 pixel groups of one row lands as
         // [plane][18][128 B], i.e. 144 consecutive pixels per plane
         cuuint64_t dims5[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)H, (cuuint64_t)sb.planes, (cuuint64_t)n};
@@ -323,7 +329,9 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       if (c.pack_buf >= 0) {
         rsb::PackParams& k = c.pk;
         memset(&k, 0, sizeof k);
-        k.n = n, k.H = H, k.W = W, k.cin = d.cin, k.kh = d.kh, k.kw = d.kw, k.pad_t = d.pad_t, k.pad_l = d.pad_l;
+        k.n = n, k.H = H, k.W = W, k.cin = d.cin;
+        k.kh = c.pack_planar ? 1 : d.kh, k.kw = c.pack_planar ? 1 : d.kw;
+        k.pad_t = c.pack_planar ? 0 : d.pad_t, k.pad_l = c.pack_planar ? 0 : d.pad_l;
         k.kplanes = c.pack_k / 8;
         for (int i = 0; i < 4; ++i) k.in_mean[i] = d.in_mean[i];
         k.in_scale = d.in_scale;
@@ -564,11 +572,13 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
   c.tc_src_buf = d.src_buf, c.tc_src_ch_off = d.src_ch_off, c.tc_cin = c.cin_pad16, c.tc_kh = d.kh, c.tc_kw = d.kw;
   if (p->dtype == RSB_BF16 && d.src_buf == RSB_EXTERNAL_INPUT && d.cin * d.kh * d.kw <= 256) {
     Buffer hb;
-    c.pack_k = ceil_div(d.cin * d.kh * d.kw, 16) * 16;
+    c.pack_planar = d.kh * d.kw > 1 && c.cin_pad16 <= 64;
+    c.pack_k = c.pack_planar ? c.cin_pad16 : ceil_div(d.cin * d.kh * d.kw, 16) * 16;
     hb.channels = c.pack_k, hb.planes = c.pack_k / 8, hb.scale = 1;
     p->bufs.push_back(hb);
     c.pack_buf = (int)p->bufs.size() - 1;
-    c.tc_src_buf = c.pack_buf, c.tc_src_ch_off = 0, c.tc_cin = c.pack_k, c.tc_kh = 1, c.tc_kw = 1;
+    c.tc_src_buf = c.pack_buf, c.tc_src_ch_off = 0, c.tc_cin = c.pack_k;
+    c.tc_kh = c.pack_planar ? d.kh : 1, c.tc_kw = c.pack_planar ? d.kw : 1;
   }
   p->convs.push_back(std::move(c));
   p->ops.push_back({0, (int)p->convs.size() - 1});
@@ -706,7 +716,7 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       RSB_CUDA(cudaMalloc(&c.d_slopes, cmax * sizeof(float)));
       RSB_CUDA(cudaMemcpy(c.d_slopes, slopes.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (c.tc_ok && c.pack_buf >= 0) {
+    if (c.tc_ok && c.pack_buf >= 0 && !c.pack_planar) {
       // packed conv == 1x1 conv over k = (ci*kh + ky)*kw + kx, which is the OIHW flattening of the weight
       const int k8 = c.pack_k / 8, kreal = d.cin * taps;
       std::vector<uint16_t> wp((size_t)k8 * c.npad * 8, 0);
@@ -857,7 +867,7 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           if (t.epi.dst_external) t.epi.dst = y, t.epi.out_dtype = y_dtype;
           t.epi.base = x, t.epi.base_dtype = x_dtype;
           static const bool pair_kernel = getenv("RSB_TC2") != nullptr;
-          if (c.use_rs && force_direct != 2) {
+          if (c.rs_ready && force_direct != 2 && (c.rs_pref || force_direct == 3)) {
             rsb::ConvRsParams q = c.rsp;
             q.epi = t.epi;
             e = rsb::launch_conv_rs(c.map_rs, q, p->num_sms, stream);

@@ -50,7 +50,7 @@ def run_case(cin, cout, n, H, W, act, gate):
     plan = pb.finalize(torch.device(DEV))
     xd = x.to(DEV, torch.bfloat16)
     got = {}
-    for mode, fd in (('rs', 0), ('tc', 2)):
+    for mode, fd in (('rs', 3), ('tc', 2)):
         plan.force_direct = fd
         plan.forward(xd)
         torch.cuda.synchronize()
@@ -91,7 +91,7 @@ def time_layers():
         plan = pb.finalize(torch.device(DEV))
         x = torch.rand(1, 3, 1080, 1920, device=DEV, dtype=torch.bfloat16)
         plan.forward(x)
-        for mode, fd in (('rs', 0), ('tc', 2)):
+        for mode, fd in (('rs', 3), ('tc', 2)):
             plan.force_direct = fd
             for _ in range(3):
                 plan.forward(x, ops=(1, 2))
