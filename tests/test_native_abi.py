@@ -61,8 +61,8 @@ def test_plan_building_and_argument_validation(lib):
     nbytes = C.c_size_t()
     assert lib.rsb_plan_workspace_bytes(pb._h, 1, 16, 16, C.byref(nbytes)) == 0
     # planar-8 bf16 planes of 16x16 pixels x 16 B: 48 ch -> 6, 12 ch -> 2 (whole 16-channel K steps),
-    # + the hidden im2col buffer of the first conv (3*3*3 = 27 -> 32 channels -> 4 planes)
-    assert nbytes.value == (6 + 2 + 4) * 16 * 16 * 16
+    # + the hidden planar copy of the normalised input feeding the 3x3 stem (3 -> 16 channels -> 2 planes)
+    assert nbytes.value == (6 + 2 + 2) * 16 * 16 * 16
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-device behaviour')
