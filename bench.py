@@ -251,7 +251,7 @@ def run_engine(args):
                  api='resselt_b200.runner.FramePipeline over load_from_state_dict(...) module, pinned host frames'),
         gpu_launches=plan.launches_per_forward * args.steps,
         roofline=dict(bound='tensor', achieved=achieved, peak=peaks['bf16_burst'], unit='TFLOP/s', frac=achieved / peaks['bf16_burst'],
-                      traffic=traffic, kernel='conv_tc 3x3 48->48 + SiLU, 1080p', kernel_ms=kernel_ms, flops_per_launch=kernel_flops,
+                      traffic=traffic, kernel='conv_rs (row-streaming tcgen05) 3x3 48->48 + SiLU, 1080p', kernel_ms=kernel_ms, flops_per_launch=kernel_flops,
                       peak_source=peaks['source'] + ' burst bf16 (kernel timed alone)',
                       step_tflops=step_tflops, step_frac_of_sustained=step_tflops / (peaks['bf16_sustained'] * world)),
         cpu_baseline=dict(value=cpu_value, unit='MP/s', cores=cpu_threads, kind='port',
