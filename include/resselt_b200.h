@@ -192,7 +192,9 @@ int rsb_plan_workspace_bytes(const rsb_plan* plan, int n, int h, int w, size_t* 
  * stream: a cudaStream_t passed as void*.  force_direct selects the conv kernels: 0 = fastest available,
  * 1 = every conv on the CUDA-core kernel (debug cross-check of the tensor-core kernels), 2 = tensor-core tile
  * kernel only (no row-streaming 3x3 kernel; cross-check of the two tensor-core formulations), 3 = row-streaming
- * kernel for every eligible 3x3 conv even where the tile kernel would be preferred (small images). */
+ * kernel for every eligible 3x3 conv even where the tile kernel would be preferred (small images), 4 = like 0 but with
+ * the experimental fused conv-pair kernel (two consecutive 3x3 convs in one launch, the intermediate map kept in shared
+ * memory; bit-identical to 0; also enabled for mode 0 by the environment variable RSB_PAIR=1). */
 int rsb_plan_forward(rsb_plan* plan, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype,
                      void* workspace, size_t workspace_bytes, void* stream, int force_direct);
 

@@ -168,12 +168,12 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       while (next_strip(p, u, u1, s)) {
         const int ya = max(s.y0 - 1, 0), yb = min(s.y1, p.H - 1);
         for (int yi = ya; yi <= yb; ++yi) {
-          mbar_wait(&empty[st], st_par);
+          mbar_wait_parked(&empty[st], st_par);
           // output rows that receive their first contribution from this input row: yi + 1, and row 0 at yi == 0
           for (int r = (yi == 0 ? 0 : yi + 1); r <= yi + 1; ++r)
             if (r >= s.y0 && r < s.y1) {
               const int q = qbase + (r - s.y0);
-              mbar_wait(&tempty[q % NS], (((uint32_t)(q / NS)) & 1u) ^ 1u);
+              mbar_wait_parked(&tempty[q % NS], (((uint32_t)(q / NS)) & 1u) ^ 1u);
             }
           if (p.dbg & 2) {
             mbar_arrive(&full[st]);
@@ -318,7 +318,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               if (k * 8 < cstore) pre[k] = *reinterpret_cast<const uint4*>(rp + k * plane_stride);
           }
         }
-        mbar_wait(&tfull[slot], par);
+        mbar_wait_parked(&tfull[slot], par);
         tc_fence_after();
         if (te) te[1] = clock64();
         if (qd == 0 && lane == 0) {

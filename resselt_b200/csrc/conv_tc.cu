@@ -113,7 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const int rem = tile - n * tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_parked(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], p.stage_bytes);
           tma_load_4d(stage0 + (size_t)s * st_al, &src_map, &full[s], 8 * (tx * kTileW - p.pad_l),
                       ty * kTileH - p.pad_t, p.src_plane0 + c * cp8, n);
@@ -224,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 if (j * 8 < cstore) pre[j] = *reinterpret_cast<const uint4*>(rp + j * plane_stride);
             }
           }
-          mbar_wait(&tfull[g], aph);
+          mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
           // software-pipelined accumulator reads: chunk ci+1 is in flight while chunk ci goes through the epilogue
           uint32_t r[2][16];
@@ -251,7 +251,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             }
           }
         } else {
-          mbar_wait(&tfull[g], aph);
+          mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
           for (int c = part * 16; c < p.npad; c += 16 * parts) {
             uint32_t r[16];

@@ -348,49 +348,53 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
 // one pixel -> bias / activation / combine (same arithmetic as epilogue8) -> two 16-byte stores at drow + plane * stride.
 // `pre` holds the prefetched residual chunks of this pixel (COMB != NONE).
 template <int ACT, int COMB>
+__device__ __forceinline__ void epilogue8_planar(const Epi& e, const float* bias, const float* slopes, const uint32_t* acc8, int c0,
+                                                 __nv_bfloat16* drow, size_t plane_stride, const uint4* pre) {
+  float v[8];
+  const float4 b0 = reinterpret_cast<const float4*>(bias + c0)[0];
+  const float4 b1 = reinterpret_cast<const float4*>(bias + c0)[1];
+  v[0] = __uint_as_float(acc8[0]) + b0.x, v[1] = __uint_as_float(acc8[1]) + b0.y;
+  v[2] = __uint_as_float(acc8[2]) + b0.z, v[3] = __uint_as_float(acc8[3]) + b0.w;
+  v[4] = __uint_as_float(acc8[4]) + b1.x, v[5] = __uint_as_float(acc8[5]) + b1.y;
+  v[6] = __uint_as_float(acc8[6]) + b1.z, v[7] = __uint_as_float(acc8[7]) + b1.w;
+  if (COMB == RSB_COMB_SPAB_GATE) {
+    float r[8];
+    unpack8<__nv_bfloat16>(*pre, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = spab_gate_fast(v[i], r[i]);
+  } else {
+    if (ACT != RSB_ACT_NONE) {
+      float sl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (ACT == RSB_ACT_PRELU) {
+        const float4 s0 = reinterpret_cast<const float4*>(slopes + c0)[0];
+        const float4 s1 = reinterpret_cast<const float4*>(slopes + c0)[1];
+        sl[0] = s0.x, sl[1] = s0.y, sl[2] = s0.z, sl[3] = s0.w, sl[4] = s1.x, sl[5] = s1.y, sl[6] = s1.z, sl[7] = s1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = activate<true, ACT>(ACT, v[i], e.act_param, sl[i]);
+    }
+    if (COMB == RSB_COMB_MUL) {
+      float r[8];
+      unpack8<__nv_bfloat16>(*pre, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= r[i];
+    } else if (COMB == RSB_COMB_AXPY) {
+      float r[8];
+      unpack8<__nv_bfloat16>(*pre, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(e.alpha, v[i], e.beta1 * r[i]);
+    }
+  }
+  store8<__nv_bfloat16>(drow + (size_t)(c0 >> 3) * plane_stride, v);
+}
+
+template <int ACT, int COMB>
 __device__ __forceinline__ void epilogue16_planar(const Epi& e, const float* bias, const float* slopes, const uint32_t (&acc)[16], int c,
                                                   int cstore, __nv_bfloat16* drow, size_t plane_stride, const uint4* pre) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int c0 = c + 8 * half;
-    if (c0 < cstore) {
-      float v[8];
-      const float4 b0 = reinterpret_cast<const float4*>(bias + c0)[0];
-      const float4 b1 = reinterpret_cast<const float4*>(bias + c0)[1];
-      v[0] = __uint_as_float(acc[8 * half + 0]) + b0.x, v[1] = __uint_as_float(acc[8 * half + 1]) + b0.y;
-      v[2] = __uint_as_float(acc[8 * half + 2]) + b0.z, v[3] = __uint_as_float(acc[8 * half + 3]) + b0.w;
-      v[4] = __uint_as_float(acc[8 * half + 4]) + b1.x, v[5] = __uint_as_float(acc[8 * half + 5]) + b1.y;
-      v[6] = __uint_as_float(acc[8 * half + 6]) + b1.z, v[7] = __uint_as_float(acc[8 * half + 7]) + b1.w;
-      if (COMB == RSB_COMB_SPAB_GATE) {
-        float r[8];
-        unpack8<__nv_bfloat16>(pre[half], r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = spab_gate_fast(v[i], r[i]);
-      } else {
-        if (ACT != RSB_ACT_NONE) {
-          float sl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (ACT == RSB_ACT_PRELU) {
-            const float4 s0 = reinterpret_cast<const float4*>(slopes + c0)[0];
-            const float4 s1 = reinterpret_cast<const float4*>(slopes + c0)[1];
-            sl[0] = s0.x, sl[1] = s0.y, sl[2] = s0.z, sl[3] = s0.w, sl[4] = s1.x, sl[5] = s1.y, sl[6] = s1.z, sl[7] = s1.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = activate<true, ACT>(ACT, v[i], e.act_param, sl[i]);
-        }
-        if (COMB == RSB_COMB_MUL) {
-          float r[8];
-          unpack8<__nv_bfloat16>(pre[half], r);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] *= r[i];
-        } else if (COMB == RSB_COMB_AXPY) {
-          float r[8];
-          unpack8<__nv_bfloat16>(pre[half], r);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaf(e.alpha, v[i], e.beta1 * r[i]);
-        }
-      }
-      store8<__nv_bfloat16>(drow + (size_t)(c0 >> 3) * plane_stride, v);
-    }
+    if (c0 < cstore) epilogue8_planar<ACT, COMB>(e, bias, slopes, &acc[8 * half], c0, drow, plane_stride, pre != nullptr ? &pre[half] : nullptr);
   }
 }
 
@@ -432,6 +436,29 @@ struct ConvRsParams {
   unsigned long long* timeline;  // bring-up: [4] = min CTA start, max CTA end, CTA 0 after grid-dependency wait, CTA 0 first MMA (globaltimer ns)
   int dbg;               // bring-up switches (env RSB_RS_DBG): 1 no epilogue work, 2 no TMA loads, 4 no MMAs, 8 no tcgen05.ld, 16 no tcgen05.st
   Epi epi;
+};
+
+// Fused pair of 3x3 convs (conv_pair.cu): A's activated output rows stay in shared memory and feed B
+struct ConvPairParams {
+  int n, H, W;
+  int cols;   // strips of 120 owned output pixels (conv_pair_cols)
+  int units;  // n * cols * H
+  int cin0;   // conv A input channels (multiple of 16)
+  int np;     // A's output channels == B's input channels == UMMA N per kernel row of both convs (multiple of 16)
+  int src_plane0;
+  const void* wpackA;  // bf16 [3 kw][cin0/8][5 * np][8], N blocks hold kernel rows [2, 1, 0, 2, 1]
+  uint32_t wbytesA;
+  const void* wpackB;  // bf16 [3 kw][np/8][5 * np][8]
+  uint32_t wbytesB;
+  uint32_t stage_bytes;  // cin0/8 planes x 18 groups x 128 B
+  const float* biasA;    // [np]
+  int actA;
+  float actA_param;
+  int lag;  // B consumes A's output row j at step j + lag
+  int res_prefetch;  // res_map is valid: the producer prefetches B's residual rows into L2
+  long long* trace;  // bring-up: clock stamps of CTA 1 (env RSB_PAIR_TRACE=<file>)
+  int dbg;  // bring-up switches (env RSB_PAIR_DBG): 1 no A epilogue math/stores, 2 no B epilogue math/stores
+  Epi epi;  // conv B's tail
 };
 
 struct ConvDirectParams {
@@ -569,6 +596,12 @@ size_t conv_rs_smem_bytes(int cin, int np, int stages);
 uint32_t conv_rs_stage_bytes(int cin);
 cudaError_t conv_rs_configure(size_t max_smem);
 cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, int num_sms, cudaStream_t stream);
+uint32_t conv_pair_weight_bytes(int cin, int np);
+size_t conv_pair_smem_bytes(int cin0, int np);
+int conv_pair_cols(int W);
+bool conv_pair_supported(int cin0, int np, int actA, int actB, int combB);
+cudaError_t conv_pair_configure(size_t max_smem);
+cudaError_t launch_conv_pair(const CUtensorMap& src_map, const CUtensorMap& res_map, const ConvPairParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cudaStream_t stream);
 cudaError_t launch_pack_input(const PackParams& p, cudaStream_t stream);
 cudaError_t launch_groupnorm(const GroupNormParams& p, bool bf16_storage, cudaStream_t stream);

@@ -80,10 +80,15 @@ struct ConvOp {
   int rs_stages = 0;
   void* d_wrs = nullptr;
   uint32_t wbytes_rs = 0;
+  // fused pair kernel (conv_pair.cu): this conv is the head (A) of a pair with the next op; decided at finalize
+  bool pair_head = false, pair_ready = false;
+  void* d_wrot = nullptr;  // [3 kw][cin/8][5 * npad][8]: kernel rows [2, 1, 0, 2, 1] side by side on the N axis
+  uint32_t wbytes_rot = 0;
   // bound state
-  CUtensorMap map, map_rs;
+  CUtensorMap map, map_rs, map_res;  // map_res: the pair's second conv's residual rows (L2 prefetch)
   rsb::ConvTcParams tcp;
   rsb::ConvRsParams rsp;
+  rsb::ConvPairParams prp;
   rsb::ConvDirectParams dp;
 };
 
@@ -200,6 +205,76 @@ int layout(const rsb_plan* p, int n, int h, int w, std::vector<size_t>* offsets,
   off += align_up(aux, kWsAlign);
   *total = off == 0 ? kWsAlign : off;
   return 0;
+}
+
+// ---- fused conv pairs (conv_pair.cu)
+struct Region {
+  int buf, c0, c1;  // channels [c0, c1) of a plan buffer (whole planes)
+};
+inline bool overlaps(const Region& a, const Region& b) { return a.buf >= 0 && a.buf == b.buf && a.c0 < b.c1 && b.c0 < a.c1; }
+inline bool covers(const Region& a, const Region& b) { return a.buf >= 0 && a.buf == b.buf && a.c0 <= b.c0 && a.c1 >= b.c1; }
+inline Region conv_src(const ConvOp& c) { return {c.d.src_buf, c.d.src_ch_off, c.d.src_ch_off + c.cin_pad16}; }
+inline Region conv_dst(const ConvOp& c) { return {c.d.dst_buf, c.d.dst_ch_off, c.d.dst_ch_off + ceil_div(c.d.cout, 8) * 8}; }
+
+// Is `r` (written by op `writer`) never read by an op after `last_reader`?  Scans forward until an op overwrites all of it.
+bool region_dead_after(const rsb_plan* p, const Region& r, size_t last_reader) {
+  for (size_t j = last_reader + 1; j < p->ops.size(); ++j) {
+    const Op& op = p->ops[j];
+    if (op.kind == 0) {
+      const ConvOp& c = p->convs[op.index];
+      const rsb_conv_desc& d = c.d;
+      if (overlaps(conv_src(c), r)) return false;
+      if (d.combine != RSB_COMB_NONE) {
+        const int ch = ceil_div(d.cout, 8) * 8;
+        if (overlaps({d.res1_buf, d.res1_ch_off, d.res1_ch_off + ch}, r)) return false;
+        if (d.res2_buf >= 0 && overlaps({d.res2_buf, d.res2_ch_off, d.res2_ch_off + ch}, r)) return false;
+      }
+      const bool plain_dst = d.dst_buf >= 0 && d.dst_ps <= 1 && d.dst2_buf < 0;
+      if (plain_dst && covers(conv_dst(c), r)) return true;
+      if (d.dst_buf == r.buf || d.dst2_buf == r.buf) return false;  // partial overwrite: keep it simple, call it live
+    } else if (op.kind == 1) {
+      const rsb_groupnorm_desc& d = p->gns[op.index].d;
+      if (d.src_buf == r.buf || d.dst_buf == r.buf || d.skip_buf == r.buf) return false;
+    } else {
+      const rsb_op_desc& d = p->auxs[op.index].d;
+      if (d.src_buf == r.buf || d.src2_buf == r.buf || d.dst_buf == r.buf) return false;
+    }
+  }
+  return true;  // the next forward rewrites it before anything reads it
+}
+
+// Mark conv i as the head of a fused pair with conv i + 1 when A's output is only ever read by B.
+void find_pairs(rsb_plan* p) {
+  static const bool no_pair = getenv("RSB_NO_PAIR") != nullptr;
+  if (no_pair || p->dtype != RSB_BF16) return;
+  // two passes: first the pairs whose second conv reads a residual (the unfused layer is the most HBM-bound one: three
+  // maps per launch), then whatever is left
+  std::vector<char> taken(p->ops.size(), 0);
+  for (int pass = 0; pass < 2; ++pass)
+  for (size_t i = 0; i + 1 < p->ops.size(); ++i) {
+    if (p->ops[i].kind != 0 || p->ops[i + 1].kind != 0 || taken[i] || taken[i + 1]) continue;
+    if (pass == 0 && p->convs[p->ops[i + 1].index].d.combine == RSB_COMB_NONE) continue;
+    ConvOp& a = p->convs[p->ops[i].index];
+    ConvOp& b = p->convs[p->ops[i + 1].index];
+    const rsb_conv_desc &da = a.d, &db = b.d;
+    if (!a.rs_elig || !b.rs_elig || a.d_wrot == nullptr || b.d_wrot == nullptr) continue;
+    if (a.pack_buf >= 0 || b.pack_buf >= 0 || a.scale != b.scale) continue;
+    if (da.combine != RSB_COMB_NONE || da.act == RSB_ACT_PRELU || da.dst_buf < 0 || da.dst_ps > 1 || da.dst2_buf >= 0) continue;
+    if (da.cout != a.npad || b.npad != a.npad) continue;  // one UMMA N for both convs, no padded channels in the ring
+    if (db.src_buf != da.dst_buf || db.src_ch_off != da.dst_ch_off || db.cin != da.cout || db.src_upsample2) continue;
+    if (db.dst_buf < 0 || db.dst_ps > 1 || db.dst2_buf >= 0 || db.res2_buf >= 0 || db.act == RSB_ACT_PRELU) continue;
+    const Region mid = conv_dst(a), bdst = conv_dst(b), asrc = conv_src(a);
+    if (overlaps(bdst, asrc) || overlaps(bdst, mid)) continue;  // B's rows are written while A still reads its source
+    if (db.combine != RSB_COMB_NONE) {
+      const Region res = {db.res1_buf, db.res1_ch_off, db.res1_ch_off + ceil_div(db.cout, 8) * 8};
+      if (overlaps(res, mid) || overlaps(res, bdst)) continue;
+    }
+    if (!rsb::conv_pair_supported(a.tc_cin, a.npad, da.act, db.act, db.combine)) continue;
+    if (rsb::conv_pair_smem_bytes(a.tc_cin, a.npad) > kMaxSmem) continue;
+    if (!region_dead_after(p, mid, i + 1)) continue;
+    a.pair_head = true;
+    taken[i] = taken[i + 1] = 1;  // pairs do not overlap
+  }
 }
 
 void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi& e) {
@@ -358,6 +433,43 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     q.wpack = c.d_wdirect;
     fill_epi(p, c, n, H, W, ws, q.epi);
   }
+  for (size_t i = 0; i + 1 < p->ops.size(); ++i) {
+    if (p->ops[i].kind != 0) continue;
+    ConvOp& a = p->convs[p->ops[i].index];
+    a.pair_ready = false;
+    if (!a.pair_head) continue;
+    ConvOp& b = p->convs[p->ops[i + 1].index];
+    const int H = h * a.scale, W = w * a.scale;
+    const int cols = rsb::conv_pair_cols(W);
+    // same eligibility as the row-streaming kernel (W % 8 == 0, enough rows per CTA to amortise the run ends)
+    if (!a.rs_ready || !b.rs_ready || (long long)n * cols * H < 8ll * p->num_sms) continue;
+    rsb::ConvPairParams& q = a.prp;
+    memset(&q, 0, sizeof q);
+    q.n = n, q.H = H, q.W = W;
+    q.cols = cols, q.units = n * cols * H;
+    q.cin0 = a.tc_cin, q.np = a.npad;
+    q.src_plane0 = a.tc_src_ch_off / 8;
+    q.wpackA = a.d_wrot, q.wbytesA = a.wbytes_rot;
+    q.wpackB = b.d_wrot, q.wbytesB = b.wbytes_rot;
+    q.stage_bytes = rsb::conv_rs_stage_bytes(a.tc_cin);
+    q.biasA = a.d_bias, q.actA = a.d.act, q.actA_param = a.d.act_param;
+    q.epi = b.tcp.epi;
+    memset(&a.map_res, 0, sizeof a.map_res);
+    if (b.d.combine != RSB_COMB_NONE) {
+      EncodeTiledFn enc = get_encode_fn();
+      const Buffer& rb = p->bufs[b.d.res1_buf];
+      cuuint64_t dims5[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)H, (cuuint64_t)rb.planes, (cuuint64_t)n};
+      cuuint64_t strides5[4] = {128, (cuuint64_t)W * 16, (cuuint64_t)W * 16 * H, (cuuint64_t)W * 16 * H * rb.planes};
+      cuuint32_t box5[5] = {64, 16, 1, (cuuint32_t)(a.npad / 8), 1};
+      cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+      CUresult r5 = enc(&a.map_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ws + rb.offset, dims5, strides5, box5, estr5,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r5 != CUDA_SUCCESS) return fail(RSB_ERR_INVALID, "cuTensorMapEncodeTiled (pair residual) failed with CUresult %d", (int)r5);
+      q.res_prefetch = 1;
+    }
+    a.pair_ready = true;
+  }
   for (size_t i = 0; i < p->gns.size(); ++i) {
     GnOp& g = p->gns[i];
     const int H = h * g.scale, W = w * g.scale;
@@ -475,7 +587,7 @@ int rsb_plan_destroy(rsb_plan* p) {
     cudaGetDevice(&prev);
     cudaSetDevice(p->device);
     for (ConvOp& c : p->convs) {
-      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wrs), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
+      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wrs), cudaFree(c.d_wrot), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
     for (AuxOp& a : p->auxs)
@@ -674,6 +786,7 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
   RSB_CUDA(rsb::conv_tc_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_tc2_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_rs_configure(kMaxSmem));
+  RSB_CUDA(rsb::conv_pair_configure(kMaxSmem));
   static const bool no_rs = getenv("RSB_NO_RS") != nullptr;
 
   for (ConvOp& c : p->convs) {
@@ -753,6 +866,21 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
           RSB_CUDA(cudaMalloc(&c.d_wrs, c.wbytes_rs));
           RSB_CUDA(cudaMemcpy(c.d_wrs, wr.data(), c.wbytes_rs, cudaMemcpyHostToDevice));
           c.rs_elig = true;
+          if (c.tc_cin <= 64 && c.npad <= 64) {
+            // fused-pair layout: five N blocks holding kernel rows [2, 1, 0, 2, 1]
+            const int n5 = 5 * c.npad;
+            static const int kh_of_block[5] = {2, 1, 0, 2, 1};
+            std::vector<uint16_t> wq((size_t)3 * cin8 * n5 * 8, 0);
+            for (int o = 0; o < d.cout; ++o)
+              for (int ci = 0; ci < d.cin; ++ci)
+                for (int j = 0; j < 5; ++j)
+                  for (int kx = 0; kx < 3; ++kx)
+                    wq[(((size_t)kx * cin8 + ci / 8) * n5 + j * c.npad + o) * 8 + (ci & 7)] =
+                        f32_to_bf16(c.w[((size_t)o * d.cin + ci) * 9 + kh_of_block[j] * 3 + kx]);
+            c.wbytes_rot = (uint32_t)(wq.size() * 2);
+            RSB_CUDA(cudaMalloc(&c.d_wrot, c.wbytes_rot));
+            RSB_CUDA(cudaMemcpy(c.d_wrot, wq.data(), c.wbytes_rot, cudaMemcpyHostToDevice));
+          }
         }
       }
       if (c.npad % 16 == 0 && c.kchunk == c.tc_cin) {
@@ -781,6 +909,7 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
     }
     std::vector<float>().swap(c.w);
   }
+  find_pairs(p);
   for (GnOp& g : p->gns) {
     RSB_CUDA(cudaMalloc(&g.d_gamma, g.gamma.size() * sizeof(float)));
     RSB_CUDA(cudaMalloc(&g.d_beta, g.beta.size() * sizeof(float)));
@@ -807,7 +936,11 @@ int rsb_plan_launches_per_forward(const rsb_plan* p) {
   for (const ConvOp& c : p->convs) packed += (c.pack_buf >= 0 && c.tc_ok) ? 1 : 0;
   int aux = 0;
   for (const AuxOp& a : p->auxs) aux += (a.d.kind == RSB_OP_CHANATTN || a.d.kind == RSB_OP_AIM) ? 3 : 1;
-  return (int)p->convs.size() + packed + 2 * (int)p->gns.size() + aux;
+  int fused = 0;  // a fused pair is one launch for two convs (opt-in: RSB_PAIR=1)
+  static const bool pair_env = getenv("RSB_PAIR") != nullptr;
+  if (pair_env)
+    for (const ConvOp& c : p->convs) fused += (c.pair_head && (p->bws == nullptr || c.pair_ready)) ? 1 : 0;
+  return (int)p->convs.size() - fused + packed + 2 * (int)p->gns.size() + aux;
 }
 
 int rsb_plan_flops(const rsb_plan* p, int n, int h, int w, double* flops) {
@@ -853,7 +986,13 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
       cudaError_t e;
       if (op.kind == 0) {
         ConvOp& c = p->convs[op.index];
-        if (c.tc_ok && force_direct != 1) {
+        static const bool pair_env = getenv("RSB_PAIR") != nullptr;
+        if (c.pair_ready && ((force_direct == 0 && pair_env) || force_direct == 4) && oi + 1 < op_end) {
+          // this conv and the next one as one fused launch; the intermediate map is not materialised
+          rsb::ConvPairParams q = c.prp;
+          e = rsb::launch_conv_pair(c.map_rs, q.res_prefetch ? c.map_res : c.map_rs, q, p->num_sms, stream);
+          ++oi;
+        } else if (c.tc_ok && force_direct != 1) {
           if (c.pack_buf >= 0) {
             rsb::PackParams k = c.pk;
             k.src = x, k.src_dtype = x_dtype;

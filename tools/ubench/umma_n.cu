@@ -56,7 +56,7 @@ int main() {
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int reps = 9 * 400;
   for (int nc = 0; nc <= 2; ++nc)
-    for (int N : {48, 144, 192, 256}) {
+    for (int N : {16, 48, 96, 144, 192, 256}) {
       bench<<<148, 128, 64 * 1024>>>(N, reps, 128, 2304, 1, 1, d, nc);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
