@@ -433,6 +433,7 @@ const RsVariant kRsVariants[] = {
     RSB_V(4, 4, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_V(4, 4, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_V(4, 4, RSB_ACT_NONE, RSB_COMB_AXPY),
+    RSB_V(6, 4, RSB_ACT_NONE, RSB_COMB_AXPY),  // the two K halves of ESRGAN's 192 -> 64 conv
     RSB_V(4, 4, RSB_ACT_SIGMOID, RSB_COMB_MUL),
     RSB_V(8, 4, RSB_ACT_NONE, RSB_COMB_NONE),
     // upsampler convs storing PixelShuffle'd into the caller's tensor

@@ -438,6 +438,21 @@ struct ConvRsParams {
   Epi epi;
 };
 
+// Large-kernel row-streaming conv (conv_lk.cu): K x K, all kernel rows stacked on the UMMA N axis, 16 output channels
+struct ConvLkParams {
+  int n, H, W;
+  int cols;   // ceil(W / 128)
+  int units;  // n * cols * H
+  int cin;    // multiple of 16
+  int k;      // kernel extent (odd, 5..17); padding k / 2
+  int src_plane0;
+  const void* wpack;  // bf16 [k kw][cin/8][k * 16][8]: N block j holds kernel row k-1-j
+  uint32_t wbytes;
+  int stages;
+  uint32_t stage_bytes;  // cin/8 planes x 18 groups x 128 B
+  Epi epi;
+};
+
 // Fused pair of 3x3 convs (conv_pair.cu): A's activated output rows stay in shared memory and feed B
 struct ConvPairParams {
   int n, H, W;
@@ -596,6 +611,10 @@ size_t conv_rs_smem_bytes(int cin, int np, int stages);
 uint32_t conv_rs_stage_bytes(int cin);
 cudaError_t conv_rs_configure(size_t max_smem);
 cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, int num_sms, cudaStream_t stream);
+uint32_t conv_lk_weight_bytes(int cin, int k);
+size_t conv_lk_smem_bytes(int cin, int k, int stages);
+cudaError_t conv_lk_configure(size_t max_smem);
+cudaError_t launch_conv_lk(const CUtensorMap& src_map, const ConvLkParams& p, int num_sms, cudaStream_t stream);
 uint32_t conv_pair_weight_bytes(int cin, int np);
 size_t conv_pair_smem_bytes(int cin0, int np);
 int conv_pair_cols(int W);

@@ -80,6 +80,12 @@ struct ConvOp {
   int rs_stages = 0;
   void* d_wrs = nullptr;
   uint32_t wbytes_rs = 0;
+  // large-kernel row-streaming kernel (conv_lk.cu): K x K (odd, 5..17), <= 16 output channels
+  bool lk_elig = false, lk_ready = false;
+  int lk_stages = 0;
+  void* d_wlk = nullptr;
+  uint32_t wbytes_lk = 0;
+  rsb::ConvLkParams lkp;
   // fused pair kernel (conv_pair.cu): this conv is the head (A) of a pair with the next op; decided at finalize
   bool pair_head = false, pair_ready = false;
   void* d_wrot = nullptr;  // [3 kw][cin/8][5 * npad][8]: kernel rows [2, 1, 0, 2, 1] side by side on the N axis
@@ -377,8 +383,9 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       fill_epi(p, c, n, H, W, ws, t.epi);
       // each CTA streams a contiguous run of rows and pays ~2 halo rows per run: worth it from ~8 rows per CTA
       c.rs_ready = c.rs_elig && W % 8 == 0;
+      c.lk_ready = c.lk_elig && W % 8 == 0;
       c.rs_pref = (long long)n * ceil_div(W, 128) * H >= 8ll * p->num_sms;
-      if (c.rs_ready) {
+      if (c.rs_ready || c.lk_ready) {
         // the same tensor viewed as [n][plane][H][W/8][8 px x 8 ch]: a box of 18 pixel groups of one row lands as
         // [plane][18][128 B], i.e. 144 consecutive pixels per plane
         cuuint64_t dims5[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)H, (cuuint64_t)sb.planes, (cuuint64_t)n};
@@ -400,6 +407,19 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
         q.stages = c.rs_stages;
         q.stage_bytes = rsb::conv_rs_stage_bytes(c.tc_cin);
         q.epi = t.epi;
+        if (c.lk_ready) {
+          rsb::ConvLkParams& k = c.lkp;
+          memset(&k, 0, sizeof k);
+          k.n = n, k.H = H, k.W = W;
+          k.cols = ceil_div(W, 128);
+          k.units = n * k.cols * H;
+          k.cin = c.tc_cin, k.k = d.kh;
+          k.src_plane0 = c.tc_src_ch_off / 8;
+          k.wpack = c.d_wlk, k.wbytes = c.wbytes_lk;
+          k.stages = c.lk_stages;
+          k.stage_bytes = rsb::conv_rs_stage_bytes(c.tc_cin);
+          k.epi = t.epi;
+        }
       }
       if (c.pack_buf >= 0) {
         rsb::PackParams& k = c.pk;
@@ -587,7 +607,7 @@ int rsb_plan_destroy(rsb_plan* p) {
     cudaGetDevice(&prev);
     cudaSetDevice(p->device);
     for (ConvOp& c : p->convs) {
-      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wrs), cudaFree(c.d_wrot), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
+      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wrs), cudaFree(c.d_wrot), cudaFree(c.d_wlk), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
     for (AuxOp& a : p->auxs)
@@ -787,6 +807,7 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
   RSB_CUDA(rsb::conv_tc2_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_rs_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_pair_configure(kMaxSmem));
+  RSB_CUDA(rsb::conv_lk_configure(kMaxSmem));
   static const bool no_rs = getenv("RSB_NO_RS") != nullptr;
 
   for (ConvOp& c : p->convs) {
@@ -881,6 +902,26 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
             RSB_CUDA(cudaMalloc(&c.d_wrot, c.wbytes_rot));
             RSB_CUDA(cudaMemcpy(c.d_wrot, wq.data(), c.wbytes_rot, cudaMemcpyHostToDevice));
           }
+        }
+      }
+      if (!no_rs && d.kh == d.kw && d.kh % 2 == 1 && d.kh >= 5 && d.kh <= 17 && d.pad_t == d.kh / 2 && d.pad_l == d.kw / 2 && c.npad == 16 &&
+          c.tc_cin <= 64) {
+        // large-kernel row-streaming kernel: [kw][cin/8][K * 16][8], N block j holds kernel row K-1-j
+        const int K = d.kh, nk = K * 16;
+        for (int sg = 8; sg >= 4 && c.lk_stages == 0; --sg)
+          if (rsb::conv_lk_smem_bytes(c.tc_cin, K, sg) <= kMaxSmem) c.lk_stages = sg;
+        if (c.lk_stages > 0) {
+          std::vector<uint16_t> wl((size_t)K * cin8 * nk * 8, 0);
+          for (int o = 0; o < d.cout; ++o)
+            for (int ci = 0; ci < d.cin; ++ci)
+              for (int j = 0; j < K; ++j)
+                for (int kx = 0; kx < K; ++kx)
+                  wl[(((size_t)kx * cin8 + ci / 8) * nk + j * 16 + o) * 8 + (ci & 7)] =
+                      f32_to_bf16(c.w[((size_t)o * d.cin + ci) * K * K + (K - 1 - j) * K + kx]);
+          c.wbytes_lk = (uint32_t)(wl.size() * 2);
+          RSB_CUDA(cudaMalloc(&c.d_wlk, c.wbytes_lk));
+          RSB_CUDA(cudaMemcpy(c.d_wlk, wl.data(), c.wbytes_lk, cudaMemcpyHostToDevice));
+          c.lk_elig = true;
         }
       }
       if (c.npad % 16 == 0 && c.kchunk == c.tc_cin) {
@@ -1006,7 +1047,11 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           if (t.epi.dst_external) t.epi.dst = y, t.epi.out_dtype = y_dtype;
           t.epi.base = x, t.epi.base_dtype = x_dtype;
           static const bool pair_kernel = getenv("RSB_TC2") != nullptr;
-          if (c.rs_ready && force_direct != 2 && (c.rs_pref || force_direct == 3)) {
+          if (c.lk_ready && force_direct != 2 && (c.rs_pref || force_direct == 3)) {
+            rsb::ConvLkParams q = c.lkp;
+            q.epi = t.epi;
+            e = rsb::launch_conv_lk(c.map_rs, q, p->num_sms, stream);
+          } else if (c.rs_ready && force_direct != 2 && (c.rs_pref || force_direct == 3)) {
             rsb::ConvRsParams q = c.rsp;
             q.epi = t.epi;
             e = rsb::launch_conv_rs(c.map_rs, q, p->num_sms, stream);

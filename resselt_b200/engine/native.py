@@ -14,7 +14,7 @@ import threading
 
 CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'csrc'))
 LIB_PATH = os.path.join(CSRC_DIR, 'libresselt_b200.so')
-SOURCES = ('conv_tc.cu', 'conv_tc2.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_direct.cu', 'dat_ops.cu', 'plan.cu')
+SOURCES = ('conv_tc.cu', 'conv_tc2.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_lk.cu', 'conv_direct.cu', 'dat_ops.cu', 'plan.cu')
 HEADERS = ('kernels.cuh', 'ptx.cuh', os.path.join('..', '..', 'include', 'resselt_b200.h'))
 NVCC_FLAGS = (
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
