@@ -119,6 +119,75 @@ __global__ void __launch_bounds__(256) dwconv3_kernel(const __grid_constant__ To
   }
 }
 
+// bf16 storage: each thread owns one pixel column of one 8-channel plane over a vertical run of rows.  The plane's 72
+// weights live in registers for the whole run and the 3 x 3 window of 16-byte pixel chunks slides down, so an output costs
+// three loads (two of them L1 hits) instead of nine plus 72 weight loads; GELU uses the MUFU erf approximation of the
+// conv epilogues (|err| <= 1.5e-7).  First version: 170 us per launch on DAT 4x 512^2.
+constexpr int kDwRows = 8;
+__global__ void __launch_bounds__(128) dwconv3_bf16_kernel(const __grid_constant__ TokenOpParams p) {
+  using T = __nv_bfloat16;
+  const int C = p.channels, planes = (C + 7) >> 3;
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int yb = blockIdx.y * kDwRows;
+  const int pl = blockIdx.z % planes, n = blockIdx.z / planes;
+  if (x >= p.W) return;
+  const T* src = reinterpret_cast<const T*>(p.src) + planar_index(n, p.src_planes, p.src_plane0 + pl, p.H, p.W, 0, 0);
+  const T* mul = reinterpret_cast<const T*>(p.src2);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  float w[9][8], bias[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = pl * 8 + k;
+    bias[k] = c < C ? p.w1[c] : 0.0f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[t][k] = c < C ? p.w0[c * 9 + t] : 0.0f;
+  }
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  auto ldrow = [&](int y, uint4 (&o)[3]) {
+    if (y < 0 || y >= p.H) {
+      o[0] = o[1] = o[2] = zero;
+      return;
+    }
+    const uint4* r = reinterpret_cast<const uint4*>(src + ((size_t)y * p.W + x) * 8);
+    o[0] = x > 0 ? r[-1] : zero;
+    o[1] = r[0];
+    o[2] = x + 1 < p.W ? r[1] : zero;
+  };
+  uint4 win[3][3];
+  ldrow(yb - 1, win[0]);
+  ldrow(yb, win[1]);
+#pragma unroll
+  for (int r = 0; r < kDwRows; ++r) {
+    const int y = yb + r;
+    if (y < p.H) {
+      ldrow(y + 1, win[(r + 2) % 3]);
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = bias[k];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          float v[8];
+          unpack8<T>(win[(r + ky) % 3][kx], v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(v[k], w[ky * 3 + kx][k], acc[k]);
+        }
+      if (p.i0 == RSB_ACT_GELU) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = activate<true, RSB_ACT_GELU>(RSB_ACT_GELU, acc[k], 0.0f, 0.0f);
+      }
+      if (mul != nullptr) {
+        float g[8];
+        load8<T>(mul + planar_index(n, p.src2_planes, p.src2_plane0 + pl, p.H, p.W, y, x), g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= g[k];
+      }
+      store8<T>(dst + planar_index(n, p.dst_planes, p.dst_plane0 + pl, p.H, p.W, y, x), acc);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ window attention
 constexpr int kHD = 32;  // head_dim padded (<= 32 supported)
 
@@ -224,60 +293,106 @@ __global__ void __launch_bounds__(256) winattn_kernel(const __grid_constant__ Wi
 }
 
 // ------------------------------------------------------------------------------------------------ channel attention
-constexpr int kTok = 32;  // tokens per shared-memory tile of the Gram reduction
+constexpr int kTok = 64;  // tokens per shared-memory tile of the Gram reduction
 
-// partial[n][head][block][d*d + 2d]: Gram q^T k and squared column norms of q and k over this block's token range
+// partial[n][head][block][d*d + 2d]: Gram q^T k and squared column norms of q and k over this block's token range.
+// Register-tiled: the 32 x 32 (head_dim padded) Gram matrix is cut into 8 x 8 tiles of 4 x 4 accumulators; the 256
+// threads are 4 token groups x 64 tiles, so one token costs a thread two 16-byte shared-memory loads for 16 FMAs (the
+// first version read two scalars per FMA and was shared-memory bound: 769 us per launch on DAT 4x 512^2).  Loads are
+// whole 16-byte pixel chunks of the planes the head's channels live in (coalesced along tokens).  Summation order is
+// fixed (token groups are reduced in order), so results are run-to-run deterministic.
 template <typename T>
 __global__ void __launch_bounds__(256) chanattn_reduce_kernel(const __grid_constant__ ChanAttnParams p) {
-  __shared__ float qs[kTok][kHD + 1], ks[kTok][kHD + 1];
+  constexpr int kRow = kHD + 4;  // 144-byte rows: float4-aligned, and the per-token scatter of the load phase is 4-way
+                                 // instead of 32-way bank-conflicted
+  __shared__ __align__(16) float qs[kTok][kRow], ks[kTok][kRow];
+  __shared__ float red[3][kHD * kHD + 2 * kHD];
   const int h = blockIdx.y, n = blockIdx.z, d = p.head_dim;
   const size_t hw = (size_t)p.H * p.W;
   const size_t chunk = (hw + gridDim.x - 1) / gridDim.x;
   const size_t t0 = (size_t)blockIdx.x * chunk, t1 = min(hw, t0 + chunk);
   const T* src = reinterpret_cast<const T*>(p.src);
   const int cq = p.src_ch_off + h * d, ck = cq + p.qkv_stride;
-  float acc[4] = {0, 0, 0, 0};
-  float nrm = 0.0f;
+  const int grp = threadIdx.x >> 6, tile = threadIdx.x & 63;
+  const int i0 = (tile >> 3) * 4, j0 = (tile & 7) * 4;
+  float acc[4][4] = {};
+  float nq[4] = {0, 0, 0, 0}, nk[4] = {0, 0, 0, 0};
+  // planes touched by the head's channel range (at most 5 for head_dim <= 32)
+  const int pq0 = cq >> 3, npq = ((cq + d - 1) >> 3) - pq0 + 1;
+  const int pk0 = ck >> 3, npk = ((ck + d - 1) >> 3) - pk0 + 1;
+  for (int e = threadIdx.x; e < kTok * kRow; e += blockDim.x) (&qs[0][0])[e] = 0.0f, (&ks[0][0])[e] = 0.0f;  // padded columns stay zero
+  __syncthreads();
   for (size_t base = t0; base < t1; base += kTok) {
-    for (int e = threadIdx.x; e < kTok * d * 2; e += blockDim.x) {
-      const int which = e / (kTok * d), r = e - which * kTok * d;
-      const int tt = r / d, c = r - tt * d;
+    for (int e = threadIdx.x; e < kTok * (npq + npk); e += blockDim.x) {
+      const int pl = e / kTok, tt = e - pl * kTok;
+      const bool isk = pl >= npq;
+      const int plane = isk ? pk0 + (pl - npq) : pq0 + pl;
+      const int c0 = isk ? ck : cq;
       const size_t tok = base + tt;
-      float v = 0.0f;
-      if (tok < t1) {
-        const int ch = (which ? ck : cq) + c;
-        v = (float)src[(((size_t)n * p.src_planes + (ch >> 3)) * hw + tok) * 8 + (ch & 7)];
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (tok < t1) load8<T>(src + (((size_t)n * p.src_planes + plane) * hw + tok) * 8, v);
+      float* row = isk ? ks[tt] : qs[tt];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = plane * 8 + k - c0;
+        if (c >= 0 && c < d) row[c] = v[k];
       }
-      (which ? ks : qs)[tt][c] = v;
     }
     __syncthreads();
+#pragma unroll 4
+    for (int tt = grp; tt < kTok; tt += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(&qs[tt][i0]);
+      const float4 b = *reinterpret_cast<const float4*>(&ks[tt][j0]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int e = threadIdx.x + r * 256;
-      if (e < d * d) {
-        const int i = e / d, j = e - i * d;
-        float a = acc[r];
-#pragma unroll 8
-        for (int tt = 0; tt < kTok; ++tt) a = fmaf(qs[tt][i], ks[tt][j], a);
-        acc[r] = a;
-      }
-    }
-    if (threadIdx.x < 2 * d) {
-      const int c = threadIdx.x < d ? threadIdx.x : threadIdx.x - d;
-      for (int tt = 0; tt < kTok; ++tt) {
-        const float v = threadIdx.x < d ? qs[tt][c] : ks[tt][c];
-        nrm = fmaf(v, v, nrm);
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        nq[i] = fmaf(av[i], av[i], nq[i]);
+        nk[i] = fmaf(bv[i], bv[i], nk[i]);
       }
     }
     __syncthreads();
   }
-  float* out = p.partial + (((size_t)n * p.heads + h) * gridDim.x + blockIdx.x) * (d * d + 2 * d);
+  // reduce the four token groups in fixed order: groups 1..3 park their tiles, group 0 adds them up and writes
+  const int len = d * d + 2 * d;
+  if (grp > 0) {
+    float* r = red[grp - 1];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int e = threadIdx.x + r * 256;
-    if (e < d * d) out[e] = acc[r];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[(i0 + i) * kHD + j0 + j] = acc[i][j];
+    if (j0 == 0)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[kHD * kHD + i0 + i] = nq[i];
+    if (i0 == 0)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[kHD * kHD + kHD + j0 + j] = nk[j];
   }
-  if (threadIdx.x < 2 * d) out[d * d + threadIdx.x] = nrm;
+  __syncthreads();
+  if (grp == 0) {
+    float* out = p.partial + (((size_t)n * p.heads + h) * gridDim.x + blockIdx.x) * len;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (i0 + i) * kHD + j0 + j;
+        const float v = ((acc[i][j] + red[0][e]) + red[1][e]) + red[2][e];
+        if (i0 + i < d && j0 + j < d) out[(i0 + i) * d + j0 + j] = v;
+      }
+    if (j0 == 0)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = kHD * kHD + i0 + i;
+        if (i0 + i < d) out[d * d + i0 + i] = ((nq[i] + red[0][e]) + red[1][e]) + red[2][e];
+      }
+    if (i0 == 0)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = kHD * kHD + kHD + j0 + j;
+        if (j0 + j < d) out[d * d + d + j0 + j] = ((nk[j] + red[0][e]) + red[1][e]) + red[2][e];
+      }
+  }
 }
 
 // attn[n][head][i][j] = softmax_j( G[i][j] / (max(|q_i|, eps) max(|k_j|, eps)) * temperature[head] )
@@ -466,7 +581,9 @@ cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s) 
 
 cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s) {
   const int g = grid_for((size_t)p.n * ((p.channels + 7) / 8) * p.H * p.W);
-  if (bf16)
+  if (bf16 && (long long)p.n * ((p.channels + 7) / 8) <= 65535)
+    dwconv3_bf16_kernel<<<dim3((p.W + 127) / 128, (p.H + kDwRows - 1) / kDwRows, p.n * ((p.channels + 7) / 8)), 128, 0, s>>>(p);
+  else if (bf16)
     dwconv3_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
   else
     dwconv3_kernel<float><<<g, 256, 0, s>>>(p);
