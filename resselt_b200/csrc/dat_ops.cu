@@ -292,6 +292,211 @@ __global__ void __launch_bounds__(256) winattn_kernel(const __grid_constant__ Wi
   }
 }
 
+// ---- tensor-core version (bf16 storage): one CTA per (window, head), one warp per 16 queries, FlashAttention-2 style.
+// S = Q K^T and O = P V run on warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) over 64-key chunks with an online
+// softmax in registers; the score scale, position bias, shift mask and softmax are fp32, P is rounded to bf16 for the PV
+// product (as in every bf16 attention kernel).  Q / K rows and V^T rows sit in shared memory as bf16 with padded strides
+// (conflict-free fragment loads).  The CUDA-core version above issues ~95 instructions per (query, key) pair and took
+// 2.35 ms per launch on DAT 4x 512^2 (46 % of the forward); this one is bound by the 65 536 exponentials per window-head.
+// A tcgen05 formulation (S in TMEM) is the next step; at head_dim 30 and 256 keys the softmax, not the MMA, is the limit.
+constexpr int kWaQS = kHD + 8;  // Q / K row stride in bf16 elements (80 B: fragment loads hit 32 distinct banks)
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+size_t winattn_mma_smem_bytes(int split_h, int split_w) {
+  const int N = split_h * split_w, NK = (N + 63) / 64 * 64, NQ = (N + 15) / 16 * 16;
+  return (size_t)(NQ + NK) * kWaQS * 2 + (size_t)kHD * (NK + 8) * 2 + (size_t)(2 * split_h - 1) * (2 * split_w - 1) * 4 + (size_t)NK * 4;
+}
+
+__global__ void __launch_bounds__(512) winattn_mma_kernel(const __grid_constant__ WinAttnParams p) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  using T = __nv_bfloat16;
+  const int br = blockIdx.z, h = blockIdx.y;
+  const int Hs = br == 0 ? p.split_h : p.split_w, Ws = br == 0 ? p.split_w : p.split_h;
+  const int N = Hs * Ws, NK = (N + 63) / 64 * 64, NQ = (N + 15) / 16 * 16, VS = NK + 8;
+  const int sh = p.shifted ? Hs / 2 : 0, sw = p.shifted ? Ws / 2 : 0;
+  const int nWx = p.Wp / Ws, nWy = p.Hp / Hs;
+  const int win = blockIdx.x % (nWx * nWy), n = blockIdx.x / (nWx * nWy);
+  const int wy = win / nWx, wx = win - wy * nWx;
+  const int d = p.head_dim;
+  const int tab_w = 2 * Ws - 1, tab_n = (2 * Hs - 1) * tab_w;
+  T* Qs = reinterpret_cast<T*>(smraw);            // [NQ][kWaQS]
+  T* Ks = Qs + (size_t)NQ * kWaQS;                // [NK][kWaQS]
+  T* Vt = Ks + (size_t)NK * kWaQS;                // [kHD][VS]   (V transposed: keys contiguous)
+  float* tab = reinterpret_cast<float*>(Vt + (size_t)kHD * VS);  // [tab_n] bias of this head
+  int* kinfo = reinterpret_cast<int*>(tab + tab_n);              // [NK] (jy * tab_w + jx) | label << 20
+  const float* table = br == 0 ? p.table0 : p.table1;
+  const int hpb = p.heads / 2;
+  for (int i = threadIdx.x; i < tab_n; i += blockDim.x) tab[i] = table[(size_t)i * hpb + h];
+
+  const T* src = reinterpret_cast<const T*>(p.src);
+  const int half = p.dim / 2;
+  const int cq = p.src_ch_off + br * half + h * d;
+  const T zero = __float2bfloat16_rn(0.0f);
+  for (int t = threadIdx.x; t < max(NQ, NK); t += blockDim.x) {
+    const bool active = t < N;
+    const int ty = active ? t / Ws : 0, tx = active ? t - ty * Ws : 0;
+    const int yr = wy * Hs + ty, xr = wx * Ws + tx;          // coordinates in the rolled, padded image
+    const int yo = (yr + sh) % p.Hp, xo = (xr + sw) % p.Wp;  // where that token lives in the un-rolled image
+    const bool inb = active && yo < p.H && xo < p.W;         // padded tokens have q = k = v = 0
+    for (int c = 0; c < kHD; ++c) {
+      T qv = zero, kv = zero, vv = zero;
+      if (inb && c < d) {
+        const size_t base = planar_index(n, p.src_planes, 0, p.H, p.W, yo, xo);
+        const int c1 = cq + c, c2 = c1 + p.qkv_stride, c3 = c2 + p.qkv_stride;
+        const size_t ps = (size_t)p.H * p.W * 8;
+        qv = src[base + (size_t)(c1 >> 3) * ps + (c1 & 7)];
+        kv = src[base + (size_t)(c2 >> 3) * ps + (c2 & 7)];
+        vv = src[base + (size_t)(c3 >> 3) * ps + (c3 & 7)];
+      }
+      if (t < NQ) Qs[t * kWaQS + c] = qv;
+      if (t < NK) Ks[t * kWaQS + c] = kv, Vt[c * VS + t] = vv;
+    }
+    if (t < NK) {
+      int lab = 0;
+      if (p.shifted && active) {
+        const int ry = yr < p.Hp - Hs ? 0 : (yr < p.Hp - sh ? 1 : 2);
+        const int rx = xr < p.Wp - Ws ? 0 : (xr < p.Wp - sw ? 1 : 2);
+        lab = 3 * ry + rx;
+      }
+      kinfo[t] = (ty * tab_w + tx) | (lab << 20) | (active ? 0 : 1 << 30);
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = warp * 16;
+  if (r0 >= NQ) return;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const int qa = r0 + g4, qb = qa + 8;  // the two query rows this thread holds fragments of
+  // query-side halves of the bias index and the shift-mask labels
+  int qpos[2], qlab[2];
+  bool qact[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int t = e == 0 ? qa : qb;
+    qact[e] = t < N;
+    const int tt = qact[e] ? t : 0;
+    const int ty = tt / Ws, tx = tt - ty * Ws;
+    qpos[e] = (ty + Hs - 1) * tab_w + tx + Ws - 1;
+    qlab[e] = (kinfo[tt] >> 20) & 0xF;
+  }
+  uint32_t qf[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const T* qr = Qs + ks * 16 + t4 * 2;
+    qf[ks][0] = *reinterpret_cast<const uint32_t*>(qr + (size_t)qa * kWaQS);
+    qf[ks][1] = *reinterpret_cast<const uint32_t*>(qr + (size_t)qb * kWaQS);
+    qf[ks][2] = *reinterpret_cast<const uint32_t*>(qr + (size_t)qa * kWaQS + 8);
+    qf[ks][3] = *reinterpret_cast<const uint32_t*>(qr + (size_t)qb * kWaQS + 8);
+  }
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.0f, 0.0f};
+  float o[4][4];
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[dt][e] = 0.0f;
+
+  for (int kc = 0; kc < NK; kc += 64) {
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[nt][e] = 0.0f;
+      const T* kr = Ks + (size_t)(kc + nt * 8 + g4) * kWaQS + t4 * 2;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma_bf16_16816(sc[nt], qf[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16), *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+    }
+    // scale, position bias, shift mask; chunk maxima
+    float cm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = kc + nt * 8 + t4 * 2 + (e & 1);
+        const int ki = kinfo[j];
+        const int r = e >> 1;
+        float v = sc[nt][e] * p.scale + tab[qpos[r] - (ki & 0xFFFFF)];
+        if (p.shifted && ((ki >> 20) & 0xF) != qlab[r]) v += -100.0f;
+        if (ki >> 30) v = -INFINITY;  // keys beyond the window (chunk padding)
+        sc[nt][e] = v;
+        cm[r] = fmaxf(cm[r], v);
+      }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      cm[r] = fmaxf(cm[r], __shfl_xor_sync(0xffffffffu, cm[r], 1));
+      cm[r] = fmaxf(cm[r], __shfl_xor_sync(0xffffffffu, cm[r], 2));
+      const float mn = fmaxf(m[r], cm[r]);
+      corr[r] = __expf(m[r] - mn);  // first chunk: exp(-inf) = 0
+      m[r] = mn;
+      l[r] *= corr[r];
+    }
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) {
+      o[dt][0] *= corr[0], o[dt][1] *= corr[0];
+      o[dt][2] *= corr[1], o[dt][3] *= corr[1];
+    }
+    // P = exp(S - m) as bf16 A fragments; row sums accumulate the ROUNDED values so that O / l is a true weighted mean
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = __expf(sc[nt][0] - m[0]), p1 = __expf(sc[nt][1] - m[0]);
+      const float p2 = __expf(sc[nt][2] - m[1]), p3 = __expf(sc[nt][3] - m[1]);
+      const uint32_t lo = pack_bf16x2(p0, p1), hi = pack_bf16x2(p2, p3);
+      l[0] += __uint_as_float(lo << 16) + __uint_as_float(lo & 0xFFFF0000u);
+      l[1] += __uint_as_float(hi << 16) + __uint_as_float(hi & 0xFFFF0000u);
+      pf[nt >> 1][(nt & 1) * 2 + 0] = lo;
+      pf[nt >> 1][(nt & 1) * 2 + 1] = hi;
+    }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) {
+        const T* vr = Vt + (size_t)(dt * 8 + g4) * VS + kc + kt * 16 + t4 * 2;
+        mma_bf16_16816(o[dt], pf[kt], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  T* dst = reinterpret_cast<T*>(p.dst);
+  const int co = p.dst_ch_off + br * half + h * d;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = r == 0 ? qa : qb;
+    if (t >= N) continue;
+    const int ty = t / Ws, tx = t - ty * Ws;
+    const int yo = (wy * Hs + ty + sh) % p.Hp, xo = (wx * Ws + tx + sw) % p.Wp;
+    if (yo >= p.H || xo >= p.W) continue;
+    const float inv = 1.0f / l[r];
+    const size_t base = planar_index(n, p.dst_planes, 0, p.H, p.W, yo, xo);
+    const size_t ps = (size_t)p.H * p.W * 8;
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) {
+      const int c = dt * 8 + t4 * 2;  // dims c, c + 1
+      const int ch = co + c;
+      if (c + 1 < d && (ch & 1) == 0) {
+        *reinterpret_cast<uint32_t*>(dst + base + (size_t)(ch >> 3) * ps + (ch & 7)) = pack_bf16x2(o[dt][2 * r] * inv, o[dt][2 * r + 1] * inv);
+      } else {
+        if (c < d) dst[base + (size_t)(ch >> 3) * ps + (ch & 7)] = __float2bfloat16_rn(o[dt][2 * r] * inv);
+        if (c + 1 < d) dst[base + (size_t)((ch + 1) >> 3) * ps + ((ch + 1) & 7)] = __float2bfloat16_rn(o[dt][2 * r + 1] * inv);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ channel attention
 constexpr int kTok = 64;  // tokens per shared-memory tile of the Gram reduction
 
@@ -598,6 +803,8 @@ size_t winattn_smem_bytes(int split_h, int split_w) {
 cudaError_t winattn_configure() {
   cudaError_t e = cudaFuncSetAttribute(winattn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(winattn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(winattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
@@ -605,7 +812,12 @@ cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
   const int windows = (p.Hp / p.split_h) * (p.Wp / p.split_w);
   const dim3 grid(windows * p.n, p.heads / 2, 2);
   const size_t smem = winattn_smem_bytes(p.split_h, p.split_w);
-  if (bf16)
+  static const bool no_mma = getenv("RSB_WINATTN_SIMT") != nullptr;
+  const int N = p.split_h * p.split_w;
+  if (bf16 && !no_mma && N <= 256 && p.head_dim <= kHD && winattn_mma_smem_bytes(p.split_h, p.split_w) <= 160 * 1024) {
+    const int warps = (N + 15) / 16;
+    winattn_mma_kernel<<<grid, 32 * warps, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
+  } else if (bf16)
     winattn_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
   else
     winattn_kernel<float><<<grid, 256, smem, s>>>(p);
