@@ -22,4 +22,5 @@ from .sr_forward import (  # noqa: F401
     realplksr_forward,
     span_forward,
     spanplus_forward,
+    swinir_forward,
 )

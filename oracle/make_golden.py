@@ -42,6 +42,14 @@ def cases():
                                    expansion_factor=2.0, upscale=4), 22, (1, 3, 40, 56), 112),
         'dat_x2_d3_2_s4_8': ('DAT', dict(img_size=32, in_chans=3, embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2],
                                       expansion_factor=2.0, upscale=2), 23, (2, 3, 19, 27), 113),
+        'swinir_x2_ps_d2_3': ('SwinIR', dict(img_size=64, in_chans=3, embed_dim=60, depths=[2, 3], num_heads=[6, 6], window_size=8, mlp_ratio=2.0,
+                                             upscale=2, upsampler='pixelshuffle', resi_connection='1conv'), 24, (1, 3, 24, 32), 114),
+        'swinir_x3_psd_180': ('SwinIR', dict(img_size=64, in_chans=3, embed_dim=180, depths=[2], num_heads=[6], window_size=8, mlp_ratio=2.0,
+                                             upscale=3, upsampler='pixelshuffledirect', resi_connection='1conv'), 25, (2, 3, 19, 27), 115),
+        'swinir_x4_nearest_3conv': ('SwinIR', dict(img_size=64, in_chans=3, embed_dim=64, depths=[2, 2], num_heads=[4, 4], window_size=8, mlp_ratio=4.0,
+                                                   upscale=4, upsampler='nearest+conv', resi_connection='3conv'), 26, (1, 3, 21, 30), 116),
+        'swinir_jpeg_w7_gray': ('SwinIR', dict(img_size=126, in_chans=1, embed_dim=48, depths=[2, 2], num_heads=[6, 6], window_size=7, mlp_ratio=2.0,
+                                               upscale=1, img_range=255.0, upsampler='', resi_connection='1conv'), 27, (1, 1, 30, 23), 117),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
     }
@@ -52,7 +60,7 @@ def engine_model(kind: str, kwargs: dict, seed: int):
 
     cls = {'SPAN': archs.SPAN, 'SPANPlus': archs.SpanPlus, 'Compact': archs.SRVGGNetCompact}
     extra = {k: getattr(archs, k) for k in ('RRDBNet', 'RealPLKSR') if hasattr(archs, k)}
-    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None)})
+    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None)})
     return cls[kind](seed=seed, **kwargs)
 
 

@@ -356,7 +356,109 @@ def dat_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, img_range: float =
     return _conv(sd, 'conv_last', t, 1) / img_range + mean
 
 
+# ---------------------------------------------------------------------------------------------- SwinIR
+def _swin_mask(H, W, ws, shift, dtype):
+    """SwinTransformerBlock.calculate_mask (/root/reference/resselt/archs/swinir/arch.py:268-293)."""
+    img = torch.zeros(H, W, dtype=dtype)
+    cnt = 0
+    for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[hs, wsl] = cnt
+            cnt += 1
+    win = img.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    diff = win.unsqueeze(1) - win.unsqueeze(2)
+    return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
+
+
+def _swin_block(sd: SD, p: str, x, H, W, ws, shift, heads):
+    """SwinTransformerBlock.forward (/root/reference/resselt/archs/swinir/arch.py:295-335) with WindowAttention.forward
+    (:133-170) and Mlp.forward (:34-40) inlined; x: [B, H*W, C]."""
+    B, L, C = x.shape
+    t = _ln(sd, f'{p}.norm1', x).view(B, H, W, C)
+    if shift > 0:
+        t = torch.roll(t, shifts=(-shift, -shift), dims=(1, 2))
+    N = ws * ws
+    win = t.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, N, C)  # window_partition (:43-56)
+    qkv = _lin(sd, f'{p}.attn.qkv', win).reshape(-1, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * (C // heads) ** -0.5, qkv[1], qkv[2]
+    attn = q @ k.transpose(-2, -1)
+    idx = sd[f'{p}.attn.relative_position_index'].long().view(-1)
+    bias = sd[f'{p}.attn.relative_position_bias_table'].to(x.dtype)[idx].view(N, N, -1).permute(2, 0, 1)
+    attn = attn + bias.unsqueeze(0)
+    if shift > 0:
+        mask = _swin_mask(H, W, ws, shift, x.dtype)
+        nW = mask.shape[0]
+        attn = (attn.view(B, nW, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, N, C)
+    o = _lin(sd, f'{p}.attn.proj', o)
+    o = o.view(B, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)  # window_reverse (:59-72)
+    if shift > 0:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    x = x + o.reshape(B, L, C)
+    return x + _lin(sd, f'{p}.mlp.fc2', F.gelu(_lin(sd, f'{p}.mlp.fc1', _ln(sd, f'{p}.norm2', x))))
+
+
+def _swin_resi_conv(sd: SD, name: str, t):
+    """'1conv' (a single 3x3) or '3conv' (3x3 -> lrelu(0.2) -> 1x1 -> lrelu(0.2) -> 3x3), arch.py:564-574 / :890-901."""
+    if f'{name}.weight' in sd:
+        return _conv(sd, name, t, 1)
+    t = F.leaky_relu(_conv(sd, f'{name}.0', t, 1), 0.2)
+    t = F.leaky_relu(_conv(sd, f'{name}.2', t, 0), 0.2)
+    return _conv(sd, f'{name}.4', t, 1)
+
+
+def swinir_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """SwinIR.forward (/root/reference/resselt/archs/swinir/arch.py:962-1011; forward_features :947-960, RSTB.forward
+    :592-593), all four reconstruction heads; hyper-parameters re-derived like the loader does
+    (/root/reference/resselt/archs/swinir/__init__.py:35-96).  ape=False, patch_norm=True, start_unshuffle=1."""
+    x = x.to(dtype)
+    if 'conv_before_upsample.0.weight' in sd:
+        upsampler = 'nearest+conv' if 'conv_up1.weight' in sd else 'pixelshuffle'
+    else:
+        upsampler = 'pixelshuffledirect' if 'upsample.0.weight' in sd else ''
+    ws = int(math.isqrt(sd['layers.0.residual_group.blocks.0.attn.relative_position_index'].shape[0]))
+    img_range = 255.0 if ws == 7 else 1.0
+    B, in_ch, H0, W0 = x.shape
+    x = F.pad(x, (0, (ws - W0 % ws) % ws, 0, (ws - H0 % ws) % ws), 'reflect') if (H0 % ws or W0 % ws) else x  # check_image_size
+    H, W = x.shape[2:]
+    mean = torch.tensor((0.4488, 0.4371, 0.4040), dtype=dtype).view(1, 3, 1, 1) if in_ch == 3 else torch.zeros(1, 1, 1, 1, dtype=dtype)
+    x = (x - mean) * img_range
+    feat = _conv(sd, 'conv_first', x, 1)
+    t = _ln(sd, 'patch_embed.norm', feat.flatten(2).transpose(1, 2))
+    for i in range(_seq_len(sd, 'layers')):
+        res = t
+        heads = sd[f'layers.{i}.residual_group.blocks.0.attn.relative_position_bias_table'].shape[1]
+        for b in range(_seq_len(sd, f'layers.{i}.residual_group.blocks')):
+            t = _swin_block(sd, f'layers.{i}.residual_group.blocks.{b}', t, H, W, ws, 0 if b % 2 == 0 else ws // 2, heads)
+        t = _swin_resi_conv(sd, f'layers.{i}.conv', t.transpose(1, 2).reshape(B, -1, H, W)).flatten(2).transpose(1, 2) + res
+    t = _ln(sd, 'norm', t).transpose(1, 2).reshape(B, -1, H, W)
+    t = _swin_resi_conv(sd, 'conv_after_body', t) + feat
+    up = 1
+    if upsampler == 'pixelshuffle':
+        t = F.leaky_relu(_conv(sd, 'conv_before_upsample.0', t, 1), 0.01)
+        for i in range(0, _seq_len(sd, 'upsample'), 2):
+            r = int(math.isqrt(sd[f'upsample.{i}.weight'].shape[0] // sd[f'upsample.{i}.weight'].shape[1]))
+            t = F.pixel_shuffle(_conv(sd, f'upsample.{i}', t, 1), r)
+            up *= r
+        t = _conv(sd, 'conv_last', t, 1)
+    elif upsampler == 'pixelshuffledirect':
+        up = int(math.isqrt(sd['upsample.0.weight'].shape[0] // in_ch))
+        t = F.pixel_shuffle(_conv(sd, 'upsample.0', t, 1), up)
+    elif upsampler == 'nearest+conv':
+        t = F.leaky_relu(_conv(sd, 'conv_before_upsample.0', t, 1), 0.01)
+        for n in (1, 2, 3):
+            if f'conv_up{n}.weight' in sd:
+                t = F.leaky_relu(_conv(sd, f'conv_up{n}', F.interpolate(t, scale_factor=2, mode='nearest'), 1), 0.2)
+                up *= 2
+        t = _conv(sd, 'conv_last', F.leaky_relu(_conv(sd, 'conv_hr', t, 1), 0.2), 1)
+    else:
+        t = x + _conv(sd, 'conv_last', t, 1)
+    t = t / img_range + mean
+    return t[:, :, : H0 * up, : W0 * up]
+
+
 _FORWARDS: Dict[str, Callable] = {
+    'SwinIR': swinir_forward,
     'DAT': dat_forward,
     'RealPLKSR': realplksr_forward,
     'ESRGAN': esrgan_forward,

@@ -11,9 +11,10 @@ from .esrgan import ESRGANArch, RRDBNet
 from .plksr import PLKSRArch, RealPLKSR
 from .span import SPAN, SPANArch
 from .spanplus import SpanPlus, SpanPlusArch
+from .swinir import SwinIR, SwinIRArch
 
 internal_registry = Registry()
-for _arch in (SPANArch, SpanPlusArch, CompactArch, ESRGANArch, PLKSRArch, DatArch):
+for _arch in (SPANArch, SpanPlusArch, CompactArch, ESRGANArch, PLKSRArch, DatArch, SwinIRArch):
     internal_registry.add(_arch())
 
-__all__ = ['internal_registry', 'SPAN', 'SPANArch', 'SpanPlus', 'SpanPlusArch', 'SRVGGNetCompact', 'CompactArch', 'RRDBNet', 'ESRGANArch', 'RealPLKSR', 'PLKSRArch', 'DAT', 'DatArch']
+__all__ = ['internal_registry', 'SPAN', 'SPANArch', 'SpanPlus', 'SpanPlusArch', 'SRVGGNetCompact', 'CompactArch', 'RRDBNet', 'ESRGANArch', 'RealPLKSR', 'PLKSRArch', 'DAT', 'DatArch', 'SwinIR', 'SwinIRArch']

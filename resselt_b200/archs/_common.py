@@ -8,10 +8,11 @@ import torch
 from ..engine import ParamSpec
 
 
-def conv_specs(prefix: str, cin: int, cout: int, k: int) -> List[ParamSpec]:
-    """Names/shapes of one ``nn.Conv2d(cin, cout, k)`` with bias."""
+def conv_specs(prefix: str, cin: int, cout: int, k: int, gain: float = 1.0) -> List[ParamSpec]:
+    """Names/shapes of one ``nn.Conv2d(cin, cout, k)`` with bias (``gain`` scales the random-init weight range)."""
     fan_in = cin * k * k
-    return [(f'{prefix}.weight', (cout, cin, k, k), 'conv_w'), (f'{prefix}.bias', (cout,), f'bias:{fan_in}')]
+    kind = 'conv_w' if gain == 1.0 else f'conv_w*{gain}'
+    return [(f'{prefix}.weight', (cout, cin, k, k), kind), (f'{prefix}.bias', (cout,), f'bias:{fan_in}')]
 
 
 def conv3xc_specs(prefix: str, cin: int, cout: int, gain: int = 2) -> List[ParamSpec]:

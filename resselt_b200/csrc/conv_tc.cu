@@ -126,7 +126,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     // enough to keep the tensor pipe full with N = 48 MMAs (~24 math cycles each).  Each tile's MMAs stay in order
     // inside one warp, so the accumulation order per output pixel is fixed.  The whole warp walks the loop (so every
     // operand stays in uniform registers); one elected lane issues.
-    const int first = warp == 1 ? 0 : 1;
+    // K-chunked tiles share one ring of stages in chunk order.  A warp waiting for fill k of a stage must already have
+    // seen fill k-1 of it complete (mbarrier waits only know the phase parity): with two warps alternating tiles that
+    // holds only while a tile's chunks occupy fewer stages than the ring has (nchunks <= S - 1); wider K (e.g. a
+    // 384 -> 192 1x1 conv: 6 chunks of 64 channels over 4 stages) is issued by warp 1 alone, in tile order.
+    const bool solo = p.nchunks >= S;
+    const int first = (warp == 1 || solo) ? 0 : 1;
+    const int tstep = solo ? 1 : 2;
     const bool leader = elect_one();
     mbar_wait(wbar, 0);
     const uint32_t idesc = make_idesc_bf16(128, p.npad);
@@ -137,7 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const uint32_t a_kstep = 2u * (a_lbo >> 4);  // descriptor address units (16 B) per 16-channel K step
     const uint32_t b_kstep = 2u * (b_lbo >> 4);
     int i = first;
-    for (int tile = blockIdx.x + first * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, i += 2) {
+    for (int tile = blockIdx.x + first * gridDim.x; tile < p.num_tiles && !(solo && warp == 3); tile += tstep * gridDim.x, i += tstep) {
       const int acc = i % A;
       const uint32_t aph = (uint32_t)(i / A) & 1u;
       mbar_wait(&tempty[acc], aph ^ 1);

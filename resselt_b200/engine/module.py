@@ -22,7 +22,7 @@ class ParamGroup(nn.Module):
 
 
 ParamSpec = Tuple[str, Tuple[int, ...], str]  # (dotted name, shape, kind)
-# kinds: 'conv_w', 'bias:<fan_in>', 'prelu', 'ones', 'zeros', 'buffer_zeros', 'normal:<std>'
+# kinds: 'conv_w[*gain]', 'bias:<fan_in>', 'prelu', 'ones', 'zeros', 'buffer_zeros', 'normal:<std>'
 
 
 def _init_tensor(shape, kind: str, rng: np.random.RandomState) -> torch.Tensor:
@@ -34,9 +34,9 @@ def _init_tensor(shape, kind: str, rng: np.random.RandomState) -> torch.Tensor:
         return torch.from_numpy(rng.uniform(0.5, 1.5, size=shape).astype(np.float32))
     if kind.startswith('buffer_normal:'):
         return torch.from_numpy(np.asarray(rng.normal(0.0, float(kind.split(':')[1]), size=shape), dtype=np.float32))
-    if kind == 'conv_w':
+    if kind.startswith('conv_w'):  # 'conv_w' or 'conv_w*<gain>'
         fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
-        bound = 1.0 / math.sqrt(max(fan_in, 1))
+        bound = (float(kind.split('*')[1]) if '*' in kind else 1.0) / math.sqrt(max(fan_in, 1))
         a = rng.uniform(-bound, bound, size=shape)
     elif kind.startswith('bias:'):
         bound = 1.0 / math.sqrt(max(int(kind.split(':')[1]), 1))

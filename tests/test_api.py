@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import resselt_b200
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, internal_registry
+from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR, internal_registry
 from resselt_b200.factory import Architecture, KeyCondition
 from resselt_b200.factory.arch import ModelMetadata
 from resselt_b200.registry import ArchitectureNotFound, Registry
@@ -20,7 +20,7 @@ def _sd(model):
 
 def test_public_surface():
     assert resselt_b200.__all__ == ['add', 'get', 'load_from_file', 'load_from_state_dict']
-    assert {'SPAN', 'spanplus', 'Compact', 'ESRGAN', 'PLKSR', 'dat'} <= set(internal_registry.store)
+    assert {'SPAN', 'spanplus', 'Compact', 'ESRGAN', 'PLKSR', 'dat', 'SwinIR'} <= set(internal_registry.store)
     assert resselt_b200.get('SPAN').id == 'SPAN'
     with pytest.raises(KeyError):  # same as the reference's dict lookup (registry.py:74)
         resselt_b200.get('nope')
@@ -52,6 +52,12 @@ def test_metadata_field_order():
         (RealPLKSR(dim=32, n_blocks=2, upscaling_factor=2, kernel_size=13, use_ea=False), ('RealPLKSR', 3, 3, 2)),
         (DAT(depth=[3, 2], num_heads=[6, 6], upscale=4), ('DAT', 3, 3, 4)),
         (DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=2, img_size=32), ('DAT', 3, 3, 2)),
+        (SwinIR(embed_dim=60, depths=[2, 3], num_heads=[6, 6], upscale=2), ('SwinIR', 3, 3, 2)),
+        (SwinIR(embed_dim=180, depths=[2], num_heads=[6], upscale=3, upsampler='pixelshuffledirect'), ('SwinIR', 3, 3, 3)),
+        (SwinIR(embed_dim=180, depths=[2], num_heads=[6], upscale=3, upsampler='pixelshuffle'), ('SwinIR', 3, 3, 3)),
+        (SwinIR(embed_dim=64, depths=[2, 2], num_heads=[4, 4], mlp_ratio=4.0, upscale=4, upsampler='nearest+conv', resi_connection='3conv', img_size=48),
+         ('SwinIR', 3, 3, 4)),
+        (SwinIR(in_chans=1, embed_dim=48, depths=[2], num_heads=[6], window_size=7, img_size=126, img_range=255.0, upsampler=''), ('SwinIR', 1, 1, 1)),
     ],
 )
 def test_detect_and_hyperparameter_inference(model, meta):
@@ -72,6 +78,10 @@ def test_detect_and_hyperparameter_inference(model, meta):
             model.num_blocks, model.plus, model.shuffle_factor, model._keys.style)
     if isinstance(model, RealPLKSR):
         assert (loaded.dim, loaded.n_blocks, loaded.kernel_size, loaded.use_ea) == (model.dim, model.n_blocks, model.kernel_size, model.use_ea)
+    if isinstance(model, SwinIR):
+        assert (loaded.dim, loaded.hidden, loaded.window_size, loaded.depths, loaded.heads, loaded.img_size, loaded.img_range, loaded.upsampler,
+                loaded.resi_connection) == (model.dim, model.hidden, model.window_size, model.depths, model.heads, model.img_size, model.img_range,
+                                            model.upsampler, model.resi_connection)
     if isinstance(model, DAT):
         assert (loaded.depth, loaded.heads, loaded.split, loaded.img_size) == (model.depth, model.heads, model.split, model.img_size)
 

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 import oracle
 import resselt_b200
 from conftest import golden_case, golden_index, norm_err, psnr
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact
+from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
 from resselt_b200.engine import INPUT, OUTPUT, PlanBuilder
 from resselt_b200.engine import native as N
 from resselt_b200.runner import FramePipeline, tiled_forward
@@ -62,6 +62,13 @@ def test_golden_fixtures_fp32_and_bf16(name):
         ('DAT', DAT(upscale=4, seed=32), (1, 3, 64, 64)),                                    # default 6x6 blocks, 180 ch, 8x32 windows
         ('DAT', DAT(depth=[3, 3], num_heads=[6, 6], upscale=2, seed=33), (2, 3, 37, 45)),      # padding + shifted-window masks
         ('DAT', DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=2, img_size=32, seed=34), (1, 3, 50, 30)),
+        ('SwinIR', SwinIR(upscale=4, seed=35), (1, 3, 64, 64)),                                # classical SR: 6x6 blocks, 180 ch, window 8
+        ('SwinIR', SwinIR(depths=[2], num_heads=[6], upscale=2, seed=39), (1, 3, 136, 200)),       # > 2 tiles per CTA in every layer
+        ('SwinIR', SwinIR(embed_dim=60, depths=[6, 6, 6, 6], num_heads=[6, 6, 6, 6], upscale=2, upsampler='pixelshuffledirect', seed=36), (2, 3, 37, 45)),
+        ('SwinIR', SwinIR(embed_dim=240, depths=[2, 2], num_heads=[8, 8], upscale=4, upsampler='nearest+conv', resi_connection='3conv', seed=37),
+         (1, 3, 40, 52)),                                                                      # real-world SR large model shape
+        ('SwinIR', SwinIR(in_chans=1, embed_dim=48, depths=[2, 2], num_heads=[6, 6], window_size=7, img_size=126, img_range=255.0, upsampler='', seed=38),
+         (1, 1, 33, 47)),                                                                      # JPEG-artifact model: window 7, residual head
     ],
 )
 def test_against_oracle_on_seeded_inputs(kind, model, shape):
@@ -94,6 +101,8 @@ LAYER_CASES = [
     (32, 256, 3, 1, 16, 24, N.ACT_NONE),
     (48, 48, 3, 1, 5, 7, N.ACT_GELU),      # image smaller than one 16x8 tile
     (80, 40, 3, 1, 19, 23, N.ACT_SIGMOID),  # channel counts that are not multiples of 16
+    (384, 192, 1, 1, 200, 176, N.ACT_NONE),  # 6 K chunks over a 4-stage ring, several tiles per CTA (single issuing warp)
+    (192, 32, 3, 1, 136, 200, N.ACT_NONE),   # 3 K chunks per tile, two issuing warps alternating tiles
 ]
 
 

@@ -6,7 +6,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from resselt_b200.archs import SPAN, SpanPlus, SRVGGNetCompact, RRDBNet
+from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
 
 arch = sys.argv[1] if len(sys.argv) > 1 else 'span'
 h = int(sys.argv[2]) if len(sys.argv) > 2 else 1080
@@ -16,7 +16,10 @@ dev = torch.device('cuda:0')
 m = {'span': lambda: SPAN(feature_channels=48, upscale=2, seed=3),
      'spanplus': lambda: SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=4),
      'compact': lambda: SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=5),
-     'esrgan': lambda: RRDBNet(num_blocks=23, scale=4, seed=6)}[arch]().eval().to(dev).bfloat16()
+     'esrgan': lambda: RRDBNet(num_blocks=23, scale=4, seed=6),
+     'plksr': lambda: RealPLKSR(n_blocks=28, upscaling_factor=4, seed=7),
+     'dat': lambda: DAT(upscale=4, seed=8),
+     'swinir': lambda: SwinIR(upscale=4, seed=9)}[arch]().eval().to(dev).bfloat16()
 x = torch.rand(1, 3, h, w, device=dev).bfloat16()
 plan = m.plan_for(dev, torch.bfloat16)
 out = torch.empty(1, 3, m.upscale * h, m.upscale * w, device=dev, dtype=torch.bfloat16)
