@@ -313,10 +313,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 size_t winattn_mma_smem_bytes(int split_h, int split_w) {
   const int N = split_h * split_w, NK = (N + 63) / 64 * 64, NQ = (N + 15) / 16 * 16;
-  return (size_t)(NQ + NK) * kWaQS * 2 + (size_t)kHD * (NK + 8) * 2 + (size_t)(2 * split_h - 1) * (2 * split_w - 1) * 4 + (size_t)NK * 4;
+  return (size_t)(NQ + NK) * kWaQS * 2 + (size_t)kHD * (NK + 8) * 2 + (size_t)(2 * split_h - 1) * (2 * split_w - 1) * 4 + (size_t)NK * 8;
 }
 
-__global__ void __launch_bounds__(512) winattn_mma_kernel(const __grid_constant__ WinAttnParams p) {
+// kThreads = 128 serves windows of <= 64 tokens (SwinIR's 8x8): a tighter register budget keeps 5 CTAs per SM resident
+// (the kernel's phases — stage, attend, store — are latency-bound chains; residency is what overlaps them).
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const __grid_constant__ WinAttnParams p) {
   extern __shared__ __align__(16) uint8_t smraw[];
   using T = __nv_bfloat16;
   const int br = blockIdx.z, h = blockIdx.y;
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(512) winattn_mma_kernel(const __grid_constant_
   T* Vt = Ks + (size_t)NK * kWaQS;                // [kHD][VS]   (V transposed: keys contiguous)
   float* tab = reinterpret_cast<float*>(Vt + (size_t)kHD * VS);  // [tab_n] bias of this head
   int* kinfo = reinterpret_cast<int*>(tab + tab_n);              // [NK] (jy * tab_w + jx) | label << 20
+  int* tokoff = kinfo + NK;                                      // [NK] pixel index y * W + x of the token, -1: padding
   const float* table = br == 0 ? p.table0 : p.table1;
   const int hpb = p.heads / 2;
   for (int i = threadIdx.x; i < tab_n; i += blockDim.x) tab[i] = table[(size_t)i * hpb + h];
@@ -340,34 +344,84 @@ __global__ void __launch_bounds__(512) winattn_mma_kernel(const __grid_constant_
   const T* src = reinterpret_cast<const T*>(p.src);
   const int half = p.dim / 2;
   const int cq = p.src_ch_off + br * half + h * d;
-  const T zero = __float2bfloat16_rn(0.0f);
-  for (int t = threadIdx.x; t < max(NQ, NK); t += blockDim.x) {
+  // Staging.  Q / K / V^T tiles are zero-filled first (padded tokens, head dims d..31 and chunk padding must read as 0),
+  // then every (matrix, 8-channel plane, token) item is ONE 16-byte load — consecutive threads take consecutive tokens,
+  // i.e. consecutive 16-byte chunks of a plane row — whose channels inside [cq, cq + d) are scattered to shared memory.
+  // A head's 30 channels start at any channel offset, so it touches up to 5 planes per matrix.  (The first version
+  // issued one 2-byte load per (token, channel); on SwinIR's 8x8 windows this staging plus the per-token div/mod
+  // address arithmetic was half of the kernel's instructions: 442 -> 254 us per launch at 4x 512^2.)
+  {
+    uint4* z = reinterpret_cast<uint4*>(smraw);
+    const int nz = ((NQ + NK) * kWaQS * 2 + kHD * VS * 2) / 16;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int t = threadIdx.x; t < NK; t += blockDim.x) {
     const bool active = t < N;
     const int ty = active ? t / Ws : 0, tx = active ? t - ty * Ws : 0;
-    const int yr = wy * Hs + ty, xr = wx * Ws + tx;          // coordinates in the rolled, padded image
-    const int yo = (yr + sh) % p.Hp, xo = (xr + sw) % p.Wp;  // where that token lives in the un-rolled image
-    const bool inb = active && yo < p.H && xo < p.W;         // padded tokens have q = k = v = 0
-    for (int c = 0; c < kHD; ++c) {
-      T qv = zero, kv = zero, vv = zero;
-      if (inb && c < d) {
-        const size_t base = planar_index(n, p.src_planes, 0, p.H, p.W, yo, xo);
-        const int c1 = cq + c, c2 = c1 + p.qkv_stride, c3 = c2 + p.qkv_stride;
-        const size_t ps = (size_t)p.H * p.W * 8;
-        qv = src[base + (size_t)(c1 >> 3) * ps + (c1 & 7)];
-        kv = src[base + (size_t)(c2 >> 3) * ps + (c2 & 7)];
-        vv = src[base + (size_t)(c3 >> 3) * ps + (c3 & 7)];
-      }
-      if (t < NQ) Qs[t * kWaQS + c] = qv;
-      if (t < NK) Ks[t * kWaQS + c] = kv, Vt[c * VS + t] = vv;
+    const int yr = wy * Hs + ty, xr = wx * Ws + tx;  // coordinates in the rolled, padded image
+    int yo = yr + sh, xo = xr + sw;                  // where that token lives in the un-rolled image
+    if (yo >= p.Hp) yo -= p.Hp;
+    if (xo >= p.Wp) xo -= p.Wp;
+    int lab = 0;
+    if (p.shifted && active) {
+      const int ry = yr < p.Hp - Hs ? 0 : (yr < p.Hp - sh ? 1 : 2);
+      const int rx = xr < p.Wp - Ws ? 0 : (xr < p.Wp - sw ? 1 : 2);
+      lab = 3 * ry + rx;
     }
-    if (t < NK) {
-      int lab = 0;
-      if (p.shifted && active) {
-        const int ry = yr < p.Hp - Hs ? 0 : (yr < p.Hp - sh ? 1 : 2);
-        const int rx = xr < p.Wp - Ws ? 0 : (xr < p.Wp - sw ? 1 : 2);
-        lab = 3 * ry + rx;
+    kinfo[t] = (ty * tab_w + tx) | (lab << 20) | (active ? 0 : 1 << 30);
+    tokoff[t] = (active && yo < p.H && xo < p.W) ? yo * p.W + xo : -1;  // padded tokens have q = k = v = 0
+  }
+  __syncthreads();
+  {
+    // thread = one token, walking the (matrix, plane) items with a stride of blockDim / N: no per-item index arithmetic
+    constexpr int kPl = (kHD + 7 + 7) / 8;  // planes a head can straddle
+    const size_t ps = (size_t)p.H * p.W * 8;
+    const int g = threadIdx.x / N, t = threadIdx.x - g * N, groups = blockDim.x / N;
+    const int po = g < groups ? tokoff[t] : -1;
+    if (po >= 0) {
+      const T* tok = src + ((size_t)n * p.src_planes * p.H * p.W + po) * 8;
+      // all of a thread's loads are issued before the first value is used: one DRAM round trip per CTA, not one per item
+      constexpr int kItems = (3 * kPl + 1) / 2;  // groups >= 2 whenever the block has twice as many threads as tokens
+      if (groups >= 2) {
+        uint4 v[kItems];
+#pragma unroll
+        for (int it = 0; it < kItems; ++it) {
+          const int mp = g + it * groups;
+          const int m = mp / kPl, pl = mp - m * kPl;
+          const int cm = cq + m * p.qkv_stride;
+          const int plane = (cm >> 3) + pl;
+          if (mp < 3 * kPl && plane * 8 - cm < d) v[it] = *reinterpret_cast<const uint4*>(tok + (size_t)plane * ps);
+        }
+#pragma unroll
+        for (int it = 0; it < kItems; ++it) {
+          const int mp = g + it * groups;
+          const int m = mp / kPl, pl = mp - m * kPl;
+          const int cm = cq + m * p.qkv_stride;
+          const int cbase = ((cm >> 3) + pl) * 8 - cm;  // head dim of the plane's first channel (negative: previous head's)
+          if (mp >= 3 * kPl || cbase >= d) continue;
+          const T* e = reinterpret_cast<const T*>(&v[it]);
+          T* out = m == 0 ? Qs + t * kWaQS : (m == 1 ? Ks + t * kWaQS : Vt + t);
+          const int stride = m == 2 ? VS : 1;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if ((unsigned)(cbase + k) < (unsigned)d) out[(cbase + k) * stride] = e[k];
+        }
+      } else {
+        for (int mp = 0; mp < 3 * kPl; ++mp) {
+          const int m = mp / kPl, pl = mp - m * kPl;
+          const int cm = cq + m * p.qkv_stride;
+          const int plane = (cm >> 3) + pl;
+          const int cbase = plane * 8 - cm;
+          if (cbase >= d) continue;
+          const uint4 v = *reinterpret_cast<const uint4*>(tok + (size_t)plane * ps);
+          const T* e = reinterpret_cast<const T*>(&v);
+          T* out = m == 0 ? Qs + t * kWaQS : (m == 1 ? Ks + t * kWaQS : Vt + t);
+          const int stride = m == 2 ? VS : 1;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if ((unsigned)(cbase + k) < (unsigned)d) out[(cbase + k) * stride] = e[k];
+        }
       }
-      kinfo[t] = (ty * tab_w + tx) | (lab << 20) | (active ? 0 : 1 << 30);
     }
   }
   __syncthreads();
@@ -476,12 +530,10 @@ __global__ void __launch_bounds__(512) winattn_mma_kernel(const __grid_constant_
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int t = r == 0 ? qa : qb;
-    if (t >= N) continue;
-    const int ty = t / Ws, tx = t - ty * Ws;
-    const int yo = (wy * Hs + ty + sh) % p.Hp, xo = (wx * Ws + tx + sw) % p.Wp;
-    if (yo >= p.H || xo >= p.W) continue;
+    const int po = t < N ? tokoff[t] : -1;
+    if (po < 0) continue;
     const float inv = 1.0f / l[r];
-    const size_t base = planar_index(n, p.dst_planes, 0, p.H, p.W, yo, xo);
+    const size_t base = ((size_t)n * p.dst_planes * p.H * p.W + po) * 8;
     const size_t ps = (size_t)p.H * p.W * 8;
 #pragma unroll
     for (int dt = 0; dt < 4; ++dt) {
@@ -803,7 +855,10 @@ size_t winattn_smem_bytes(int split_h, int split_w) {
 cudaError_t winattn_configure() {
   cudaError_t e = cudaFuncSetAttribute(winattn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(winattn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  e = cudaFuncSetAttribute(winattn_mma_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(winattn_mma_kernel<128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(winattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
@@ -816,7 +871,10 @@ cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
   const int N = p.split_h * p.split_w;
   if (bf16 && !no_mma && N <= 256 && p.head_dim <= kHD && winattn_mma_smem_bytes(p.split_h, p.split_w) <= 160 * 1024) {
     const int warps = (N + 15) / 16;
-    winattn_mma_kernel<<<grid, 32 * warps, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
+    if (warps <= 4)  // (a 6-CTA / 80-register variant spills and measured no faster: 260 vs 254 us)
+      winattn_mma_kernel<128, 5><<<grid, 128, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
+    else
+      winattn_mma_kernel<512, 1><<<grid, 32 * warps, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
   } else if (bf16)
     winattn_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
   else

@@ -6,7 +6,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact
+from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
 
 arch = sys.argv[1] if len(sys.argv) > 1 else 'span'
 h = int(sys.argv[2]) if len(sys.argv) > 2 else 1080
@@ -20,7 +20,9 @@ model = {'span': lambda: SPAN(feature_channels=48, upscale=2, seed=3),
          'compact': lambda: SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=5),
          'esrgan': lambda: RRDBNet(num_blocks=23, scale=4, seed=6),
          'plksr': lambda: RealPLKSR(n_blocks=28, upscaling_factor=4, seed=8),
-         'dat': lambda: DAT(upscale=4, seed=9)}[arch]().eval().to(dev).bfloat16()
+         'dat': lambda: DAT(upscale=4, seed=9),
+         'swinir': lambda: SwinIR(upscale=4, seed=10),
+         'swinir1': lambda: SwinIR(upscale=4, depths=[2], num_heads=[6], seed=10)}[arch]().eval().to(dev).bfloat16()
 x = torch.rand(batch, 3, h, w, device=dev).bfloat16()
 with torch.inference_mode():
     for _ in range(warm):
