@@ -73,6 +73,91 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ 
   }
 }
 
+// bf16 storage, register-resident: a pixel's channels are split over the four quarter-warps (quarter q takes planes q, q + 4,
+// ...; lanes 0..7 are 8 neighbouring pixels, so every load instruction covers 4 x 128 contiguous bytes), each thread
+// issues all of its <= kPP 16-byte loads before the first use and the three LayerNorm passes (mean, centred variance,
+// normalise) run out of registers: one HBM read + one write per element.  The generic kernel above re-reads the pixel three
+// times through L1/L2 (62 us per 180-channel 512^2 map against 29 us of pure traffic).
+template <int kPP>
+__global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_constant__ TokenOpParams p) {
+  using T = __nv_bfloat16;
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t total = (size_t)p.n * hw;
+  const int C = p.channels, planes = (C + 7) >> 3;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  const int lane = threadIdx.x & 31, sub = lane >> 3;
+  const size_t pix_in_block = (size_t)(threadIdx.x >> 5) * 8 + (lane & 7);  // 64 pixels per 256-thread block
+  const float inv_c = 1.0f / (float)C;
+  for (size_t i0 = (size_t)blockIdx.x * 64; i0 < total; i0 += (size_t)gridDim.x * 64) {
+    const size_t i = i0 + pix_in_block;
+    const bool live = i < total;
+    const int n = live ? (int)(i / hw) : 0;
+    const size_t pix = live ? i - (size_t)n * hw : 0;
+    const T* s = src + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8 + pix * 8;
+    uint4 raw[kPP];
+#pragma unroll
+    for (int j = 0; j < kPP; ++j) {
+      const int pl = 4 * j + sub;
+      raw[j] = (live && pl < planes) ? *reinterpret_cast<const uint4*>(s + (size_t)pl * hw * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kPP; ++j) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h2[k]);
+        if ((4 * j + sub) * 8 + 2 * k < C) sum += f.x;
+        if ((4 * j + sub) * 8 + 2 * k + 1 < C) sum += f.y;
+      }
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    const float mean = sum * inv_c;
+    float sq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kPP; ++j) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h2[k]);
+        if ((4 * j + sub) * 8 + 2 * k < C) sq += (f.x - mean) * (f.x - mean);
+        if ((4 * j + sub) * 8 + 2 * k + 1 < C) sq += (f.y - mean) * (f.y - mean);
+      }
+    }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+    const float rstd = rsqrtf(sq * inv_c + p.f0);
+    T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
+#pragma unroll
+    for (int j = 0; j < kPP; ++j) {
+      const int pl = 4 * j + sub;
+      if (!live || pl >= planes) continue;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h2[k]);
+        v[2 * k] = f.x, v[2 * k + 1] = f.y;
+      }
+      float g[8], b[8];
+      if (pl * 8 + 8 <= C) {  // gamma / beta hold exactly C floats: vector loads only for whole planes
+        const float4 g0 = *reinterpret_cast<const float4*>(p.w0 + pl * 8), g1 = *reinterpret_cast<const float4*>(p.w0 + pl * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(p.w1 + pl * 8), b1 = *reinterpret_cast<const float4*>(p.w1 + pl * 8 + 4);
+        g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w, g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
+        b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w, b[4] = b1.x, b[5] = b1.y, b[6] = b1.z, b[7] = b1.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = pl * 8 + k < C ? p.w0[pl * 8 + k] : 0.0f, b[k] = pl * 8 + k < C ? p.w1[pl * 8 + k] : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = pl * 8 + k < C ? (v[k] - mean) * rstd * g[k] + b[k] : 0.0f;
+      store8<T>(d + (size_t)pl * hw * 8, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv3_kernel(const __grid_constant__ TokenOpParams p) {
@@ -829,7 +914,18 @@ inline int grid_for(size_t total, int threads = 256, int cap = 148 * 32) {
 
 cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s) {
   const int g = grid_for((size_t)p.n * p.H * p.W);
-  if (bf16)
+  const int planes = (p.channels + 7) / 8;
+  const size_t pixels = (size_t)p.n * p.H * p.W;
+  const int g2 = (int)std::min<size_t>((pixels + 63) / 64, (size_t)148 * 128);
+  if (bf16 && planes <= 8)
+    layernorm_bf16_kernel<2><<<g2, 256, 0, s>>>(p);
+  else if (bf16 && planes <= 16)
+    layernorm_bf16_kernel<4><<<g2, 256, 0, s>>>(p);
+  else if (bf16 && planes <= 24)
+    layernorm_bf16_kernel<6><<<g2, 256, 0, s>>>(p);
+  else if (bf16 && planes <= 32)
+    layernorm_bf16_kernel<8><<<g2, 256, 0, s>>>(p);
+  else if (bf16)
     layernorm_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
   else
     layernorm_kernel<float><<<g, 256, 0, s>>>(p);

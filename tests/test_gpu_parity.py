@@ -254,3 +254,22 @@ def test_workspace_argument_checks():
     ws = torch.empty(2048, dtype=torch.uint8, device=DEV)
     rc = plan._lib.rsb_plan_forward(plan._h, x.data_ptr(), N.F32, 1, 8, 8, y.data_ptr(), N.F32, ws.data_ptr(), 16, None, 0)
     assert rc == -4 and b'workspace too small' in plan._lib.rsb_last_error()
+
+
+@pytest.mark.parametrize('C,n,H,W', [(180, 1, 37, 45), (60, 2, 16, 24), (64, 1, 9, 130), (240, 1, 20, 33), (96, 1, 64, 64), (360, 1, 12, 12)])
+def test_layernorm_op_bf16_against_fp64(C, n, H, W):
+    # register-resident bf16 LayerNorm (4 threads per pixel) for C <= 256, generic three-pass kernel above that
+    g = torch.Generator().manual_seed(C * 7 + H)
+    x = torch.randn(n, C, H, W, generator=g) * 2.0 + 0.5
+    gamma, beta = 1.0 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    pb = PlanBuilder(torch.bfloat16, C, C, 1)
+    a, b = pb.buffer(C), pb.buffer(C)
+    pb.conv(INPUT, a, torch.eye(C).view(C, C, 1, 1))
+    pb.layernorm(a, b, gamma, beta)
+    pb.conv(b, OUTPUT, torch.eye(C).view(C, C, 1, 1))
+    plan = pb.finalize(torch.device(DEV))
+    plan.forward(x.to(DEV, torch.bfloat16))
+    got = plan.read_buffer(b).double().cpu()
+    xq = x.to(torch.bfloat16).double()
+    ref = F.layer_norm(xq.permute(0, 2, 3, 1), (C,), gamma.double(), beta.double(), 1e-5).permute(0, 3, 1, 2)
+    assert (got - ref).abs().max() <= 2.0 ** -8 * max(1.0, float(ref.abs().max()))  # one bf16 rounding of the result
