@@ -404,6 +404,7 @@ struct ConvTcParams {
   int tiles_x, tiles_y, num_tiles;
   int cin;   // multiple of 16
   int kchunk, nchunks;  // K chunking of the shared-memory stages: cin == kchunk * nchunks, kchunk % 16 == 0
+  int solo_issue;       // K-chunked tiles only: 1 = one MMA-issuing warp walks every tile (see conv_tc.cu)
   int npad;  // UMMA N, multiple of 16, <= 256
   int kh, kw, pad_t, pad_l;
   int src_plane0;

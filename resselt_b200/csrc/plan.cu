@@ -367,6 +367,13 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.num_tiles = t.tiles_x * t.tiles_y * n;
       t.cin = c.tc_cin, t.npad = c.npad;
       t.kchunk = c.kchunk, t.nchunks = c.tc_cin / c.kchunk;
+      {
+        // two issuing warps alternate tiles over ONE ring of stages; a warp may only wait for fill k of a stage after it has
+        // itself seen fill k-1 complete (mbarrier waits know the phase parity only).  That is guaranteed when the previous
+        // fill of every stage a tile uses belongs to the warp's own previous tile: 2 * nchunks <= stages (or one chunk).
+        static const bool two_env = getenv("RSB_TC_TWO") != nullptr;  // bring-up: the looser nchunks < stages rule
+        t.solo_issue = t.nchunks > 1 && (two_env ? t.nchunks >= c.stages : 2 * t.nchunks > c.stages);
+      }
       t.kh = c.tc_kh, t.kw = c.tc_kw;
       const bool im2col = c.pack_buf >= 0 && !c.pack_planar;
       t.pad_t = im2col ? 0 : d.pad_t, t.pad_l = im2col ? 0 : d.pad_l;

@@ -273,3 +273,22 @@ def test_layernorm_op_bf16_against_fp64(C, n, H, W):
     xq = x.to(torch.bfloat16).double()
     ref = F.layer_norm(xq.permute(0, 2, 3, 1), (C,), gamma.double(), beta.double(), 1e-5).permute(0, 3, 1, 2)
     assert (got - ref).abs().max() <= 2.0 ** -8 * max(1.0, float(ref.abs().max()))  # one bf16 rounding of the result
+
+
+def test_large_swinir_after_span_is_repeatable():
+    # regression: K-chunked tensor-core convs (3 K chunks over a 4-stage ring, two issuing warps) once faulted at 512^2 when
+    # a 1080p SPAN forward had run earlier in the process (timing-dependent mbarrier phase aliasing); they are now issued
+    # by one warp unless 2 * chunks <= stages.  Whole forwards back to back, no synchronisation in between.
+    span = SPAN(feature_channels=48, upscale=2, seed=3).eval().to(DEV).bfloat16()
+    swin = SwinIR(upscale=4, seed=9).eval().to(DEV).bfloat16()
+    g = torch.Generator().manual_seed(5)
+    xs = torch.rand(1, 3, 1080, 1920, generator=g).to(DEV, torch.bfloat16)
+    xw = torch.rand(1, 3, 512, 512, generator=g).to(DEV, torch.bfloat16)
+    with torch.inference_mode():
+        for _ in range(3):
+            span(xs)
+        outs = [swin(xw) for _ in range(4)]
+        torch.cuda.synchronize()
+    assert bool(torch.isfinite(outs[0].float()).all())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
