@@ -17,8 +17,11 @@
  *                            SPAB gate span/arch.py:176-177; residual adds utilities/block.py:344,465;
  *                            PixelShuffle span/arch.py:55, compact/arch.py:54-64, rplksr.py:143-147).
  *   rsb_plan_add_groupnorm <- nn.GroupNorm + skip (resselt/archs/plksr/rplksr.py:83,91-93)
+ *   rsb_plan_add_op      <- LayerNorm / depthwise conv / window + channel attention / AIM call sites of DAT and SwinIR
+ *                           (listed at rsb_op_kind below)
  *   rsb_plan_forward     <- <Module>.forward (span/arch.py:231-250, spanplus/arch.py:199-201,
- *                           compact/arch.py:56-65, esrgan/arch.py:129-138, plksr/rplksr.py:145-147)
+ *                           compact/arch.py:56-65, esrgan/arch.py:129-138, plksr/rplksr.py:145-147,
+ *                           dat/arch.py:970-990, swinir/arch.py:962-1011)
  *
  * Conventions: plain C types only; every function returns 0 on success, a negative rsb_status for
  * argument/state errors, or a positive cudaError_t value; rsb_last_error() returns a thread-local
@@ -129,16 +132,22 @@ typedef struct rsb_groupnorm_desc {
   int32_t skip_buf, skip_ch_off; /* RSB_NO_BUFFER: no skip */
 } rsb_groupnorm_desc;
 
-/* Token-wise / attention ops of the transformer architectures (DAT).  A token is a pixel of a planar buffer.
+/* Token-wise / attention ops of the transformer architectures (DAT, SwinIR).  A token is a pixel of a planar buffer.
  * Call sites replaced: /root/reference/resselt/archs/dat/arch.py:48,636,672,897,924 (LayerNorm), :49,345,547
  * (depthwise conv), :224-267 + :456-482 (shifted-window attention), :565-589 (channel attention), :492-508 and
- * :594-607 (adaptive interaction module). */
+ * :594-607 (adaptive interaction module); /root/reference/resselt/archs/swinir/arch.py:253,262,299,334,878,956
+ * (LayerNorm), :133-170 + :268-332 (W-MSA / SW-MSA: window partition, relative-position bias gathered through
+ * relative_position_index, cyclic shift and mask, window reverse). */
 enum rsb_op_kind {
   RSB_OP_LAYERNORM = 1, /* dst = LN_channels(src) * w[0] + w[1];  f[0] = eps                                         */
   RSB_OP_DWCONV3 = 2,   /* dst = act(dwconv3x3(src; w[0] = [C][9], w[1] = bias[C])) [* src2];  i[0] = rsb_act          */
   RSB_OP_WINATTN = 3,   /* src = [q | k | v]; i[0] heads, i[1] split_h, i[2] split_w, i[3] shifted, i[4] channel stride
                            between q, k and v (0: channels);
-                           f[0] = qk scale; w[0] / w[1] = position-bias tables of the two branches                    */
+                           f[0] = qk scale; w[0] / w[1] = position-bias tables of the two branches
+                           ([(2 sh - 1)(2 sw - 1)][heads / 2], offset index (dy + sh - 1)(2 sw - 1) + dx + sw - 1).
+                           Branch 0 (first half of the channels / heads) uses split_h x split_w windows, branch 1 the
+                           transposed shape; square windows (split_h == split_w) give plain Swin attention, the two
+                           tables then being the two head halves of the learned relative_position_bias_table           */
   RSB_OP_CHANATTN = 4,  /* src = [q | k | v]; i[0] heads, i[1] q/k/v channel stride (0: channels); w[0] = temperature[heads] */
   RSB_OP_AIM = 5        /* src = attention output, src2 = conv branch, dst = gated sum; i[0] mode (0 window block,
                            1 channel block), i[1] / i[2] hidden widths of the channel / spatial MLPs;
