@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace rsb {
 namespace {
@@ -77,7 +78,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ 
 // ...; lanes 0..7 are 8 neighbouring pixels, so every load instruction covers 4 x 128 contiguous bytes), each thread
 // issues all of its <= kPP 16-byte loads before the first use and the three LayerNorm passes (mean, centred variance,
 // normalise) run out of registers: one HBM read + one write per element.  The generic kernel above re-reads the pixel three
-// times through L1/L2 (62 us per 180-channel 512^2 map against 29 us of pure traffic).
+// times through L1/L2.  Measured: all three formulations tried (three-pass, this one, and a cp.async.bulk-staged one with
+// 184 KB per SM in flight) take 59-64 us per 180-channel 512^2 map (2.5 TB/s) — neither issue slots nor bytes in flight
+// are what limits it; see DESIGN.md 3.5.
 template <int kPP>
 __global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_constant__ TokenOpParams p) {
   using T = __nv_bfloat16;
@@ -101,46 +104,51 @@ __global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_con
       const int pl = 4 * j + sub;
       raw[j] = (live && pl < planes) ? *reinterpret_cast<const uint4*>(s + (size_t)pl * hw * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
-    float sum = 0.0f;
+    // fp32 copies, converted once (bf16 -> fp32 is a shift / mask); channels >= C of the last plane are forced to zero so
+    // that none of the three passes below needs a per-element bound check
+    float v[kPP][8];
 #pragma unroll
     for (int j = 0; j < kPP; ++j) {
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+      const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(h2[k]);
-        if ((4 * j + sub) * 8 + 2 * k < C) sum += f.x;
-        if ((4 * j + sub) * 8 + 2 * k + 1 < C) sum += f.y;
+      for (int k = 0; k < 4; ++k) v[j][2 * k] = __uint_as_float(w4[k] << 16), v[j][2 * k + 1] = __uint_as_float(w4[k] & 0xFFFF0000u);
+      const int c0 = (4 * j + sub) * 8;
+      if (c0 + 8 > C && c0 < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c0 + k >= C) v[j][k] = 0.0f;
       }
     }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kPP; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[j][k];
     sum += __shfl_xor_sync(0xffffffffu, sum, 8);
     sum += __shfl_xor_sync(0xffffffffu, sum, 16);
     const float mean = sum * inv_c;
+    // centred second moment: planes that do not exist (and the zeroed tail) would each add mean^2 — count them out exactly
     float sq = 0.0f;
+    int cnt = 0;
 #pragma unroll
     for (int j = 0; j < kPP; ++j) {
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+      const int c0 = (4 * j + sub) * 8;
+      if (c0 < C) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(h2[k]);
-        if ((4 * j + sub) * 8 + 2 * k < C) sq += (f.x - mean) * (f.x - mean);
-        if ((4 * j + sub) * 8 + 2 * k + 1 < C) sq += (f.y - mean) * (f.y - mean);
+        for (int k = 0; k < 8; ++k) sq = fmaf(v[j][k] - mean, v[j][k] - mean, sq);
+        cnt += c0 + 8 > C ? c0 + 8 - C : 0;
       }
     }
+    sq -= (float)cnt * mean * mean;
     sq += __shfl_xor_sync(0xffffffffu, sq, 8);
     sq += __shfl_xor_sync(0xffffffffu, sq, 16);
-    const float rstd = rsqrtf(sq * inv_c + p.f0);
+    const float rstd = rsqrtf(fmaxf(sq, 0.0f) * inv_c + p.f0);
+    const float shift = -mean * rstd;
     T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
 #pragma unroll
     for (int j = 0; j < kPP; ++j) {
       const int pl = 4 * j + sub;
       if (!live || pl >= planes) continue;
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(h2[k]);
-        v[2 * k] = f.x, v[2 * k + 1] = f.y;
-      }
       float g[8], b[8];
       if (pl * 8 + 8 <= C) {  // gamma / beta hold exactly C floats: vector loads only for whole planes
         const float4 g0 = *reinterpret_cast<const float4*>(p.w0 + pl * 8), g1 = *reinterpret_cast<const float4*>(p.w0 + pl * 8 + 4);
@@ -151,9 +159,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = pl * 8 + k < C ? p.w0[pl * 8 + k] : 0.0f, b[k] = pl * 8 + k < C ? p.w1[pl * 8 + k] : 0.0f;
       }
+      float o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = pl * 8 + k < C ? (v[k] - mean) * rstd * g[k] + b[k] : 0.0f;
-      store8<T>(d + (size_t)pl * hw * 8, v);
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(fmaf(v[j][k], rstd, shift), g[k], b[k]);  // tail channels: g = b = 0 -> 0
+      store8<T>(d + (size_t)pl * hw * 8, o);
     }
   }
 }
@@ -391,6 +400,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&t);
@@ -424,7 +439,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
   int* tokoff = kinfo + NK;                                      // [NK] pixel index y * W + x of the token, -1: padding
   const float* table = br == 0 ? p.table0 : p.table1;
   const int hpb = p.heads / 2;
-  for (int i = threadIdx.x; i < tab_n; i += blockDim.x) tab[i] = table[(size_t)i * hpb + h];
+  for (int i = threadIdx.x; i < tab_n; i += blockDim.x) tab[i] = table[(size_t)i * hpb + h] * kLog2e;  // softmax in base 2
+  const float scale2 = p.scale * kLog2e;
+  const bool ones_row = d < kHD;  // spare V^T row carries the softmax denominators (see below)
 
   const T* src = reinterpret_cast<const T*>(p.src);
   const int half = p.dim / 2;
@@ -457,6 +474,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
     tokoff[t] = (active && yo < p.H && xo < p.W) ? yo * p.W + xo : -1;  // padded tokens have q = k = v = 0
   }
   __syncthreads();
+  if (ones_row)
+    for (int t = threadIdx.x; t < NK; t += blockDim.x) Vt[(kHD - 1) * VS + t] = __float2bfloat16_rn(1.0f);
   {
     // thread = one token, walking the (matrix, plane) items with a stride of blockDim / N: no per-item index arithmetic
     constexpr int kPl = (kHD + 7 + 7) / 8;  // planes a head can straddle
@@ -555,28 +574,44 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
       for (int ks = 0; ks < 2; ++ks)
         mma_bf16_16816(sc[nt], qf[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16), *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
     }
-    // scale, position bias, shift mask; chunk maxima
-    float cm[2] = {-INFINITY, -INFINITY};
+    // scale + position bias (both pre-multiplied by log2 e: the softmax runs on ex2), then — only where they exist — the
+    // shift mask and the chunk padding, as warp-uniform branches around their own loops; chunk maxima last
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int j = kc + nt * 8 + t4 * 2 + (e & 1);
-        const int ki = kinfo[j];
-        const int r = e >> 1;
-        float v = sc[nt][e] * p.scale + tab[qpos[r] - (ki & 0xFFFFF)];
-        if (p.shifted && ((ki >> 20) & 0xF) != qlab[r]) v += -100.0f;
-        if (ki >> 30) v = -INFINITY;  // keys beyond the window (chunk padding)
-        sc[nt][e] = v;
-        cm[r] = fmaxf(cm[r], v);
+        const int ki = kinfo[kc + nt * 8 + t4 * 2 + (e & 1)];
+        sc[nt][e] = fmaf(sc[nt][e], scale2, tab[qpos[e >> 1] - (ki & 0xFFFFF)]);
       }
+    if (p.shifted) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ki = kinfo[kc + nt * 8 + t4 * 2 + (e & 1)];
+          if (((ki >> 20) & 0xF) != qlab[e >> 1]) sc[nt][e] += -100.0f * kLog2e;
+        }
+    }
+    if (NK != N) {  // keys beyond the window (chunk padding)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (kinfo[kc + nt * 8 + t4 * 2 + (e & 1)] >> 30) sc[nt][e] = -INFINITY;
+    }
+    float cm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      cm[0] = fmaxf(cm[0], fmaxf(sc[nt][0], sc[nt][1]));
+      cm[1] = fmaxf(cm[1], fmaxf(sc[nt][2], sc[nt][3]));
+    }
     float corr[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       cm[r] = fmaxf(cm[r], __shfl_xor_sync(0xffffffffu, cm[r], 1));
       cm[r] = fmaxf(cm[r], __shfl_xor_sync(0xffffffffu, cm[r], 2));
       const float mn = fmaxf(m[r], cm[r]);
-      corr[r] = __expf(m[r] - mn);  // first chunk: exp(-inf) = 0
+      corr[r] = ex2_approx(m[r] - mn);  // first chunk: 2^(-inf) = 0
       m[r] = mn;
       l[r] *= corr[r];
     }
@@ -585,15 +620,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
       o[dt][0] *= corr[0], o[dt][1] *= corr[0];
       o[dt][2] *= corr[1], o[dt][3] *= corr[1];
     }
-    // P = exp(S - m) as bf16 A fragments; row sums accumulate the ROUNDED values so that O / l is a true weighted mean
+    // P = 2^(S - m) as bf16 A fragments.  O / l must be a true weighted mean of the ROUNDED probabilities: with head_dim < 32 the
+    // row sums come for free from the PV product itself (row kHD-1 of V^T is all ones, so column kHD-1 of O accumulates
+    // sum_j P_ij); only head_dim == 32 adds the rounded values up by hand.
     uint32_t pf[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = __expf(sc[nt][0] - m[0]), p1 = __expf(sc[nt][1] - m[0]);
-      const float p2 = __expf(sc[nt][2] - m[1]), p3 = __expf(sc[nt][3] - m[1]);
+      const float p0 = ex2_approx(sc[nt][0] - m[0]), p1 = ex2_approx(sc[nt][1] - m[0]);
+      const float p2 = ex2_approx(sc[nt][2] - m[1]), p3 = ex2_approx(sc[nt][3] - m[1]);
       const uint32_t lo = pack_bf16x2(p0, p1), hi = pack_bf16x2(p2, p3);
-      l[0] += __uint_as_float(lo << 16) + __uint_as_float(lo & 0xFFFF0000u);
-      l[1] += __uint_as_float(hi << 16) + __uint_as_float(hi & 0xFFFF0000u);
+      if (!ones_row) {
+        l[0] += __uint_as_float(lo << 16) + __uint_as_float(lo & 0xFFFF0000u);
+        l[1] += __uint_as_float(hi << 16) + __uint_as_float(hi & 0xFFFF0000u);
+      }
       pf[nt >> 1][(nt & 1) * 2 + 0] = lo;
       pf[nt >> 1][(nt & 1) * 2 + 1] = hi;
     }
@@ -607,8 +646,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
-    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    if (ones_row) {
+      l[r] = __shfl_sync(0xffffffffu, o[3][2 * r + 1], lane | 3);  // column kHD-1 = 31 lives in the t4 == 3 lane of each row group
+    } else {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
   }
   T* dst = reinterpret_cast<T*>(p.dst);
   const int co = p.dst_ch_off + br * half + h * d;
@@ -744,8 +787,14 @@ __global__ void __launch_bounds__(256) chanattn_finalize_kernel(const __grid_con
   const int len = d * d + 2 * d;
   const float* in = p.partial + ((size_t)n * p.heads + h) * p.blocks * len;
   for (int e = threadIdx.x; e < len; e += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < p.blocks; ++b) s += in[(size_t)b * len + e];  // fixed order: run-to-run deterministic
+    double s = 0.0;  // fixed order: run-to-run deterministic; 16 loads in flight (the loop used to be one L2 round trip per block)
+    for (int b0 = 0; b0 < p.blocks; b0 += 16) {
+      float t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = b0 + u < p.blocks ? in[(size_t)(b0 + u) * len + e] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += t[u];
+    }
     g[e] = (float)s;
   }
   __syncthreads();
@@ -800,6 +849,75 @@ __global__ void __launch_bounds__(256) chanattn_apply_kernel(const __grid_consta
   }
 }
 
+// bf16 plan: the per-token 30 x 30 apply on warp-level tensor-core MMAs.  out[tok][i] = sum_j attn[i][j] v[tok][j] is a
+// [tokens x d] x [d x d] GEMM per head: a warp takes 16 tokens, its A fragments (tokens x head dims) are 4-byte loads straight
+// from the planar buffer (8 neighbouring tokens x 16 bytes per request), the B fragments (the head's softmaxed attention matrix,
+// rounded to bf16 like P in the window kernel) live in 16 registers for the CTA's lifetime, results leave as 4-byte bf16 pairs.
+// The CUDA-core version above spends one shared-memory load per FMA (251 us per launch on DAT 4x 512^2, 85 % issue-bound).
+// Needs even head_dim and even channel offsets (pairs must not straddle a plane); anything else stays on the kernel above.
+__global__ void __launch_bounds__(256) chanattn_apply_mma_kernel(const __grid_constant__ ChanAttnParams p) {
+  using T = __nv_bfloat16;
+  const int h = blockIdx.y, n = blockIdx.z, d = p.head_dim;
+  const size_t hw = (size_t)p.H * p.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g4 = lane >> 2, t4 = lane & 3;
+  const float* a = p.attn + ((size_t)n * p.heads + h) * d * d;
+  uint32_t bf[4][2][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i = nt * 8 + g4, j = ks * 16 + 2 * t4 + 8 * half;
+        const float lo = (i < d && j < d) ? a[i * d + j] : 0.0f, hi = (i < d && j + 1 < d) ? a[i * d + j + 1] : 0.0f;
+        bf[nt][ks][half] = pack_bf16x2(lo, hi);
+      }
+  const T* src = reinterpret_cast<const T*>(p.src) + (size_t)n * p.src_planes * hw * 8;
+  T* dst = reinterpret_cast<T*>(p.dst) + (size_t)n * p.dst_planes * hw * 8;
+  const int cv = p.src_ch_off + 2 * p.qkv_stride + h * d, co = p.dst_ch_off + h * d;
+  size_t aoff[2][2], ooff[4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int ch = cv + ks * 16 + 2 * t4 + 8 * half;
+      aoff[ks][half] = (size_t)(ch >> 3) * hw * 8 + (ch & 7);
+    }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int ch = co + nt * 8 + 2 * t4;
+    ooff[nt] = (size_t)(ch >> 3) * hw * 8 + (ch & 7);
+  }
+  const size_t tiles = (hw + 15) / 16;
+  for (size_t tile = (size_t)blockIdx.x * 8 + warp; tile < tiles; tile += (size_t)gridDim.x * 8) {
+    const size_t t0 = tile * 16 + g4, t1 = t0 + 8;
+    const bool v0 = t0 < hw, v1 = t1 < hw;
+    uint32_t af[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const bool in = ks * 16 + 2 * t4 + 8 * half < d;  // head dims >= d belong to the next head: read them as zero
+        af[ks][half * 2 + 0] = (v0 && in) ? *reinterpret_cast<const uint32_t*>(src + aoff[ks][half] + t0 * 8) : 0u;
+        af[ks][half * 2 + 1] = (v1 && in) ? *reinterpret_cast<const uint32_t*>(src + aoff[ks][half] + t1 * 8) : 0u;
+      }
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) mma_bf16_16816(acc[nt], af[ks], bf[nt][ks][0], bf[nt][ks][1]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt * 8 + 2 * t4 >= d) continue;
+      if (v0) *reinterpret_cast<uint32_t*>(dst + ooff[nt] + t0 * 8) = pack_bf16x2(acc[nt][0], acc[nt][1]);
+      if (v1) *reinterpret_cast<uint32_t*>(dst + ooff[nt] + t1 * 8) = pack_bf16x2(acc[nt][2], acc[nt][3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ AIM
 // pool partial sums: partial[n][block][plane*8 + k]
 template <typename T>
@@ -833,19 +951,30 @@ __global__ void __launch_bounds__(256) aim_cmap_kernel(const __grid_constant__ A
   const int n = blockIdx.x, C = p.channels;
   const float inv = 1.0f / ((float)p.H * (float)p.W);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < p.blocks; ++b) s += p.partial[((size_t)n * p.blocks + b) * p.cpad + c];
+    double s = 0.0;  // fixed order, 16 loads in flight
+    for (int b0 = 0; b0 < p.blocks; b0 += 16) {
+      float t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = b0 + u < p.blocks ? p.partial[((size_t)n * p.blocks + b0 + u) * p.cpad + c] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += t[u];
+    }
     mean[c] = (float)s * inv;
   }
   __syncthreads();
-  if (threadIdx.x < p.ci_hidden) {
-    float s = p.ci_b1[threadIdx.x];
-    for (int c = 0; c < C; ++c) s = fmaf(p.ci_w1[threadIdx.x * C + c], mean[c], s);
-    hid[threadIdx.x] = gelu_f(s);
+  // hidden layer: one warp per hidden unit, lanes stride over the channels (coalesced weight rows), shuffle tree (fixed order)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < p.ci_hidden; k += blockDim.x >> 5) {
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) s = fmaf(p.ci_w1[k * C + c], mean[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hid[k] = gelu_f(s + p.ci_b1[k]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = p.ci_b2[c];
+#pragma unroll 8
     for (int k = 0; k < p.ci_hidden; ++k) s = fmaf(p.ci_w2[c * p.ci_hidden + k], hid[k], s);
     p.cmap[(size_t)n * p.cpad + c] = sigm_f(s);
   }
@@ -986,7 +1115,11 @@ cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, cudaStream_t s) 
   else
     chanattn_reduce_kernel<float><<<g1, 256, 0, s>>>(p);
   chanattn_finalize_kernel<<<g2, 256, 0, s>>>(p);
-  if (bf16)
+  const bool pairs_ok = p.head_dim % 2 == 0 && p.head_dim <= kHD && (p.src_ch_off + 2 * p.qkv_stride) % 2 == 0 && p.dst_ch_off % 2 == 0;
+  if (bf16 && pairs_ok) {
+    const unsigned gx = (unsigned)std::min<size_t>((hw + 127) / 128, 296);  // 8 warps x 16 tokens per block step
+    chanattn_apply_mma_kernel<<<dim3(gx, p.heads, p.n), 256, 0, s>>>(p);
+  } else if (bf16)
     chanattn_apply_kernel<__nv_bfloat16><<<g3, 256, 0, s>>>(p);
   else
     chanattn_apply_kernel<float><<<g3, 256, 0, s>>>(p);

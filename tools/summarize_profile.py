@@ -2,6 +2,7 @@
 
     python tools/summarize_profile.py launches <launches.csv> <out.md> [title]
     python tools/summarize_profile.py full <report.ncu-rep> <out.md> [title]
+    python tools/summarize_profile.py rows <report.ncu-rep> <out.md> [title]
 """
 import csv
 import json
@@ -68,11 +69,42 @@ def full(path, out, title):
     return traffic
 
 
+def rows_mode(path, out, title):
+    """One row per captured launch (kernels as rows): what a bandwidth-bound kernel needs to be judged."""
+    raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {k: hdr.index(k) for k in ('Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+                                     'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+                                     'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+                                     'smsp__issue_active.avg.pct_of_peak_sustained_active', 'launch__grid_size', 'launch__block_size',
+                                     'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active')}
+    mult = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}
+    tmult = {'us': 1.0, 'ms': 1e3, 'ns': 1e-3, 's': 1e6}
+    with open(out, 'w') as f:
+        f.write(f'# {title}\n\nSource: `ncu --set full --clock-control none --import-source on` on `{os.path.basename(path)}` (one row per captured '
+                'launch; cold-cache, serialised). GB/s = (DRAM read + write) / duration; HBM peak in MEASURED_PEAKS.json: 6546 GB/s.\n\n')
+        f.write('| kernel | grid x block | us | DRAM read MB | DRAM write MB | GB/s | DRAM % of peak | tensor pipe % | MUFU pipe % | warps active % | issue active % | regs |\n')
+        f.write('|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n')
+        for r in rows[2:]:
+            name = r[col['Kernel Name']].replace('rsb::<unnamed>::', '').split('(')[0]
+            us = float(r[col['gpu__time_duration.sum']]) * tmult.get(units[col['gpu__time_duration.sum']], 1.0)
+            rd = float(r[col['dram__bytes_read.sum']]) * mult.get(units[col['dram__bytes_read.sum']], 1.0)
+            wr = float(r[col['dram__bytes_write.sum']]) * mult.get(units[col['dram__bytes_write.sum']], 1.0)
+            g = lambda k: float(r[col[k]])
+            f.write(f"| `{name}` | {r[col['launch__grid_size']]} x {r[col['launch__block_size']]} | {us:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {(rd + wr) / us / 1e3:.0f} | "
+                    f"{g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{g('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'):.1f} | {g('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | {r[col['launch__registers_per_thread']]} |\n")
+
+
 if __name__ == '__main__':
     mode, src, dst = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else os.path.basename(src)
     if mode == 'launches':
         launches(src, dst, title)
+    elif mode == 'rows':
+        rows_mode(src, dst, title)
     else:
         t = full(src, dst, title)
         print(json.dumps(t, indent=1))
