@@ -175,11 +175,16 @@ __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const __grid_con
     const size_t pix = i - (size_t)pl * hw;
     float v[8];
     load8<T>(reinterpret_cast<const T*>(p.src) + (((size_t)n * p.src_planes + p.src_plane0 + g * planes_per_group + pl) * hw + pix) * 8, v);
+    // fp32 inside one 8-channel chunk, fp64 across chunks: 2 double adds per 8 elements instead of 16 (fp64 issue was half
+    // of this kernel's time); still a fixed summation order
+    float s8 = 0.0f, ss8 = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      s += v[k];
-      ss += (double)v[k] * v[k];
+      s8 += v[k];
+      ss8 = fmaf(v[k], v[k], ss8);
     }
+    s += (double)s8;
+    ss += (double)ss8;
   }
   __shared__ double sh[2][256];
   sh[0][threadIdx.x] = s;
@@ -207,13 +212,29 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __grid_const
   const int planes_per_group = cpg / 8;
   const size_t hw = (size_t)p.H * p.W;
   __shared__ float s_mean, s_rstd;
-  if (threadIdx.x == 0) {
+  __shared__ double red[2][256];
+  {
+    // all 256 threads fetch partials at once and reduce them as a fixed tree (one thread walking them serially cost every
+    // block ~25 us of dependent L2 round trips before its first load)
     const double* in = p.partial + ((size_t)n * p.groups + g) * p.blocks_per_group * 2;
     double s = 0.0, ss = 0.0;
-    for (int b = 0; b < p.blocks_per_group; ++b) {
+    for (int b = threadIdx.x; b < p.blocks_per_group; b += blockDim.x) {
       s += in[2 * b];
       ss += in[2 * b + 1];
     }
+    red[0][threadIdx.x] = s;
+    red[1][threadIdx.x] = ss;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        red[0][threadIdx.x] += red[0][threadIdx.x + o];
+        red[1][threadIdx.x] += red[1][threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const double s = red[0][0], ss = red[1][0];
     const double cnt = (double)hw * cpg;
     const double mean = s / cnt;
     double var = ss / cnt - mean * mean;
