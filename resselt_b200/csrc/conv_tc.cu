@@ -62,11 +62,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   uint64_t* const tempty = tfull + kMaxAcc;
   uint64_t* const wbar = tempty + kMaxAcc;
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  // seen[s] = number of fills of stage s whose completion an MMA warp has observed.  mbarrier waits only know the phase
+  // PARITY: a warp that asks for fill k of a stage while fill k-1 has not completed yet is told "done" (it sees fill k-2).
+  // With two issuing warps the previous fill of a stage may be the OTHER warp's tile, and TMA loads complete out of order
+  // (L2 hit vs miss), so before waiting for fill k a warp first waits until whoever owned fill k-1 has seen it land.
+  volatile uint32_t* const seen = tmem_slot + 4;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      seen[s] = 0;
     }
     for (int a = 0; a < kMaxAcc; ++a) {
       mbar_init(&tfull[a], 1);
@@ -150,7 +156,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       const uint32_t d = tmem_base + (uint32_t)acc * p.acc_stride;
       if constexpr (KH > 0) {
         const int s = i % S;  // static geometry: one chunk per tile
-        mbar_wait(&full[s], (uint32_t)(i / S) & 1u);
+        const uint32_t fill = (uint32_t)(i / S);
+        while (seen[s] < fill) {
+        }
+        mbar_wait(&full[s], fill & 1u);
+        if (leader) seen[s] = fill + 1;
         tc_fence_after();
         constexpr uint32_t kPlane = (uint32_t)((kTileH + KH - 1) * (kTileW + KW - 1));  // 16-byte units per 8-ch plane
         const uint64_t da = make_smem_desc(smem_u32(stage0 + (size_t)s * st_al), kPlane * 16u, (uint32_t)(kTileW + KW - 1) * 16u);
@@ -176,7 +186,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         for (int c = 0; c < p.nchunks; ++c) {
           const int j = i * p.nchunks + c;
           const int s = j % S;
-          mbar_wait(&full[s], (uint32_t)(j / S) & 1u);
+          const uint32_t fill = (uint32_t)(j / S);
+          while (seen[s] < fill) {
+          }
+          mbar_wait(&full[s], fill & 1u);
+          if (leader) seen[s] = fill + 1;
           tc_fence_after();
           const uint32_t a_lo0 = a_lo_const + (smem_u32(stage0 + (size_t)s * st_al) >> 4);
           uint32_t b_tap = b_lo0 + (uint32_t)(c * (p.kchunk >> 3)) * (b_lbo >> 4);
@@ -362,7 +376,7 @@ size_t conv_tc_smem_bytes(int cin, int kchunk, int npad, int kh, int kw, int sta
   const uint32_t wbytes = (uint32_t)kh * kw * cin * npad * 2u;
   const uint32_t stage = (uint32_t)(kTileH + kh - 1) * (kTileW + kw - 1) * kchunk * 2u;
   return (size_t)align_up(wbytes, kAlign) + (size_t)stages * align_up(stage, kAlign) + 2 * npad * sizeof(float) +
-         (2 * stages + 2 * kMaxAcc + 1) * 8 + 16;
+         (2 * stages + 2 * kMaxAcc + 1) * 8 + 16 + 8 * sizeof(uint32_t);  // barriers, TMEM slot, seen[] (<= 8 stages)
 }
 
 int conv_tc_num_acc(int npad) {

@@ -352,8 +352,14 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       if (!enc) return fail(RSB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
       const Buffer& sb = p->bufs[c.tc_src_buf];
       const int HT = rsb::kTileH + c.tc_kh - 1, WT = rsb::kTileW + c.tc_kw - 1;
-      cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)sb.planes, (cuuint64_t)n};
-      cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)W * 16 * H, (cuuint64_t)W * 16 * H * sb.planes};
+      // 1x1 convs between planar buffers have no neighbourhood: view the image as (H*W/8) rows of 8 pixels, so that a
+      // 16 x 8 tile is 128 CONSECUTIVE pixels — 2 KB contiguous per plane for the TMA load, the residual read and the store
+      // instead of sixteen 128-byte pieces one image row apart.  Same linear addresses, same arithmetic, different tile shape.
+      static const bool no_linear = getenv("RSB_NO_LINEAR1X1") != nullptr;
+      const bool linear = !no_linear && c.tc_kh == 1 && c.tc_kw == 1 && d.dst_buf >= 0 && d.dst_ps <= 1 && ((long long)H * W) % 8 == 0;
+      const int Hm = linear ? (int)((long long)H * W / 8) : H, Wm = linear ? 8 : W;
+      cuuint64_t dims[4] = {(cuuint64_t)Wm * 8, (cuuint64_t)Hm, (cuuint64_t)sb.planes, (cuuint64_t)n};
+      cuuint64_t strides[3] = {(cuuint64_t)Wm * 16, (cuuint64_t)Wm * 16 * Hm, (cuuint64_t)Wm * 16 * Hm * sb.planes};
       cuuint32_t box[4] = {(cuuint32_t)(8 * WT), (cuuint32_t)HT, (cuuint32_t)(c.kchunk / 8), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(&c.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ws + sb.offset, dims, strides, box, estr,
@@ -362,8 +368,8 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       if (r != CUDA_SUCCESS) return fail(RSB_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
       rsb::ConvTcParams& t = c.tcp;
       memset(&t, 0, sizeof t);
-      t.n = n, t.H = H, t.W = W;
-      t.tiles_x = ceil_div(W, rsb::kTileW), t.tiles_y = ceil_div(H, rsb::kTileH);
+      t.n = n, t.H = Hm, t.W = Wm;
+      t.tiles_x = ceil_div(Wm, rsb::kTileW), t.tiles_y = ceil_div(Hm, rsb::kTileH);
       t.num_tiles = t.tiles_x * t.tiles_y * n;
       t.cin = c.tc_cin, t.npad = c.npad;
       t.kchunk = c.kchunk, t.nchunks = c.tc_cin / c.kchunk;
@@ -387,7 +393,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       uint32_t cols = 32;
       while (cols < (uint32_t)t.num_acc * c.npad) cols <<= 1;
       t.tmem_cols = cols;
-      fill_epi(p, c, n, H, W, ws, t.epi);
+      fill_epi(p, c, n, Hm, Wm, ws, t.epi);
       // each CTA streams a contiguous run of rows and pays ~2 halo rows per run: worth it from ~8 rows per CTA
       c.rs_ready = c.rs_elig && W % 8 == 0;
       c.lk_ready = c.lk_elig && W % 8 == 0;
