@@ -418,7 +418,7 @@ size_t winattn_mma_smem_bytes(int split_h, int split_w) {
 
 // kThreads = 128 serves windows of <= 64 tokens (SwinIR's 8x8): a tighter register budget keeps 5 CTAs per SM resident
 // (the kernel's phases — stage, attend, store — are latency-bound chains; residency is what overlaps them).
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, bool kLoop>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const __grid_constant__ WinAttnParams p) {
   extern __shared__ __align__(16) uint8_t smraw[];
   using T = __nv_bfloat16;
@@ -485,12 +485,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
     if (po >= 0) {
       const T* tok = src + ((size_t)n * p.src_planes * p.H * p.W + po) * 8;
       // all of a thread's loads are issued before the first value is used: one DRAM round trip per CTA, not one per item
-      constexpr int kItems = (3 * kPl + 1) / 2;  // groups >= 2 whenever the block has twice as many threads as tokens
-      if (groups >= 2) {
+      constexpr int kItems = (3 * kPl + 1) / 2;  // loads per batch: one batch when the block has two threads per token, else two
+      for (int mp0 = g; mp0 < 3 * kPl; mp0 += groups * kItems) {
         uint4 v[kItems];
 #pragma unroll
         for (int it = 0; it < kItems; ++it) {
-          const int mp = g + it * groups;
+          const int mp = mp0 + it * groups;
           const int m = mp / kPl, pl = mp - m * kPl;
           const int cm = cq + m * p.qkv_stride;
           const int plane = (cm >> 3) + pl;
@@ -498,27 +498,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
         }
 #pragma unroll
         for (int it = 0; it < kItems; ++it) {
-          const int mp = g + it * groups;
+          const int mp = mp0 + it * groups;
           const int m = mp / kPl, pl = mp - m * kPl;
           const int cm = cq + m * p.qkv_stride;
           const int cbase = ((cm >> 3) + pl) * 8 - cm;  // head dim of the plane's first channel (negative: previous head's)
           if (mp >= 3 * kPl || cbase >= d) continue;
           const T* e = reinterpret_cast<const T*>(&v[it]);
-          T* out = m == 0 ? Qs + t * kWaQS : (m == 1 ? Ks + t * kWaQS : Vt + t);
-          const int stride = m == 2 ? VS : 1;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if ((unsigned)(cbase + k) < (unsigned)d) out[(cbase + k) * stride] = e[k];
-        }
-      } else {
-        for (int mp = 0; mp < 3 * kPl; ++mp) {
-          const int m = mp / kPl, pl = mp - m * kPl;
-          const int cm = cq + m * p.qkv_stride;
-          const int plane = (cm >> 3) + pl;
-          const int cbase = plane * 8 - cm;
-          if (cbase >= d) continue;
-          const uint4 v = *reinterpret_cast<const uint4*>(tok + (size_t)plane * ps);
-          const T* e = reinterpret_cast<const T*>(&v);
           T* out = m == 0 ? Qs + t * kWaQS : (m == 1 ? Ks + t * kWaQS : Vt + t);
           const int stride = m == 2 ? VS : 1;
 #pragma unroll
@@ -531,9 +516,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = warp * 16;
-  if (r0 >= NQ) return;
   const int g4 = lane >> 2, t4 = lane & 3;
+  T* dst = reinterpret_cast<T*>(p.dst);
+  const int co = p.dst_ch_off + br * half + h * d;
+  // a warp takes 16 queries at a time; with 256-token windows a 256-thread CTA walks two query tiles per warp, so that two
+  // CTAs fit an SM and one window's staging overlaps the other's attention (one 512-thread CTA per SM left the SM idle
+  // during every staging phase)
+  int r0 = warp * 16;
+  if (r0 >= NQ) return;
+  do {  // (single pass, known at compile time, for the 128-thread variant)
   const int qa = r0 + g4, qb = qa + 8;  // the two query rows this thread holds fragments of
   // query-side halves of the bias index and the shift-mask labels
   int qpos[2], qlab[2];
@@ -653,8 +644,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
       l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
     }
   }
-  T* dst = reinterpret_cast<T*>(p.dst);
-  const int co = p.dst_ch_off + br * half + h * d;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int t = r == 0 ? qa : qb;
@@ -675,6 +664,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
       }
     }
   }
+  r0 += kThreads / 2;
+  } while (kLoop && r0 < NQ);  // query tiles
 }
 
 // ------------------------------------------------------------------------------------------------ channel attention
@@ -1080,9 +1071,11 @@ size_t winattn_smem_bytes(int split_h, int split_w) {
 cudaError_t winattn_configure() {
   cudaError_t e = cudaFuncSetAttribute(winattn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(winattn_mma_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  e = cudaFuncSetAttribute(winattn_mma_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(winattn_mma_kernel<128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  e = cudaFuncSetAttribute(winattn_mma_kernel<128, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(winattn_mma_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(winattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -1094,12 +1087,18 @@ cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
   const size_t smem = winattn_smem_bytes(p.split_h, p.split_w);
   static const bool no_mma = getenv("RSB_WINATTN_SIMT") != nullptr;
   const int N = p.split_h * p.split_w;
-  if (bf16 && !no_mma && N <= 256 && p.head_dim <= kHD && winattn_mma_smem_bytes(p.split_h, p.split_w) <= 160 * 1024) {
+  if (bf16 && !no_mma && N <= 256 && p.head_dim <= kHD && winattn_mma_smem_bytes(p.split_h, p.split_w) <= 100 * 1024) {
     const int warps = (N + 15) / 16;
+    // > 64 tokens: 128-thread CTAs, every warp walks NQ / 64 query tiles; three CTAs per SM (shared-memory bound) overlap one
+    // window's staging with the others' attention.  Measured on DAT's 8x32 windows at 4x 512^2: one 512-thread CTA per SM
+    // 565 us, two 256-thread CTAs 473 us, three 128-thread CTAs 395 us per launch (RSB_WA_T256=1 selects the middle one).
+    static const bool t128 = getenv("RSB_WA_T256") == nullptr;
     if (warps <= 4)  // (a 6-CTA / 80-register variant spills and measured no faster: 260 vs 254 us)
-      winattn_mma_kernel<128, 5><<<grid, 128, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
+      winattn_mma_kernel<128, 5, false><<<grid, 128, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
+    else if (t128)
+      winattn_mma_kernel<128, 3, true><<<grid, 128, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
     else
-      winattn_mma_kernel<512, 1><<<grid, 32 * warps, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
+      winattn_mma_kernel<256, 2, true><<<grid, 32 * std::min(warps, 8), winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
   } else if (bf16)
     winattn_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
   else
