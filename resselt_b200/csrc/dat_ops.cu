@@ -480,8 +480,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
     // thread = one token, walking the (matrix, plane) items with a stride of blockDim / N: no per-item index arithmetic
     constexpr int kPl = (kHD + 7 + 7) / 8;  // planes a head can straddle
     const size_t ps = (size_t)p.H * p.W * 8;
-    const int g = threadIdx.x / N, t = threadIdx.x - g * N, groups = blockDim.x / N;
-    const int po = g < groups ? tokoff[t] : -1;
+    // blocks with at least N threads: `groups` threads share a token; smaller blocks: each thread walks several tokens
+    const int groups = max(1, (int)blockDim.x / N), g = threadIdx.x / N;
+    const int tstep = (int)blockDim.x >= N ? N : (int)blockDim.x;
+    for (int t = threadIdx.x - g * N; t < N && g < groups; t += tstep) {
+    const int po = tokoff[t];
     if (po >= 0) {
       const T* tok = src + ((size_t)n * p.src_planes * p.H * p.W + po) * 8;
       // all of a thread's loads are issued before the first value is used: one DRAM round trip per CTA, not one per item
@@ -512,6 +515,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
         }
       }
     }
+    }  // tokens of this thread
   }
   __syncthreads();
 
@@ -1074,8 +1078,7 @@ cudaError_t winattn_configure() {
   e = cudaFuncSetAttribute(winattn_mma_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(winattn_mma_kernel<128, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(winattn_mma_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+
 
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(winattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -1089,14 +1092,11 @@ cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
   const int N = p.split_h * p.split_w;
   if (bf16 && !no_mma && N <= 256 && p.head_dim <= kHD && winattn_mma_smem_bytes(p.split_h, p.split_w) <= 100 * 1024) {
     const int warps = (N + 15) / 16;
-    // > 64 tokens: 128-thread CTAs, every warp walks NQ / 64 query tiles; three CTAs per SM (shared-memory bound) overlap one
-    // window's staging with the others' attention.  Measured on DAT's 8x32 windows at 4x 512^2: one 512-thread CTA per SM
-    // 565 us, two 256-thread CTAs 473 us, three 128-thread CTAs 395 us per launch (RSB_WA_T256=1 selects the middle one).
-    static const bool t128 = getenv("RSB_WA_T256") == nullptr;
+    // > 64 tokens: 256-thread CTAs, every warp walks NQ / 128 query tiles; two CTAs per SM overlap one window's staging with
+    // the other's attention.  DAT's 8x32 windows at 4x 512^2: one 512-thread CTA per SM 565 us, two 256-thread CTAs 473 us per
+    // launch (three 128-thread CTAs measured the same as two of 256).
     if (warps <= 4)  // (a 6-CTA / 80-register variant spills and measured no faster: 260 vs 254 us)
       winattn_mma_kernel<128, 5, false><<<grid, 128, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
-    else if (t128)
-      winattn_mma_kernel<128, 3, true><<<grid, 128, winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
     else
       winattn_mma_kernel<256, 2, true><<<grid, 32 * std::min(warps, 8), winattn_mma_smem_bytes(p.split_h, p.split_w), s>>>(p);
   } else if (bf16)
