@@ -19,6 +19,7 @@ from .sr_forward import (  # noqa: F401
     dat_forward,
     esrgan_forward,
     forward_by_name,
+    plksr_forward,
     realplksr_forward,
     span_forward,
     spanplus_forward,

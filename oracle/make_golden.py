@@ -50,6 +50,12 @@ def cases():
                                                    upscale=4, upsampler='nearest+conv', resi_connection='3conv'), 26, (1, 3, 21, 30), 116),
         'swinir_jpeg_w7_gray': ('SwinIR', dict(img_size=126, in_chans=1, embed_dim=48, depths=[2, 2], num_heads=[6, 6], window_size=7, mlp_ratio=2.0,
                                                upscale=1, img_range=255.0, upsampler='', resi_connection='1conv'), 27, (1, 1, 30, 23), 117),
+        'plksr_x4_dccm_plk17': ('PLKSR', dict(dim=64, n_blocks=2, upscaling_factor=4, ccm_type='DCCM', kernel_size=17, split_ratio=0.25, lk_type='PLK',
+                                              use_ea=True), 28, (1, 3, 22, 26), 118),
+        'plksr_x3_iccm_sparse': ('PLKSR', dict(dim=64, n_blocks=2, upscaling_factor=3, ccm_type='ICCM', kernel_size=17, split_ratio=0.25,
+                                               lk_type='SparsePLK', use_ea=True), 29, (2, 3, 18, 16), 119),
+        'plksr_x2_ccm_rect13_noea': ('PLKSR', dict(dim=32, n_blocks=3, upscaling_factor=2, ccm_type='CCM', kernel_size=15, split_ratio=0.25,
+                                                   lk_type='RectSparsePLK', use_ea=False), 30, (1, 3, 20, 20), 120),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
     }
@@ -60,7 +66,7 @@ def engine_model(kind: str, kwargs: dict, seed: int):
 
     cls = {'SPAN': archs.SPAN, 'SPANPlus': archs.SpanPlus, 'Compact': archs.SRVGGNetCompact}
     extra = {k: getattr(archs, k) for k in ('RRDBNet', 'RealPLKSR') if hasattr(archs, k)}
-    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None)})
+    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None)})
     return cls[kind](seed=seed, **kwargs)
 
 

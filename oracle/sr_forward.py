@@ -193,6 +193,47 @@ def realplksr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, norm_groups:
     return F.pixel_shuffle(t + torch.repeat_interleave(x, r2, dim=1), math.isqrt(r2))
 
 
+def plksr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, sparse_dilations=(1, 2, 3, 4), with_idt: bool = False) -> torch.Tensor:
+    """plksr.forward (/root/reference/resselt/archs/plksr/plksr.py:374-377) with PLKBlock.forward (:301-308), the CCM / ICCM /
+    DCCM mixers (:18-52, exact GELU), the three partial large-kernel layers in their un-converted eval form (PLKConv2d :70-81,
+    SparsePLKConv2d :153-164 with the loader's default dilations, RectSparsePLKConv2d :116-117) and EA (:239-248)."""
+    x = x.to(dtype)
+    n_feats = _seq_len(sd, 'feats')
+    t = _conv(sd, 'feats.0', x, 1)
+    for i in range(1, n_feats - 1):
+        p = f'feats.{i}'
+        skip = t
+        k0, k2 = sd[f'{p}.channe_mixer.0.weight'].shape[2], sd[f'{p}.channe_mixer.2.weight'].shape[2]
+        t = _conv(sd, f'{p}.channe_mixer.2', F.gelu(_conv(sd, f'{p}.channe_mixer.0', t, k0 // 2)), k2 // 2)
+        cw = lambda name, inp, **kw: F.conv2d(inp, sd[f'{p}.lk.{name}.weight'].to(dtype), sd[f'{p}.lk.{name}.bias'].to(dtype), **kw)
+        if f'{p}.lk.conv.weight' in sd:
+            pdim, k = sd[f'{p}.lk.conv.weight'].shape[0], sd[f'{p}.lk.conv.weight'].shape[2]
+            x1 = t[:, :pdim]
+            lk = cw('conv', x1, padding=k // 2)
+        elif f'{p}.lk.convs.0.weight' in sd:
+            pdim = sd[f'{p}.lk.convs.0.weight'].shape[0]
+            x1 = t[:, :pdim]
+            lk = 0.0
+            for j in range(_seq_len(sd, f'{p}.lk.convs')):
+                k = sd[f'{p}.lk.convs.{j}.weight'].shape[2]
+                d = sparse_dilations[j] if j < len(sparse_dilations) else 1
+                lk = lk + cw(f'convs.{j}', x1, padding=(k // 2) * d, dilation=d)
+        else:
+            pdim = sd[f'{p}.lk.mn_conv.weight'].shape[0]
+            x1 = t[:, :pdim]
+            m, n = sd[f'{p}.lk.mn_conv.weight'].shape[2:]
+            lk = cw('mn_conv', x1, padding=(m // 2, n // 2)) + cw('nm_conv', x1, padding=(n // 2, m // 2)) + cw('nn_conv', x1, padding=n // 2)
+        if with_idt:
+            lk = lk + x1
+        t = torch.cat([lk, t[:, pdim:]], 1)
+        if f'{p}.attn.f.0.weight' in sd:
+            t = t * torch.sigmoid(_conv(sd, f'{p}.attn.f.0', t, 1))
+        t = _conv(sd, f'{p}.refine', t, 0) + skip
+    t = _conv(sd, f'feats.{n_feats - 1}', t, 1)
+    r2 = t.shape[1] // x.shape[1]
+    return F.pixel_shuffle(t + torch.repeat_interleave(x, r2, dim=1), int(math.isqrt(r2)))
+
+
 # ---------------------------------------------------------------------------------------------- DAT
 def _lin(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
     b = sd.get(name + '.bias')
@@ -461,6 +502,7 @@ _FORWARDS: Dict[str, Callable] = {
     'SwinIR': swinir_forward,
     'DAT': dat_forward,
     'RealPLKSR': realplksr_forward,
+    'PLKSR': plksr_forward,
     'ESRGAN': esrgan_forward,
     'SPAN': span_forward,
     'SPANPlus': spanplus_forward,

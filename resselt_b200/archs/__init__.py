@@ -8,7 +8,7 @@ from ..registry import Registry
 from .compact import CompactArch, SRVGGNetCompact
 from .dat import DAT, DatArch
 from .esrgan import ESRGANArch, RRDBNet
-from .plksr import PLKSRArch, RealPLKSR
+from .plksr import PLKSR, PLKSRArch, RealPLKSR
 from .span import SPAN, SPANArch
 from .spanplus import SpanPlus, SpanPlusArch
 from .swinir import SwinIR, SwinIRArch
@@ -17,4 +17,4 @@ internal_registry = Registry()
 for _arch in (SPANArch, SpanPlusArch, CompactArch, ESRGANArch, PLKSRArch, DatArch, SwinIRArch):
     internal_registry.add(_arch())
 
-__all__ = ['internal_registry', 'SPAN', 'SPANArch', 'SpanPlus', 'SpanPlusArch', 'SRVGGNetCompact', 'CompactArch', 'RRDBNet', 'ESRGANArch', 'RealPLKSR', 'PLKSRArch', 'DAT', 'DatArch', 'SwinIR', 'SwinIRArch']
+__all__ = ['internal_registry', 'SPAN', 'SPANArch', 'SpanPlus', 'SpanPlusArch', 'SRVGGNetCompact', 'CompactArch', 'RRDBNet', 'ESRGANArch', 'RealPLKSR', 'PLKSR', 'PLKSRArch', 'DAT', 'DatArch', 'SwinIR', 'SwinIRArch']

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import resselt_b200
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR, internal_registry
+from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR, internal_registry
 from resselt_b200.factory import Architecture, KeyCondition
 from resselt_b200.factory.arch import ModelMetadata
 from resselt_b200.registry import ArchitectureNotFound, Registry
@@ -50,6 +50,10 @@ def test_metadata_field_order():
         (RRDBNet(num_blocks=1, scale=2, key_style='bsrgan'), ('ESRGAN', 3, 3, 2)),
         (RealPLKSR(n_blocks=2, upscaling_factor=4), ('RealPLKSR', 3, 3, 4)),
         (RealPLKSR(dim=32, n_blocks=2, upscaling_factor=2, kernel_size=13, use_ea=False), ('RealPLKSR', 3, 3, 2)),
+        (PLKSR(n_blocks=2, upscaling_factor=4), ('PLKSR', 3, 3, 4)),
+        (PLKSR(dim=32, n_blocks=2, upscaling_factor=2, ccm_type='CCM', kernel_size=13, use_ea=False), ('PLKSR', 3, 3, 2)),
+        (PLKSR(n_blocks=1, upscaling_factor=3, ccm_type='ICCM', lk_type='SparsePLK'), ('PLKSR', 3, 3, 3)),
+        (PLKSR(n_blocks=1, upscaling_factor=2, lk_type='RectSparsePLK', kernel_size=15), ('PLKSR', 3, 3, 2)),
         (DAT(depth=[3, 2], num_heads=[6, 6], upscale=4), ('DAT', 3, 3, 4)),
         (DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=2, img_size=32), ('DAT', 3, 3, 2)),
         (SwinIR(embed_dim=60, depths=[2, 3], num_heads=[6, 6], upscale=2), ('SwinIR', 3, 3, 2)),
@@ -78,6 +82,9 @@ def test_detect_and_hyperparameter_inference(model, meta):
             model.num_blocks, model.plus, model.shuffle_factor, model._keys.style)
     if isinstance(model, RealPLKSR):
         assert (loaded.dim, loaded.n_blocks, loaded.kernel_size, loaded.use_ea) == (model.dim, model.n_blocks, model.kernel_size, model.use_ea)
+    if isinstance(model, PLKSR):
+        assert (loaded.dim, loaded.n_blocks, loaded.ccm_type, loaded.lk_type, loaded.kernel_size, loaded.kmax, loaded.use_ea) == (
+            model.dim, model.n_blocks, model.ccm_type, model.lk_type, model.kernel_size, model.kmax, model.use_ea)
     if isinstance(model, SwinIR):
         assert (loaded.dim, loaded.hidden, loaded.window_size, loaded.depths, loaded.heads, loaded.img_size, loaded.img_range, loaded.upsampler,
                 loaded.resi_connection) == (model.dim, model.hidden, model.window_size, model.depths, model.heads, model.img_size, model.img_range,

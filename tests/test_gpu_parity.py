@@ -10,7 +10,7 @@ import torch.nn.functional as F
 import oracle
 import resselt_b200
 from conftest import golden_case, golden_index, norm_err, psnr
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
 from resselt_b200.engine import INPUT, OUTPUT, PlanBuilder
 from resselt_b200.engine import native as N
 from resselt_b200.runner import FramePipeline, tiled_forward
@@ -59,6 +59,10 @@ def test_golden_fixtures_fp32_and_bf16(name):
         ('ESRGAN', RRDBNet(in_nc=12, out_nc=3, num_blocks=2, scale=4, shuffle_factor=2, seed=29), (1, 3, 33, 27)),
         ('RealPLKSR', RealPLKSR(n_blocks=28, upscaling_factor=4, seed=30), (1, 3, 48, 56)),  # full depth
         ('RealPLKSR', RealPLKSR(dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, use_ea=False, seed=31), (2, 3, 21, 30)),
+        ('PLKSR', PLKSR(n_blocks=28, upscaling_factor=4, seed=40), (1, 3, 48, 56)),                                   # full depth, DCCM + 17x17 PLK + EA
+        ('PLKSR', PLKSR(n_blocks=3, upscaling_factor=2, ccm_type='ICCM', lk_type='SparsePLK', seed=41), (2, 3, 33, 30)),  # dilated branches -> one 17x17
+        ('PLKSR', PLKSR(dim=32, n_blocks=3, upscaling_factor=3, ccm_type='CCM', lk_type='RectSparsePLK', kernel_size=15, use_ea=False, seed=42),
+         (1, 3, 40, 41)),
         ('DAT', DAT(upscale=4, seed=32), (1, 3, 64, 64)),                                    # default 6x6 blocks, 180 ch, 8x32 windows
         ('DAT', DAT(depth=[3, 3], num_heads=[6, 6], upscale=2, seed=33), (2, 3, 37, 45)),      # padding + shifted-window masks
         ('DAT', DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=2, img_size=32, seed=34), (1, 3, 50, 30)),

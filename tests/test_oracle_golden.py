@@ -60,3 +60,26 @@ def test_spab_second_output_is_activated():
     x = torch.randn(1, 48, 8, 8, generator=torch.Generator().manual_seed(5))
     _, o1 = _spab(sd, 'block_6', x, F.silu)
     assert torch.allclose(o1, F.silu(_conv3xc(sd, 'block_6.c1_r', x)))
+
+
+@pytest.mark.parametrize('lk_type,kw', [('PLK', dict(kernel_size=13)), ('SparsePLK', dict()), ('RectSparsePLK', dict(kernel_size=15))])
+def test_plksr_large_kernel_layers_merge_into_one_dense_kernel(lk_type, kw):
+    # the engine runs every partial large-kernel layer of the original PLKSR as ONE dense conv (archs/plksr.py::_dense_lk_kernel):
+    # the merged kernel must equal the sum of the (dilated / rectangular) branch convs the reference evaluates (plksr.py:153-164, 116-117)
+    from resselt_b200.archs import PLKSR
+    from resselt_b200.archs.plksr import _dense_lk_kernel
+
+    m = PLKSR(n_blocks=1, upscaling_factor=2, lk_type=lk_type, seed=9, **kw)
+    w = {k: v.double() for k, v in m.state_dict().items()}
+    k, b = _dense_lk_kernel(w, 'feats.1.lk', lk_type, m.pdim, m.kmax, m.sparse_dilations, with_idt=True)
+    x = torch.randn(2, m.pdim, 23, 19, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    cw = lambda name, **kk: F.conv2d(x, w[f'feats.1.lk.{name}.weight'], w[f'feats.1.lk.{name}.bias'], **kk)
+    if lk_type == 'PLK':
+        ref = cw('conv', padding=m.kernel_size // 2)
+    elif lk_type == 'SparsePLK':
+        ref = sum(cw(f'convs.{j}', padding=(5 // 2) * d, dilation=d) for j, d in enumerate(m.sparse_dilations))
+    else:
+        mm, nn_ = m.kernel_size, m.kernel_size // 3
+        ref = cw('mn_conv', padding=(mm // 2, nn_ // 2)) + cw('nm_conv', padding=(nn_ // 2, mm // 2)) + cw('nn_conv', padding=nn_ // 2)
+    ref = ref + x  # with_idt
+    assert (F.conv2d(x, k, b, padding=m.kmax // 2) - ref).abs().max() < 1e-12
