@@ -174,6 +174,8 @@ def run_engine(args):
     sampler = ClockSampler(local) if rank == 0 else None
     # ---------------------------------------------------------------- device-resident throughput
     with torch.inference_mode():
+        for i in range(n_inputs):  # untimed priming: every (frame, out) pair is seen once, so its CUDA graph exists before the warm-up
+            model.forward_into(dev_frames[i], out)
         for i in range(args.warmup):
             model.forward_into(dev_frames[i % n_inputs], out)
         barrier()
@@ -245,6 +247,7 @@ def run_engine(args):
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
         config=dict(workload=WORKLOAD, frames_per_step_per_gpu=1, sharding='frames round-robin over ranks, no collective',
                     l2='per-step working set (1.6 GB of activations) exceeds the 126 MB L2; inputs rotate over 8 frames',
+                    launch='whole forward replayed as a CUDA graph per (frame, out) pair (Plan.forward graph=True); captured in an untimed priming pass',
                     weights='random init (seeded), loaded through resselt_b200.load_from_state_dict'),
         clocks=clocks,
         e2e=dict(value=e2e_value, unit='MP/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps,

@@ -148,8 +148,9 @@ class EngineModule(nn.Module):
         return self.plan_for(x.device, x.dtype).forward(x)
 
     def forward_into(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        """Forward writing into a caller-owned NCHW tensor (streaming runners reuse their output slots)."""
-        return self.plan_for(x.device, x.dtype).forward(x, out=out)
+        """Forward writing into a caller-owned NCHW tensor (streaming runners reuse their output slots); repeated calls
+        with the same tensors replay a captured CUDA graph (Plan.forward, ``graph=True``)."""
+        return self.plan_for(x.device, x.dtype).forward(x, out=out, graph=True)
 
     @property
     def receptive_radius(self) -> int:

@@ -296,3 +296,25 @@ def test_large_swinir_after_span_is_repeatable():
     assert bool(torch.isfinite(outs[0].float()).all())
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+
+
+def test_forward_into_replays_a_cuda_graph_and_tracks_new_inputs():
+    # forward_into(x, out) captures the forward once per (x, out) address pair and replays it; the replay must read the tensors'
+    # CURRENT contents and be bit-identical to plain launches
+    m = _load(SPAN(feature_channels=48, upscale=2, seed=51).state_dict(), torch.bfloat16)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(1, 3, 96, 128, generator=g).to(DEV, torch.bfloat16)
+    out = torch.empty(1, 3, 192, 256, device=DEV, dtype=torch.bfloat16)
+    plan = m.plan_for(torch.device(DEV), torch.bfloat16)
+    with torch.inference_mode():
+        for _ in range(3):
+            m.forward_into(x, out)
+        assert len(plan._graphs) == 1 and plan._graphs_enabled
+        assert torch.equal(out, m(x))
+        x.copy_(torch.rand(1, 3, 96, 128, generator=g))
+        m.forward_into(x, out)  # replay on new contents
+        assert len(plan._graphs) == 1
+        assert torch.equal(out, m(x))
+        other = torch.empty_like(out)
+        m.forward_into(x, other)  # new address pair: second graph
+        assert len(plan._graphs) == 2 and torch.equal(other, out)
