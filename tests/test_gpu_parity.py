@@ -318,3 +318,45 @@ def test_forward_into_replays_a_cuda_graph_and_tracks_new_inputs():
         other = torch.empty_like(out)
         m.forward_into(x, other)  # new address pair: second graph
         assert len(plan._graphs) == 2 and torch.equal(other, out)
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 1, 1), (1, 3, 2, 3), (3, 3, 7, 5), (2, 3, 9, 130), (1, 3, 129, 8)])
+@pytest.mark.parametrize('kind', ['SPAN', 'Compact', 'ESRGAN'])
+def test_degenerate_image_sizes(kind, shape):
+    # images smaller than one tile / one 128-pixel strip, single rows and columns, odd batches: the fp32 path must still match the
+    # oracle to 1e-4 and the bf16 path (tensor-core tile kernel with TMA zero fill on every side) the 50 dB bar
+    model = {'SPAN': lambda: SPAN(feature_channels=48, upscale=2, seed=61),
+             'Compact': lambda: SRVGGNetCompact(num_feat=64, num_conv=4, upscale=4, seed=62),
+             'ESRGAN': lambda: RRDBNet(num_blocks=1, scale=4, seed=63)}[kind]()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(sum(shape)))
+    ref = oracle.forward_by_name(kind, sd, x, torch.float32)
+    with torch.inference_mode():
+        y32 = _load(sd)(x.to(DEV)).cpu()
+        y16 = _load(sd, torch.bfloat16)(x.to(DEV, torch.bfloat16)).float().cpu()
+    assert y32.shape == ref.shape
+    assert norm_err(y32, ref) <= FP32_TOL
+    if ref.numel() >= 1024:
+        assert psnr(y16, ref) >= BF16_PSNR_DB
+    else:  # a PSNR over a few dozen samples is noise: bound the error by a few bf16 roundings of the largest value instead
+        assert float((y16 - ref).abs().max()) <= 4 * 2.0 ** -8 * max(1.0, float(ref.abs().max()))
+
+
+def test_input_layouts_and_dtypes():
+    # non-contiguous (channels-last, sliced) inputs are made contiguous by the module; fp16 tensors take the exact-fp32 path and
+    # come back as fp16; CPU tensors and wrong channel counts raise instead of falling back
+    sd = SRVGGNetCompact(num_feat=32, num_conv=3, upscale=2, seed=64).state_dict()
+    m = _load(sd)
+    x = torch.rand(2, 3, 20, 24, generator=torch.Generator().manual_seed(3)).to(DEV)
+    with torch.inference_mode():
+        y = m(x)
+        assert torch.equal(m(x.contiguous(memory_format=torch.channels_last)), y)
+        big = torch.rand(2, 3, 40, 48, device=DEV)
+        big[:, :, 10:30, 12:36] = x
+        assert torch.equal(m(big[:, :, 10:30, 12:36]), y)
+        y_half = m(x.half())
+        assert y_half.dtype == torch.float16 and (y_half.float() - m(x.half().float())).abs().max() <= 2e-3
+        with pytest.raises(RuntimeError):
+            m(x.cpu())
+        with pytest.raises(RuntimeError):
+            m(torch.rand(1, 4, 8, 8, device=DEV))
