@@ -132,10 +132,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     // enough to keep the tensor pipe full with N = 48 MMAs (~24 math cycles each).  Each tile's MMAs stay in order
     // inside one warp, so the accumulation order per output pixel is fixed.  The whole warp walks the loop (so every
     // operand stays in uniform registers); one elected lane issues.
-    // K-chunked tiles share one ring of stages in chunk order.  A warp waiting for fill k of a stage must already have
-    // seen fill k-1 of it complete (mbarrier waits only know the phase parity): with two warps alternating tiles that is
-    // guaranteed only when the previous fill of each of its stages was its own previous tile's (2 * nchunks <= S); wider
-    // K (e.g. a 384 -> 192 1x1 conv: 6 chunks of 64 channels over 4 stages) is issued by warp 1 alone, in tile order.
+    // K-chunked tiles share one ring of stages in chunk order; the seen[] protocol below keeps the parity waits exact for
+    // both warps.  solo (bring-up switch): warp 1 alone issues every tile.
     const bool solo = p.solo_issue != 0;
     const int first = (warp == 1 || solo) ? 0 : 1;
     const int tstep = solo ? 1 : 2;

@@ -374,11 +374,11 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.cin = c.tc_cin, t.npad = c.npad;
       t.kchunk = c.kchunk, t.nchunks = c.tc_cin / c.kchunk;
       {
-        // two issuing warps alternate tiles over ONE ring of stages; a warp may only wait for fill k of a stage after it has
-        // itself seen fill k-1 complete (mbarrier waits know the phase parity only).  That is guaranteed when the previous
-        // fill of every stage a tile uses belongs to the warp's own previous tile: 2 * nchunks <= stages (or one chunk).
-        static const bool two_env = getenv("RSB_TC_TWO") != nullptr;  // bring-up: the looser nchunks < stages rule
-        t.solo_issue = t.nchunks > 1 && (two_env ? t.nchunks >= c.stages : 2 * t.nchunks > c.stages);
+        // K-chunked tiles: both issuing warps share ONE ring of stages in chunk order.  The seen[] counters of the kernel make
+        // every full-barrier wait phase-exact, so two warps are safe for any chunk / stage count (measured +2..4 % on RealPLKSR,
+        // SwinIR, DAT over a single issuing warp).  RSB_TC_SOLO=1 restores one issuing warp whenever 2 * chunks > stages.
+        static const bool solo_env = getenv("RSB_TC_SOLO") != nullptr;
+        t.solo_issue = solo_env && t.nchunks > 1 && 2 * t.nchunks > c.stages;
       }
       t.kh = c.tc_kh, t.kw = c.tc_kw;
       const bool im2col = c.pack_buf >= 0 && !c.pack_planar;

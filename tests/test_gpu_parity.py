@@ -105,7 +105,7 @@ LAYER_CASES = [
     (32, 256, 3, 1, 16, 24, N.ACT_NONE),
     (48, 48, 3, 1, 5, 7, N.ACT_GELU),      # image smaller than one 16x8 tile
     (80, 40, 3, 1, 19, 23, N.ACT_SIGMOID),  # channel counts that are not multiples of 16
-    (384, 192, 1, 1, 200, 176, N.ACT_NONE),  # 6 K chunks over a 4-stage ring, several tiles per CTA (single issuing warp)
+    (384, 192, 1, 1, 200, 176, N.ACT_NONE),  # 6 K chunks over a 4-stage ring, several tiles per CTA
     (192, 32, 3, 1, 136, 200, N.ACT_NONE),   # 3 K chunks per tile, two issuing warps alternating tiles
 ]
 
@@ -281,8 +281,8 @@ def test_layernorm_op_bf16_against_fp64(C, n, H, W):
 
 def test_large_swinir_after_span_is_repeatable():
     # regression: K-chunked tensor-core convs (3 K chunks over a 4-stage ring, two issuing warps) once faulted at 512^2 when
-    # a 1080p SPAN forward had run earlier in the process (timing-dependent mbarrier phase aliasing); they are now issued
-    # by one warp unless 2 * chunks <= stages.  Whole forwards back to back, no synchronisation in between.
+    # a 1080p SPAN forward had run earlier in the process (timing-dependent mbarrier phase aliasing between the two MMA-issuing
+    # warps, fixed by the seen[] counters of conv_tc).  Whole forwards back to back, no synchronisation in between.
     span = SPAN(feature_channels=48, upscale=2, seed=3).eval().to(DEV).bfloat16()
     swin = SwinIR(upscale=4, seed=9).eval().to(DEV).bfloat16()
     g = torch.Generator().manual_seed(5)
