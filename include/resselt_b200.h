@@ -132,7 +132,8 @@ typedef struct rsb_groupnorm_desc {
   int32_t skip_buf, skip_ch_off; /* RSB_NO_BUFFER: no skip */
 } rsb_groupnorm_desc;
 
-/* Token-wise / attention ops of the transformer architectures (DAT, SwinIR).  A token is a pixel of a planar buffer.
+/* Token-wise / attention ops of the transformer architectures (DAT, SwinIR) and the DySample head.  A token is a pixel of a
+ * planar buffer.
  * Call sites replaced: /root/reference/resselt/archs/dat/arch.py:48,636,672,897,924 (LayerNorm), :49,345,547
  * (depthwise conv), :224-267 + :456-482 (shifted-window attention), :565-589 (channel attention), :492-508 and
  * :594-607 (adaptive interaction module); /root/reference/resselt/archs/swinir/arch.py:253,262,299,334,878,956
@@ -153,6 +154,14 @@ enum rsb_op_kind {
                            1 channel block), i[1] / i[2] hidden widths of the channel / spatial MLPs;
                            w[0..3] = channel MLP (W1 [h1][C], b1, W2 [C][h1], b2), w[4..7] = spatial MLP
                            (W1 [h2][C], b1, w2 [h2], b2 [1]); BatchNorm folded by the caller                           */
+  ,
+  RSB_OP_DYSAMPLE = 6   /* DySample head (resselt/utilities/dysample.py:46-83) with its 1x1 end_conv fused, written to the caller's
+                           NCHW output: src = features [C] on the low-res grid, src2 = 0.5 * offset(x) * sigmoid(scope(x))
+                           [2 * groups * s^2 channels, produced by two 1x1 conv ops], dst_buf = RSB_EXTERNAL_OUTPUT;
+                           i[0] groups, i[1] s (up-sampling factor of this head), i[2] out channels;
+                           w[0] = init_pos [2 * groups * s^2], w[1] = end_conv weight [out][C], w[2] = end_conv bias [out].
+                           Sampling position of output pixel (h*s+i, w*s+j), group g: (w + off_x, h + off_y) in input pixels,
+                           clamped to the image (grid_sample bilinear, align_corners=False, padding_mode='border')            */
 };
 
 typedef struct rsb_op_desc {

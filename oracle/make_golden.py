@@ -56,6 +56,12 @@ def cases():
                                                lk_type='SparsePLK', use_ea=True), 29, (2, 3, 18, 16), 119),
         'plksr_x2_ccm_rect13_noea': ('PLKSR', dict(dim=32, n_blocks=3, upscaling_factor=2, ccm_type='CCM', kernel_size=15, split_ratio=0.25,
                                                    lk_type='RectSparsePLK', use_ea=False), 30, (1, 3, 20, 20), 120),
+        'spanplus_x2_dys': ('SPANPlus', dict(num_in_ch=3, num_out_ch=3, blocks=[2], feature_channels=48, upscale=2, upsampler='dys'), 31, (1, 3, 22, 26), 121),
+        'spanplus_x4_dys_f32': ('SPANPlus', dict(num_in_ch=3, num_out_ch=3, blocks=[1], feature_channels=32, upscale=4, upsampler='dys'), 32, (2, 3, 14, 17), 122),
+        'realplksr_x4_dys': ('RealPLKSR', dict(in_ch=3, dim=64, n_blocks=2, upscaling_factor=4, kernel_size=17, split_ratio=0.25, use_ea=True,
+                                               norm_groups=4, dysample=True), 33, (1, 3, 20, 24), 123),
+        'realplksr_x3_dys': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=1, upscaling_factor=3, kernel_size=13, split_ratio=0.25, use_ea=True,
+                                               norm_groups=4, dysample=True), 34, (2, 3, 15, 13), 124),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
     }
@@ -71,6 +77,15 @@ def engine_model(kind: str, kwargs: dict, seed: int):
 
 
 def main():
+    # The reference's DySample builds one tensor with pin_memory=True (resselt/utilities/dysample.py:62), which needs a CUDA driver
+    # this container does not have.  Dropping that flag (values unchanged) is the only deviation from the unmodified package.
+    _orig_tensor = torch.tensor
+
+    def _tensor_without_pinning(*args, **kwargs):
+        kwargs.pop('pin_memory', None)
+        return _orig_tensor(*args, **kwargs)
+
+    torch.tensor = _tensor_without_pinning
     import resselt as reference  # the unmodified reference package
 
     os.makedirs(GOLDEN_DIR, exist_ok=True)

@@ -77,8 +77,29 @@ def span_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, img_range: float 
     return F.pixel_shuffle(_conv(sd, 'upsampler.0', out, 1), r)
 
 
+def _dysample(sd: SD, p: str, x: torch.Tensor, groups: int) -> torch.Tensor:
+    """DySample.forward (/root/reference/resselt/utilities/dysample.py:46-83), restated with the same ATen calls: offsets
+    ``offset(x) * sigmoid(scope(x)) * 0.5 + init_pos``, a coordinate grid in normalised [-1, 1] units, pixel_shuffle of the
+    coordinates, ``grid_sample(bilinear, align_corners=False, padding_mode='border')`` per channel group, 1x1 ``end_conv``.
+    (The reference builds its normaliser with ``pin_memory=True`` (:62), which needs a CUDA driver; the value is the same.)"""
+    B, C, H, W = x.shape
+    s = math.isqrt(sd[f'{p}.offset.weight'].shape[0] // (2 * groups))
+    offset = _conv(sd, f'{p}.offset', x, 0) * torch.sigmoid(F.conv2d(x, sd[f'{p}.scope.weight'].to(x.dtype))) * 0.5 + sd[f'{p}.init_pos'].to(x.dtype)
+    offset = offset.view(B, 2, -1, H, W)
+    coords_h = torch.arange(H) + 0.5
+    coords_w = torch.arange(W) + 0.5
+    coords = torch.stack(torch.meshgrid([coords_w, coords_h], indexing='ij')).transpose(1, 2).unsqueeze(1).unsqueeze(0).type(x.dtype)
+    normalizer = torch.tensor([W, H], dtype=x.dtype).view(1, 2, 1, 1, 1)
+    coords = 2 * (coords + offset) / normalizer - 1
+    coords = F.pixel_shuffle(coords.reshape(B, -1, H, W), s).view(B, 2, -1, s * H, s * W).permute(0, 2, 3, 4, 1).contiguous().flatten(0, 1)
+    out = F.grid_sample(x.reshape(B * groups, -1, H, W), coords, mode='bilinear', align_corners=False, padding_mode='border').view(B, -1, s * H, s * W)
+    if f'{p}.end_conv.weight' in sd:
+        out = _conv(sd, f'{p}.end_conv', out, 0)
+    return out
+
+
 def spanplus_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
-    """SpanPlus.forward with the 'ps' upsampler, eval mode
+    """SpanPlus.forward with the 'ps' or 'dys' upsampler, eval mode
     (/root/reference/resselt/archs/spanplus/arch.py:199-201, SPABS.forward :146-151)."""
     x = x.to(dtype)
     groups = _seq_len(sd, 'feats') - 1
@@ -92,6 +113,8 @@ def spanplus_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tens
         end, o1 = _spab(sd, f'{pre}.block_end', t, F.mish)
         tail = _conv3xc(sd, f'{pre}.conv_2', end)
         cur = _conv(sd, f'{pre}.conv_cat', torch.cat([cur, tail, b1, o1], 1), 0)
+    if 'upsampler.0.weight' not in sd:  # 'dys' head: DySample(feature_channels, out_ch, upscale), groups = 4 (spanplus/arch.py:186)
+        return _dysample(sd, 'upsampler', cur, 4)
     in_ch = sd['feats.0.eval_conv.weight'].shape[1]
     r = math.isqrt(sd['upsampler.0.weight'].shape[0] // in_ch)
     return F.pixel_shuffle(_conv(sd, 'upsampler.0', cur, 1), r)
@@ -190,7 +213,11 @@ def realplksr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, norm_groups:
         t = t + skip
     t = _conv(sd, f'feats.{total - 1}', t, 1)
     r2 = t.shape[1] // x.shape[1]
-    return F.pixel_shuffle(t + torch.repeat_interleave(x, r2, dim=1), math.isqrt(r2))
+    t = t + torch.repeat_interleave(x, r2, dim=1)
+    if 'to_img.init_pos' in sd:  # DySample head: groups = out_ch for odd factors, else 4 (rplksr.py:133-140)
+        r = math.isqrt(r2)
+        return _dysample(sd, 'to_img', t, x.shape[1] if r % 2 != 0 else 4)
+    return F.pixel_shuffle(t, math.isqrt(r2))
 
 
 def plksr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, sparse_dilations=(1, 2, 3, 4), with_idt: bool = False) -> torch.Tensor:

@@ -45,3 +45,39 @@ def merge_conv3xc(w: Dict[str, torch.Tensor], prefix: str):
     inner_bias = torch.einsum('nmhw,m->n', w2, b1) + b2
     bias = w3 @ inner_bias + b3 + sk_b
     return merged, bias
+
+
+# ------------------------------------------------------------------------------------------------ DySample head
+def dysample_init_pos(scale: int, groups: int) -> torch.Tensor:
+    """The ``init_pos`` buffer exactly as DySample._init_pos builds it (/root/reference/resselt/utilities/dysample.py:42-44)."""
+    h = torch.arange((-scale + 1) / 2, (scale - 1) / 2 + 1) / scale
+    return torch.stack(torch.meshgrid([h, h], indexing='ij')).transpose(1, 2).repeat(1, groups, 1).reshape(1, -1, 1, 1)
+
+
+def dysample_specs(prefix: str, in_channels: int, out_ch: int, scale: int, groups: int = 4, end_convolution: bool = True) -> List[ParamSpec]:
+    """Parameter / buffer names of a DySample module (dysample.py:12-40): end_conv (1x1), offset (1x1), scope (1x1, no bias), init_pos."""
+    if in_channels < groups or in_channels % groups != 0:
+        raise ValueError('Incorrect in_channels and groups values.')  # dysample.py:23-27
+    k = 2 * groups * scale * scale
+    specs: List[ParamSpec] = []
+    if end_convolution:
+        specs += conv_specs(f'{prefix}.end_conv', in_channels, out_ch, 1, gain=3.0)
+    specs += [(f'{prefix}.offset.weight', (k, in_channels, 1, 1), 'conv_w*2.0'), (f'{prefix}.offset.bias', (k,), f'bias:{in_channels}')]
+    specs += [(f'{prefix}.scope.weight', (k, in_channels, 1, 1), 'conv_w*2.0')]
+    specs += [(f'{prefix}.init_pos', dysample_init_pos(scale, groups), 'buffer_tensor')]
+    return specs
+
+
+def emit_dysample(pb, w: Dict[str, torch.Tensor], prefix: str, x, out_ch: int, scale: int, groups: int = 4) -> None:
+    """DySample.forward (dysample.py:46-83) on the engine: ``0.5 * offset(x) * sigmoid(scope(x))`` is two 1x1 conv ops (the 0.5
+    folded into the offset conv, the product in its epilogue); the sampling + 1x1 end_conv is one fused op writing the caller's
+    NCHW output.  ``x`` is the feature buffer range the head reads (it must hold exactly the head's input channels)."""
+    from ..engine import OUTPUT
+    from ..engine import native as N
+
+    k = 2 * groups * scale * scale
+    gate, off = pb.buffer(k, scale=pb.scales[x.buf]), pb.buffer(k, scale=pb.scales[x.buf])
+    pb.conv(x, gate, w[f'{prefix}.scope.weight'], None, act=N.ACT_SIGMOID)
+    pb.conv(x, off, 0.5 * w[f'{prefix}.offset.weight'], 0.5 * w[f'{prefix}.offset.bias'], combine=N.COMB_MUL, res1=gate)
+    pb.op(N.OP_DYSAMPLE, x, OUTPUT, x.channels, src2=off, ints=(groups, scale, out_ch),
+          weights=(w[f'{prefix}.init_pos'], w[f'{prefix}.end_conv.weight'], w[f'{prefix}.end_conv.bias']))

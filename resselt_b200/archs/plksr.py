@@ -24,7 +24,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import get_seq_len, pixelshuffle_scale
-from ._common import conv_specs
+from ._common import conv_specs, dysample_specs, emit_dysample
 
 
 class RealPLKSR(EngineModule):
@@ -41,8 +41,8 @@ class RealPLKSR(EngineModule):
         dysample: bool = False,
         seed: int = 0,
     ):
-        if dysample:
-            raise NotImplementedError('RealPLKSR with the DySample head is not supported by the B200 engine (see DESIGN.md)')
+        if dysample and upscaling_factor == 1:
+            raise NotImplementedError('RealPLKSR 1x with DySample (no end convolution, rplksr.py:139) is not supported')
         pdim = int(dim * split_ratio)
         if pdim % 8 != 0 or dim % 8 != 0 or (dim // norm_groups) % 8 != 0:
             raise NotImplementedError('dim, dim*split_ratio and dim/norm_groups must be multiples of 8 (planar-8 layout)')
@@ -58,7 +58,11 @@ class RealPLKSR(EngineModule):
             specs += conv_specs(f'{p}.refine', dim, dim, 1)
             specs += [(f'{p}.norm.weight', (dim,), 'affine_w'), (f'{p}.norm.bias', (dim,), f'bias:{dim}')]
         specs += conv_specs(f'feats.{n_blocks + 2}', dim, in_ch * r2, 3)  # feats.{n_blocks+1} is the (param-free) Dropout2d
+        self_groups = in_ch if upscaling_factor % 2 != 0 else 4  # rplksr.py:134
+        if dysample:
+            specs += dysample_specs('to_img', in_ch * r2, in_ch, upscaling_factor, groups=self_groups)
         super().__init__(specs, in_ch, in_ch, upscaling_factor, seed=seed)
+        self.dysample, self.dys_groups = dysample, self_groups
         self.dim, self.pdim, self.n_blocks, self.kernel_size = dim, pdim, n_blocks, kernel_size
         self.use_ea, self.norm_groups = use_ea, norm_groups
 
@@ -84,7 +88,19 @@ class RealPLKSR(EngineModule):
             pb.conv(cur, refined, w[f'{p}.refine.weight'], w[f'{p}.refine.bias'])
             pb.groupnorm(refined, x_out, self.norm_groups, w[f'{p}.norm.weight'], w[f'{p}.norm.bias'], eps=1e-5, skip=x_in)
         last = f'feats.{self.n_blocks + 2}'
-        pb.conv(xs[self.n_blocks % 2], OUTPUT, w[f'{last}.weight'], w[f'{last}.bias'], ps=self.upscale, add_base=True)
+        if not self.dysample:
+            pb.conv(xs[self.n_blocks % 2], OUTPUT, w[f'{last}.weight'], w[f'{last}.bias'], ps=self.upscale, add_base=True)
+            return
+        # DySample head (rplksr.py:133-147): it reads feats(x) + repeat_interleave(x, r^2) as a 3 r^2-channel low-res map.  The
+        # repeated input is a 1-tap conv of the caller's tensor (channel c r^2 + k copies input channel c); the last conv adds it.
+        r2, cin = self.upscale * self.upscale, self.in_channels
+        rep_w = torch.zeros(cin * r2, cin, 3, 3, dtype=torch.float64)
+        for c in range(cin):
+            rep_w[c * r2:(c + 1) * r2, c, 1, 1] = 1.0
+        rep, pre = pb.buffer(cin * r2), pb.buffer(cin * r2)
+        pb.conv(INPUT, rep, rep_w, None)
+        pb.conv(xs[self.n_blocks % 2], pre, w[f'{last}.weight'], w[f'{last}.bias'], combine=N.COMB_AXPY, res1=rep)
+        emit_dysample(pb, w, 'to_img', pre, self.out_channels, self.upscale, groups=self.dys_groups)
 
 
 def _dense_lk_kernel(w, p: str, lk_type: str, pdim: int, kmax: int, dilations: Sequence[int], with_idt: bool):

@@ -13,7 +13,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import dysample_scale, get_seq_len, pixelshuffle_scale
-from ._common import conv3xc_specs, conv_specs, merge_conv3xc
+from ._common import conv3xc_specs, conv_specs, dysample_specs, emit_dysample, merge_conv3xc
 from .span import emit_spab
 
 
@@ -29,10 +29,9 @@ class SpanPlus(EngineModule):
         upsampler: str = 'ps',
         seed: int = 0,
     ):
-        if upsampler != 'ps':
-            raise NotImplementedError(
-                f"SPANPlus upsampler '{upsampler}' is not supported by the B200 engine (only 'ps'; see DESIGN.md)"
-            )
+        if upsampler not in ('ps', 'dys'):
+            # 'conv' (1x only) cannot even be loaded by the reference (spanplus/__init__.py:20-27 reads upsampler.end_conv)
+            raise NotImplementedError(f"SPANPlus upsampler '{upsampler}' is not supported by the B200 engine (only 'ps' and 'dys')")
         blocks = [int(blocks)] if not isinstance(blocks, (list, tuple)) else [int(b) for b in blocks]
         f = feature_channels
         specs = conv3xc_specs('feats.0', num_in_ch, f)
@@ -43,16 +42,23 @@ class SpanPlus(EngineModule):
                     specs += conv3xc_specs(f'feats.{g}.{b}.{c}', f, f)
             specs += conv3xc_specs(f'feats.{g}.conv_2', f, f)
             specs += conv_specs(f'feats.{g}.conv_cat', 4 * f, f, 1)
-        out_ch = num_in_ch  # 'ps' models emit as many channels as they take (spanplus/arch.py:170)
-        specs += conv_specs('upsampler.0', f, out_ch * upscale * upscale, 3)
+        if upsampler == 'ps':
+            out_ch = num_in_ch  # 'ps' models emit as many channels as they take (spanplus/arch.py:172)
+            specs += conv_specs('upsampler.0', f, out_ch * upscale * upscale, 3)
+        else:
+            out_ch = num_out_ch
+            specs += dysample_specs('upsampler', f, out_ch, upscale)  # DySample(feature_channels, out_channels, upscale) (spanplus/arch.py:186)
         super().__init__(specs, num_in_ch, out_ch, upscale, seed=seed)
         self.blocks: List[int] = blocks
         self.feature_channels = f
+        self.upsampler_kind = upsampler
         if f % 8 != 0:
             raise ValueError('feature_channels must be a multiple of 8 for the planar-8 activation layout')
 
     @property
     def receptive_radius(self) -> int:
+        if self.upsampler_kind != 'ps':
+            raise NotImplementedError('DySample samples at learned, data-dependent offsets: no exact halo exists')
         # stem (1) + per group: (n + 2) SPABs x 3 convs + conv_2 (1); + upsampler conv (1)
         return 1 + sum(3 * (n + 2) + 1 for n in self.blocks) + 1
 
@@ -77,7 +83,10 @@ class SpanPlus(EngineModule):
             pb.conv(end_out, tail, *merge_conv3xc(w, f'{pre}.conv_2'))  # Dropout2d is the identity in eval
             dst = cats[g].slice(0, f) if g < len(self.blocks) else t1
             pb.conv(cat, dst, w[f'{pre}.conv_cat.weight'], w[f'{pre}.conv_cat.bias'])
-        pb.conv(t1, OUTPUT, w['upsampler.0.weight'], w['upsampler.0.bias'], ps=self.upscale)
+        if self.upsampler_kind == 'ps':
+            pb.conv(t1, OUTPUT, w['upsampler.0.weight'], w['upsampler.0.bias'], ps=self.upscale)
+        else:
+            emit_dysample(pb, w, 'upsampler', t1, self.out_channels, self.upscale)
 
 
 class SpanPlusArch(Architecture[SpanPlus]):

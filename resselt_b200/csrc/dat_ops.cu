@@ -1030,6 +1030,66 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ DySample head
+// One thread per OUTPUT pixel: for each group, the learned offset of this sub-pixel gives one sampling position in the
+// low-res feature map (border-clamped bilinear, exactly grid_sample(align_corners=False, padding_mode='border') after the
+// reference's normalise / un-normalise round trip cancels: position = (w + off_x, h + off_y)); the group's channels are
+// gathered as 16-byte plane chunks at the four neighbours, blended, and fed straight into the 1x1 end_conv, so the sampled
+// high-res feature map (C channels at s^2 times the pixels) is never materialised — only out_ch values per pixel are written.
+constexpr int kDyMaxOut = 4, kDyMaxC = 256, kDyMaxOff = 256;
+template <typename T>
+__global__ void __launch_bounds__(256) dysample_kernel(const __grid_constant__ DySampleParams p) {
+  __shared__ float w_sm[kDyMaxOut * kDyMaxC];
+  __shared__ float ip_sm[kDyMaxOff];
+  const int C = p.channels, G = p.groups, s = p.s, s2 = s * s, cg = C / G;
+  for (int e = threadIdx.x; e < p.out_ch * C; e += blockDim.x) w_sm[e] = p.weight[e];
+  for (int e = threadIdx.x; e < 2 * G * s2; e += blockDim.x) ip_sm[e] = p.init_pos[e];
+  __syncthreads();
+  const int OH = p.H * s, OW = p.W * s;
+  const size_t total = (size_t)p.n * OH * OW;
+  const size_t hw = (size_t)p.H * p.W;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % OW), Y = (int)((idx / OW) % OH), n = (int)(idx / ((size_t)OW * OH));
+    const int w = X / s, j = X - w * s, h = Y / s, i = Y - h * s;
+    const T* src = reinterpret_cast<const T*>(p.src) + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8;
+    const T* off = reinterpret_cast<const T*>(p.off) + ((size_t)n * p.off_planes + p.off_plane0) * hw * 8 + ((size_t)h * p.W + w) * 8;
+    float acc[kDyMaxOut];
+#pragma unroll
+    for (int o = 0; o < kDyMaxOut; ++o) acc[o] = o < p.out_ch ? p.bias[o] : 0.0f;
+    for (int g = 0; g < G; ++g) {
+      const int cx = g * s2 + i * s + j, cy = (G + g) * s2 + i * s + j;
+      const float ox = (float)off[(size_t)(cx >> 3) * hw * 8 + (cx & 7)] + ip_sm[cx];
+      const float oy = (float)off[(size_t)(cy >> 3) * hw * 8 + (cy & 7)] + ip_sm[cy];
+      const float px = fminf(fmaxf((float)w + ox, 0.0f), (float)(p.W - 1));
+      const float py = fminf(fmaxf((float)h + oy, 0.0f), (float)(p.H - 1));
+      const int x0 = (int)floorf(px), y0 = (int)floorf(py);
+      const int x1 = min(x0 + 1, p.W - 1), y1 = min(y0 + 1, p.H - 1);
+      const float fx = px - (float)x0, fy = py - (float)y0;
+      const float w00 = (1.0f - fx) * (1.0f - fy), w01 = fx * (1.0f - fy), w10 = (1.0f - fx) * fy, w11 = fx * fy;
+      const size_t o00 = ((size_t)y0 * p.W + x0) * 8, o01 = ((size_t)y0 * p.W + x1) * 8, o10 = ((size_t)y1 * p.W + x0) * 8, o11 = ((size_t)y1 * p.W + x1) * 8;
+      const int c_lo = g * cg, c_hi = c_lo + cg;
+      for (int pl = c_lo >> 3; pl <= (c_hi - 1) >> 3; ++pl) {
+        const T* base = src + (size_t)pl * hw * 8;
+        float a[8], b[8], c[8], d[8];
+        load8<T>(base + o00, a);
+        load8<T>(base + o01, b);
+        load8<T>(base + o10, c);
+        load8<T>(base + o11, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int ch = pl * 8 + k;
+          if (ch < c_lo || ch >= c_hi) continue;
+          const float v = fmaf(w00, a[k], fmaf(w01, b[k], fmaf(w10, c[k], w11 * d[k])));
+#pragma unroll
+          for (int o = 0; o < kDyMaxOut; ++o)
+            if (o < p.out_ch) acc[o] = fmaf(w_sm[o * C + ch], v, acc[o]);
+        }
+      }
+    }
+    for (int o = 0; o < p.out_ch; ++o) st_any(p.dst, p.dst_dtype, (((size_t)n * p.out_ch + o) * OH + Y) * OW + X, acc[o]);
+  }
+}
+
 inline int grid_for(size_t total, int threads = 256, int cap = 148 * 32) {
   return (int)std::max<size_t>(1, std::min<size_t>((total + threads - 1) / threads, (size_t)cap));
 }
@@ -1139,6 +1199,15 @@ cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s) {
     aim_combine_kernel<__nv_bfloat16><<<g3, 256, smem, s>>>(p);
   else
     aim_combine_kernel<float><<<g3, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dysample(const DySampleParams& p, bool bf16, cudaStream_t s) {
+  const int g = grid_for((size_t)p.n * p.H * p.s * p.W * p.s, 256, 148 * 64);
+  if (bf16)
+    dysample_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    dysample_kernel<float><<<g, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 

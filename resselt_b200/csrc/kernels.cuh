@@ -578,6 +578,20 @@ struct AimParams {
   float* cmap;     // [n][cpad]
 };
 
+struct DySampleParams {
+  int n, H, W, channels, groups, s, out_ch;  // H x W: the low-res grid; output is (H*s) x (W*s)
+  const void* src;  // features
+  int src_planes, src_plane0;
+  const void* off;  // 0.5 * offset * sigmoid(scope): 2 * groups * s^2 channels
+  int off_planes, off_plane0;
+  void* dst;  // caller's NCHW output
+  int dst_dtype;
+  const float* init_pos;  // [2 * groups * s^2]
+  const float* weight;    // end_conv [out_ch][channels]
+  const float* bias;      // [out_ch]
+};
+
+cudaError_t launch_dysample(const DySampleParams& p, bool bf16, cudaStream_t s);
 cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s);
 cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s);
 size_t winattn_smem_bytes(int split_h, int split_w);

@@ -118,6 +118,7 @@ struct AuxOp {
   rsb::WinAttnParams win;
   rsb::ChanAttnParams chan;
   rsb::AimParams aim;
+  rsb::DySampleParams dys;
 };
 
 struct Op {
@@ -527,6 +528,16 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     const rsb_op_desc& d = a.d;
     const int H = h * a.scale, W = w * a.scale;
     const Buffer& sb = p->bufs[d.src_buf];
+    if (d.kind == RSB_OP_DYSAMPLE) {
+      rsb::DySampleParams& t = a.dys;
+      memset(&t, 0, sizeof t);
+      const Buffer& ob = p->bufs[d.src2_buf];
+      t.n = n, t.H = H, t.W = W, t.channels = d.channels, t.groups = d.i[0], t.s = d.i[1], t.out_ch = d.i[2];
+      t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_plane0 = d.src_ch_off / 8;
+      t.off = ws + ob.offset, t.off_planes = ob.planes, t.off_plane0 = d.src2_ch_off / 8;
+      t.init_pos = a.dw[0], t.weight = a.dw[1], t.bias = a.dw[2];
+      continue;
+    }
     const Buffer& db = p->bufs[d.dst_buf];
     uint8_t* scratch = ws + aux_off;
     if (d.kind == RSB_OP_LAYERNORM || d.kind == RSB_OP_DWCONV3) {
@@ -756,8 +767,28 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
   if (!p || !desc) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: NULL argument");
   if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_op: plan already finalized");
   const rsb_op_desc& d = *desc;
-  if (d.kind < RSB_OP_LAYERNORM || d.kind > RSB_OP_AIM) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown kind %d", d.kind);
+  if (d.kind < RSB_OP_LAYERNORM || d.kind > RSB_OP_DYSAMPLE) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown kind %d", d.kind);
   if (d.channels < 1) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: bad channel count");
+  if (d.kind == RSB_OP_DYSAMPLE) {
+    const int g = d.i[0], s = d.i[1], oc = d.i[2];
+    if (d.dst_buf != RSB_EXTERNAL_OUTPUT) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: DySample writes the external output (end_conv fused)");
+    if (g < 1 || s < 1 || d.channels % g != 0 || d.channels > 256 || 2 * g * s * s > 256 || oc < 1 || oc > 4 || oc != p->out_ch)
+      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: DySample needs channels %% groups == 0, channels <= 256, 2*groups*s^2 <= 256, out channels <= 4");
+    if (int e = check_buf(p, d.src_buf, d.src_ch_off, d.channels, "rsb_plan_add_op(DySample src)")) return e;
+    if (int e = check_buf(p, d.src2_buf, d.src2_ch_off, 2 * g * s * s, "rsb_plan_add_op(DySample offsets)")) return e;
+    if (p->bufs[d.src_buf].scale != p->bufs[d.src2_buf].scale || p->bufs[d.src_buf].scale * s != p->upscale)
+      return fail(RSB_ERR_INVALID, "rsb_plan_add_op: DySample grid mismatch (buffer scale %d x %d != upscale %d)", p->bufs[d.src_buf].scale, s, p->upscale);
+    if (!d.w[0] || d.wn[0] != 2 * g * s * s || !d.w[1] || d.wn[1] != (int64_t)oc * d.channels || !d.w[2] || d.wn[2] != oc)
+      return fail(RSB_ERR_INVALID, "rsb_plan_add_op: DySample needs init_pos [2*groups*s^2], end_conv weight [out][C] and bias [out]");
+    AuxOp a;
+    a.d = d;
+    for (int k = 0; k < 3; ++k) a.w[k].assign(d.w[k], d.w[k] + d.wn[k]);
+    for (int k = 0; k < 8; ++k) a.d.w[k] = nullptr;
+    a.scale = p->bufs[d.src_buf].scale;
+    p->auxs.push_back(std::move(a));
+    p->ops.push_back({2, (int)p->auxs.size() - 1});
+    return 0;
+  }
   const bool qkv = d.kind == RSB_OP_WINATTN || d.kind == RSB_OP_CHANATTN;
   if (d.src_buf < 0 || d.src_buf >= (int)p->bufs.size() || d.dst_buf < 0 || d.dst_buf >= (int)p->bufs.size())
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown buffer");
@@ -1089,6 +1120,12 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           case RSB_OP_DWCONV3: e = rsb::launch_dwconv3(a.tok, bf, stream); break;
           case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, stream); break;
           case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, stream); break;
+          case RSB_OP_DYSAMPLE: {
+            rsb::DySampleParams q = a.dys;
+            q.dst = y, q.dst_dtype = y_dtype;
+            e = rsb::launch_dysample(q, bf, stream);
+            break;
+          }
           default: e = rsb::launch_aim(a.aim, bf, stream); break;
         }
       }

@@ -39,6 +39,10 @@ def test_metadata_field_order():
         (SPAN(num_in_ch=1, num_out_ch=1, feature_channels=56, upscale=2, norm=False), ('SPAN', 1, 1, 2)),
         (SpanPlus(blocks=[4], upscale=2), ('SPANPlus', 3, 3, 2)),
         (SpanPlus(blocks=[2, 3], feature_channels=32, upscale=4), ('SPANPlus', 3, 3, 4)),
+        (SpanPlus(blocks=[2], upscale=2, upsampler='dys'), ('SPANPlus', 3, 3, 2)),
+        (SpanPlus(blocks=[1], feature_channels=32, upscale=4, upsampler='dys'), ('SPANPlus', 3, 3, 4)),
+        (RealPLKSR(n_blocks=1, upscaling_factor=4, dysample=True), ('RealPLKSR', 3, 3, 4)),
+        (RealPLKSR(dim=32, n_blocks=1, upscaling_factor=3, kernel_size=13, dysample=True), ('RealPLKSR', 3, 3, 3)),
         (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4), ('Compact', 3, 3, 4)),
         (SRVGGNetCompact(num_feat=24, num_conv=8, upscale=2), ('Compact', 3, 3, 2)),
         (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=1), ('Compact', 3, 3, 1)),
@@ -74,14 +78,15 @@ def test_detect_and_hyperparameter_inference(model, meta):
     for k, v in loaded.state_dict().items():
         assert torch.equal(v, sd[k])
     if isinstance(model, SpanPlus):
-        assert loaded.blocks == model.blocks
+        assert loaded.blocks == model.blocks and loaded.upsampler_kind == model.upsampler_kind
     if isinstance(model, SPAN):
         assert loaded.norm == model.norm
     if isinstance(model, RRDBNet):
         assert (loaded.num_blocks, loaded.plus, loaded.shuffle_factor, loaded._keys.style) == (
             model.num_blocks, model.plus, model.shuffle_factor, model._keys.style)
     if isinstance(model, RealPLKSR):
-        assert (loaded.dim, loaded.n_blocks, loaded.kernel_size, loaded.use_ea) == (model.dim, model.n_blocks, model.kernel_size, model.use_ea)
+        assert (loaded.dim, loaded.n_blocks, loaded.kernel_size, loaded.use_ea, loaded.dysample) == (
+            model.dim, model.n_blocks, model.kernel_size, model.use_ea, model.dysample)
     if isinstance(model, PLKSR):
         assert (loaded.dim, loaded.n_blocks, loaded.ccm_type, loaded.lk_type, loaded.kernel_size, loaded.kmax, loaded.use_ea) == (
             model.dim, model.n_blocks, model.ccm_type, model.lk_type, model.kernel_size, model.kmax, model.use_ea)
@@ -171,10 +176,17 @@ def test_state_dict_helpers():
     assert pixelshuffle_scale(48, 3) == 4 and pixelshuffle_scale(12, 3) == 2
 
 
-def test_spanplus_dysample_checkpoint_is_refused_explicitly():
-    sd = _sd(SpanPlus(blocks=[1], feature_channels=16, upscale=2))
-    del sd['upsampler.0.weight'], sd['upsampler.0.bias']
-    sd['upsampler.end_conv.weight'] = torch.zeros(3, 16, 1, 1)
-    sd['upsampler.offset.weight'] = torch.zeros(32, 16, 1, 1)
+def test_unsupported_heads_are_refused_explicitly():
+    # what the engine does not run must fail loudly at load time, never fall back: SPANPlus 'conv' (1x) head is not loadable by the
+    # reference either (spanplus/__init__.py:20-27); RealPLKSR 1x DySample has no end convolution (rplksr.py:139)
     with pytest.raises(NotImplementedError):
+        SpanPlus(blocks=[1], feature_channels=16, upscale=1, upsampler='conv')
+    with pytest.raises(NotImplementedError):
+        RealPLKSR(n_blocks=1, upscaling_factor=1, dysample=True)
+
+
+def test_dysample_checkpoint_with_incomplete_keys_fails_strict_load():
+    sd = _sd(SpanPlus(blocks=[1], feature_channels=16, upscale=2, upsampler='dys'))
+    del sd['upsampler.scope.weight']
+    with pytest.raises(RuntimeError):
         resselt_b200.load_from_state_dict(sd)

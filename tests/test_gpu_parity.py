@@ -51,6 +51,10 @@ def test_golden_fixtures_fp32_and_bf16(name):
         ('SPAN', SPAN(feature_channels=48, upscale=2, seed=21), (1, 3, 67, 93)),
         ('SPAN', SPAN(feature_channels=48, upscale=4, seed=22), (2, 3, 33, 40)),
         ('SPANPlus', SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=23), (1, 3, 70, 50)),
+        ('SPANPlus', SpanPlus(blocks=[4], feature_channels=48, upscale=2, upsampler='dys', seed=43), (1, 3, 70, 50)),   # DySample head (default upsampler)
+        ('SPANPlus', SpanPlus(blocks=[2], feature_channels=48, upscale=4, upsampler='dys', seed=44), (2, 3, 33, 47)),
+        ('RealPLKSR', RealPLKSR(n_blocks=4, upscaling_factor=4, dysample=True, seed=45), (1, 3, 48, 56)),
+        ('RealPLKSR', RealPLKSR(dim=32, n_blocks=2, upscaling_factor=3, kernel_size=13, dysample=True, seed=46), (2, 3, 21, 30)),  # odd factor: groups = 3
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=24), (3, 3, 45, 61)),
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=1, seed=25), (1, 3, 40, 40)),
         ('ESRGAN', RRDBNet(num_blocks=23, scale=4, seed=26), (1, 3, 48, 40)),           # full depth: 69 dense blocks
