@@ -17,8 +17,8 @@
  *                            SPAB gate span/arch.py:176-177; residual adds utilities/block.py:344,465;
  *                            PixelShuffle span/arch.py:55, compact/arch.py:54-64, rplksr.py:143-147).
  *   rsb_plan_add_groupnorm <- nn.GroupNorm + skip (resselt/archs/plksr/rplksr.py:83,91-93)
- *   rsb_plan_add_op      <- LayerNorm / depthwise conv / window + channel attention / AIM call sites of DAT and SwinIR
- *                           (listed at rsb_op_kind below)
+ *   rsb_plan_add_op      <- LayerNorm / depthwise conv / window + channel attention / AIM call sites of DAT and SwinIR, and the
+ *                           DySample head of SPANPlus / RealPLKSR (resselt/utilities/dysample.py:46-83) (listed at rsb_op_kind below)
  *   rsb_plan_forward     <- <Module>.forward (span/arch.py:231-250, spanplus/arch.py:199-201,
  *                           compact/arch.py:56-65, esrgan/arch.py:129-138, plksr/rplksr.py:145-147,
  *                           dat/arch.py:970-990, swinir/arch.py:962-1011)

@@ -23,6 +23,8 @@ model = {'span': lambda: SPAN(feature_channels=48, upscale=2, seed=3),
          'dat': lambda: DAT(upscale=4, seed=9),
          'swinir': lambda: SwinIR(upscale=4, seed=10),
          'swinir1': lambda: SwinIR(upscale=4, depths=[2], num_heads=[6], seed=10),
+         'spanplus_dys': lambda: SpanPlus(blocks=[4], feature_channels=48, upscale=2, upsampler='dys', seed=4),
+         'plksr_dys': lambda: RealPLKSR(n_blocks=28, upscaling_factor=4, dysample=True, seed=8),
          'plksr1': lambda: RealPLKSR(n_blocks=1, upscaling_factor=4, seed=8),
          'dat1': lambda: DAT(upscale=4, depth=[4], num_heads=[6], seed=9)}[arch]().eval().to(dev).bfloat16()
 x = torch.rand(batch, 3, h, w, device=dev).bfloat16()
