@@ -158,7 +158,9 @@ enum rsb_op_kind {
   RSB_OP_DYSAMPLE = 6   /* DySample head (resselt/utilities/dysample.py:46-83) with its 1x1 end_conv fused, written to the caller's
                            NCHW output: src = features [C] on the low-res grid, src2 = 0.5 * offset(x) * sigmoid(scope(x))
                            [2 * groups * s^2 channels, produced by two 1x1 conv ops], dst_buf = RSB_EXTERNAL_OUTPUT;
-                           i[0] groups, i[1] s (up-sampling factor of this head), i[2] out channels;
+                           i[0] groups, i[1] s (up-sampling factor of this head), i[2] out channels, i[3] != 0: src already
+                           holds the per-group end_conv projections z[g*4 + o] = sum_{c in group g} W[o][c] x[c] (4 channels
+                           per group, produced by a 1x1 conv op; sampling and end_conv commute) and w[1] is ignored;
                            w[0] = init_pos [2 * groups * s^2], w[1] = end_conv weight [out][C], w[2] = end_conv bias [out].
                            Sampling position of output pixel (h*s+i, w*s+j), group g: (w + off_x, h + off_y) in input pixels,
                            clamped to the image (grid_sample bilinear, align_corners=False, padding_mode='border')            */

@@ -79,5 +79,15 @@ def emit_dysample(pb, w: Dict[str, torch.Tensor], prefix: str, x, out_ch: int, s
     gate, off = pb.buffer(k, scale=pb.scales[x.buf]), pb.buffer(k, scale=pb.scales[x.buf])
     pb.conv(x, gate, w[f'{prefix}.scope.weight'], None, act=N.ACT_SIGMOID)
     pb.conv(x, off, 0.5 * w[f'{prefix}.offset.weight'], 0.5 * w[f'{prefix}.offset.bias'], combine=N.COMB_MUL, res1=gate)
-    pb.op(N.OP_DYSAMPLE, x, OUTPUT, x.channels, src2=off, ints=(groups, scale, out_ch),
-          weights=(w[f'{prefix}.init_pos'], w[f'{prefix}.end_conv.weight'], w[f'{prefix}.end_conv.bias']))
+    # sampling (bilinear, per group) and the 1x1 end_conv are both linear and commute: project every group through its slice of
+    # end_conv on the low-res grid first (4 channels per group, out_ch of them used), then gather 4 values per neighbour instead
+    # of the group's feature channels
+    end_w = w[f'{prefix}.end_conv.weight'].reshape(out_ch, x.channels)
+    cg = x.channels // groups
+    zw = torch.zeros(4 * groups, x.channels, 1, 1, dtype=end_w.dtype)
+    for g in range(groups):
+        zw[4 * g:4 * g + out_ch, g * cg:(g + 1) * cg, 0, 0] = end_w[:, g * cg:(g + 1) * cg]
+    z = pb.buffer(4 * groups, scale=pb.scales[x.buf])
+    pb.conv(x, z, zw, None)
+    pb.op(N.OP_DYSAMPLE, z, OUTPUT, 4 * groups, src2=off, ints=(groups, scale, out_ch, 1),
+          weights=(w[f'{prefix}.init_pos'], end_w, w[f'{prefix}.end_conv.bias']))

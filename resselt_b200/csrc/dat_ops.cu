@@ -1036,7 +1036,7 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
 // reference's normalise / un-normalise round trip cancels: position = (w + off_x, h + off_y)); the group's channels are
 // gathered as 16-byte plane chunks at the four neighbours, blended, and fed straight into the 1x1 end_conv, so the sampled
 // high-res feature map (C channels at s^2 times the pixels) is never materialised — only out_ch values per pixel are written.
-constexpr int kDyMaxOut = 4, kDyMaxC = 256, kDyMaxOff = 256;
+constexpr int kDyMaxOut = 4, kDyMaxC = 256, kDyMaxOff = 256, kDyMaxGroups = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) dysample_kernel(const __grid_constant__ DySampleParams p) {
   __shared__ float w_sm[kDyMaxOut * kDyMaxC];
@@ -1088,6 +1088,119 @@ __global__ void __launch_bounds__(256) dysample_kernel(const __grid_constant__ D
     }
     for (int o = 0; o < p.out_ch; ++o) st_any(p.dst, p.dst_dtype, (((size_t)n * p.out_ch + o) * OH + Y) * OW + X, acc[o]);
   }
+}
+
+// Lean version for groups of <= 32 channels (every released model: 12 or 9): ncu showed the kernel above issue-bound (83 % of
+// the issue slots, 2 200 instructions per output pixel) on 64-bit index divisions and per-channel group-membership predicates.
+// Here the grid is (x blocks, output row, image) — no divisions by the image width — and the end_conv weights are pre-masked
+// per (group, plane of the group's span) in shared memory, zero outside the group, so the inner loop is branch-free:
+// 4 chunk loads, 8 blends, 8 x 4 FMAs per plane.
+constexpr int kDySpan = 5;  // planes a group of <= 32 channels can straddle
+template <typename T>
+__global__ void __launch_bounds__(256) dysample_lean_kernel(const __grid_constant__ DySampleParams p) {
+  __shared__ __align__(16) float wm[kDyMaxGroups * kDySpan * 8 * 4];
+  __shared__ float ip_sm[kDyMaxOff];
+  const int C = p.channels, G = p.groups, s = p.s, s2 = s * s, cg = C / G;
+  for (int e = threadIdx.x; e < G * kDySpan * 8 * 4; e += blockDim.x) {
+    const int o = e & 3, k = (e >> 2) & 7, q = (e >> 5) % kDySpan, g = (e >> 5) / kDySpan;
+    const int ch = (((g * cg) >> 3) + q) * 8 + k;
+    wm[e] = (ch >= g * cg && ch < (g + 1) * cg && o < p.out_ch) ? p.weight[o * C + ch] : 0.0f;
+  }
+  for (int e = threadIdx.x; e < 2 * G * s2; e += blockDim.x) ip_sm[e] = p.init_pos[e];
+  __syncthreads();
+  const int OW = p.W * s, OH = p.H * s;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y, n = blockIdx.z;
+  if (X >= OW) return;
+  const int h = Y / s, i = Y - h * s, w = X / s, j = X - w * s;
+  const size_t hw = (size_t)p.H * p.W;
+  const T* src = reinterpret_cast<const T*>(p.src) + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8;
+  const T* off = reinterpret_cast<const T*>(p.off) + ((size_t)n * p.off_planes + p.off_plane0) * hw * 8 + ((size_t)h * p.W + w) * 8;
+  float acc[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = o < p.out_ch ? p.bias[o] : 0.0f;
+  for (int g = 0; g < G; ++g) {
+    const int cx = g * s2 + i * s + j, cy = (G + g) * s2 + i * s + j;
+    const float ox = (float)off[(size_t)(cx >> 3) * hw * 8 + (cx & 7)] + ip_sm[cx];
+    const float oy = (float)off[(size_t)(cy >> 3) * hw * 8 + (cy & 7)] + ip_sm[cy];
+    const float px = fminf(fmaxf((float)w + ox, 0.0f), (float)(p.W - 1));
+    const float py = fminf(fmaxf((float)h + oy, 0.0f), (float)(p.H - 1));
+    const int x0 = (int)px, y0 = (int)py;  // px, py >= 0: truncation == floor
+    const int x1 = min(x0 + 1, p.W - 1), y1 = min(y0 + 1, p.H - 1);
+    const float fx = px - (float)x0, fy = py - (float)y0;
+    const float w00 = (1.0f - fx) * (1.0f - fy), w01 = fx * (1.0f - fy), w10 = (1.0f - fx) * fy, w11 = fx * fy;
+    const size_t o00 = ((size_t)y0 * p.W + x0) * 8, o01 = ((size_t)y0 * p.W + x1) * 8, o10 = ((size_t)y1 * p.W + x0) * 8, o11 = ((size_t)y1 * p.W + x1) * 8;
+    const int pl0 = (g * cg) >> 3, span = (((g + 1) * cg - 1) >> 3) - pl0 + 1;
+    for (int q = 0; q < span; ++q) {
+      const T* bp = src + (size_t)(pl0 + q) * hw * 8;
+      float a[8], b[8], c[8], d[8];
+      load8<T>(bp + o00, a);
+      load8<T>(bp + o01, b);
+      load8<T>(bp + o10, c);
+      load8<T>(bp + o11, d);
+      const float4* wq = reinterpret_cast<const float4*>(wm) + (g * kDySpan + q) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float v = fmaf(w00, a[k], fmaf(w01, b[k], fmaf(w10, c[k], w11 * d[k])));
+        const float4 ww = wq[k];
+        acc[0] = fmaf(ww.x, v, acc[0]);
+        acc[1] = fmaf(ww.y, v, acc[1]);
+        acc[2] = fmaf(ww.z, v, acc[2]);
+        acc[3] = fmaf(ww.w, v, acc[3]);
+      }
+    }
+  }
+  for (int o = 0; o < p.out_ch; ++o) st_any(p.dst, p.dst_dtype, (((size_t)n * p.out_ch + o) * OH + Y) * OW + X, acc[o]);
+}
+
+// Pre-projected form (DySampleParams::projected): sampling and the 1x1 end_conv are both linear, so the end_conv is applied
+// FIRST, per group, on the low-res grid by an ordinary tensor-core 1x1 conv op: z[g*4 + o] = sum_{c in group g} W[o][c] x[c]
+// (4 channels per group, out_ch of them used).  The head then gathers 4 values per (group, neighbour) — one 8-byte load in
+// bf16 — instead of the group's 12-16 feature channels: a quarter of the loads, conversions and FMAs of the kernels above.
+// out[o](Y, X) = bias[o] + sum_g bilinear_g(z[g*4 + o]).
+template <typename T>
+__global__ void __launch_bounds__(256) dysample_proj_kernel(const __grid_constant__ DySampleParams p) {
+  __shared__ float ip_sm[kDyMaxOff];
+  const int G = p.groups, s = p.s, s2 = s * s;
+  for (int e = threadIdx.x; e < 2 * G * s2; e += blockDim.x) ip_sm[e] = p.init_pos[e];
+  __syncthreads();
+  const int OW = p.W * s, OH = p.H * s;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y, n = blockIdx.z;
+  if (X >= OW) return;
+  const int h = Y / s, i = Y - h * s, w = X / s, j = X - w * s;
+  const size_t hw = (size_t)p.H * p.W;
+  const T* src = reinterpret_cast<const T*>(p.src) + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8;
+  const T* off = reinterpret_cast<const T*>(p.off) + ((size_t)n * p.off_planes + p.off_plane0) * hw * 8 + ((size_t)h * p.W + w) * 8;
+  float acc[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = o < p.out_ch ? p.bias[o] : 0.0f;
+  for (int g = 0; g < G; ++g) {
+    const int cx = g * s2 + i * s + j, cy = (G + g) * s2 + i * s + j;
+    const float ox = (float)off[(size_t)(cx >> 3) * hw * 8 + (cx & 7)] + ip_sm[cx];
+    const float oy = (float)off[(size_t)(cy >> 3) * hw * 8 + (cy & 7)] + ip_sm[cy];
+    const float px = fminf(fmaxf((float)w + ox, 0.0f), (float)(p.W - 1));
+    const float py = fminf(fmaxf((float)h + oy, 0.0f), (float)(p.H - 1));
+    const int x0 = (int)px, y0 = (int)py;  // px, py >= 0: truncation == floor
+    const int x1 = min(x0 + 1, p.W - 1), y1 = min(y0 + 1, p.H - 1);
+    const float fx = px - (float)x0, fy = py - (float)y0;
+    const float wt[4] = {(1.0f - fx) * (1.0f - fy), fx * (1.0f - fy), (1.0f - fx) * fy, fx * fy};
+    const size_t nb[4] = {((size_t)y0 * p.W + x0) * 8, ((size_t)y0 * p.W + x1) * 8, ((size_t)y1 * p.W + x0) * 8, ((size_t)y1 * p.W + x1) * 8};
+    const T* bp = src + (size_t)(g >> 1) * hw * 8 + (g & 1) * 4;  // two groups of 4 channels per 8-channel plane
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float v[4];
+      if constexpr (sizeof(T) == 2) {
+        const uint2 r = *reinterpret_cast<const uint2*>(bp + nb[t]);
+        v[0] = __uint_as_float(r.x << 16), v[1] = __uint_as_float(r.x & 0xFFFF0000u);
+        v[2] = __uint_as_float(r.y << 16), v[3] = __uint_as_float(r.y & 0xFFFF0000u);
+      } else {
+        const float4 r = *reinterpret_cast<const float4*>(bp + nb[t]);
+        v[0] = r.x, v[1] = r.y, v[2] = r.z, v[3] = r.w;
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = fmaf(wt[t], v[o], acc[o]);
+    }
+  }
+  for (int o = 0; o < p.out_ch; ++o) st_any(p.dst, p.dst_dtype, (((size_t)n * p.out_ch + o) * OH + Y) * OW + X, acc[o]);
 }
 
 inline int grid_for(size_t total, int threads = 256, int cap = 148 * 32) {
@@ -1204,7 +1317,19 @@ cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s) {
 
 cudaError_t launch_dysample(const DySampleParams& p, bool bf16, cudaStream_t s) {
   const int g = grid_for((size_t)p.n * p.H * p.s * p.W * p.s, 256, 148 * 64);
-  if (bf16)
+  static const bool generic = getenv("RSB_DYS_GENERIC") != nullptr;  // bring-up: the straightforward kernel
+  const bool lean = !generic && p.groups <= kDyMaxGroups && p.channels / p.groups <= 32 && p.H * p.s <= 65535 && p.n <= 65535;
+  const dim3 gl((unsigned)((p.W * p.s + 255) / 256), (unsigned)(p.H * p.s), (unsigned)p.n);
+  if (p.projected) {
+    if (bf16)
+      dysample_proj_kernel<__nv_bfloat16><<<gl, 256, 0, s>>>(p);
+    else
+      dysample_proj_kernel<float><<<gl, 256, 0, s>>>(p);
+  } else if (bf16 && lean)
+    dysample_lean_kernel<__nv_bfloat16><<<gl, 256, 0, s>>>(p);
+  else if (lean)
+    dysample_lean_kernel<float><<<gl, 256, 0, s>>>(p);
+  else if (bf16)
     dysample_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
   else
     dysample_kernel<float><<<g, 256, 0, s>>>(p);

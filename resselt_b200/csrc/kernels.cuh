@@ -580,6 +580,7 @@ struct AimParams {
 
 struct DySampleParams {
   int n, H, W, channels, groups, s, out_ch;  // H x W: the low-res grid; output is (H*s) x (W*s)
+  int projected;    // 1: src holds the per-group end_conv projections (4 channels per group), see dysample_proj_kernel
   const void* src;  // features
   int src_planes, src_plane0;
   const void* off;  // 0.5 * offset * sigmoid(scope): 2 * groups * s^2 channels
