@@ -62,6 +62,8 @@ def cases():
                                                norm_groups=4, dysample=True), 33, (1, 3, 20, 24), 123),
         'realplksr_x3_dys': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=1, upscaling_factor=3, kernel_size=13, split_ratio=0.25, use_ea=True,
                                                norm_groups=4, dysample=True), 34, (2, 3, 15, 13), 124),
+        'dat_light_x3_psd_3conv': ('DAT', dict(img_size=32, in_chans=3, embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], expansion_factor=2.0,
+                                               upscale=3, upsampler='pixelshuffledirect', resi_connection='3conv'), 35, (1, 3, 21, 30), 125),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
     }

@@ -391,7 +391,7 @@ def _dat_sgfn(sd: SD, p: str, x, H, W):
 
 
 def dat_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, img_range: float = 1.0) -> torch.Tensor:
-    """DAT.forward, 'pixelshuffle' head and '1conv' residual connection (/root/reference/resselt/archs/dat/arch.py:970-990,
+    """DAT.forward, both heads ('pixelshuffle', 'pixelshuffledirect') and both residual connections ('1conv', '3conv') (/root/reference/resselt/archs/dat/arch.py:970-990,
     forward_features :959-968, ResidualGroup.forward :763-780, DATB.forward :674-683).  Which blocks shift follows
     :335 / :456: (rg even and b in {2, 6, ..}) or (rg odd and b % 4 == 0)."""
     x = x.to(dtype)
@@ -415,9 +415,12 @@ def dat_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, img_range: float =
                 t = t + _dat_channel_block(sd, f'{p}.attn', n1, H, W, sd[f'{p}.attn.temperature'].shape[0])
             t = t + _dat_sgfn(sd, f'{p}.ffn', _ln(sd, f'{p}.norm2', t), H, W)
         img = t.transpose(1, 2).reshape(B, -1, H, W)
-        t = res + _conv(sd, f'layers.{rg}.conv', img, 1).flatten(2).transpose(1, 2)
+        t = res + _swin_resi_conv(sd, f'layers.{rg}.conv', img).flatten(2).transpose(1, 2)  # '1conv' or '3conv' (:750-759)
     t = _ln(sd, 'norm', t).transpose(1, 2).reshape(B, -1, H, W)
-    t = _conv(sd, 'conv_after_body', t, 1) + feat
+    t = _swin_resi_conv(sd, 'conv_after_body', t) + feat
+    if 'conv_last.weight' not in sd:  # 'pixelshuffledirect' head: UpsampleOneStep (:804-825, forward :981-984)
+        r = math.isqrt(sd['upsample.0.weight'].shape[0] // in_ch)
+        return F.pixel_shuffle(_conv(sd, 'upsample.0', t, 1), r) / img_range + mean
     t = F.leaky_relu(_conv(sd, 'conv_before_upsample.0', t, 1), 0.01)
     for i in range(0, _seq_len(sd, 'upsample'), 2):
         t = F.pixel_shuffle(_conv(sd, f'upsample.{i}', t, 1), 2)

@@ -91,3 +91,27 @@ def emit_dysample(pb, w: Dict[str, torch.Tensor], prefix: str, x, out_ch: int, s
     pb.conv(x, z, zw, None)
     pb.op(N.OP_DYSAMPLE, z, OUTPUT, 4 * groups, src2=off, ints=(groups, scale, out_ch, 1),
           weights=(w[f'{prefix}.init_pos'], end_w, w[f'{prefix}.end_conv.bias']))
+
+
+# ------------------------------------------------------------------------------------------------ '1conv' / '3conv' residual connections
+def resi_conv_specs(prefix: str, dim: int, resi_connection: str) -> List[ParamSpec]:
+    """The conv closing a residual group of SwinIR / DAT: one 3x3 ('1conv') or 3x3 -> lrelu(0.2) -> 1x1 -> lrelu(0.2) -> 3x3 through a
+    dim/4 bottleneck ('3conv') (/root/reference/resselt/archs/swinir/arch.py:564-574, dat/arch.py:750-759)."""
+    if resi_connection == '1conv':
+        return conv_specs(prefix, dim, dim, 3)
+    # random init only: the bottleneck attenuates the signal, a gain keeps the output range of seeded test models sane
+    return (conv_specs(f'{prefix}.0', dim, dim // 4, 3, gain=2.0) + conv_specs(f'{prefix}.2', dim // 4, dim // 4, 1, gain=2.0)
+            + conv_specs(f'{prefix}.4', dim // 4, dim, 3, gain=2.0))
+
+
+def emit_resi_conv(pb, w: Dict[str, torch.Tensor], name: str, resi_connection: str, src, dst, res, tmp_a, tmp_b) -> None:
+    """dst = conv(src) + res with conv = '1conv' or '3conv'; tmp_a / tmp_b: dim/4-channel scratch buffers for '3conv'."""
+    from ..engine import native as N
+
+    if resi_connection == '1conv':
+        pb.conv(src, dst, w[f'{name}.weight'], w[f'{name}.bias'], combine=N.COMB_AXPY, res1=res)
+        return
+    lrelu = dict(act=N.ACT_LRELU, act_param=0.2)
+    pb.conv(src, tmp_a, w[f'{name}.0.weight'], w[f'{name}.0.bias'], **lrelu)
+    pb.conv(tmp_a, tmp_b, w[f'{name}.2.weight'], w[f'{name}.2.bias'], **lrelu)
+    pb.conv(tmp_b, dst, w[f'{name}.4.weight'], w[f'{name}.4.bias'], combine=N.COMB_AXPY, res1=res)

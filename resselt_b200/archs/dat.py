@@ -1,4 +1,4 @@
-"""DAT (Dual Aggregation Transformer) on the B200 engine — 'pixelshuffle' head, '1conv' residual connection.
+"""DAT (Dual Aggregation Transformer) on the B200 engine — 'pixelshuffle' and 'pixelshuffledirect' heads, '1conv' / '3conv'.
 
 Reference: /root/reference/resselt/archs/dat/arch.py:828-990 (model), :615-683 (DATB), :270-513 (Adaptive_Spatial_Attention),
 :516-612 (Adaptive_Channel_Attention), :40-101 (SGFN / SpatialGate), :104-143 (DynamicPosBias), :686-780 (ResidualGroup),
@@ -24,7 +24,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import get_seq_len, pixelshuffle_scale
-from ._common import conv_specs
+from ._common import conv_specs, emit_resi_conv, resi_conv_specs
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)
 
@@ -98,10 +98,10 @@ class DAT(EngineModule):
         upsampler: str = 'pixelshuffle',
         seed: int = 0,
     ):
-        if resi_connection != '1conv' or upsampler != 'pixelshuffle':
-            raise NotImplementedError("only DAT with resi_connection='1conv' and upsampler='pixelshuffle' is supported (see DESIGN.md)")
-        if upscale & (upscale - 1):
-            raise NotImplementedError('only power-of-two upscale factors')
+        if resi_connection not in ('1conv', '3conv') or upsampler not in ('pixelshuffle', 'pixelshuffledirect'):
+            raise ValueError(f'unknown resi_connection {resi_connection!r} / upsampler {upsampler!r}')
+        if upsampler == 'pixelshuffle' and upscale & (upscale - 1):
+            raise NotImplementedError("DAT 'pixelshuffle' head: power-of-two upscale factors only")
         dim, hidden = embed_dim, int(embed_dim * expansion_factor)
         split = [int(split_size[0]), int(split_size[1])]
         specs = conv_specs('conv_first', in_chans, dim, 3) + _ln_specs('before_RG.1', dim)
@@ -137,13 +137,17 @@ class DAT(EngineModule):
                 specs += _lin_specs(f'{f}.fc1', dim, hidden) + _ln_specs(f'{f}.sg.norm', hidden // 2)
                 specs += [(f'{f}.sg.conv.weight', (hidden // 2, 1, 3, 3), 'conv_w'), (f'{f}.sg.conv.bias', (hidden // 2,), 'bias:9')]
                 specs += _lin_specs(f'{f}.fc2', hidden // 2, dim) + _ln_specs(f'{p}.norm2', dim)
-            specs += conv_specs(f'layers.{rg}.conv', dim, dim, 3)
-        specs += _ln_specs('norm', dim) + conv_specs('conv_after_body', dim, dim, 3)
-        specs += conv_specs('conv_before_upsample.0', dim, 64, 3)
-        for i in range(int(math.log2(upscale))):
-            specs += conv_specs(f'upsample.{2 * i}', 64, 256, 3)
-        specs += conv_specs('conv_last', 64, in_chans, 3)
+            specs += resi_conv_specs(f'layers.{rg}.conv', dim, resi_connection)
+        specs += _ln_specs('norm', dim) + resi_conv_specs('conv_after_body', dim, resi_connection)
+        if upsampler == 'pixelshuffle':
+            specs += conv_specs('conv_before_upsample.0', dim, 64, 3)
+            for i in range(int(math.log2(upscale))):
+                specs += conv_specs(f'upsample.{2 * i}', 64, 256, 3)
+            specs += conv_specs('conv_last', 64, in_chans, 3)
+        else:  # UpsampleOneStep (arch.py:804-825): one conv + PixelShuffle straight to the image
+            specs += conv_specs('upsample.0', dim, upscale * upscale * in_chans, 3, gain=2.0)
         super().__init__(specs, in_chans, in_chans, upscale, seed=seed)
+        self.resi_connection, self.upsampler_kind = resi_connection, upsampler
         self.dim, self.hidden, self.split, self.depth, self.heads = dim, hidden, split, list(depth), list(num_heads)
         self.img_range, self.img_size = float(img_range), img_size
 
@@ -178,6 +182,9 @@ class DAT(EngineModule):
         hpad = (half + 15) // 16 * 16
         hid, gate_n, gated = pb.buffer(2 * hpad), pb.buffer(half), pb.buffer(half)
         rg_res, img = pb.buffer(dim), pb.buffer(dim)
+        tmp_a = tmp_b = None
+        if self.resi_connection == '3conv':
+            tmp_a, tmp_b = pb.buffer(dim // 4), pb.buffer(dim // 4)
         mean = RGB_MEAN if self.in_channels == 3 else (0.0, 0.0, 0.0)
         pb.conv(INPUT, feat, w['conv_first.weight'], w['conv_first.bias'], in_mean=mean, in_scale=self.img_range)
         pb.layernorm(feat, x, w['before_RG.1.weight'], w['before_RG.1.bias'])
@@ -216,10 +223,14 @@ class DAT(EngineModule):
                 pb.layernorm(hid.slice(hpad, half), gate_n, w[f'{f}.sg.norm.weight'], w[f'{f}.sg.norm.bias'])
                 pb.dwconv3(gate_n, gated, w[f'{f}.sg.conv.weight'], w[f'{f}.sg.conv.bias'], gate=hid.slice(0, half))
                 pb.conv(gated, x, lin_w(f'{f}.fc2'), lin_b(f'{f}.fc2'), combine=N.COMB_AXPY, res1=x)      # x += fc2(...)
-            pb.conv(x, img, w[f'layers.{rg}.conv.weight'], w[f'layers.{rg}.conv.bias'], combine=N.COMB_AXPY, res1=rg_res)
+            emit_resi_conv(pb, w, f'layers.{rg}.conv', self.resi_connection, x, img, rg_res, tmp_a, tmp_b)
             x, img = img, x
         pb.layernorm(x, xn, w['norm.weight'], w['norm.bias'])
-        pb.conv(xn, y, w['conv_after_body.weight'], w['conv_after_body.bias'], combine=N.COMB_AXPY, res1=feat)
+        emit_resi_conv(pb, w, 'conv_after_body', self.resi_connection, xn, y, feat, tmp_a, tmp_b)
+        omean = mean if self.in_channels == 3 else (0.0, 0.0, 0.0)
+        if self.upsampler_kind == 'pixelshuffledirect':
+            pb.conv(y, OUTPUT, w['upsample.0.weight'], w['upsample.0.bias'], ps=self.upscale, out_scale=1.0 / self.img_range, out_mean=omean)
+            return
         cur = pb.buffer(64)
         pb.conv(y, cur, w['conv_before_upsample.0.weight'], w['conv_before_upsample.0.bias'], act=N.ACT_LRELU, act_param=0.01)
         grid = 1
@@ -232,7 +243,6 @@ class DAT(EngineModule):
                 sel = perm[phase * 64:(phase + 1) * 64]
                 pb.conv(cur, nxt, wk[sel], bk[sel], dst_ps=2, dst_phase=phase)
             cur, grid = nxt, grid * 2
-        omean = mean if self.in_channels == 3 else (0.0, 0.0, 0.0)
         pb.conv(cur, OUTPUT, w['conv_last.weight'], w['conv_last.bias'], ps=1, out_scale=1.0 / self.img_range, out_mean=omean)
 
 

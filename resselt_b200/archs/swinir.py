@@ -28,7 +28,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import get_pixelshuffle_params, get_seq_len
-from ._common import conv_specs
+from ._common import conv_specs, emit_resi_conv, resi_conv_specs
 from .dat import RGB_MEAN, _lin_specs, _ln_specs
 from .esrgan import upconv_phase_kernels
 
@@ -57,14 +57,6 @@ def _shift_mask(size: int, ws: int, shift: int) -> torch.Tensor:
     win = img.view(size // ws, ws, size // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
     diff = win.unsqueeze(1) - win.unsqueeze(2)
     return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
-
-
-def _resi_specs(prefix: str, dim: int, resi_connection: str):
-    if resi_connection == '1conv':
-        return conv_specs(prefix, dim, dim, 3)
-    # random init only: the dim/4 bottleneck attenuates the signal, a gain keeps the output range of seeded test models sane
-    return (conv_specs(f'{prefix}.0', dim, dim // 4, 3, gain=2.0) + conv_specs(f'{prefix}.2', dim // 4, dim // 4, 1, gain=2.0)
-            + conv_specs(f'{prefix}.4', dim // 4, dim, 3, gain=2.0))
 
 
 class SwinIR(EngineModule):
@@ -110,8 +102,8 @@ class SwinIR(EngineModule):
                 specs += _lin_specs(f'{p}.attn.qkv', dim, 3 * dim, qkv_bias) + _lin_specs(f'{p}.attn.proj', dim, dim)
                 specs += _ln_specs(f'{p}.norm2', dim)
                 specs += _lin_specs(f'{p}.mlp.fc1', dim, hidden) + _lin_specs(f'{p}.mlp.fc2', hidden, dim)
-            specs += _resi_specs(f'layers.{i}.conv', dim, resi_connection)
-        specs += _ln_specs('norm', dim) + _resi_specs('conv_after_body', dim, resi_connection)
+            specs += resi_conv_specs(f'layers.{i}.conv', dim, resi_connection)
+        specs += _ln_specs('norm', dim) + resi_conv_specs('conv_after_body', dim, resi_connection)
         if upsampler == 'pixelshuffle':
             specs += conv_specs('conv_before_upsample.0', dim, NUM_FEAT, 3)
             steps = [3] if upscale == 3 else [2] * int(math.log2(upscale))
@@ -135,14 +127,7 @@ class SwinIR(EngineModule):
 
     # ------------------------------------------------------------------ plan
     def _resi_conv(self, pb: PlanBuilder, w, name: str, src, dst, res, tmp_a, tmp_b) -> None:
-        """dst = conv(src) + res with conv = '1conv' or '3conv' (arch.py:564-574, 890-901)."""
-        if self.resi_connection == '1conv':
-            pb.conv(src, dst, w[f'{name}.weight'], w[f'{name}.bias'], combine=N.COMB_AXPY, res1=res)
-            return
-        lrelu = dict(act=N.ACT_LRELU, act_param=0.2)
-        pb.conv(src, tmp_a, w[f'{name}.0.weight'], w[f'{name}.0.bias'], **lrelu)
-        pb.conv(tmp_a, tmp_b, w[f'{name}.2.weight'], w[f'{name}.2.bias'], **lrelu)
-        pb.conv(tmp_b, dst, w[f'{name}.4.weight'], w[f'{name}.4.bias'], combine=N.COMB_AXPY, res1=res)
+        emit_resi_conv(pb, w, name, self.resi_connection, src, dst, res, tmp_a, tmp_b)
 
     def build_plan(self, pb: PlanBuilder, w) -> None:
         dim, hidden, ws = self.dim, self.hidden, self.window_size

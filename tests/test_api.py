@@ -60,6 +60,8 @@ def test_metadata_field_order():
         (PLKSR(n_blocks=1, upscaling_factor=2, lk_type='RectSparsePLK', kernel_size=15), ('PLKSR', 3, 3, 2)),
         (DAT(depth=[3, 2], num_heads=[6, 6], upscale=4), ('DAT', 3, 3, 4)),
         (DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=2, img_size=32), ('DAT', 3, 3, 2)),
+        (DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=3, img_size=32, upsampler='pixelshuffledirect', resi_connection='3conv'),
+         ('DAT', 3, 3, 3)),
         (SwinIR(embed_dim=60, depths=[2, 3], num_heads=[6, 6], upscale=2), ('SwinIR', 3, 3, 2)),
         (SwinIR(embed_dim=180, depths=[2], num_heads=[6], upscale=3, upsampler='pixelshuffledirect'), ('SwinIR', 3, 3, 3)),
         (SwinIR(embed_dim=180, depths=[2], num_heads=[6], upscale=3, upsampler='pixelshuffle'), ('SwinIR', 3, 3, 3)),
@@ -95,7 +97,8 @@ def test_detect_and_hyperparameter_inference(model, meta):
                 loaded.resi_connection) == (model.dim, model.hidden, model.window_size, model.depths, model.heads, model.img_size, model.img_range,
                                             model.upsampler, model.resi_connection)
     if isinstance(model, DAT):
-        assert (loaded.depth, loaded.heads, loaded.split, loaded.img_size) == (model.depth, model.heads, model.split, model.img_size)
+        assert (loaded.depth, loaded.heads, loaded.split, loaded.img_size, loaded.resi_connection, loaded.upsampler_kind) == (
+            model.depth, model.heads, model.split, model.img_size, model.resi_connection, model.upsampler_kind)
 
 
 def test_wrapped_and_prefixed_checkpoints():

@@ -70,6 +70,8 @@ def test_golden_fixtures_fp32_and_bf16(name):
         ('DAT', DAT(upscale=4, seed=32), (1, 3, 64, 64)),                                    # default 6x6 blocks, 180 ch, 8x32 windows
         ('DAT', DAT(depth=[3, 3], num_heads=[6, 6], upscale=2, seed=33), (2, 3, 37, 45)),      # padding + shifted-window masks
         ('DAT', DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=2, img_size=32, seed=34), (1, 3, 50, 30)),
+        ('DAT', DAT(embed_dim=60, split_size=[8, 32], depth=[3, 2], num_heads=[6, 6], upscale=3, upsampler='pixelshuffledirect', resi_connection='3conv', seed=47),
+         (1, 3, 40, 70)),                                                                      # DAT-light layout: one-step head, 3conv residual connections
         ('SwinIR', SwinIR(upscale=4, seed=35), (1, 3, 64, 64)),                                # classical SR: 6x6 blocks, 180 ch, window 8
         ('SwinIR', SwinIR(depths=[2], num_heads=[6], upscale=2, seed=39), (1, 3, 136, 200)),       # > 2 tiles per CTA in every layer
         ('SwinIR', SwinIR(embed_dim=60, depths=[6, 6, 6, 6], num_heads=[6, 6, 6, 6], upscale=2, upsampler='pixelshuffledirect', seed=36), (2, 3, 37, 45)),
