@@ -231,6 +231,7 @@ class Plan:
 
     def _workspace_for(self, n: int, h: int, w: int) -> torch.Tensor:
         if self._ws_shape != (n, h, w):
+            self._graphs.clear()    # captured graphs point into the old workspace
             self._workspace = None  # release before allocating the next one
             nbytes = self.workspace_bytes(n, h, w)
             raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
