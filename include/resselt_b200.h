@@ -161,6 +161,8 @@ enum rsb_op_kind {
                            i[0] groups, i[1] s (up-sampling factor of this head), i[2] out channels, i[3] != 0: src already
                            holds the per-group end_conv projections z[g*4 + o] = sum_{c in group g} W[o][c] x[c] (4 channels
                            per group, produced by a 1x1 conv op; sampling and end_conv commute) and w[1] is ignored;
+                           i[4] > 0: src2 holds [0.5 * offset(x) | scope(x)] (scope i[4] channels after offset, one conv op for
+                           both) and the op applies the sigmoid gate itself;
                            w[0] = init_pos [2 * groups * s^2], w[1] = end_conv weight [out][C], w[2] = end_conv bias [out].
                            Sampling position of output pixel (h*s+i, w*s+j), group g: (w + off_x, h + off_y) in input pixels,
                            clamped to the image (grid_sample bilinear, align_corners=False, padding_mode='border')            */

@@ -69,16 +69,22 @@ def dysample_specs(prefix: str, in_channels: int, out_ch: int, scale: int, group
 
 
 def emit_dysample(pb, w: Dict[str, torch.Tensor], prefix: str, x, out_ch: int, scale: int, groups: int = 4) -> None:
-    """DySample.forward (dysample.py:46-83) on the engine: ``0.5 * offset(x) * sigmoid(scope(x))`` is two 1x1 conv ops (the 0.5
-    folded into the offset conv, the product in its epilogue); the sampling + 1x1 end_conv is one fused op writing the caller's
-    NCHW output.  ``x`` is the feature buffer range the head reads (it must hold exactly the head's input channels)."""
+    """DySample.forward (dysample.py:46-83) on the engine: ``0.5 * offset(x)`` and ``scope(x)`` come out of ONE 1x1 conv op (the 0.5
+    folded into the weights), the per-group end_conv projections out of another; sigmoid gate, sampling and the sum over groups
+    are one fused op writing the caller's NCHW output.  ``x`` is the feature buffer range the head reads (it must hold exactly the head's input channels)."""
     from ..engine import OUTPUT
     from ..engine import native as N
 
     k = 2 * groups * scale * scale
-    gate, off = pb.buffer(k, scale=pb.scales[x.buf]), pb.buffer(k, scale=pb.scales[x.buf])
-    pb.conv(x, gate, w[f'{prefix}.scope.weight'], None, act=N.ACT_SIGMOID)
-    pb.conv(x, off, 0.5 * w[f'{prefix}.offset.weight'], 0.5 * w[f'{prefix}.offset.bias'], combine=N.COMB_MUL, res1=gate)
+    kp = (k + 7) // 8 * 8  # scope starts on a plane boundary
+    # one conv op produces [0.5 * offset | scope]; the head applies sigmoid(scope) to the offsets it reads
+    ow, ob = w[f'{prefix}.offset.weight'], w[f'{prefix}.offset.bias']
+    both_w = torch.zeros(kp + k, x.channels, 1, 1, dtype=ow.dtype)
+    both_b = torch.zeros(kp + k, dtype=ow.dtype)
+    both_w[:k], both_b[:k] = 0.5 * ow, 0.5 * ob
+    both_w[kp:] = w[f'{prefix}.scope.weight']
+    off = pb.buffer(kp + k, scale=pb.scales[x.buf])
+    pb.conv(x, off, both_w, both_b)
     # sampling (bilinear, per group) and the 1x1 end_conv are both linear and commute: project every group through its slice of
     # end_conv on the low-res grid first (4 channels per group, out_ch of them used), then gather 4 values per neighbour instead
     # of the group's feature channels
@@ -89,7 +95,7 @@ def emit_dysample(pb, w: Dict[str, torch.Tensor], prefix: str, x, out_ch: int, s
         zw[4 * g:4 * g + out_ch, g * cg:(g + 1) * cg, 0, 0] = end_w[:, g * cg:(g + 1) * cg]
     z = pb.buffer(4 * groups, scale=pb.scales[x.buf])
     pb.conv(x, z, zw, None)
-    pb.op(N.OP_DYSAMPLE, z, OUTPUT, 4 * groups, src2=off, ints=(groups, scale, out_ch, 1),
+    pb.op(N.OP_DYSAMPLE, z, OUTPUT, 4 * groups, src2=off, ints=(groups, scale, out_ch, 1, kp),
           weights=(w[f'{prefix}.init_pos'], end_w, w[f'{prefix}.end_conv.bias']))
 
 

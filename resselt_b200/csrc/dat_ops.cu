@@ -1037,6 +1037,17 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
 // gathered as 16-byte plane chunks at the four neighbours, blended, and fed straight into the 1x1 end_conv, so the sampled
 // high-res feature map (C channels at s^2 times the pixels) is never materialised — only out_ch values per pixel are written.
 constexpr int kDyMaxOut = 4, kDyMaxC = 256, kDyMaxOff = 256, kDyMaxGroups = 8;
+// offset channel c of the pixel `off` points at; with gate_off > 0 the buffer holds [0.5 * offset | scope] and the gate
+// sigmoid(scope) is applied here (one conv op produces both halves)
+template <typename T>
+__device__ __forceinline__ float dys_offset(const T* off, size_t hw, int c, int gate_off) {
+  float v = (float)off[(size_t)(c >> 3) * hw * 8 + (c & 7)];
+  if (gate_off > 0) {
+    const int cg2 = c + gate_off;
+    v *= sigm_f((float)off[(size_t)(cg2 >> 3) * hw * 8 + (cg2 & 7)]);
+  }
+  return v;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) dysample_kernel(const __grid_constant__ DySampleParams p) {
   __shared__ float w_sm[kDyMaxOut * kDyMaxC];
@@ -1058,8 +1069,8 @@ __global__ void __launch_bounds__(256) dysample_kernel(const __grid_constant__ D
     for (int o = 0; o < kDyMaxOut; ++o) acc[o] = o < p.out_ch ? p.bias[o] : 0.0f;
     for (int g = 0; g < G; ++g) {
       const int cx = g * s2 + i * s + j, cy = (G + g) * s2 + i * s + j;
-      const float ox = (float)off[(size_t)(cx >> 3) * hw * 8 + (cx & 7)] + ip_sm[cx];
-      const float oy = (float)off[(size_t)(cy >> 3) * hw * 8 + (cy & 7)] + ip_sm[cy];
+      const float ox = dys_offset<T>(off, hw, cx, p.gate_off) + ip_sm[cx];
+      const float oy = dys_offset<T>(off, hw, cy, p.gate_off) + ip_sm[cy];
       const float px = fminf(fmaxf((float)w + ox, 0.0f), (float)(p.W - 1));
       const float py = fminf(fmaxf((float)h + oy, 0.0f), (float)(p.H - 1));
       const int x0 = (int)floorf(px), y0 = (int)floorf(py);
@@ -1120,8 +1131,8 @@ __global__ void __launch_bounds__(256) dysample_lean_kernel(const __grid_constan
   for (int o = 0; o < 4; ++o) acc[o] = o < p.out_ch ? p.bias[o] : 0.0f;
   for (int g = 0; g < G; ++g) {
     const int cx = g * s2 + i * s + j, cy = (G + g) * s2 + i * s + j;
-    const float ox = (float)off[(size_t)(cx >> 3) * hw * 8 + (cx & 7)] + ip_sm[cx];
-    const float oy = (float)off[(size_t)(cy >> 3) * hw * 8 + (cy & 7)] + ip_sm[cy];
+    const float ox = dys_offset<T>(off, hw, cx, p.gate_off) + ip_sm[cx];
+    const float oy = dys_offset<T>(off, hw, cy, p.gate_off) + ip_sm[cy];
     const float px = fminf(fmaxf((float)w + ox, 0.0f), (float)(p.W - 1));
     const float py = fminf(fmaxf((float)h + oy, 0.0f), (float)(p.H - 1));
     const int x0 = (int)px, y0 = (int)py;  // px, py >= 0: truncation == floor
@@ -1175,8 +1186,8 @@ __global__ void __launch_bounds__(256) dysample_proj_kernel(const __grid_constan
   for (int o = 0; o < 4; ++o) acc[o] = o < p.out_ch ? p.bias[o] : 0.0f;
   for (int g = 0; g < G; ++g) {
     const int cx = g * s2 + i * s + j, cy = (G + g) * s2 + i * s + j;
-    const float ox = (float)off[(size_t)(cx >> 3) * hw * 8 + (cx & 7)] + ip_sm[cx];
-    const float oy = (float)off[(size_t)(cy >> 3) * hw * 8 + (cy & 7)] + ip_sm[cy];
+    const float ox = dys_offset<T>(off, hw, cx, p.gate_off) + ip_sm[cx];
+    const float oy = dys_offset<T>(off, hw, cy, p.gate_off) + ip_sm[cy];
     const float px = fminf(fmaxf((float)w + ox, 0.0f), (float)(p.W - 1));
     const float py = fminf(fmaxf((float)h + oy, 0.0f), (float)(p.H - 1));
     const int x0 = (int)px, y0 = (int)py;  // px, py >= 0: truncation == floor

@@ -581,6 +581,7 @@ struct AimParams {
 struct DySampleParams {
   int n, H, W, channels, groups, s, out_ch;  // H x W: the low-res grid; output is (H*s) x (W*s)
   int projected;    // 1: src holds the per-group end_conv projections (4 channels per group), see dysample_proj_kernel
+  int gate_off;     // > 0: the offsets buffer is [0.5 * offset | scope], scope starting gate_off channels after offset
   const void* src;  // features
   int src_planes, src_plane0;
   const void* off;  // 0.5 * offset * sigmoid(scope): 2 * groups * s^2 channels

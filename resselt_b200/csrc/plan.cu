@@ -534,6 +534,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       const Buffer& ob = p->bufs[d.src2_buf];
       t.n = n, t.H = H, t.W = W, t.channels = d.channels, t.groups = d.i[0], t.s = d.i[1], t.out_ch = d.i[2];
       t.projected = d.i[3] != 0;
+      t.gate_off = d.i[4];
       t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_plane0 = d.src_ch_off / 8;
       t.off = ws + ob.offset, t.off_planes = ob.planes, t.off_plane0 = d.src2_ch_off / 8;
       t.init_pos = a.dw[0], t.weight = a.dw[1], t.bias = a.dw[2];
@@ -778,7 +779,8 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
     if (g < 1 || s < 1 || d.channels % g != 0 || d.channels > 256 || 2 * g * s * s > 256 || oc < 1 || oc > 4 || oc != p->out_ch)
       return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: DySample needs channels %% groups == 0, channels <= 256, 2*groups*s^2 <= 256, out channels <= 4");
     if (int e = check_buf(p, d.src_buf, d.src_ch_off, d.channels, "rsb_plan_add_op(DySample src)")) return e;
-    if (int e = check_buf(p, d.src2_buf, d.src2_ch_off, 2 * g * s * s, "rsb_plan_add_op(DySample offsets)")) return e;
+    if (d.i[4] != 0 && d.i[4] < 2 * g * s * s) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: DySample gate offset overlaps the offsets");
+    if (int e = check_buf(p, d.src2_buf, d.src2_ch_off, (d.i[4] > 0 ? d.i[4] : 0) + 2 * g * s * s, "rsb_plan_add_op(DySample offsets)")) return e;
     if (p->bufs[d.src_buf].scale != p->bufs[d.src2_buf].scale || p->bufs[d.src_buf].scale * s != p->upscale)
       return fail(RSB_ERR_INVALID, "rsb_plan_add_op: DySample grid mismatch (buffer scale %d x %d != upscale %d)", p->bufs[d.src_buf].scale, s, p->upscale);
     if (!d.w[0] || d.wn[0] != 2 * g * s * s || !d.w[1] || (!proj && d.wn[1] != (int64_t)oc * d.channels) || !d.w[2] || d.wn[2] != oc)

@@ -17,6 +17,7 @@ m = {'span': lambda: SPAN(feature_channels=48, upscale=2, seed=3),
      'spanplus': lambda: SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=4),
      'compact': lambda: SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=5),
      'esrgan': lambda: RRDBNet(num_blocks=23, scale=4, seed=6),
+     'spanplus_dys': lambda: SpanPlus(blocks=[4], feature_channels=48, upscale=2, upsampler='dys', seed=4),
      'plksr': lambda: RealPLKSR(n_blocks=28, upscaling_factor=4, seed=7),
      'dat': lambda: DAT(upscale=4, seed=8),
      'swinir': lambda: SwinIR(upscale=4, seed=9)}[arch]().eval().to(dev).bfloat16()
