@@ -868,14 +868,17 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       const Buffer& sb = p->bufs[c.tc_src_buf];
       const bool planes_ok = c.tc_src_ch_off / 8 + c.tc_cin / 8 <= sb.planes;
       const int WT = rsb::kTileW + c.tc_kw - 1, HT = rsb::kTileH + c.tc_kh - 1;
-      // prefer the whole Cin per stage (static-geometry kernels); otherwise stage K chunks of 64/48/32/16 channels
+      // prefer the whole Cin per stage (static-geometry kernels); otherwise stage K chunks of 64/48/32/16 channels.
+      // Up to 8 stages: a 48-channel 1x1 conv stages only 12 KB per tile, and four of those in flight per SM cap the kernel at
+      // ~2 TB/s (bytes in flight = bandwidth x latency); big stages still get as many as fit.
+      static const int kMaxTcStages = getenv("RSB_TC_STAGES4") ? 4 : 8;
       int stages = 0, kchunk = 0;
       const int cands[5] = {c.tc_cin, 64, 48, 32, 16};
       for (int ci = 0; ci < 5 && stages == 0; ++ci) {
         const int kc = cands[ci];
         if (kc > c.tc_cin || c.tc_cin % kc != 0) continue;
         const int min_stages = ci == 0 ? 2 : 3;
-        for (int s = 4; s >= min_stages; --s)
+        for (int s = kMaxTcStages; s >= min_stages; --s)
           if (rsb::conv_tc_smem_bytes(c.tc_cin, kc, c.npad, c.tc_kh, c.tc_kw, s) <= kMaxSmem) {
             stages = s, kchunk = kc;
             break;
