@@ -924,7 +924,8 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       RSB_CUDA(cudaMemcpy(c.d_wtc, wp.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
       if (!no_rs && d.kh == 3 && d.kw == 3 && d.pad_t == 1 && d.pad_l == 1 && 3 * c.npad <= 256 && 512 / c.npad >= 5) {
         // row-streaming kernel: [kw][cin/8][kh * npad + o][8] — the three kernel rows side by side on the N axis
-        for (int s = 8; s >= 3 && c.rs_stages == 0; --s)
+        static const int kMaxRsStages = getenv("RSB_RS_STAGES") ? atoi(getenv("RSB_RS_STAGES")) : 8;  // bring-up: deeper input ring
+        for (int s = kMaxRsStages; s >= 3 && c.rs_stages == 0; --s)
           if (rsb::conv_rs_smem_bytes(c.tc_cin, c.npad, s) <= kMaxSmem) c.rs_stages = s;
         if (c.rs_stages > 0) {
           const int n3 = 3 * c.npad;
