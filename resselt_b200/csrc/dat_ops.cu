@@ -167,6 +167,117 @@ __global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_con
   }
 }
 
+// bf16 storage, streaming form: persistent CTAs (one per SM), a producer warp keeps a ring of kLnStages tiles in flight with
+// 1-D bulk copies (cp.async.bulk, one 2 KB row of 128 pixels per 8-channel plane, mbarrier complete_tx), eight consumer warps
+// normalise the tile that has landed.  Why: a streaming kernel needs bandwidth x latency bytes in flight (~70 KB per SM at
+// 6.5 TB/s and ~1.7 us loaded latency); the register-resident kernel above holds 49 KB per SM only while its threads are in
+// their load phase (measured 2.5 TB/s), whereas here the ring (4 x 46 KB for 180 channels) stays full while the consumers
+// compute.  Consumer thread = (pixel, half): the two half-warps split the planes, statistics meet through one shuffle.
+constexpr int kLnTile = 128;  // pixels per tile
+constexpr int kLnConsumers = 256;
+__global__ void __launch_bounds__(kLnConsumers + 32, 1) layernorm_stream_kernel(const __grid_constant__ TokenOpParams p, int stages) {
+  using T = __nv_bfloat16;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const size_t hw = (size_t)p.H * p.W;
+  const int C = p.channels, planes = (C + 7) >> 3;
+  const int tiles_per_img = (int)((hw + kLnTile - 1) / kLnTile);
+  const int total_tiles = p.n * tiles_per_img;
+  const uint32_t stage_bytes = (uint32_t)planes * kLnTile * 16u;
+  uint8_t* ring = ln_smem;
+  float* gam = reinterpret_cast<float*>(ring + (size_t)stages * stage_bytes);  // [planes * 8]
+  float* bet = gam + planes * 8;
+  uint64_t* full = reinterpret_cast<uint64_t*>(bet + planes * 8);
+  uint64_t* empty = full + stages;
+  for (int c = threadIdx.x; c < planes * 8; c += blockDim.x) gam[c] = c < C ? p.w0[c] : 0.0f, bet[c] = c < C ? p.w1[c] : 0.0f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], kLnConsumers / 32);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == kLnConsumers / 32) {
+    // ---- producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, t = tile - n * tiles_per_img;
+        const size_t pix0 = (size_t)t * kLnTile;
+        const uint32_t npix = (uint32_t)min((size_t)kLnTile, hw - pix0);
+        const T* src = reinterpret_cast<const T*>(p.src) + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8 + pix0 * 8;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&full[s], (uint32_t)planes * npix * 16u);
+        for (int pl = 0; pl < planes; ++pl)
+          ptx::bulk_load_1d(ring + (size_t)s * stage_bytes + (size_t)pl * kLnTile * 16, src + (size_t)pl * hw * 8, npix * 16u, &full[s]);
+        if (++s == stages) s = 0, ph ^= 1;
+      }
+    }
+    return;
+  }
+  // ---- consumers: warp w takes pixels [16 w, 16 w + 16) of the tile; lanes 0..15 the even planes, lanes 16..31 the odd ones
+  const int half = lane >> 4, px = warp * 16 + (lane & 15);
+  const int full_planes = C >> 3, tail = C & 7;
+  const float inv_c = 1.0f / (float)C;
+  auto unpack = [](const uint4& r, float (&v)[8]) {
+    const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[2 * k] = __uint_as_float(w4[k] << 16), v[2 * k + 1] = __uint_as_float(w4[k] & 0xFFFF0000u);
+  };
+  int s = 0;
+  uint32_t ph = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img, t = tile - n * tiles_per_img;
+    const size_t pix0 = (size_t)t * kLnTile;
+    const int npix = (int)min((size_t)kLnTile, hw - pix0);
+    ptx::mbar_wait(&full[s], ph);
+    const uint4* mine = reinterpret_cast<const uint4*>(ring + (size_t)s * stage_bytes) + px;
+    const bool live = px < npix;
+    float sum = 0.0f;
+    if (live)
+      for (int pl = half; pl < planes; pl += 2) {
+        float v[8];
+        unpack(mine[pl * kLnTile], v);
+        const int lim = pl < full_planes ? 8 : tail;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += k < lim ? v[k] : 0.0f;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    const float mean = sum * inv_c;
+    float sq = 0.0f;
+    if (live)
+      for (int pl = half; pl < planes; pl += 2) {
+        float v[8];
+        unpack(mine[pl * kLnTile], v);
+        const int lim = pl < full_planes ? 8 : tail;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sq += k < lim ? (v[k] - mean) * (v[k] - mean) : 0.0f;
+      }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+    const float rstd = rsqrtf(sq * inv_c + p.f0);
+    const float shift = -mean * rstd;
+    if (live) {
+      T* d = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8;
+      for (int pl = half; pl < planes; pl += 2) {
+        float v[8], o[8];
+        unpack(mine[pl * kLnTile], v);
+        const float4 g0 = *reinterpret_cast<const float4*>(gam + pl * 8), g1 = *reinterpret_cast<const float4*>(gam + pl * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bet + pl * 8), b1 = *reinterpret_cast<const float4*>(bet + pl * 8 + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(fmaf(v[k], rstd, shift), g[k], b[k]);  // tail channels: gamma = beta = 0 -> 0
+        store8<T>(d + (size_t)pl * hw * 8, o);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[s]);  // this warp is done reading the stage
+    if (++s == stages) s = 0, ph ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv3_kernel(const __grid_constant__ TokenOpParams p) {
@@ -1225,6 +1336,19 @@ cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s) 
   const int planes = (p.channels + 7) / 8;
   const size_t pixels = (size_t)p.n * p.H * p.W;
   const int g2 = (int)std::min<size_t>((pixels + 63) / 64, (size_t)148 * 128);
+  static const bool no_stream = getenv("RSB_LN_REG") != nullptr;  // bring-up: the register-resident kernel instead
+  if (bf16 && !no_stream && planes <= 64) {
+    const size_t stage = (size_t)planes * kLnTile * 16;
+    int stages = (int)std::min<size_t>(8, (200 * 1024 - (size_t)planes * 64 - 256) / stage);
+    const size_t hw = (size_t)p.H * p.W;
+    const size_t tiles = (size_t)p.n * ((hw + kLnTile - 1) / kLnTile);
+    if (stages >= 2 && tiles >= 1) {
+      const size_t smem = (size_t)stages * stage + (size_t)planes * 64 + (size_t)stages * 16 + 16;
+      const int grid = (int)std::min<size_t>(tiles, 148);
+      layernorm_stream_kernel<<<grid, kLnConsumers + 32, smem, s>>>(p, stages);
+      return cudaGetLastError();
+    }
+  }
   if (bf16 && planes <= 8)
     layernorm_bf16_kernel<2><<<g2, 256, 0, s>>>(p);
   else if (bf16 && planes <= 16)
@@ -1257,6 +1381,10 @@ size_t winattn_smem_bytes(int split_h, int split_w) {
 }
 
 cudaError_t winattn_configure() {
+  {
+    cudaError_t e0 = cudaFuncSetAttribute(layernorm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e0 != cudaSuccess) return e0;
+  }
   cudaError_t e = cudaFuncSetAttribute(winattn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(winattn_mma_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
