@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RSB_VERSION 100
+#define RSB_VERSION 200
 
 typedef struct rsb_plan rsb_plan;
 
@@ -201,6 +201,36 @@ int rsb_plan_add_groupnorm(rsb_plan* plan, const rsb_groupnorm_desc* desc);
 int rsb_plan_finalize(rsb_plan* plan, int device);
 
 int rsb_plan_num_ops(const rsb_plan* plan);
+/* bf16 plans: convolutions that do not fit the tensor-core kernels and run on the CUDA-core kernel instead (0 for every
+ * BASELINE configuration; a warning is printed to stderr once per process when it is not) */
+int rsb_plan_num_direct_convs(const rsb_plan* plan);
+
+/* What one op of a finalised plan runs as (in the mode of the last forward, at the shape it bound): for launch accounting and
+ * per-kernel timing (bench.py times every launch unit inside a CUDA graph and reports the dominant kernel's roofline). */
+enum rsb_kernel_id {
+  RSB_K_CONV_DIRECT = 0, /* CUDA-core FFMA conv (the whole fp32 plan)                       */
+  RSB_K_CONV_TC = 1,     /* tcgen05 tile kernel (1x1 convs / linears, wide 3x3)             */
+  RSB_K_CONV_RS = 2,     /* tcgen05 row-streaming 3x3                                       */
+  RSB_K_CONV_LK = 3,     /* tcgen05 row-streaming K x K                                     */
+  RSB_K_CONV_PAIR = 4,   /* two 3x3 convs fused, intermediate rows in shared memory         */
+  RSB_K_GROUPNORM = 5,
+  RSB_K_LAYERNORM = 6,
+  RSB_K_DWCONV3 = 7,
+  RSB_K_WINATTN = 8,
+  RSB_K_CHANATTN = 9,
+  RSB_K_AIM = 10,
+  RSB_K_DYSAMPLE = 11
+};
+typedef struct rsb_op_info {
+  int32_t kind;       /* 0 convolution, 1 GroupNorm, 2 token / attention op                                        */
+  int32_t kernel;     /* rsb_kernel_id of the (main) kernel                                                        */
+  int32_t fused_next; /* 1: this conv and the next op run as ONE fused launch; the totals below cover both ops      */
+  int32_t launches;   /* kernels launched for this op (0 for the second op of a fused pair)                         */
+  double flops;       /* 2 * MACs at the bound shape (convolutions; 0 otherwise)                                    */
+  double bytes;       /* algorithmic HBM bytes at the bound shape: inputs + residuals read, outputs written (convs) */
+} rsb_op_info;
+int rsb_plan_op_info(const rsb_plan* plan, int op_index, rsb_op_info* out);
+const char* rsb_kernel_name(int kernel_id);
 /* kernels launched by one rsb_plan_forward call (for launch accounting) */
 int rsb_plan_launches_per_forward(const rsb_plan* plan);
 /* 2 * MACs of all convolutions for an n x h x w input */
@@ -211,12 +241,13 @@ int rsb_plan_workspace_bytes(const rsb_plan* plan, int n, int h, int w, size_t* 
 /* x: contiguous NCHW [n][in_channels][h][w] of x_dtype on the plan's device;
  * y: contiguous NCHW [n][out_channels][h*upscale][w*upscale] of y_dtype;
  * workspace: 1024-byte aligned device memory of at least rsb_plan_workspace_bytes() bytes.
- * stream: a cudaStream_t passed as void*.  force_direct selects the conv kernels: 0 = fastest available,
- * 1 = every conv on the CUDA-core kernel (debug cross-check of the tensor-core kernels), 2 = tensor-core tile
- * kernel only (no row-streaming 3x3 kernel; cross-check of the two tensor-core formulations), 3 = row-streaming
- * kernel for every eligible 3x3 conv even where the tile kernel would be preferred (small images), 4 = like 0 but with
- * the experimental fused conv-pair kernel (two consecutive 3x3 convs in one launch, the intermediate map kept in shared
- * memory; bit-identical to 0; also enabled for mode 0 by the environment variable RSB_PAIR=1). */
+ * stream: a cudaStream_t passed as void*.  force_direct selects the conv kernels: 0 = fastest available (row-streaming 3x3,
+ * tile kernel), 1 = every conv on the CUDA-core kernel (debug cross-check of the tensor-core kernels), 2 = tensor-core tile
+ * kernel only (no row-streaming 3x3 kernel; cross-check of the two tensor-core formulations), 3 = row-streaming kernel for
+ * every eligible 3x3 conv even where the tile kernel would be preferred (small images), 4 = like 0 but chains of 48-channel
+ * 3x3 convs run as fused conv pairs (two convs per launch, the intermediate rows kept in shared memory; bit-identical to 0;
+ * measured on B200 it is bound by shared-memory bandwidth at the speed of the two HBM-bound single launches, so it is opt-in),
+ * 5 = same as 0. */
 int rsb_plan_forward(rsb_plan* plan, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype,
                      void* workspace, size_t workspace_bytes, void* stream, int force_direct);
 

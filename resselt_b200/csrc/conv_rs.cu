@@ -72,17 +72,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
-  if (p.timeline != nullptr && threadIdx.x == 0) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    atomicMin(&p.timeline[0], gt);
-  }
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[8 * 159 + 0] = clock64();
-  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 160) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.trace[2000 + 2 * blockIdx.x] = (long long)gt;
-  }
   const int S = p.stages;
   const int NS = NCH > 0 ? (512 / (16 * (NCH > 0 ? NCH : 1)) > kRsMaxSlots ? kRsMaxSlots : 512 / (16 * (NCH > 0 ? NCH : 1))) : p.nslots;
   const int NP = NCH > 0 ? 16 * NCH : p.np;
@@ -143,12 +132,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   tc_fence_after();
 
   pdl_wait();  // everything below reads or writes activation buffers
-  if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.timeline[2] = gt;
-  }
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[8 * 159 + 1] = clock64();
   const int u0 = (int)((long long)p.units * blockIdx.x / gridDim.x);
   const int u1 = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
 
@@ -175,12 +158,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               const int q = qbase + (r - s.y0);
               mbar_wait_parked(&tempty[q % NS], (((uint32_t)(q / NS)) & 1u) ^ 1u);
             }
-          if (p.dbg & 2) {
-            mbar_arrive(&full[st]);
-          } else {
-            mbar_expect_tx(&full[st], p.stage_bytes);
-            tma_load_5d(stage0 + (size_t)st * st_al, &src_map, &full[st], 0, s.cx * 16 - 1, yi, p.src_plane0, s.n);
-          }
+          mbar_expect_tx(&full[st], p.stage_bytes);
+          tma_load_5d(stage0 + (size_t)st * st_al, &src_map, &full[st], 0, s.cx * 16 - 1, yi, p.src_plane0, s.n);
           if (++st == S) st = 0, st_par ^= 1u;
         }
         qbase += s.y1 - s.y0;
@@ -199,7 +178,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const int ksteps = KS > 0 ? KS : (p.cin >> 4);
     const int cin8 = 2 * ksteps;
     const uint32_t tfull_s = smem_u32(tfull);
-    int st = 0, qbase = 0, u = u0, trow = 0;
+    int st = 0, qbase = 0, u = u0;
     uint32_t st_par = 0;
     Strip s;
     while (next_strip(p, u, u1, s)) {
@@ -208,22 +187,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const uint32_t a_lo = a_lo0 + (uint32_t)st * st_units;
         const int qn = qbase + (yi + 1 - s.y0);  // CTA-local index of output row yi + 1
         const int slot_n = qn % NS;
-        long long* const tr = (p.trace != nullptr && blockIdx.x == 0 && leader && trow < 160) ? p.trace + 8 * trow : nullptr;
-        ++trow;
-        if (tr) {
-          tr[0] = clock64();
-          unsigned long long gt;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-          tr[1] = (long long)gt;
-        }
         mbar_wait(&full[st], st_par);
         tc_fence_after();
-        if (tr) tr[2] = clock64();
-        if (p.timeline != nullptr && trow == 1 && blockIdx.x == 0 && leader) {
-          unsigned long long gt;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-          p.timeline[3] = gt;
-        }
         // every accumulator slot is zero when it is handed over (the epilogue clears it after reading): all MMAs accumulate
         if (KS > 0 && NCH > 0 && yi - 1 >= s.y0 && yi + 1 < s.y1 && slot_n >= 2) {
           // steady state: rows yi+1, yi, yi-1 sit in three consecutive slots -> one N = 3 * npad MMA per (dx, k step)
@@ -231,14 +196,12 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           constexpr uint32_t kI3 = make_idesc_bf16(128, (int)(3 * kN));
           const uint32_t d0 = tmem_base + (uint32_t)(NS - 1 - slot_n) * kN;
           if (leader) {
-            if (!(p.dbg & 4)) {
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx)
+            for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                for (int kk = 0; kk < (KS > 0 ? KS : 1); ++kk)
-                  umma_bf16_lohi<true>(d0, a_lo + (uint32_t)(dx + kk * 2 * (int)(kRsPlaneBytes >> 4)), a_hi,
-                                       b_lo0 + (uint32_t)((dx * 2 * KS + 2 * kk) * 3 * (int)kN), b_hi, kI3);
-            }
+              for (int kk = 0; kk < (KS > 0 ? KS : 1); ++kk)
+                umma_bf16_lohi<true>(d0, a_lo + (uint32_t)(dx + kk * 2 * (int)(kRsPlaneBytes >> 4)), a_hi,
+                                     b_lo0 + (uint32_t)((dx * 2 * KS + 2 * kk) * 3 * (int)kN), b_hi, kI3);
             umma_commit_addr(tfull_s + 8u * (uint32_t)(slot_n - 2));  // output row yi - 1 is complete
           }
         } else {
@@ -263,26 +226,23 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           idg[1] = n1 ? idesc0 | ((uint32_t)((n1 * NP) >> 3) << 17) : 0u;
           idg[2] = n2 ? idesc0 | ((uint32_t)((n2 * NP) >> 3) << 17) : 0u;
           if (leader) {
-            if (!(p.dbg & 4)) {
-              uint32_t b_dx = b_lo0;
-              for (int dx = 0; dx < 3; ++dx) {
-                uint32_t a = a_lo + (uint32_t)dx, b = b_dx;
-                for (int kk = 0; kk < ksteps; ++kk) {
+            uint32_t b_dx = b_lo0;
+            for (int dx = 0; dx < 3; ++dx) {
+              uint32_t a = a_lo + (uint32_t)dx, b = b_dx;
+              for (int kk = 0; kk < ksteps; ++kk) {
 #pragma unroll
-                  for (int g = 0; g < 3; ++g)
-                    if (idg[g] != 0u) umma_bf16_lohi<true>(tmem_base + col[g], a, a_hi, b + (uint32_t)(g * NP), b_hi, idg[g]);
-                  a += 2u * (kRsPlaneBytes >> 4);
-                  b += 2u * (uint32_t)(3 * NP);
-                }
-                b_dx += (uint32_t)(cin8 * 3 * NP);
+                for (int g = 0; g < 3; ++g)
+                  if (idg[g] != 0u) umma_bf16_lohi<true>(tmem_base + col[g], a, a_hi, b + (uint32_t)(g * NP), b_hi, idg[g]);
+                a += 2u * (kRsPlaneBytes >> 4);
+                b += 2u * (uint32_t)(3 * NP);
               }
+              b_dx += (uint32_t)(cin8 * 3 * NP);
             }
             // output rows whose last contribution this was: r = yi - 1 always, r = yi on the image's last row
             if (v[2]) umma_commit_addr(tfull_s + 8u * (uint32_t)((qn - 2) % NS));
             if (v[1] && yi == p.H - 1) umma_commit_addr(tfull_s + 8u * (uint32_t)((qn - 1) % NS));
           }
         }
-        if (tr) tr[3] = clock64();
         if (++st == S) st = 0, st_par ^= 1u;
       }
       qbase += s.y1 - s.y0;
@@ -298,14 +258,12 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       const int ya = max(s.y0 - 1, 0), yb = min(s.y1, p.H - 1);
       const int n = s.n;
       const int x = s.cx * 128 + qd * 32 + lane;
-      const bool valid = x < p.W && !(p.dbg & 1);
+      const bool valid = x < p.W;
       for (int y = s.y0 + ((wg - qbase) & (kRsWG - 1)); y < s.y1; y += kRsWG) {
         const int q = qbase + (y - s.y0);  // q % kRsWG == wg
         const int slot = q % NS;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((NS - 1 - slot) * NP);
         const uint32_t par = ((uint32_t)(q / NS)) & 1u;
-        long long* const te = (p.trace != nullptr && blockIdx.x == 0 && qd == 0 && lane == 0 && q < 160) ? p.trace + 8 * 160 + 4 * q : nullptr;
-        if (te) te[0] = clock64();
         constexpr bool kUsesRes = NCH > 0 && (COMB == RSB_COMB_SPAB_GATE || COMB == RSB_COMB_MUL || COMB == RSB_COMB_AXPY);
         uint4 pre[kUsesRes ? 2 * NCH : 1];
         if constexpr (kUsesRes) {
@@ -320,7 +278,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         }
         mbar_wait_parked(&tfull[slot], par);
         tc_fence_after();
-        if (te) te[1] = clock64();
         if (qd == 0 && lane == 0) {
           // every MMA up to input row min(y + 1, H - 1) has completed: hand those rows' stages back to the producer
           // (row y + 1 by its predecessor's epilogue; the strip's first output row also covers the rows before it)
@@ -381,7 +338,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[slot]);
         }
-        if (te) te[2] = clock64();
       }
       qbase += s.y1 - s.y0;
       jbase += yb - ya + 1;
@@ -390,17 +346,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (p.timeline != nullptr && threadIdx.x == 0) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    atomicMax(&p.timeline[1], gt);
-  }
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[8 * 159 + 2] = clock64();
-  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 160) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.trace[2000 + 2 * blockIdx.x + 1] = (long long)gt;
-  }
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -489,69 +434,6 @@ cudaError_t launch_conv_rs(const CUtensorMap& src_map, const ConvRsParams& p, in
   if (smem < 120 * 1024) smem = 120 * 1024;
   const int grid = p.units < num_sms ? p.units : num_sms;
   RsKernelFn fn = rs_pick(p);
-  static const char* tl_file = getenv("RSB_RS_TIMELINE");
-  if (tl_file != nullptr) {
-    // bring-up: globaltimer stamps of the first 64 launches, dumped after the 64th
-    static unsigned long long* d_tl = nullptr;
-    static int count = 0;
-    if (d_tl == nullptr) {
-      cudaMalloc(&d_tl, 64 * 4 * sizeof(unsigned long long));
-      static unsigned long long init[64 * 4];
-      for (int i = 0; i < 64; ++i) init[4 * i] = ~0ull, init[4 * i + 1] = 0, init[4 * i + 2] = 0, init[4 * i + 3] = 0;
-      cudaMemcpy(d_tl, init, sizeof init, cudaMemcpyHostToDevice);
-    }
-    if (count < 64) {
-      ConvRsParams q = p;
-      q.timeline = d_tl + 4 * count;
-      ++count;
-      cudaError_t e = launch_pdl(fn, dim3(grid), dim3(kRsThreads), smem, stream, src_map, q);
-      if (count == 64) {
-        static unsigned long long h[64 * 4];
-        cudaStreamSynchronize(stream);
-        cudaMemcpy(h, d_tl, sizeof h, cudaMemcpyDeviceToHost);
-        FILE* f = fopen(tl_file, "w");
-        if (f != nullptr) {
-          for (int i = 0; i < 64; ++i)
-            fprintf(f, "%d start %llu end %llu dur %llu gap_from_prev_end %lld wait_done+%lld first_mma+%lld\n", i, h[4 * i] - h[0], h[4 * i + 1] - h[0],
-                    h[4 * i + 1] - h[4 * i], i ? (long long)(h[4 * i] - h[4 * i - 3]) : 0ll, (long long)(h[4 * i + 2] - h[4 * i]),
-                    (long long)(h[4 * i + 3] - h[4 * i]));
-          fclose(f);
-        }
-      }
-      return e;
-    }
-  }
-  const char* dbg = getenv("RSB_RS_DBG");
-  const char* trace = getenv("RSB_RS_TRACE");
-  if (dbg != nullptr || trace != nullptr) {
-    ConvRsParams q = p;
-    q.dbg = dbg != nullptr ? atoi(dbg) : 0;
-    static long long* d_trace = nullptr;
-    const size_t tbytes = (2000 + 2 * 160) * sizeof(long long);
-    if (trace != nullptr) {
-      if (d_trace == nullptr) cudaMalloc(&d_trace, tbytes);
-      cudaMemsetAsync(d_trace, 0, tbytes, stream);
-      q.trace = d_trace;
-    }
-    launch_pdl(fn, dim3(grid), dim3(kRsThreads), smem, stream, src_map, q);
-    if (trace != nullptr) {
-      static long long h[2000 + 2 * 160];
-      cudaStreamSynchronize(stream);
-      cudaMemcpy(h, d_trace, tbytes, cudaMemcpyDeviceToHost);
-      FILE* f = fopen(trace, "w");
-      if (f != nullptr) {
-        for (int r = 0; r < 160; ++r) {
-          fprintf(f, "%d", r);
-          for (int k = 0; k < 5; ++k) fprintf(f, " %lld", h[8 * r + k]);
-          for (int k = 0; k < 3; ++k) fprintf(f, " %lld", h[8 * 160 + 4 * r + k]);
-          fprintf(f, " %lld %lld", h[2000 + 2 * r], h[2000 + 2 * r + 1]);
-          fprintf(f, "\n");
-        }
-        fclose(f);
-      }
-    }
-    return cudaGetLastError();
-  }
   return launch_pdl(fn, dim3(grid), dim3(kRsThreads), smem, stream, src_map, p);
 }
 

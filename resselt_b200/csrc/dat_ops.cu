@@ -1331,12 +1331,13 @@ inline int grid_for(size_t total, int threads = 256, int cap = 148 * 32) {
 
 }  // namespace
 
-cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s) {
-  const int g = grid_for((size_t)p.n * p.H * p.W);
+cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s) {
+  const int sms = num_sms > 0 ? num_sms : 148;
+  const int g = grid_for((size_t)p.n * p.H * p.W, 256, sms * 32);
   const int planes = (p.channels + 7) / 8;
   const size_t pixels = (size_t)p.n * p.H * p.W;
-  const int g2 = (int)std::min<size_t>((pixels + 63) / 64, (size_t)148 * 128);
-  static const bool no_stream = getenv("RSB_LN_REG") != nullptr;  // bring-up: the register-resident kernel instead
+  const int g2 = (int)std::min<size_t>((pixels + 63) / 64, (size_t)sms * 128);
+  static const bool no_stream = rsb_env("RSB_LN_REG") != nullptr;  // bring-up: the register-resident kernel instead
   if (bf16 && !no_stream && planes <= 64) {
     const size_t stage = (size_t)planes * kLnTile * 16;
     int stages = (int)std::min<size_t>(8, (200 * 1024 - (size_t)planes * 64 - 256) / stage);
@@ -1344,7 +1345,7 @@ cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s) 
     const size_t tiles = (size_t)p.n * ((hw + kLnTile - 1) / kLnTile);
     if (stages >= 2 && tiles >= 1) {
       const size_t smem = (size_t)stages * stage + (size_t)planes * 64 + (size_t)stages * 16 + 16;
-      const int grid = (int)std::min<size_t>(tiles, 148);
+      const int grid = (int)std::min<size_t>(tiles, (size_t)sms);  // persistent: one CTA per SM
       layernorm_stream_kernel<<<grid, kLnConsumers + 32, smem, s>>>(p, stages);
       return cudaGetLastError();
     }
@@ -1400,7 +1401,7 @@ cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
   const int windows = (p.Hp / p.split_h) * (p.Wp / p.split_w);
   const dim3 grid(windows * p.n, p.heads / 2, 2);
   const size_t smem = winattn_smem_bytes(p.split_h, p.split_w);
-  static const bool no_mma = getenv("RSB_WINATTN_SIMT") != nullptr;
+  static const bool no_mma = rsb_env("RSB_WINATTN_SIMT") != nullptr;
   const int N = p.split_h * p.split_w;
   if (bf16 && !no_mma && N <= 256 && p.head_dim <= kHD && winattn_mma_smem_bytes(p.split_h, p.split_w) <= 100 * 1024) {
     const int warps = (N + 15) / 16;
@@ -1456,7 +1457,7 @@ cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s) {
 
 cudaError_t launch_dysample(const DySampleParams& p, bool bf16, cudaStream_t s) {
   const int g = grid_for((size_t)p.n * p.H * p.s * p.W * p.s, 256, 148 * 64);
-  static const bool generic = getenv("RSB_DYS_GENERIC") != nullptr;  // bring-up: the straightforward kernel
+  static const bool generic = rsb_env("RSB_DYS_GENERIC") != nullptr;  // bring-up: the straightforward kernel
   const bool lean = !generic && p.groups <= kDyMaxGroups && p.channels / p.groups <= 32 && p.H * p.s <= 65535 && p.n <= 65535;
   const dim3 gl((unsigned)((p.W * p.s + 255) / 256), (unsigned)(p.H * p.s), (unsigned)p.n);
   if (p.projected) {

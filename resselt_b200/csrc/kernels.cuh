@@ -409,14 +409,12 @@ struct ConvTcParams {
   int kh, kw, pad_t, pad_l;
   int src_plane0;
   const void* wpack;  // bf16 [kh*kw][cin/8][npad][8]
-  const void* wpack2; // bf16 [2][kh*kw][cin/8][npad/2][8]: per-CTA halves for the cta_group::2 kernel (or null)
   uint32_t wbytes;
   int stages;
   uint32_t stage_bytes;  // (kTileH+kh-1) * (kTileW+kw-1) * kchunk * 2
   int num_acc;           // accumulator buffers in TMEM == epilogue warpgroups (1..4)
   uint32_t acc_stride;   // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;    // allocation (power of two >= 32)
-  int dbg;               // bring-up switches of the CTA-pair kernel (env RSB_TC2_DBG)
   Epi epi;
 };
 
@@ -433,9 +431,6 @@ struct ConvRsParams {
   uint32_t wbytes;
   int stages;
   uint32_t stage_bytes;  // cin/8 planes x 18 groups x 128 B
-  long long* trace;      // bring-up: per-row clock stamps of CTA 0 (env RSB_RS_TRACE=<file>)
-  unsigned long long* timeline;  // bring-up: [4] = min CTA start, max CTA end, CTA 0 after grid-dependency wait, CTA 0 first MMA (globaltimer ns)
-  int dbg;               // bring-up switches (env RSB_RS_DBG): 1 no epilogue work, 2 no TMA loads, 4 no MMAs, 8 no tcgen05.ld, 16 no tcgen05.st
   Epi epi;
 };
 
@@ -454,7 +449,7 @@ struct ConvLkParams {
   Epi epi;
 };
 
-// Fused pair of 3x3 convs (conv_pair.cu): A's activated output rows stay in shared memory and feed B
+// Fused pair of 3x3 convs (conv_pair.cu): A's finished output rows stay in shared memory and feed B
 struct ConvPairParams {
   int n, H, W;
   int cols;   // strips of 120 owned output pixels (conv_pair_cols)
@@ -462,18 +457,22 @@ struct ConvPairParams {
   int cin0;   // conv A input channels (multiple of 16)
   int np;     // A's output channels == B's input channels == UMMA N per kernel row of both convs (multiple of 16)
   int src_plane0;
-  const void* wpackA;  // bf16 [3 kw][cin0/8][5 * np][8], N blocks hold kernel rows [2, 1, 0, 2, 1]
+  const void* wpackA;  // bf16 [3 kw][cin0/8][3 kh * np][8] (the row-streaming layout of conv_rs)
   uint32_t wbytesA;
-  const void* wpackB;  // bf16 [3 kw][np/8][5 * np][8]
+  const void* wpackB;  // bf16 [3 kw][np/8][3 kh * np][8]
   uint32_t wbytesB;
   uint32_t stage_bytes;  // cin0/8 planes x 18 groups x 128 B
+  // conv A's tail: bias, then activation actA or (combA == RSB_COMB_SPAB_GATE) the gate with residual resA
   const float* biasA;    // [np]
   int actA;
   float actA_param;
-  int lag;  // B consumes A's output row j at step j + lag
-  int res_prefetch;  // res_map is valid: the producer prefetches B's residual rows into L2
-  long long* trace;  // bring-up: clock stamps of CTA 1 (env RSB_PAIR_TRACE=<file>)
-  int dbg;  // bring-up switches (env RSB_PAIR_DBG): 1 no A epilogue math/stores, 2 no B epilogue math/stores
+  int combA;
+  const void* resA;
+  int resA_planes, resA_plane0;
+  void* dstA;  // non-null: A's rows are also written to this planar buffer (a later layer reads them)
+  int dstA_planes, dstA_plane0;
+  int res_prefetch;  // res_map is valid (the gate's residual rows travel through it): 1 = conv B's residual, 2 = conv A's
+  int res_plane0;    // first plane of that residual inside res_map's buffer
   Epi epi;  // conv B's tail
 };
 
@@ -594,7 +593,7 @@ struct DySampleParams {
 };
 
 cudaError_t launch_dysample(const DySampleParams& p, bool bf16, cudaStream_t s);
-cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, cudaStream_t s);
+cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s);
 cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s);
 size_t winattn_smem_bytes(int split_h, int split_w);
 cudaError_t winattn_configure();
@@ -602,11 +601,20 @@ cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s);
 cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, cudaStream_t s);
 cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s);
 
+// Kernel-selection switches read from the environment (RSB_NO_PAIR, RSB_NO_RS, RSB_NO_PDL, RSB_LN_REG, ...) exist only in
+// bring-up builds (-DRSB_BRINGUP): the product library ignores the environment, so a stray variable cannot change what a
+// benchmark measures.  None of them skips work; they select between kernels that compute the same result.
+#ifdef RSB_BRINGUP
+inline const char* rsb_env(const char* name) { return getenv(name); }
+#else
+inline const char* rsb_env(const char*) { return nullptr; }
+#endif
+
 // Launch with programmatic stream serialization: the kernel may be scheduled while the previous kernel of the stream
-// drains; it must call ptx::pdl_wait() before touching activation memory.  RSB_NO_PDL=1 restores plain launches.
+// drains; it must call ptx::pdl_wait() before touching activation memory.  (Bring-up builds: RSB_NO_PDL=1 restores plain launches.)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  static const bool no_pdl = getenv("RSB_NO_PDL") != nullptr;
+  static const bool no_pdl = rsb_env("RSB_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -621,9 +629,6 @@ cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, in
 size_t conv_tc_smem_bytes(int cin, int kchunk, int npad, int kh, int kw, int stages);
 int conv_tc_num_acc(int npad);
 cudaError_t conv_tc_configure(size_t max_smem);
-bool conv_tc2_supported(const ConvTcParams& p);
-cudaError_t conv_tc2_configure(size_t max_smem);
-cudaError_t launch_conv_tc2(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream);
 size_t conv_rs_smem_bytes(int cin, int np, int stages);
 uint32_t conv_rs_stage_bytes(int cin);
 cudaError_t conv_rs_configure(size_t max_smem);
@@ -632,10 +637,9 @@ uint32_t conv_lk_weight_bytes(int cin, int k);
 size_t conv_lk_smem_bytes(int cin, int k, int stages);
 cudaError_t conv_lk_configure(size_t max_smem);
 cudaError_t launch_conv_lk(const CUtensorMap& src_map, const ConvLkParams& p, int num_sms, cudaStream_t stream);
-uint32_t conv_pair_weight_bytes(int cin, int np);
 size_t conv_pair_smem_bytes(int cin0, int np);
 int conv_pair_cols(int W);
-bool conv_pair_supported(int cin0, int np, int actA, int actB, int combB);
+bool conv_pair_supported(int cin0, int np, int actA, int combA, int storeA, int actB, int combB);
 cudaError_t conv_pair_configure(size_t max_smem);
 cudaError_t launch_conv_pair(const CUtensorMap& src_map, const CUtensorMap& res_map, const ConvPairParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_direct(const ConvDirectParams& p, bool bf16_storage, cudaStream_t stream);

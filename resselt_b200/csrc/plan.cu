@@ -40,6 +40,21 @@ constexpr size_t kMaxSmem = 227 * 1024;
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Makes `device` current for a scope and restores the caller's device on every exit path (error returns included).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 uint16_t f32_to_bf16(float f) {  // round-to-nearest-even, same as __float2bfloat16_rn
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -70,7 +85,6 @@ struct ConvOp {
   int tc_src_buf = -1, tc_src_ch_off = 0, tc_cin = 0, tc_kh = 0, tc_kw = 0;
   rsb::PackParams pk;
   void* d_wtc = nullptr;
-  void* d_wtc2 = nullptr;  // per-CTA halves for the CTA-pair kernel
   uint32_t wbytes_tc = 0;
   float* d_wdirect = nullptr;
   float* d_bias = nullptr;
@@ -88,8 +102,7 @@ struct ConvOp {
   rsb::ConvLkParams lkp;
   // fused pair kernel (conv_pair.cu): this conv is the head (A) of a pair with the next op; decided at finalize
   bool pair_head = false, pair_ready = false;
-  void* d_wrot = nullptr;  // [3 kw][cin/8][5 * npad][8]: kernel rows [2, 1, 0, 2, 1] side by side on the N axis
-  uint32_t wbytes_rot = 0;
+  bool pair_store = false;  // a later op reads this conv's output: the pair kernel writes it to its buffer as well
   // bound state
   CUtensorMap map, map_rs, map_res;  // map_res: the pair's second conv's residual rows (L2 prefetch)
   rsb::ConvTcParams tcp;
@@ -155,6 +168,8 @@ struct rsb_plan {
   bool finalized = false;
   int device = -1;
   int num_sms = 0;
+  int num_direct = 0;  // bf16 plans: convs that fell back to the CUDA-core kernel
+  int info_mode = 0;   // force_direct of the last forward: what rsb_plan_op_info describes
   std::mutex mu;
   // binding
   int bn = 0, bh = 0, bw = 0;
@@ -250,37 +265,41 @@ bool region_dead_after(const rsb_plan* p, const Region& r, size_t last_reader) {
   return true;  // the next forward rewrites it before anything reads it
 }
 
-// Mark conv i as the head of a fused pair with conv i + 1 when A's output is only ever read by B.
+// Cut the plan's chains of row-streamable 3x3 convs into fused pairs (conv_pair.cu): conv i becomes the head (A) of a pair
+// with conv i + 1 (B) when B reads exactly what A writes.  A may end in an activation or in the SPAB gate; when a later op
+// still reads A's output the pair kernel also writes it to its buffer (pair_store), otherwise the map never reaches HBM.
+// Greedy from the front: SPAN's conv_1, 6 x (c1_r, c2_r, c3_r), conv_2 become ten pairs.
 void find_pairs(rsb_plan* p) {
-  static const bool no_pair = getenv("RSB_NO_PAIR") != nullptr;
+  static const bool no_pair = rsb::rsb_env("RSB_NO_PAIR") != nullptr;
   if (no_pair || p->dtype != RSB_BF16) return;
-  // two passes: first the pairs whose second conv reads a residual (the unfused layer is the most HBM-bound one: three
-  // maps per launch), then whatever is left
-  std::vector<char> taken(p->ops.size(), 0);
-  for (int pass = 0; pass < 2; ++pass)
   for (size_t i = 0; i + 1 < p->ops.size(); ++i) {
-    if (p->ops[i].kind != 0 || p->ops[i + 1].kind != 0 || taken[i] || taken[i + 1]) continue;
-    if (pass == 0 && p->convs[p->ops[i + 1].index].d.combine == RSB_COMB_NONE) continue;
+    if (p->ops[i].kind != 0 || p->ops[i + 1].kind != 0) continue;
     ConvOp& a = p->convs[p->ops[i].index];
     ConvOp& b = p->convs[p->ops[i + 1].index];
     const rsb_conv_desc &da = a.d, &db = b.d;
-    if (!a.rs_elig || !b.rs_elig || a.d_wrot == nullptr || b.d_wrot == nullptr) continue;
-    if (a.pack_buf >= 0 || b.pack_buf >= 0 || a.scale != b.scale) continue;
-    if (da.combine != RSB_COMB_NONE || da.act == RSB_ACT_PRELU || da.dst_buf < 0 || da.dst_ps > 1 || da.dst2_buf >= 0) continue;
+    if (!a.rs_elig || !b.rs_elig || a.tc_cin > 64 || a.npad > 64) continue;
+    if ((a.pack_buf >= 0 && !a.pack_planar) || b.pack_buf >= 0 || a.scale != b.scale) continue;
+    if ((da.combine != RSB_COMB_NONE && da.combine != RSB_COMB_SPAB_GATE) || da.res2_buf >= 0 || da.act == RSB_ACT_PRELU) continue;
+    if (da.dst_buf < 0 || da.dst_ps > 1 || da.dst2_buf >= 0) continue;
     if (da.cout != a.npad || b.npad != a.npad) continue;  // one UMMA N for both convs, no padded channels in the ring
     if (db.src_buf != da.dst_buf || db.src_ch_off != da.dst_ch_off || db.cin != da.cout || db.src_upsample2) continue;
     if (db.dst_buf < 0 || db.dst_ps > 1 || db.dst2_buf >= 0 || db.res2_buf >= 0 || db.act == RSB_ACT_PRELU) continue;
     const Region mid = conv_dst(a), bdst = conv_dst(b), asrc = conv_src(a);
     if (overlaps(bdst, asrc) || overlaps(bdst, mid)) continue;  // B's rows are written while A still reads its source
+    if (da.combine != RSB_COMB_NONE) {
+      const Region res = {da.res1_buf, da.res1_ch_off, da.res1_ch_off + ceil_div(da.cout, 8) * 8};
+      if (overlaps(res, mid) || overlaps(res, bdst)) continue;
+    }
     if (db.combine != RSB_COMB_NONE) {
       const Region res = {db.res1_buf, db.res1_ch_off, db.res1_ch_off + ceil_div(db.cout, 8) * 8};
       if (overlaps(res, mid) || overlaps(res, bdst)) continue;
     }
-    if (!rsb::conv_pair_supported(a.tc_cin, a.npad, da.act, db.act, db.combine)) continue;
+    const bool store = !region_dead_after(p, mid, i + 1);
+    if (!rsb::conv_pair_supported(a.tc_cin, a.npad, da.act, da.combine, store, db.act, db.combine)) continue;
     if (rsb::conv_pair_smem_bytes(a.tc_cin, a.npad) > kMaxSmem) continue;
-    if (!region_dead_after(p, mid, i + 1)) continue;
     a.pair_head = true;
-    taken[i] = taken[i + 1] = 1;  // pairs do not overlap
+    a.pair_store = store;
+    ++i;  // pairs do not overlap
   }
 }
 
@@ -356,7 +375,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       // 1x1 convs between planar buffers have no neighbourhood: view the image as (H*W/8) rows of 8 pixels, so that a
       // 16 x 8 tile is 128 CONSECUTIVE pixels — 2 KB contiguous per plane for the TMA load, the residual read and the store
       // instead of sixteen 128-byte pieces one image row apart.  Same linear addresses, same arithmetic, different tile shape.
-      static const bool no_linear = getenv("RSB_NO_LINEAR1X1") != nullptr;
+      static const bool no_linear = rsb::rsb_env("RSB_NO_LINEAR1X1") != nullptr;
       const bool linear = !no_linear && c.tc_kh == 1 && c.tc_kw == 1 && d.dst_buf >= 0 && d.dst_ps <= 1 && ((long long)H * W) % 8 == 0;
       const int Hm = linear ? (int)((long long)H * W / 8) : H, Wm = linear ? 8 : W;
       cuuint64_t dims[4] = {(cuuint64_t)Wm * 8, (cuuint64_t)Hm, (cuuint64_t)sb.planes, (cuuint64_t)n};
@@ -378,7 +397,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
         // K-chunked tiles: both issuing warps share ONE ring of stages in chunk order.  The seen[] counters of the kernel make
         // every full-barrier wait phase-exact, so two warps are safe for any chunk / stage count (measured +2..4 % on RealPLKSR,
         // SwinIR, DAT over a single issuing warp).  RSB_TC_SOLO=1 restores one issuing warp whenever 2 * chunks > stages.
-        static const bool solo_env = getenv("RSB_TC_SOLO") != nullptr;
+        static const bool solo_env = rsb::rsb_env("RSB_TC_SOLO") != nullptr;
         t.solo_issue = solo_env && t.nchunks > 1 && 2 * t.nchunks > c.stages;
       }
       t.kh = c.tc_kh, t.kw = c.tc_kw;
@@ -386,7 +405,6 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.pad_t = im2col ? 0 : d.pad_t, t.pad_l = im2col ? 0 : d.pad_l;
       t.src_plane0 = c.tc_src_ch_off / 8;
       t.wpack = c.d_wtc, t.wbytes = c.wbytes_tc;
-      t.wpack2 = c.d_wtc2;
       t.stages = c.stages;
       t.stage_bytes = (uint32_t)HT * WT * c.kchunk * 2u;
       t.num_acc = rsb::conv_tc_num_acc(c.npad);
@@ -483,15 +501,26 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     q.cols = cols, q.units = n * cols * H;
     q.cin0 = a.tc_cin, q.np = a.npad;
     q.src_plane0 = a.tc_src_ch_off / 8;
-    q.wpackA = a.d_wrot, q.wbytesA = a.wbytes_rot;
-    q.wpackB = b.d_wrot, q.wbytesB = b.wbytes_rot;
+    q.wpackA = a.d_wrs, q.wbytesA = a.wbytes_rs;
+    q.wpackB = b.d_wrs, q.wbytesB = b.wbytes_rs;
     q.stage_bytes = rsb::conv_rs_stage_bytes(a.tc_cin);
     q.biasA = a.d_bias, q.actA = a.d.act, q.actA_param = a.d.act_param;
+    q.combA = a.d.combine;
+    if (a.d.combine != RSB_COMB_NONE) {
+      const Buffer& rb = p->bufs[a.d.res1_buf];
+      q.resA = ws + rb.offset, q.resA_planes = rb.planes, q.resA_plane0 = a.d.res1_ch_off / 8;
+    }
+    if (a.pair_store) {
+      const Buffer& db = p->bufs[a.d.dst_buf];
+      q.dstA = ws + db.offset, q.dstA_planes = db.planes, q.dstA_plane0 = a.d.dst_ch_off / 8;
+    }
     q.epi = b.tcp.epi;
     memset(&a.map_res, 0, sizeof a.map_res);
-    if (b.d.combine != RSB_COMB_NONE) {
+    const int res_of = b.d.combine != RSB_COMB_NONE ? 1 : (a.d.combine != RSB_COMB_NONE ? 2 : 0);
+    if (res_of != 0) {
+      const rsb_conv_desc& rd = res_of == 1 ? b.d : a.d;
       EncodeTiledFn enc = get_encode_fn();
-      const Buffer& rb = p->bufs[b.d.res1_buf];
+      const Buffer& rb = p->bufs[rd.res1_buf];
       cuuint64_t dims5[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)H, (cuuint64_t)rb.planes, (cuuint64_t)n};
       cuuint64_t strides5[4] = {128, (cuuint64_t)W * 16, (cuuint64_t)W * 16 * H, (cuuint64_t)W * 16 * H * rb.planes};
       cuuint32_t box5[5] = {64, 16, 1, (cuuint32_t)(a.npad / 8), 1};
@@ -500,7 +529,8 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r5 != CUDA_SUCCESS) return fail(RSB_ERR_INVALID, "cuTensorMapEncodeTiled (pair residual) failed with CUresult %d", (int)r5);
-      q.res_prefetch = 1;
+      q.res_prefetch = res_of;
+      q.res_plane0 = rd.res1_ch_off / 8;
     }
     a.pair_ready = true;
   }
@@ -628,17 +658,16 @@ int rsb_plan_create(int compute_dtype, int in_channels, int out_channels, int up
 
 int rsb_plan_destroy(rsb_plan* p) {
   if (!p) return 0;
-  if (p->finalized) {
-    int prev = -1;
-    cudaGetDevice(&prev);
-    cudaSetDevice(p->device);
+  if (p->device >= 0) {
+    // also after a finalize that failed half-way: whatever was allocated up to that point is released (null pointers are fine)
+    DeviceGuard guard(p->device);
     for (ConvOp& c : p->convs) {
-      cudaFree(c.d_wtc), cudaFree(c.d_wtc2), cudaFree(c.d_wrs), cudaFree(c.d_wrot), cudaFree(c.d_wlk), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
+      cudaFree(c.d_wtc), cudaFree(c.d_wrs), cudaFree(c.d_wlk), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
     for (AuxOp& a : p->auxs)
       for (int k = 0; k < 8; ++k) cudaFree(a.dw[k]);
-    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
   }
   delete p;
   return 0;
@@ -847,17 +876,14 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
   RSB_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return fail(RSB_ERR_NO_DEVICE, "rsb_plan_finalize: device %d is sm_%d%d; this library only contains sm_100a code", device, prop.major, prop.minor);
-  int prev = -1;
-  cudaGetDevice(&prev);
-  RSB_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);
   p->device = device;
   p->num_sms = prop.multiProcessorCount;
   RSB_CUDA(rsb::conv_tc_configure(kMaxSmem));
-  RSB_CUDA(rsb::conv_tc2_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_rs_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_pair_configure(kMaxSmem));
   RSB_CUDA(rsb::conv_lk_configure(kMaxSmem));
-  static const bool no_rs = getenv("RSB_NO_RS") != nullptr;
+  static const bool no_rs = rsb::rsb_env("RSB_NO_RS") != nullptr;
 
   for (ConvOp& c : p->convs) {
     const rsb_conv_desc& d = c.d;
@@ -871,7 +897,7 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       // prefer the whole Cin per stage (static-geometry kernels); otherwise stage K chunks of 64/48/32/16 channels.
       // Up to 8 stages: a 48-channel 1x1 conv stages only 12 KB per tile, and four of those in flight per SM cap the kernel at
       // ~2 TB/s (bytes in flight = bandwidth x latency); big stages still get as many as fit.
-      static const int kMaxTcStages = getenv("RSB_TC_STAGES4") ? 4 : 8;
+      static const int kMaxTcStages = rsb::rsb_env("RSB_TC_STAGES4") ? 4 : 8;
       int stages = 0, kchunk = 0;
       const int cands[5] = {c.tc_cin, 64, 48, 32, 16};
       for (int ci = 0; ci < 5 && stages == 0; ++ci) {
@@ -924,7 +950,9 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
       RSB_CUDA(cudaMemcpy(c.d_wtc, wp.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
       if (!no_rs && d.kh == 3 && d.kw == 3 && d.pad_t == 1 && d.pad_l == 1 && 3 * c.npad <= 256 && 512 / c.npad >= 5) {
         // row-streaming kernel: [kw][cin/8][kh * npad + o][8] — the three kernel rows side by side on the N axis
-        static const int kMaxRsStages = getenv("RSB_RS_STAGES") ? atoi(getenv("RSB_RS_STAGES")) : 8;  // bring-up: deeper input ring
+        // input-ring depth: 6 / 8 / 12 stages measured 2.09 / 2.07 / 2.05 ms on SPAN 1080p (bring-up builds: RSB_RS_STAGES, clamped
+        // to the range the barrier layout was validated with)
+        static const int kMaxRsStages = rsb::rsb_env("RSB_RS_STAGES") ? std::min(12, std::max(3, atoi(rsb::rsb_env("RSB_RS_STAGES")))) : 8;
         for (int s = kMaxRsStages; s >= 3 && c.rs_stages == 0; --s)
           if (rsb::conv_rs_smem_bytes(c.tc_cin, c.npad, s) <= kMaxSmem) c.rs_stages = s;
         if (c.rs_stages > 0) {
@@ -940,21 +968,6 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
           RSB_CUDA(cudaMalloc(&c.d_wrs, c.wbytes_rs));
           RSB_CUDA(cudaMemcpy(c.d_wrs, wr.data(), c.wbytes_rs, cudaMemcpyHostToDevice));
           c.rs_elig = true;
-          if (c.tc_cin <= 64 && c.npad <= 64) {
-            // fused-pair layout: five N blocks holding kernel rows [2, 1, 0, 2, 1]
-            const int n5 = 5 * c.npad;
-            static const int kh_of_block[5] = {2, 1, 0, 2, 1};
-            std::vector<uint16_t> wq((size_t)3 * cin8 * n5 * 8, 0);
-            for (int o = 0; o < d.cout; ++o)
-              for (int ci = 0; ci < d.cin; ++ci)
-                for (int j = 0; j < 5; ++j)
-                  for (int kx = 0; kx < 3; ++kx)
-                    wq[(((size_t)kx * cin8 + ci / 8) * n5 + j * c.npad + o) * 8 + (ci & 7)] =
-                        f32_to_bf16(c.w[((size_t)o * d.cin + ci) * 9 + kh_of_block[j] * 3 + kx]);
-            c.wbytes_rot = (uint32_t)(wq.size() * 2);
-            RSB_CUDA(cudaMalloc(&c.d_wrot, c.wbytes_rot));
-            RSB_CUDA(cudaMemcpy(c.d_wrot, wq.data(), c.wbytes_rot, cudaMemcpyHostToDevice));
-          }
         }
       }
       if (!no_rs && d.kh == d.kw && d.kh % 2 == 1 && d.kh >= 5 && d.kh <= 17 && d.pad_t == d.kh / 2 && d.pad_l == d.kw / 2 && c.npad == 16 &&
@@ -976,19 +989,6 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
           RSB_CUDA(cudaMemcpy(c.d_wlk, wl.data(), c.wbytes_lk, cudaMemcpyHostToDevice));
           c.lk_elig = true;
         }
-      }
-      if (c.npad % 16 == 0 && c.kchunk == c.tc_cin) {
-        // CTA-pair layout: CTA r of a pair holds output channels [r*N/2, (r+1)*N/2)
-        const int nh = c.npad / 2;
-        std::vector<uint16_t> w2(wp.size(), 0);
-        for (int r = 0; r < 2; ++r)
-          for (int t = 0; t < taps; ++t)
-            for (int g = 0; g < cin8; ++g)
-              for (int j = 0; j < nh; ++j)
-                for (int e = 0; e < 8; ++e)
-                  w2[((((size_t)r * taps + t) * cin8 + g) * nh + j) * 8 + e] = wp[(((size_t)t * cin8 + g) * c.npad + r * nh + j) * 8 + e];
-        RSB_CUDA(cudaMalloc(&c.d_wtc2, c.wbytes_tc));
-        RSB_CUDA(cudaMemcpy(c.d_wtc2, w2.data(), c.wbytes_tc, cudaMemcpyHostToDevice));
       }
     }
     {
@@ -1018,11 +1018,85 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
         RSB_CUDA(cudaMemcpy(a.dw[k], a.w[k].data(), a.w[k].size() * sizeof(float), cudaMemcpyHostToDevice));
       }
   p->finalized = true;
-  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  // A bf16 plan is meant to run on tensor cores; a conv that does not fit them runs on the CUDA-core kernel (~30 TFLOP/s).
+  // Correct, but a performance cliff the caller should know about: count them (rsb_plan_num_direct_convs) and say so once.
+  p->num_direct = 0;
+  if (p->dtype == RSB_BF16)
+    for (const ConvOp& c : p->convs) p->num_direct += c.tc_ok ? 0 : 1;
+  if (p->num_direct > 0) {
+    static std::once_flag warned;
+    const int nd = p->num_direct, nc = (int)p->convs.size();
+    std::call_once(warned, [nd, nc] {
+      fprintf(stderr, "resselt_b200: %d of %d convolutions of a bf16 plan do not fit the tensor-core kernels and run on the CUDA-core "
+                      "kernel (see rsb_plan_num_direct_convs)\n", nd, nc);
+    });
+  }
   return 0;
 }
 
 int rsb_plan_num_ops(const rsb_plan* p) { return p ? (int)p->ops.size() : 0; }
+int rsb_plan_num_direct_convs(const rsb_plan* p) { return p ? p->num_direct : 0; }
+
+const char* rsb_kernel_name(int k) {
+  static const char* const names[] = {"conv_direct", "conv_tc", "conv_rs", "conv_lk", "conv_pair", "groupnorm", "layernorm", "dwconv3",
+                                      "winattn", "chanattn", "aim", "dysample"};
+  return (k >= 0 && k < (int)(sizeof(names) / sizeof(names[0]))) ? names[k] : "unknown";
+}
+
+int rsb_plan_op_info(const rsb_plan* p, int op_index, rsb_op_info* out) {
+  if (!p || !out) return fail(RSB_ERR_INVALID, "rsb_plan_op_info: NULL argument");
+  if (op_index < 0 || op_index >= (int)p->ops.size()) return fail(RSB_ERR_INVALID, "rsb_plan_op_info: op %d outside [0, %zu)", op_index, p->ops.size());
+  if (!p->bws) return fail(RSB_ERR_STATE, "rsb_plan_op_info: no forward has bound a shape yet");
+  memset(out, 0, sizeof *out);
+  const Op& op = p->ops[op_index];
+  out->kind = op.kind;
+  out->launches = 1;
+  const double es = (double)p->elem();
+  if (op.kind == 0) {
+    const ConvOp& c = p->convs[op.index];
+    auto px = [&](const ConvOp& k) { return (double)p->bn * (p->bh * k.scale) * (double)(p->bw * k.scale); };
+    auto flops = [&](const ConvOp& k) { return 2.0 * k.d.cout * k.d.cin * k.d.kh * k.d.kw * px(k); };
+    auto out_bytes = [&](const ConvOp& k) { return (double)k.d.cout * px(k) * es; };
+    auto res_bytes = [&](const ConvOp& k) {
+      return k.d.combine == RSB_COMB_NONE ? 0.0 : (double)k.d.cout * px(k) * es * (k.d.combine == RSB_COMB_AXPY && k.d.res2_buf >= 0 ? 2 : 1);
+    };
+    auto in_bytes = [&](const ConvOp& k) { return (double)(k.d.src_buf == RSB_EXTERNAL_INPUT ? k.d.cin : k.tc_cin) * px(k) * es; };
+    // fused pairs are the opt-in mode 4: pair_ready says whether op_index heads one
+    const bool fused_mode = p->info_mode == 4;
+    if (fused_mode && op_index > 0 && p->ops[op_index - 1].kind == 0 && p->convs[p->ops[op_index - 1].index].pair_ready) {
+      out->kernel = RSB_K_CONV_PAIR, out->launches = 0;
+      return 0;
+    }
+    if (fused_mode && c.pair_ready && op_index + 1 < (int)p->ops.size()) {
+      const ConvOp& b = p->convs[p->ops[op_index + 1].index];
+      out->kernel = RSB_K_CONV_PAIR, out->fused_next = 1;
+      out->launches = 1 + (c.pack_buf >= 0 ? 1 : 0);
+      out->flops = flops(c) + flops(b);
+      out->bytes = in_bytes(c) + res_bytes(c) + (c.pair_store ? out_bytes(c) : 0.0) + res_bytes(b) + out_bytes(b);
+      return 0;
+    }
+    out->flops = flops(c);
+    out->bytes = in_bytes(c) + res_bytes(c) + out_bytes(c);
+    if (!c.tc_ok)
+      out->kernel = RSB_K_CONV_DIRECT;
+    else {
+      out->launches = 1 + (c.pack_buf >= 0 ? 1 : 0);
+      out->kernel = (c.lk_ready && c.rs_pref) ? RSB_K_CONV_LK : ((c.rs_ready && c.rs_pref) ? RSB_K_CONV_RS : RSB_K_CONV_TC);
+    }
+  } else if (op.kind == 1) {
+    out->kernel = RSB_K_GROUPNORM, out->launches = 2;
+  } else {
+    switch (p->auxs[op.index].d.kind) {
+      case RSB_OP_LAYERNORM: out->kernel = RSB_K_LAYERNORM; break;
+      case RSB_OP_DWCONV3: out->kernel = RSB_K_DWCONV3; break;
+      case RSB_OP_WINATTN: out->kernel = RSB_K_WINATTN; break;
+      case RSB_OP_CHANATTN: out->kernel = RSB_K_CHANATTN, out->launches = 3; break;
+      case RSB_OP_AIM: out->kernel = RSB_K_AIM, out->launches = 3; break;
+      default: out->kernel = RSB_K_DYSAMPLE; break;
+    }
+  }
+  return 0;
+}
 
 int rsb_plan_launches_per_forward(const rsb_plan* p) {
   if (!p) return 0;
@@ -1030,11 +1104,7 @@ int rsb_plan_launches_per_forward(const rsb_plan* p) {
   for (const ConvOp& c : p->convs) packed += (c.pack_buf >= 0 && c.tc_ok) ? 1 : 0;
   int aux = 0;
   for (const AuxOp& a : p->auxs) aux += (a.d.kind == RSB_OP_CHANATTN || a.d.kind == RSB_OP_AIM) ? 3 : 1;
-  int fused = 0;  // a fused pair is one launch for two convs (opt-in: RSB_PAIR=1)
-  static const bool pair_env = getenv("RSB_PAIR") != nullptr;
-  if (pair_env)
-    for (const ConvOp& c : p->convs) fused += (c.pair_head && (p->bws == nullptr || c.pair_ready)) ? 1 : 0;
-  return (int)p->convs.size() - fused + packed + 2 * (int)p->gns.size() + aux;
+  return (int)p->convs.size() + packed + 2 * (int)p->gns.size() + aux;  // mode 0; mode 4 saves one launch per fused pair
 }
 
 int rsb_plan_flops(const rsb_plan* p, int n, int h, int w, double* flops) {
@@ -1069,9 +1139,8 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
     return fail(RSB_ERR_INVALID, "rsb_plan_forward: bad tensor dtype");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   std::lock_guard<std::mutex> lock(p->mu);
-  int prev = -1;
-  cudaGetDevice(&prev);
-  if (prev != p->device) RSB_CUDA(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  p->info_mode = force_direct;
   int rc = 0;
   if (p->bn != n || p->bh != h || p->bw != w || p->bws != workspace) rc = bind(p, n, h, w, workspace, workspace_bytes, stream);
   if (rc == 0) {
@@ -1080,9 +1149,19 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
       cudaError_t e;
       if (op.kind == 0) {
         ConvOp& c = p->convs[op.index];
-        static const bool pair_env = getenv("RSB_PAIR") != nullptr;
-        if (c.pair_ready && ((force_direct == 0 && pair_env) || force_direct == 4) && oi + 1 < op_end) {
-          // this conv and the next one as one fused launch; the intermediate map is not materialised
+        if (c.pair_ready && force_direct == 4 && oi + 1 < op_end) {
+          // opt-in (mode 4): this conv and the next one as one fused launch; the intermediate map is not re-read from HBM.
+          // Not the default: measured on B200 the fused pair is bound by shared-memory bandwidth (operand reads of the N = 144 MMAs
+          // + ring / stage traffic) at about the time the two HBM-bound single launches take (profiles/r2_conv_pair_analysis.md)
+          if (c.pack_buf >= 0) {
+            rsb::PackParams k = c.pk;
+            k.src = x, k.src_dtype = x_dtype;
+            e = rsb::launch_pack_input(k, stream);
+            if (e != cudaSuccess) {
+              rc = fail_cuda(e, "kernel launch");
+              break;
+            }
+          }
           rsb::ConvPairParams q = c.prp;
           e = rsb::launch_conv_pair(c.map_rs, q.res_prefetch ? c.map_res : c.map_rs, q, p->num_sms, stream);
           ++oi;
@@ -1099,7 +1178,6 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           rsb::ConvTcParams t = c.tcp;
           if (t.epi.dst_external) t.epi.dst = y, t.epi.out_dtype = y_dtype;
           t.epi.base = x, t.epi.base_dtype = x_dtype;
-          static const bool pair_kernel = getenv("RSB_TC2") != nullptr;
           if (c.lk_ready && force_direct != 2 && (c.rs_pref || force_direct == 3)) {
             rsb::ConvLkParams q = c.lkp;
             q.epi = t.epi;
@@ -1108,9 +1186,7 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
             rsb::ConvRsParams q = c.rsp;
             q.epi = t.epi;
             e = rsb::launch_conv_rs(c.map_rs, q, p->num_sms, stream);
-          } else if (pair_kernel && rsb::conv_tc2_supported(t))
-            e = rsb::launch_conv_tc2(c.map, t, p->num_sms, stream);
-          else
+          } else
             e = rsb::launch_conv_tc(c.map, t, p->num_sms, stream);
         } else {
           rsb::ConvDirectParams q = c.dp;
@@ -1125,7 +1201,7 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
         AuxOp& a = p->auxs[op.index];
         const bool bf = p->dtype == RSB_BF16;
         switch (a.d.kind) {
-          case RSB_OP_LAYERNORM: e = rsb::launch_layernorm(a.tok, bf, stream); break;
+          case RSB_OP_LAYERNORM: e = rsb::launch_layernorm(a.tok, bf, p->num_sms, stream); break;
           case RSB_OP_DWCONV3: e = rsb::launch_dwconv3(a.tok, bf, stream); break;
           case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, stream); break;
           case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, stream); break;
@@ -1144,7 +1220,6 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
       }
     }
   }
-  if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
   return rc;
 }
 

@@ -13,13 +13,12 @@ import subprocess
 import threading
 
 CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'csrc'))
-LIB_PATH = os.path.join(CSRC_DIR, 'libresselt_b200.so')
-SOURCES = ('conv_tc.cu', 'conv_tc2.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_lk.cu', 'conv_direct.cu', 'dat_ops.cu', 'plan.cu')
+BRINGUP = bool(os.environ.get('RSB_BRINGUP'))  # bring-up flavour: separate library, never the one the product loads
+LIB_PATH = os.path.join(CSRC_DIR, 'libresselt_b200_bringup.so' if BRINGUP else 'libresselt_b200.so')
+SOURCES = ('conv_tc.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_lk.cu', 'conv_direct.cu', 'dat_ops.cu', 'plan.cu')
 HEADERS = ('kernels.cuh', 'ptx.cuh', os.path.join('..', '..', 'include', 'resselt_b200.h'))
-NVCC_FLAGS = (
-    '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-    '-Xcompiler', '-fPIC', '-shared',
-)
+NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC')
+OBJ_DIR = os.path.join(CSRC_DIR, 'build')  # git-ignored object files, one per source
 
 # enums (keep in sync with include/resselt_b200.h)
 F32, BF16, F16 = 0, 1, 2
@@ -33,6 +32,7 @@ EXPORTED_SYMBOLS = (
     'rsb_plan_add_buffer', 'rsb_plan_add_conv', 'rsb_plan_add_groupnorm', 'rsb_plan_add_op', 'rsb_plan_finalize',
     'rsb_plan_num_ops', 'rsb_plan_launches_per_forward', 'rsb_plan_flops', 'rsb_plan_workspace_bytes',
     'rsb_plan_forward', 'rsb_plan_forward_ops', 'rsb_plan_read_buffer',
+    'rsb_plan_num_direct_convs', 'rsb_plan_op_info', 'rsb_kernel_name',
 )
 
 
@@ -83,6 +83,17 @@ class OpDesc(C.Structure):
     ]
 
 
+class OpInfo(C.Structure):
+    _fields_ = [
+        ('kind', C.c_int32), ('kernel', C.c_int32), ('fused_next', C.c_int32), ('launches', C.c_int32),
+        ('flops', C.c_double), ('bytes', C.c_double),
+    ]
+
+
+def _deps_mtime() -> float:
+    return max(os.path.getmtime(os.path.join(CSRC_DIR, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC_DIR, h)))
+
+
 def library_is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -92,19 +103,41 @@ def library_is_stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into one shared library (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into one shared library (nvcc cross-compiles without a GPU).
+
+    One object per source, compiled in parallel and re-used while neither the source nor a header changed; RSB_BRINGUP=1 in
+    the environment of the BUILD adds -DRSB_BRINGUP (the kernel-selection environment switches, see kernels.cuh)."""
     if not force and not library_is_stale():
         return LIB_PATH
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libresselt_b200.so')
-    cmd = [nvcc, *NVCC_FLAGS, '-o', LIB_PATH + '.tmp', *SOURCES]
-    proc = subprocess.run(cmd, cwd=CSRC_DIR, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + proc.stdout + proc.stderr)
+    flags = list(NVCC_FLAGS) + (['-DRSB_BRINGUP'] if BRINGUP else [])
+    tag = 'bringup' if BRINGUP else 'product'
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr = _deps_mtime()
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, f'{os.path.splitext(src)[0]}.{tag}.o')
+        fresh = (not force and os.path.exists(obj)
+                 and os.path.getmtime(obj) >= max(hdr, os.path.getmtime(os.path.join(CSRC_DIR, src))))
+        jobs.append((src, obj, fresh))
+    procs = [(src, subprocess.Popen([nvcc, *flags, '-c', src, '-o', obj], cwd=CSRC_DIR, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+             for src, obj, fresh in jobs if not fresh]
+    log, failed = '', []
+    for src, proc in procs:
+        out, _ = proc.communicate()
+        log += out
+        if proc.returncode != 0:
+            failed.append(src)
+    if failed:
+        raise RuntimeError(f'nvcc failed on {failed}:\n' + log)
+    link = subprocess.run([nvcc, '-shared', '-o', LIB_PATH + '.tmp', *[obj for _, obj, _ in jobs]], cwd=CSRC_DIR, capture_output=True, text=True)
+    if link.returncode != 0:
+        raise RuntimeError('link failed:\n' + link.stdout + link.stderr)
     os.replace(LIB_PATH + '.tmp', LIB_PATH)
     if verbose:
-        print(proc.stdout + proc.stderr)
+        print(log + link.stdout + link.stderr)
     return LIB_PATH
 
 
@@ -149,6 +182,10 @@ def lib() -> C.CDLL:
             C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int,
         ]
         L.rsb_plan_read_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.rsb_plan_num_direct_convs.argtypes = [C.c_void_p]
+        L.rsb_plan_op_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(OpInfo)]
+        L.rsb_kernel_name.argtypes = [C.c_int]
+        L.rsb_kernel_name.restype = C.c_char_p
         for name in EXPORTED_SYMBOLS:
             getattr(L, name)  # AttributeError if the library does not export the declared ABI
         _lib = L

@@ -244,6 +244,33 @@ class Plan:
     def num_ops(self) -> int:
         return int(self._lib.rsb_plan_num_ops(self._h))
 
+    @property
+    def num_direct_convs(self) -> int:
+        """bf16 plans: convolutions that fell back to the CUDA-core kernel (0 for every supported configuration)."""
+        return int(self._lib.rsb_plan_num_direct_convs(self._h))
+
+    def op_info(self, index: int) -> dict:
+        """Kernel, launch count, algorithmic FLOPs / HBM bytes of op ``index`` at the shape of the last forward."""
+        info = N.OpInfo()
+        N.check(self._lib.rsb_plan_op_info(self._h, index, C.byref(info)))
+        return dict(kind=info.kind, kernel=(self._lib.rsb_kernel_name(info.kernel) or b'').decode(), fused_next=bool(info.fused_next),
+                    launches=info.launches, flops=info.flops, bytes=info.bytes)
+
+    @property
+    def fused_pairs(self) -> int:
+        """Fused conv-pair launches per forward at the shape of the last forward."""
+        return sum(1 for i in range(self.num_ops) if self.op_info(i)['fused_next'])
+
+    def launch_units(self):
+        """[(op_begin, op_end, info)] — the op ranges that run as one kernel launch group (a fused pair is one unit)."""
+        units, i = [], 0
+        while i < self.num_ops:
+            info = self.op_info(i)
+            j = i + (2 if info['fused_next'] else 1)
+            units.append((i, j, info))
+            i = j
+        return units
+
     MAX_GRAPHS = 16
 
     def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, ops: Optional[tuple] = None, graph: bool = False) -> torch.Tensor:
