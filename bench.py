@@ -8,13 +8,20 @@ frames, no collective on the compute path).  Rank 0 prints ONE JSON line.
 
   value        device-resident throughput: frames already in HBM, CUDA-event timed, max over ranks
   e2e          same metric through the public API with HOST buffers: pinned H2D copy of every frame and
-               D2H copy of every upscaled frame inside the timed region (resselt_b200.runner.FramePipeline)
-  roofline     the dominant kernel (3x3 48->48 tensor-core conv + SiLU) timed alone with CUDA events
-               against the measured dense-bf16 peak (MEASURED_PEAKS.json, burst figure)
-  cpu_baseline the CPU oracle (restatement of the reference forward) on this host's cores, bounded sample
+               D2H copy of every upscaled frame inside the timed region (resselt_b200.runner.FramePipeline);
+               e2e.copy_ceiling = the same pipeline with the forward left out (what the copies alone allow)
+  roofline     the dominant kernel of the step: every launch unit of the plan is replayed from a CUDA graph
+               (no host launch cost) and timed with CUDA events; the kernel class with the largest summed time
+               is reported against the measured dense-bf16 peak (MEASURED_PEAKS.json, burst figure: each unit
+               is timed alone), together with its share of the step and the sum of all unit times
+  cpu_baseline the reference's own forward (baseline/_ref, else the oracle port) on this host's cores: the
+               full 1080p frame, bf16 and fp32
+  gpu_library_baseline  the unmodified reference module on the same GPU in eager PyTorch (cuDNN), bf16,
+               NCHW and channels_last — the library baseline the engine has to beat
 
---impl reference times the reference's own algorithm on the host CPU (oracle port: the reference is a
-pure-Python package over PyTorch ATen and does not travel to the GPU box), all host threads.
+--impl reference times the reference's own CPU forward (resselt from baseline/_ref when it is installed:
+tools/install_reference.sh; else the oracle port) on all host threads: every step is one full 1080p frame
+in bf16, the metric's shape and dtype.
 """
 from __future__ import annotations
 
@@ -89,42 +96,117 @@ def _oracle_state_dict():
     return {k: v.clone() for k, v in SPAN(num_in_ch=3, num_out_ch=3, feature_channels=FEATURES, upscale=SCALE, seed=WEIGHT_SEED).state_dict().items()}
 
 
-def _cpu_forward_rate(h: int, w: int, steps: int, warmup: int):
-    """Oracle (CPU restatement of the reference forward) on all host threads; returns (out MP/s, ms/step, threads)."""
+def _live_reference():
+    """The unmodified reference package, if it was installed into baseline/_ref (tools/install_reference.sh); never /root/reference."""
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'resselt')):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import resselt  # noqa: PLC0415
+
+        return resselt
+    except Exception:  # noqa: BLE001 - a broken install must not take the bench down; the port is the fallback
+        return None
+
+
+def _cpu_forward(dtype_name: str):
+    """(callable x -> y on the CPU, kind) for the reference's SPAN forward: the live reference module when available, else the oracle port."""
     import torch
 
+    sd = _oracle_state_dict()
+    dtype = torch.bfloat16 if dtype_name == 'bf16' else torch.float32
+    ref = _live_reference()
+    if ref is not None:
+        model = ref.load_from_state_dict({k: v.clone() for k, v in sd.items()}).eval().to(dtype)
+        return (lambda x: model(x)), 'reference'
     import oracle
+
+    return (lambda x: oracle.forward_by_name('SPAN', sd, x, dtype)), 'port'
+
+
+def _cpu_forward_rate(h: int, w: int, steps: int, warmup: int, dtype_name: str = 'bf16'):
+    """The reference's CPU forward on all host threads; returns (out MP/s, ms/step, threads, kind)."""
+    import torch
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = _oracle_state_dict()
-    x = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(1))
-    for _ in range(warmup):
-        oracle.forward_by_name('SPAN', sd, x, torch.float32)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        oracle.forward_by_name('SPAN', sd, x, torch.float32)
-    dt = (time.perf_counter() - t0) / steps
-    return h * w * SCALE * SCALE / 1e6 / dt, dt * 1e3, threads
+    fwd, kind = _cpu_forward(dtype_name)
+    dtype = torch.bfloat16 if dtype_name == 'bf16' else torch.float32
+    x = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(1)).to(dtype)
+    with torch.inference_mode():
+        for _ in range(warmup):
+            fwd(x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fwd(x)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    return h * w * SCALE * SCALE / 1e6 / dt, dt * 1e3, threads, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    # bounded sample per step: a 270x480 crop (1/16 of a 1080p frame) so K+W steps stay within minutes
-    sh, sw = 270, 480
-    value, ms, threads = _cpu_forward_rate(sh, sw, args.steps, args.warmup)
-    sample = f'{args.steps} steps of one {sh}x{sw} crop (1/16 of a 1080p frame), fp32, torch CPU ops, {threads} threads'
+    # every step is one full 1x3x1080x1920 frame in bf16 — the metric's shape and dtype; a step takes a few seconds of CPU time
+    value, ms, threads, kind = _cpu_forward_rate(H, W, args.steps, args.warmup, 'bf16')
+    fp32_value, fp32_ms, _, _ = _cpu_forward_rate(H, W, 1, 0, 'fp32')
+    what = 'resselt (baseline/_ref) load_from_state_dict(...).eval().bfloat16() forward' if kind == 'reference' else 'oracle port of the reference forward'
+    sample = f'{args.steps} steps of one full 1x3x{H}x{W} frame, bf16, {what}, torch CPU ops, {threads} threads'
     line = dict(
         impl='reference', metric=METRIC, value=value, unit='MP/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-        ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+        ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
         config=dict(workload=WORKLOAD, sample=sample),
-        cpu_baseline=dict(value=value, unit='MP/s', cores=threads, kind='port', sample=sample),
+        cpu_baseline=dict(value=value, unit='MP/s', cores=threads, kind=kind, sample=sample, fp32_value=fp32_value, fp32_ms_per_step=fp32_ms),
         e2e=dict(value=value, unit='MP/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
     )
     print(json.dumps(line), flush=True)
+
+
+def _gpu_library_baseline(dev, frame_bf16):
+    """The unmodified reference module on this GPU through eager PyTorch (cuDNN / cuBLAS), bf16: NCHW and channels_last.
+    Same weights, same frame, CUDA events; None when the reference is not installed in baseline/_ref."""
+    import torch
+
+    ref = _live_reference()
+    if ref is None:
+        return None
+    sd = _oracle_state_dict()
+    out = dict(what='resselt.load_from_state_dict(sd).eval().cuda().bfloat16()(x), eager PyTorch %s, cuDNN %s' % (torch.__version__, torch.backends.cudnn.version()))
+    torch.backends.cudnn.benchmark = True
+    for name, fmt in (('nchw', torch.contiguous_format), ('channels_last', torch.channels_last)):
+        try:
+            model = ref.load_from_state_dict({k: v.clone() for k, v in sd.items()}).eval().to(dev).bfloat16().to(memory_format=fmt)
+            x = frame_bf16.to(memory_format=fmt)
+            with torch.inference_mode():
+                for _ in range(3):
+                    model(x)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                iters = 10
+                e0.record()
+                for _ in range(iters):
+                    model(x)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / iters
+            out[name] = dict(ms_per_step=ms, value=OUT_MP / (ms * 1e-3), unit='MP/s')
+            del model
+        except Exception as exc:  # noqa: BLE001 - report, do not fail the engine's bench
+            out[name] = dict(error=f'{type(exc).__name__}: {exc}'[:200])
+        torch.cuda.empty_cache()
+    return out
+
+
+class _CopyOnly:
+    """Stand-in model for FramePipeline that launches nothing: what the pinned H2D + D2H copies alone allow."""
+
+    out_channels = 3
+
+    def forward_into(self, din, dout):
+        return dout
 
 
 def _free_port():
@@ -200,19 +282,27 @@ def run_engine(args):
     value = world * args.steps * OUT_MP / (ms_total / 1e3)
 
     # ---------------------------------------------------------------- end to end (host buffers, copies timed)
-    pipe = FramePipeline(model, SCALE, dev, depth=3)
+    depth = 4
     frames = [host_frames[i % n_inputs] for i in range(args.steps)]
-    host_out = [torch.empty((1, 3, H * SCALE, W * SCALE), dtype=torch.bfloat16).pin_memory() for _ in range(min(args.steps, 4))]
+    host_out = [torch.empty((1, 3, H * SCALE, W * SCALE), dtype=torch.bfloat16).pin_memory() for _ in range(min(args.steps, 2 * depth))]
     outs = [host_out[i % len(host_out)] for i in range(args.steps)]
-    pipe.run(frames[: max(3, args.warmup)], outs[: max(3, args.warmup)])
-    barrier()
-    t0 = time.perf_counter()
-    pipe.run(frames, outs)
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    barrier()
+
+    def timed_pipeline(pipe):
+        pipe.run(frames[: max(depth, args.warmup)], outs[: max(depth, args.warmup)])  # warm-up: slots allocated, graphs captured
+        barrier()
+        t0 = time.perf_counter()
+        pipe.run(frames, outs)
+        torch.cuda.synchronize()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        barrier()
+        return ms
+
+    e2e_ms = timed_pipeline(FramePipeline(model, SCALE, dev, depth=depth))
+    # the same pipeline with the forward left out: the ceiling the host<->device copies set on this box at this rank count
+    copy_ms = timed_pipeline(FramePipeline(_CopyOnly(), SCALE, dev, depth=depth))
     clocks = sampler.stop() if sampler else None
     e2e_value = world * args.steps * OUT_MP / (e2e_ms / 1e3)
+    copy_value = world * args.steps * OUT_MP / (copy_ms / 1e3)
     h2d = host_frames[0].numel() * host_frames[0].element_size()
     d2h = host_out[0].numel() * host_out[0].element_size()
 
@@ -221,35 +311,35 @@ def run_engine(args):
             dist.destroy_process_group()
         return
 
-    # ---------------------------------------------------------------- dominant kernel alone (roofline)
-    # op 1 of the SPAN plan is block_1.c1_r: the 3x3 48->48 tensor-core conv + SiLU that makes up 12 of the 23
-    # launches (its gate / plain siblings share the kernel template); re-run just that op on the live buffers
+    # ---------------------------------------------------------------- dominant kernel (roofline), timed inside CUDA graphs
+    # Every launch unit of the plan is captured `reps` times into one graph and replayed: device time without host launch cost,
+    # so kernel_ms x launches <= ms_per_step holds.  Each unit re-reads the 199 MB activation maps the step left in the plan's
+    # buffers (larger than the 126 MB L2).  The class with the largest summed time is the dominant kernel.
+    from resselt_b200.engine.profiling import summarize_units, time_forward, time_units
+
     peaks = _peaks()
-    f = FEATURES
-    iters = 50
     with torch.inference_mode():
-        for _ in range(3):
-            plan.forward(dev_frames[0], out=out, ops=(1, 2))
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(iters):
-            plan.forward(dev_frames[0], out=out, ops=(1, 2))
-        k1.record()
-        torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / iters
-    kernel_flops = 2.0 * f * f * 9 * H * W
-    achieved = kernel_flops / (kernel_ms * 1e-3) / 1e12
+        units = time_units(plan, dev_frames[0], out, reps=10)
+        graph_forward_ms = time_forward(plan, dev_frames[0], out, reps=10)
+    classes = summarize_units(units)
+    dom_name = max(classes, key=lambda k: classes[k]['ms'])
+    dom = classes[dom_name]
+    # within the class, the launches that make up most of it share one shape: 3x3 48->48 at 1080p
+    dom_units = [u for u in units if u['kernel'] == dom_name]
+    kernel_ms = dom['ms'] / max(dom['units'], 1)
+    achieved = dom['tflops']
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get('dram_bytes_per_launch')
     step_tflops = plan.flops(1, H, W) * world * args.steps / (ms_total * 1e-3) / 1e12
+    sum_units_ms = sum(u['ms'] for u in units)
 
-    # ---------------------------------------------------------------- CPU baseline (bounded sample, this host)
-    cpu_h, cpu_w = 540, 960  # a quarter frame: ~10-30 s of CPU work with one warm-up
-    cpu_value, cpu_ms, cpu_threads = _cpu_forward_rate(cpu_h, cpu_w, steps=2, warmup=1)
+    # ---------------------------------------------------------------- CPU baseline (bounded sample, this host) + library baseline (this GPU)
+    cpu_value, cpu_ms, cpu_threads, cpu_kind = _cpu_forward_rate(H, W, steps=2, warmup=1, dtype_name='bf16')
+    cpu32_value, cpu32_ms, _, _ = _cpu_forward_rate(H, W, steps=1, warmup=0, dtype_name='fp32')
+    lib = _gpu_library_baseline(dev, dev_frames[0])
 
     line = dict(
         metric=METRIC, value=value, unit='MP/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -260,14 +350,26 @@ def run_engine(args):
                     weights='random init (seeded), loaded through resselt_b200.load_from_state_dict'),
         clocks=clocks,
         e2e=dict(value=e2e_value, unit='MP/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps,
-                 api='resselt_b200.runner.FramePipeline over load_from_state_dict(...) module, pinned host frames'),
+                 api='resselt_b200.runner.FramePipeline (depth 4) over load_from_state_dict(...) module, pinned host frames',
+                 copy_ceiling=dict(value=copy_value, unit='MP/s', ms_per_step=copy_ms / args.steps,
+                                   what='same pipeline, forward left out: pinned H2D + D2H copies only',
+                                   host_gbs=world * (h2d + d2h) / (copy_ms / args.steps * 1e-3) / 1e9),
+                 frac_of_copy_ceiling=e2e_value / copy_value),
         gpu_launches=plan.launches_per_forward * args.steps,
         roofline=dict(bound='tensor', achieved=achieved, peak=peaks['bf16_burst'], unit='TFLOP/s', frac=achieved / peaks['bf16_burst'],
-                      traffic=traffic, kernel='conv_rs (row-streaming tcgen05) 3x3 48->48 + SiLU, 1080p', kernel_ms=kernel_ms, flops_per_launch=kernel_flops,
-                      peak_source=peaks['source'] + ' burst bf16 (kernel timed alone)',
+                      traffic=traffic, kernel=f'{dom_name} (tcgen05 row-streaming 3x3 conv + fused epilogue), {dom["units"]} launches per forward',
+                      kernel_ms=kernel_ms, launches_per_step=dom['units'], share_of_unit_time=dom['share'],
+                      flops_per_launch=dom['flops'] / max(dom['units'], 1), algorithmic_bytes_per_launch=dom['bytes'] / max(dom['units'], 1),
+                      hbm_gbs=dom['gbs'], hbm_frac=dom['gbs'] / peaks['hbm'],
+                      timing='each launch unit replayed 10x from one CUDA graph, CUDA events, best of 2 replays',
+                      sum_of_unit_ms=sum_units_ms, graph_forward_ms=graph_forward_ms,
+                      kernel_min_ms=min(u['ms'] for u in dom_units), kernel_max_ms=max(u['ms'] for u in dom_units),
+                      classes={k: dict(units=v['units'], ms=v['ms'], share=v['share']) for k, v in classes.items()},
+                      peak_source=peaks['source'] + ' burst bf16 (each unit timed alone)',
                       step_tflops=step_tflops, step_frac_of_sustained=step_tflops / (peaks['bf16_sustained'] * world)),
-        cpu_baseline=dict(value=cpu_value, unit='MP/s', cores=cpu_threads, kind='port',
-                          sample=f'2 forwards of one {cpu_h}x{cpu_w} crop (quarter of a 1080p frame), fp32, after 1 warm-up'),
+        cpu_baseline=dict(value=cpu_value, unit='MP/s', cores=cpu_threads, kind=cpu_kind, ms_per_step=cpu_ms,
+                          sample=f'2 forwards of the full 1x3x{H}x{W} frame, bf16, after 1 warm-up', fp32_value=cpu32_value, fp32_ms_per_step=cpu32_ms),
+        gpu_library_baseline=lib,
     )
     print(json.dumps(line), flush=True)
     if world > 1:

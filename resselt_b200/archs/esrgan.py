@@ -126,8 +126,15 @@ class RRDBNet(EngineModule):
 
     @property
     def receptive_radius(self) -> int:
-        # LR pixels: first conv (1) + 15 convs per RRDB + trunk conv (1) + the HR-side convs (2 LR pixels cover them)
-        return 15 * self.num_blocks + 4
+        # plan-grid pixels: first conv (1) + 15 convs per RRDB + trunk conv (1) + the HR-side convs (2 LR pixels cover them);
+        # behind a pixel-unshuffle front end (Real-ESRGAN x2 / x1) one plan-grid pixel is shuffle_factor caller pixels
+        return (15 * self.num_blocks + 4) * (self.shuffle_factor or 1)
+
+    @property
+    def tile_multiple(self) -> int:
+        # tiles must start on multiples of shuffle_factor: otherwise pixel_unshuffle phases (and the reflect pad of odd sizes,
+        # esrgan/arch.py:130-137) differ from the untiled forward
+        return self.shuffle_factor or 1
 
     # ------------------------------------------------------------------ plan
     def _conv5(self, pb: PlanBuilder, w, name: str, src: Ref, dst: Ref, tmp: Ref, alpha: float, r_in: Ref, r_outer: Ref | None):

@@ -158,8 +158,14 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
+struct Cleared {
+  void* ws;
+  int n, h, w;
+};
+
 struct rsb_plan {
   int dtype, in_ch, out_ch, upscale;
+  std::vector<Cleared> cleared;  // (workspace, shape) pairs whose padded planes have been zeroed
   std::vector<Buffer> bufs;
   std::vector<ConvOp> convs;
   std::vector<GnOp> gns;
@@ -361,8 +367,21 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
   if ((uintptr_t)workspace % kWsAlign != 0) return fail(RSB_ERR_WORKSPACE, "workspace must be %zu-byte aligned", kWsAlign);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   for (size_t i = 0; i < p->bufs.size(); ++i) p->bufs[i].offset = offs[i];
-  // padded planes must hold finite values (they meet zero weights): clear once per binding
-  RSB_CUDA(cudaMemsetAsync(workspace, 0, total, stream));
+  // padded planes must hold finite values (they meet zero weights): clear once per (workspace, shape).  A caller that
+  // alternates between a few shapes with one workspace each (edge tiles of a tiled forward) re-binds without re-clearing:
+  // the layout for a shape is fixed, and the ops never write anything but finite values into padded channels.
+  {
+    const Cleared key = {workspace, n, h, w};
+    bool seen = false;
+    for (const Cleared& c : p->cleared) seen = seen || (c.ws == key.ws && c.n == n && c.h == h && c.w == w);
+    if (!seen) {
+      RSB_CUDA(cudaMemsetAsync(workspace, 0, total, stream));
+      // a different shape on the same memory invalidates what was recorded for it
+      p->cleared.erase(std::remove_if(p->cleared.begin(), p->cleared.end(), [&](const Cleared& c) { return c.ws == key.ws; }), p->cleared.end());
+      if (p->cleared.size() >= 8) p->cleared.erase(p->cleared.begin());
+      p->cleared.push_back(key);
+    }
+  }
 
   for (ConvOp& c : p->convs) {
     const rsb_conv_desc& d = c.d;

@@ -71,7 +71,7 @@ class EngineModule(nn.Module):
         # ... and what the native plan is built for (differs only when host-side glue reshapes the input first)
         self._plan_io = plan_io if plan_io is not None else (in_channels, out_channels, upscale)
         self._plans: Dict[Tuple[int, torch.dtype], Plan] = {}
-        self._plan_stamp: Dict[Tuple[int, torch.dtype], int] = {}
+        self._plan_stamp: Dict[Tuple[int, torch.dtype], tuple] = {}
         rng = np.random.RandomState(seed)
         for name, shape, kind in specs:
             self._register(name, _init_tensor(shape, kind, rng), is_buffer=kind.startswith('buffer'))
@@ -95,22 +95,26 @@ class EngineModule(nn.Module):
         """fp64 host copies of every parameter/buffer, keyed like the checkpoint."""
         return {k: v.detach().to('cpu', torch.float64) for k, v in self.state_dict().items()}
 
-    def _stamp(self) -> int:
-        """Cheap fingerprint of the weights: changes when a tensor is replaced or written in place."""
-        s = 0
-        for group in (self.parameters(), self.buffers()):
-            for t in group:
-                # tensors created under inference_mode carry no version counter; their storage address still moves
-                s += (0 if t.is_inference() else t._version) + (t.data_ptr() & 0xFFFFFFF)
-        return s
+    def _stamp(self) -> tuple:
+        """Fingerprint of the weights the cached native plan was packed from: one (storage address, version counter) pair per
+        parameter / buffer.  It changes when a tensor is replaced (``load_state_dict``, ``.to()``) or written in place through
+        autograd-visible ops (``p.mul_()``, ``p.copy_()``).  It does NOT see writes that bypass the version counter —
+        ``p.data.mul_(2)``, ``p.data.copy_(...)`` (the idiom of EMA / model-interpolation tools) keep both the address and the
+        version: call ``invalidate()`` (or ``refresh()``) after such edits, otherwise the plan keeps the old packed weights."""
+        return tuple((t.data_ptr(), 0 if t.is_inference() else t._version)
+                     for group in (self.parameters(), self.buffers()) for t in group)
 
     # ---------------------------------------------------------------- plan management
     def build_plan(self, pb: PlanBuilder, w: Dict[str, torch.Tensor]) -> None:  # pragma: no cover - abstract
         raise NotImplementedError
 
     def invalidate(self) -> None:
+        """Drop every cached native plan; the next forward re-merges, re-packs and re-uploads the weights.  Needed only after
+        weight edits the fingerprint cannot see (writes through ``.data``; see ``_stamp``)."""
         self._plans.clear()
         self._plan_stamp.clear()
+
+    refresh = invalidate
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate()
@@ -156,3 +160,8 @@ class EngineModule(nn.Module):
     def receptive_radius(self) -> int:
         """Input pixels beyond a tile edge that influence the tile's output (exact halo for tiled_forward)."""
         raise NotImplementedError
+
+    @property
+    def tile_multiple(self) -> int:
+        """Tile origins / sizes of an exact-halo tiling must be multiples of this (1 unless the model re-grids its input)."""
+        return 1

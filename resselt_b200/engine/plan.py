@@ -6,14 +6,18 @@
 from __future__ import annotations
 
 import ctypes as C
+import logging
 import os
 import weakref
+from collections import OrderedDict
 from typing import Optional, Sequence
 
 import numpy as np
 import torch
 
 from . import native as N
+
+_log = logging.getLogger('resselt_b200')
 
 _TORCH_TO_RSB = {torch.float32: N.F32, torch.bfloat16: N.BF16, torch.float16: N.F16}
 
@@ -206,7 +210,9 @@ class Plan:
         self.device = device
         self.compute_dtype = builder.compute_dtype
         self.in_channels, self.out_channels, self.upscale = builder.in_channels, builder.out_channels, builder.upscale
-        self._workspace: Optional[torch.Tensor] = None
+        # workspaces per input shape, least recently used first: edge tiles of tiled_forward alternate between a few shapes and
+        # must not re-allocate / re-bind (re-memset, re-encode every tensor map) on every switch
+        self._workspaces: 'OrderedDict[tuple, torch.Tensor]' = OrderedDict()
         self._ws_shape = None
         self.force_direct = False
         self._scale_of = dict(builder.scales)
@@ -229,16 +235,26 @@ class Plan:
         N.check(self._lib.rsb_plan_workspace_bytes(self._h, n, h, w, C.byref(out)))
         return int(out.value)
 
+    MAX_WORKSPACES = 4
+
     def _workspace_for(self, n: int, h: int, w: int) -> torch.Tensor:
-        if self._ws_shape != (n, h, w):
-            self._graphs.clear()    # captured graphs point into the old workspace
-            self._workspace = None  # release before allocating the next one
+        key = (n, h, w)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            while len(self._workspaces) >= self.MAX_WORKSPACES:
+                _, old = self._workspaces.popitem(last=False)
+                # captured graphs that point into the evicted workspace go with it
+                self._graphs = {k: g for k, g in self._graphs.items() if k[7] != old.data_ptr()}
+                del old
             nbytes = self.workspace_bytes(n, h, w)
             raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
             shift = (-raw.data_ptr()) % 1024
-            self._workspace = raw[shift:shift + nbytes]
-            self._ws_shape = (n, h, w)
-        return self._workspace
+            ws = raw[shift:shift + nbytes]
+            self._workspaces[key] = ws
+        else:
+            self._workspaces.move_to_end(key)
+        self._ws_shape = key
+        return ws
 
     @property
     def num_ops(self) -> int:
@@ -311,24 +327,33 @@ class Plan:
             key = (x.data_ptr(), out.data_ptr(), x.dtype, out.dtype, n, h, w, ws.data_ptr(), int(self.force_direct))
             g = self._graphs.get(key)
             if g is None and len(self._graphs) < self.MAX_GRAPHS:
+                launch()  # binds workspace / tensor maps for this shape outside the capture (and produces this call's result)
                 try:
-                    launch()  # binds workspace / tensor maps for this shape outside the capture (and produces this call's result)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, capture_error_mode='thread_local'):
                         launch()
-                    self._graphs[key] = g
-                    return out
-                except Exception:  # noqa: BLE001 - capture is an optimisation; never let it break a forward
+                except N.NativeError:
+                    raise  # a real engine error (bad workspace, failed launch) is never masked by the graph fallback
+                except RuntimeError as exc:
+                    # capture itself failed (e.g. an allocation inside the capture): graphs are an optimisation, fall back to
+                    # plain launches for this plan — and say so, once
                     self._graphs_enabled = False
                     self._graphs.clear()
+                    _log.warning('resselt_b200: CUDA-graph capture failed (%s); this plan falls back to plain launches', exc)
                     torch.cuda.synchronize(self.device)
-                    launch()
-                    return out
+                    return out  # the eager launch above already produced the result
+                self._graphs[key] = g
+                return out
             if g is not None:
                 g.replay()
                 return out
         launch()
         return out
+
+    def capture(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        """Warm-up API for streaming callers: run one forward into ``out`` and capture the CUDA graph for this (x, out) pair now —
+        outside the streaming loop, where the capture's device synchronisation would stall the copy streams."""
+        self.forward(x, out=out, graph=True)
 
     def read_buffer(self, ref: Ref) -> torch.Tensor:
         """Debug/test helper: fp32 NCHW copy of a buffer range after the last forward."""

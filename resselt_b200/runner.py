@@ -23,12 +23,18 @@ Model = Callable[[torch.Tensor], torch.Tensor]
 
 
 # ---------------------------------------------------------------------------------------- tiling
-def plan_tiles(h: int, w: int, tile_h: int, tile_w: int, halo: int) -> List[Tuple[int, int, int, int, int, int, int, int]]:
+def plan_tiles(h: int, w: int, tile_h: int, tile_w: int, halo: int, multiple: int = 1) -> List[Tuple[int, int, int, int, int, int, int, int]]:
     """Tile grid over an h x w image.  Each entry is
     (y0, y1, x0, x1, ey0, ey1, ex0, ex1): the core region [y0,y1) x [x0,x1) a tile is responsible for and
-    the halo-extended region [ey0,ey1) x [ex0,ex1) it is computed from (clipped at the image border)."""
+    the halo-extended region [ey0,ey1) x [ex0,ex1) it is computed from (clipped at the image border).
+    ``multiple`` > 1 (models that re-grid their input, e.g. a pixel-unshuffle front end): tile sizes must be multiples of it
+    and the halo is rounded up to one, so every extended region starts on the model's grid."""
     if tile_h <= 0 or tile_w <= 0 or halo < 0:
         raise ValueError('tile sizes must be positive and halo non-negative')
+    if multiple > 1:
+        if tile_h % multiple or tile_w % multiple:
+            raise ValueError(f'tile sizes must be multiples of {multiple} for this model')
+        halo = (halo + multiple - 1) // multiple * multiple
     tiles = []
     for y0 in range(0, h, tile_h):
         y1 = min(y0 + tile_h, h)
@@ -46,6 +52,7 @@ def tiled_forward(
     halo: int,
     out: Optional[torch.Tensor] = None,
     only: Optional[Sequence[int]] = None,
+    multiple: Optional[int] = None,
 ) -> torch.Tensor:
     """Run ``model`` tile by tile and stitch the centre crops on the device that holds ``x``.
 
@@ -54,9 +61,12 @@ def tiled_forward(
     receptive field lies inside the extended region, and the extended region is only clipped where
     the image itself ends (where the untiled forward zero-pads too).  ``only`` restricts the work to a
     subset of tile indices (multi-GPU sharding); untouched output pixels are left as they are.
+    ``multiple`` defaults to the model's ``tile_multiple`` (see plan_tiles).
     """
     n, _, h, w = x.shape
-    tiles = plan_tiles(h, w, tile[0], tile[1], halo)
+    if multiple is None:
+        multiple = int(getattr(model, 'tile_multiple', 1))
+    tiles = plan_tiles(h, w, tile[0], tile[1], halo, multiple)
     first = None
     for idx, (y0, y1, x0, x1, ey0, ey1, ex0, ex1) in enumerate(tiles):
         if only is not None and idx not in only:
@@ -86,34 +96,48 @@ def shard_indices(count: int, rank: int, world_size: int) -> List[int]:
 def gather_to_rank(local: Sequence[torch.Tensor], count: int, dst: int = 0, group=None) -> Optional[List[torch.Tensor]]:
     """Collect the outputs of round-robin sharded units on rank ``dst`` in unit order.
 
-    ``local`` holds this rank's outputs in the order of ``shard_indices``; all units have the same shape.
-    Returns the full list on ``dst`` and None elsewhere.  This is the only collective of the engine; it is
-    never on the compute path."""
+    ``local`` holds this rank's outputs in the order of ``shard_indices`` (possibly none, when there are fewer units than
+    ranks); units may differ in shape (edge tiles of an image that the tile grid does not divide).  Returns the full list on
+    ``dst`` and None elsewhere.  Shapes travel first (one small object gather), then every unit is one point-to-point message
+    (NCCL send/recv over NVLink on GPUs, gloo in the CPU tests) — no padding, no copy through a stacked buffer.  This is the only
+    communication of the engine; it is never on the compute path."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    local = [t.contiguous() for t in local]
+    mine = shard_indices(count, rank, world)
+    if len(local) != len(mine):
+        raise ValueError(f'rank {rank} owns {len(mine)} of {count} units but passed {len(local)} tensors')
     if world == 1:
         return list(local)
-    per_rank = (count + world - 1) // world
-    proto = local[0] if len(local) else None
-    shape_src = torch.tensor(list(proto.shape) if proto is not None else [0, 0, 0, 0], dtype=torch.int64,
-                             device=proto.device if proto is not None else None)
-    # every rank owns at least one unit in every use of this helper (count >= world); keep it simple and strict
-    if proto is None:
-        raise ValueError('gather_to_rank needs at least one unit per rank')
-    del shape_src
-    pad = per_rank - len(local)
-    stacked = torch.stack(list(local) + [torch.zeros_like(proto)] * pad)  # [per_rank, ...]
-    if rank == dst:
-        bufs = [torch.empty_like(stacked) for _ in range(world)]
-        dist.gather(stacked, bufs, dst=dst, group=group)
-        out: List[torch.Tensor] = []
-        for i in range(count):
-            out.append(bufs[i % world][i // world])
-        return out
-    dist.gather(stacked, None, dst=dst, group=group)
-    return None
+    meta = [(tuple(t.shape), t.dtype) for t in local]
+    all_meta = [None] * world if rank == dst else None
+    dist.gather_object(meta, all_meta, dst=dst, group=group)
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    if rank != dst:
+        if local:
+            for work in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, peer(dst), group) for t in local]):
+                work.wait()
+        return None
+    if local:
+        device = local[0].device
+    else:
+        device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    out: List[Optional[torch.Tensor]] = [None] * count
+    ops = []
+    for r in range(world):
+        for k, i in enumerate(shard_indices(count, r, world)):
+            if r == dst:
+                out[i] = local[k]
+            else:
+                shape, dtype = all_meta[r][k]
+                out[i] = torch.empty(shape, dtype=dtype, device=device)
+                ops.append(dist.P2POp(dist.irecv, out[i], peer(r), group))
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+    return out  # type: ignore[return-value]
 
 
 # ---------------------------------------------------------------------------------------- frame streaming

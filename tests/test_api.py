@@ -193,3 +193,59 @@ def test_dysample_checkpoint_with_incomplete_keys_fails_strict_load():
     del sd['upsampler.scope.weight']
     with pytest.raises(RuntimeError):
         resselt_b200.load_from_state_dict(sd)
+
+
+def test_weight_fingerprint_sees_replacements_and_versioned_writes_but_not_data_writes():
+    """EngineModule._stamp keys the cached native plan: tensor replacement and autograd-visible in-place writes change
+    it; writes through ``.data`` bypass the version counter and need ``invalidate()`` / ``refresh()`` — documented and pinned here."""
+    m = SRVGGNetCompact(num_feat=16, num_conv=2, upscale=2, seed=1)
+    s0 = m._stamp()
+    assert isinstance(s0, tuple) and len(s0) == len(list(m.parameters())) + len(list(m.buffers()))
+    p = next(m.parameters())
+    with torch.no_grad():
+        p.mul_(2.0)                      # versioned in-place write
+    s1 = m._stamp()
+    assert s1 != s0
+    p.data.mul_(0.5)                     # EMA-style write: invisible to the fingerprint
+    assert m._stamp() == s1
+    m._plans[(0, torch.float32)] = object()
+    m._plan_stamp[(0, torch.float32)] = s1
+    m.refresh()                          # what the caller has to do after such an edit
+    assert not m._plans and not m._plan_stamp
+    # replacing the tensors (new storage) changes the fingerprint
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    assert m._stamp() != s1
+
+
+def test_engine_plugins_register_in_the_live_reference_registry():
+    """INTEGRATION.md section 2, executed: the engine's Architecture plugins are added to the REFERENCE's own registry
+    (resselt.registry.Registry.add, /root/reference/resselt/registry.py:70-71) and its load_from_state_dict
+    (registry.py:106-116: canonicalize -> first detect() hit -> load() -> strict load_state_dict) returns engine modules."""
+    import sys
+
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'resselt')):
+        pytest.skip('reference not installed in baseline/_ref (tools/install_reference.sh)')
+    sys.path.insert(0, ref_dir)
+    try:
+        import resselt
+        from resselt.registry import Registry as RefRegistry
+
+        from resselt_b200.engine import EngineModule
+
+        reg = RefRegistry()
+        for arch in internal_registry.store.values():
+            reg.add(arch)  # the reference's add(): plain dict insert keyed by arch.id
+        for proto, name in ((SPAN(feature_channels=48, upscale=2, seed=2), 'SPAN'), (SRVGGNetCompact(num_feat=32, num_conv=4, upscale=4, seed=3), 'Compact'),
+                            (RRDBNet(num_blocks=1, scale=4, seed=4), 'ESRGAN')):
+            sd = {k: v.clone() for k, v in proto.state_dict().items()}
+            model = reg.load_from_state_dict(sd)
+            assert isinstance(model, EngineModule) and model.parameters_info.name == name
+            # and the reference's own loader accepts the very same checkpoint (same parameter names, strict)
+            ref_model = resselt.load_from_state_dict({k: v.clone() for k, v in proto.state_dict().items()})
+            assert type(ref_model).__module__.startswith('resselt.')
+            assert set(ref_model.state_dict().keys()) == set(model.state_dict().keys())
+    finally:
+        sys.path.remove(ref_dir)
+        for k in [k for k in sys.modules if k == 'resselt' or k.startswith('resselt.')]:
+            del sys.modules[k]

@@ -153,6 +153,8 @@ def test_single_conv_layer_tensor_core_vs_fp64(cin, cout, k, n, H, W, act):
         (SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=32), (70, 64), (32, 32)),
         (SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=33), (64, 100), (30, 64)),
         (RRDBNet(num_blocks=1, scale=4, seed=34), (60, 72), (24, 40)),
+        # Real-ESRGAN x2: pixel-unshuffle front end -> halo and tile origins in multiples of shuffle_factor, odd image size
+        (RRDBNet(in_nc=12, out_nc=3, num_blocks=1, scale=4, shuffle_factor=2, seed=35), (91, 118), (44, 60)),
     ],
 )
 def test_tile_seams_bit_identical(model, hw, tile, dtype):

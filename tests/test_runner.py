@@ -68,7 +68,8 @@ def _gather_worker(rank, world, port, count, tmpdir):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     model, _ = _toy_model()
-    frames = [torch.rand(1, 3, 8, 10, dtype=torch.float64, generator=torch.Generator().manual_seed(100 + i)) for i in range(count)]
+    # ragged units (edge tiles of an image the grid does not divide): every frame has its own width
+    frames = [torch.rand(1, 3, 8, 10 + i, dtype=torch.float64, generator=torch.Generator().manual_seed(100 + i)) for i in range(count)]
     mine = [model(frames[i]) for i in shard_indices(count, rank, world)]  # no collective on the compute path
     got = gather_to_rank(mine, count, dst=0)
     if rank == 0:
@@ -79,10 +80,18 @@ def _gather_worker(rank, world, port, count, tmpdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('count', [4, 5])
+@pytest.mark.parametrize('count', [4, 5, 1])  # 1: fewer units than ranks, rank 1 owns nothing
 def test_frame_sharding_and_gather_world_size_2(tmp_path, count):
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
     mp.spawn(_gather_worker, args=(2, port, count, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / 'ok').read() == '1'
+
+
+def test_plan_tiles_multiple_aligns_origins_and_rounds_the_halo():
+    tiles = plan_tiles(91, 118, 44, 60, halo=19, multiple=2)
+    assert all(t[4] % 2 == 0 and t[6] % 2 == 0 for t in tiles)          # extended origins on the model's grid
+    assert tiles[0][5] == 44 + 20 and tiles[0][7] == 60 + 20            # halo 19 -> 20
+    with pytest.raises(ValueError):
+        plan_tiles(64, 64, 33, 32, halo=4, multiple=2)
