@@ -183,6 +183,9 @@ typedef struct rsb_op_desc {
 int rsb_plan_add_op(rsb_plan* plan, const rsb_op_desc* desc);
 
 int rsb_version(void);
+/* sizeof the descriptor structs as this library was compiled (0 rsb_conv_desc, 1 rsb_groupnorm_desc, 2 rsb_op_desc, 3 rsb_op_info):
+ * lets a foreign-language binding check its own struct layout before the first call */
+int rsb_abi_struct_size(int which);
 const char* rsb_last_error(void);
 /* number of CUDA devices visible to the library (0 on a CPU-only host; never fails) */
 int rsb_device_count(void);
@@ -230,6 +233,9 @@ typedef struct rsb_op_info {
   double bytes;       /* algorithmic HBM bytes at the bound shape: inputs + residuals read, outputs written (convs) */
 } rsb_op_info;
 int rsb_plan_op_info(const rsb_plan* plan, int op_index, rsb_op_info* out);
+/* enable != 0: every op of rsb_plan_forward[_ops] runs inside an NVTX range "rsb op <index> <kernel>" (for nsys / ncu --nvtx;
+ * off by default: the names are formatted per launch) */
+int rsb_plan_set_nvtx(rsb_plan* plan, int enable);
 const char* rsb_kernel_name(int kernel_id);
 /* kernels launched by one rsb_plan_forward call (for launch accounting) */
 int rsb_plan_launches_per_forward(const rsb_plan* plan);

@@ -23,5 +23,6 @@ from .sr_forward import (  # noqa: F401
     realplksr_forward,
     span_forward,
     spanplus_forward,
+    spanpp_forward,
     swinir_forward,
 )

@@ -64,6 +64,10 @@ def cases():
                                                norm_groups=4, dysample=True), 34, (2, 3, 15, 13), 124),
         'dat_light_x3_psd_3conv': ('DAT', dict(img_size=32, in_chans=3, embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], expansion_factor=2.0,
                                                upscale=3, upsampler='pixelshuffledirect', resi_connection='3conv'), 35, (1, 3, 21, 30), 125),
+        'dat_x3_ps': ('DAT', dict(img_size=32, in_chans=3, embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], expansion_factor=2.0,
+                                  upscale=3, upsampler='pixelshuffle', resi_connection='1conv'), 36, (1, 3, 20, 26), 126),
+        'spanpp_f48': ('SpanPP', dict(num_in_ch=3, feature_channels=48, scale_list=[1, 2, 3, 4], implicit_dim=64, latent_layers=2), 37, (1, 3, 20, 28), 127),
+        'spanpp_f32_s4': ('SpanPP', dict(num_in_ch=3, feature_channels=32, scale_list=[2, 4], implicit_dim=32, latent_layers=4), 38, (2, 3, 14, 18), 128),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
     }
@@ -74,7 +78,7 @@ def engine_model(kind: str, kwargs: dict, seed: int):
 
     cls = {'SPAN': archs.SPAN, 'SPANPlus': archs.SpanPlus, 'Compact': archs.SRVGGNetCompact}
     extra = {k: getattr(archs, k) for k in ('RRDBNet', 'RealPLKSR') if hasattr(archs, k)}
-    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None)})
+    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None), 'SpanPP': getattr(archs, 'SpanPP', None)})
     return cls[kind](seed=seed, **kwargs)
 
 
@@ -91,8 +95,16 @@ def main():
     import resselt as reference  # the unmodified reference package
 
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    # `python oracle/make_golden.py name [name ...]` regenerates only those cases and merges them into index.json
+    only = set(sys.argv[1:])
     index = {}
+    index_path = os.path.join(GOLDEN_DIR, 'index.json')
+    if only and os.path.exists(index_path):
+        with open(index_path) as f:
+            index = json.load(f)['cases']
     for name, (kind, kwargs, wseed, xshape, xseed) in cases().items():
+        if only and name not in only:
+            continue
         sd = {k: v.clone() for k, v in engine_model(kind, kwargs, wseed).state_dict().items()}
         ref_model = reference.load_from_state_dict(dict(sd)).eval()
         x = torch.from_numpy(np.random.RandomState(xseed).rand(*xshape).astype(np.float32))

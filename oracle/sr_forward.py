@@ -77,6 +77,62 @@ def span_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, img_range: float 
     return F.pixel_shuffle(_conv(sd, 'upsampler.0', out, 1), r)
 
 
+def repconv_merged(sd: SD, prefix: str, dtype: torch.dtype):
+    """Fused 3x3 kernel / bias of a RepConv in eval mode: RepConv.fuse (/root/reference/resselt/archs/spanpp/arch.py:164-173) =
+    alpha[0] * SeqConv3x3.rep_params (:136-149) + alpha[1] * conv2 + alpha[2] * Conv3XC.update_params (:61-97)."""
+    g = lambda k: sd[f'{prefix}.{k}'].to(dtype)
+    k0, k1 = g('conv1.k0'), g('conv1.k1')
+    rk = F.conv2d(k1, k0.permute(1, 0, 2, 3))
+    rb = F.conv2d(torch.ones(1, k0.shape[0], 3, 3, dtype=dtype) * g('conv1.b0').view(1, -1, 1, 1), k1).view(-1) + g('conv1.b1')
+    k3, b3 = conv3xc_merged(sd, f'{prefix}.conv3', dtype)
+    a = g('alpha')
+    return a[0] * rk + a[1] * g('conv2.weight') + a[2] * k3, a[0] * rb + a[1] * g('conv2.bias') + a[2] * b3
+
+
+def _igconv_kernel(sd: SD, p: str, dim: int, ksize: int, scale: int, max_s: int, dtype) -> torch.Tensor:
+    """IGConv._implicit_representation_latent (/root/reference/resselt/archs/spanpp/arch.py:289-312) with make_coord (:219-231)."""
+    g = lambda k: sd[f'{p}.{k}'].to(dtype)
+    seq = -1 + 1 / scale + (2 / scale) * torch.arange(scale, dtype=dtype)
+    coords = torch.stack(torch.meshgrid(seq, seq, indexing='ij'), dim=-1).flip(-1).permute(2, 0, 1).unsqueeze(0)  # [1, (x, y), s, s]
+    r = torch.ones(1, 1, scale, scale, dtype=dtype) / min(scale, max_s) * 2
+    freq = g('freq').repeat(1, 1, scale, scale)
+    f1, f2 = freq.chunk(2, dim=1)
+    freq = f1 * coords[:, :1] + f2 * coords[:, 1:] + F.conv2d(r, g('phase.weight'), g('phase.bias'))
+    t = torch.cat([torch.cos(torch.pi * freq), torch.sin(torch.pi * freq)], dim=1) * g('amplitude').repeat(1, 1, scale, scale)
+    n = _seq_len(sd, f'{p}.query_kernel')
+    for i in range(0, n, 2):
+        t = F.conv2d(t, g(f'query_kernel.{i}.weight'), g(f'query_kernel.{i}.bias'))
+        t = F.relu(t) if i + 1 < n else t
+    k, rgb = t.shape[0], t.shape[1]
+    return t.view(dim, ksize, ksize, rgb, scale, scale).permute(3, 4, 5, 0, 1, 2).reshape(rgb * scale * scale, dim, ksize, ksize)
+
+
+def spanpp_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, scale: int = 2) -> torch.Tensor:
+    """SpanPP.forward in eval mode (/root/reference/resselt/archs/spanpp/arch.py:358-373; SPAB :195-216; IGConv.forward :289-297)."""
+    x = x.to(dtype)
+
+    def rep(prefix, t):
+        k, b = repconv_merged(sd, prefix, dtype)
+        return F.conv2d(t, k, b, padding=1)
+
+    def spab(prefix, t):
+        o1 = F.silu(rep(f'{prefix}.c1_r', t))          # SiLU(inplace=True): the block's second result is the activated tensor
+        o3 = rep(f'{prefix}.c3_r', F.silu(rep(f'{prefix}.c2_r', o1)))
+        return (o3 + t) * (torch.sigmoid(o3) - 0.5), o1
+
+    feat = rep('conv0', x)
+    b1, _ = spab('block_1', feat)
+    t = b1
+    for i in (2, 3, 4, 5):
+        t, _ = spab(f'block_{i}', t)
+    b6, o1 = spab('block_6', t)
+    out = _conv(sd, 'conv_cat', torch.cat([feat, rep('conv_2', b6), b1, o1], 1), 0)
+    dim = feat.shape[1]
+    scales = sd['MetaIGConv'].tolist() if 'MetaIGConv' in sd else [1, 2, 3, 4]
+    kernel = _igconv_kernel(sd, 'upsampler', dim, 3, scale, max(scales), dtype)
+    return F.pixel_shuffle(F.conv2d(out, kernel, None, padding=1), scale)
+
+
 def _dysample(sd: SD, p: str, x: torch.Tensor, groups: int) -> torch.Tensor:
     """DySample.forward (/root/reference/resselt/utilities/dysample.py:46-83), restated with the same ATen calls: offsets
     ``offset(x) * sigmoid(scope(x)) * 0.5 + init_pos``, a coordinate grid in normalised [-1, 1] units, pixel_shuffle of the
@@ -422,8 +478,9 @@ def dat_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, img_range: float =
         r = math.isqrt(sd['upsample.0.weight'].shape[0] // in_ch)
         return F.pixel_shuffle(_conv(sd, 'upsample.0', t, 1), r) / img_range + mean
     t = F.leaky_relu(_conv(sd, 'conv_before_upsample.0', t, 1), 0.01)
-    for i in range(0, _seq_len(sd, 'upsample'), 2):
-        t = F.pixel_shuffle(_conv(sd, f'upsample.{i}', t, 1), 2)
+    for i in range(0, _seq_len(sd, 'upsample'), 2):  # Upsample (:783-801): conv 64 -> 64 r^2 + PixelShuffle(r), r = 2 (n times) or 3
+        wt = sd[f'upsample.{i}.weight']
+        t = F.pixel_shuffle(_conv(sd, f'upsample.{i}', t, 1), math.isqrt(wt.shape[0] // wt.shape[1]))
     return _conv(sd, 'conv_last', t, 1) / img_range + mean
 
 
@@ -537,6 +594,7 @@ _FORWARDS: Dict[str, Callable] = {
     'SPAN': span_forward,
     'SPANPlus': spanplus_forward,
     'Compact': compact_forward,
+    'SpanPP': spanpp_forward,
 }
 
 

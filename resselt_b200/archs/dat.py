@@ -100,8 +100,8 @@ class DAT(EngineModule):
     ):
         if resi_connection not in ('1conv', '3conv') or upsampler not in ('pixelshuffle', 'pixelshuffledirect'):
             raise ValueError(f'unknown resi_connection {resi_connection!r} / upsampler {upsampler!r}')
-        if upsampler == 'pixelshuffle' and upscale & (upscale - 1):
-            raise NotImplementedError("DAT 'pixelshuffle' head: power-of-two upscale factors only")
+        if upsampler == 'pixelshuffle' and upscale & (upscale - 1) and upscale != 3:
+            raise ValueError(f'scale {upscale} is not supported. Supported scales: 2^n and 3.')  # Upsample, dat/arch.py:783-801
         dim, hidden = embed_dim, int(embed_dim * expansion_factor)
         split = [int(split_size[0]), int(split_size[1])]
         specs = conv_specs('conv_first', in_chans, dim, 3) + _ln_specs('before_RG.1', dim)
@@ -141,8 +141,8 @@ class DAT(EngineModule):
         specs += _ln_specs('norm', dim) + resi_conv_specs('conv_after_body', dim, resi_connection)
         if upsampler == 'pixelshuffle':
             specs += conv_specs('conv_before_upsample.0', dim, 64, 3)
-            for i in range(int(math.log2(upscale))):
-                specs += conv_specs(f'upsample.{2 * i}', 64, 256, 3)
+            for i, r in enumerate([3] if upscale == 3 else [2] * int(math.log2(upscale))):
+                specs += conv_specs(f'upsample.{2 * i}', 64, 64 * r * r, 3)
             specs += conv_specs('conv_last', 64, in_chans, 3)
         else:  # UpsampleOneStep (arch.py:804-825): one conv + PixelShuffle straight to the image
             specs += conv_specs('upsample.0', dim, upscale * upscale * in_chans, 3, gain=2.0)
@@ -234,15 +234,16 @@ class DAT(EngineModule):
         cur = pb.buffer(64)
         pb.conv(y, cur, w['conv_before_upsample.0.weight'], w['conv_before_upsample.0.bias'], act=N.ACT_LRELU, act_param=0.01)
         grid = 1
-        for i in range(int(math.log2(self.upscale))):
-            nxt = pb.buffer(64, scale=grid * 2)
-            # conv 64 -> 256 + PixelShuffle(2): channel c*4 + phase -> phase-major order of the sub-pixel destination
+        for i, r in enumerate([3] if self.upscale == 3 else [2] * int(math.log2(self.upscale))):
+            nxt = pb.buffer(64, scale=grid * r)
+            # conv 64 -> 64 r^2 + PixelShuffle(r) (Upsample, arch.py:783-801: 2^n as n x2 steps, 3 as one x3 step):
+            # channel c * r^2 + phase -> one conv per sub-pixel phase, stored pixel-interleaved
             wk, bk = w[f'upsample.{2 * i}.weight'], w[f'upsample.{2 * i}.bias']
-            perm = torch.arange(256).view(64, 4).t().reshape(-1)
-            for phase in range(4):
+            perm = torch.arange(64 * r * r).view(64, r * r).t().reshape(-1)
+            for phase in range(r * r):
                 sel = perm[phase * 64:(phase + 1) * 64]
-                pb.conv(cur, nxt, wk[sel], bk[sel], dst_ps=2, dst_phase=phase)
-            cur, grid = nxt, grid * 2
+                pb.conv(cur, nxt, wk[sel], bk[sel], dst_ps=r, dst_phase=phase)
+            cur, grid = nxt, grid * r
         pb.conv(cur, OUTPUT, w['conv_last.weight'], w['conv_last.bias'], ps=1, out_scale=1.0 / self.img_range, out_mean=omean)
 
 

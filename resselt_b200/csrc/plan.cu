@@ -11,11 +11,29 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.cuh"
 
 namespace {
 
 thread_local std::string g_last_error;
+
+// NVTX range around the launches of one op (per-layer ranges for nsys / ncu --nvtx); only when the caller
+// switched them on with rsb_plan_set_nvtx — the name is formatted per launch.
+struct NvtxRange {
+  bool on;
+  NvtxRange(bool enable, const char* kernel, int op) : on(enable) {
+    if (on) {
+      char name[64];
+      snprintf(name, sizeof name, "rsb op %d %s", op, kernel);
+      nvtxRangePushA(name);
+    }
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
+};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -176,6 +194,7 @@ struct rsb_plan {
   int num_sms = 0;
   int num_direct = 0;  // bf16 plans: convs that fell back to the CUDA-core kernel
   int info_mode = 0;   // force_direct of the last forward: what rsb_plan_op_info describes
+  bool nvtx = false;   // rsb_plan_set_nvtx: one NVTX range per op
   std::mutex mu;
   // binding
   int bn = 0, bh = 0, bw = 0;
@@ -653,6 +672,15 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
 extern "C" {
 
 int rsb_version(void) { return RSB_VERSION; }
+int rsb_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(rsb_conv_desc);
+    case 1: return (int)sizeof(rsb_groupnorm_desc);
+    case 2: return (int)sizeof(rsb_op_desc);
+    case 3: return (int)sizeof(rsb_op_info);
+    default: return -1;
+  }
+}
 const char* rsb_last_error(void) { return g_last_error.c_str(); }
 
 int rsb_device_count(void) {
@@ -1055,6 +1083,11 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
 
 int rsb_plan_num_ops(const rsb_plan* p) { return p ? (int)p->ops.size() : 0; }
 int rsb_plan_num_direct_convs(const rsb_plan* p) { return p ? p->num_direct : 0; }
+int rsb_plan_set_nvtx(rsb_plan* p, int enable) {
+  if (!p) return fail(RSB_ERR_INVALID, "rsb_plan_set_nvtx: NULL plan");
+  p->nvtx = enable != 0;
+  return 0;
+}
 
 const char* rsb_kernel_name(int k) {
   static const char* const names[] = {"conv_direct", "conv_tc", "conv_rs", "conv_lk", "conv_pair", "groupnorm", "layernorm", "dwconv3",
@@ -1166,6 +1199,9 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
     for (int oi = op_begin; oi < op_end; ++oi) {
       const Op& op = p->ops[oi];
       cudaError_t e;
+      rsb_op_info info;
+      if (p->nvtx) rsb_plan_op_info(p, oi, &info);
+      NvtxRange range(p->nvtx, p->nvtx ? rsb_kernel_name(info.kernel) : "", oi);
       if (op.kind == 0) {
         ConvOp& c = p->convs[op.index];
         if (c.pair_ready && force_direct == 4 && oi + 1 < op_end) {

@@ -70,8 +70,8 @@ class EngineModule(nn.Module):
         self.in_channels, self.out_channels, self.upscale = in_channels, out_channels, upscale
         # ... and what the native plan is built for (differs only when host-side glue reshapes the input first)
         self._plan_io = plan_io if plan_io is not None else (in_channels, out_channels, upscale)
-        self._plans: Dict[Tuple[int, torch.dtype], Plan] = {}
-        self._plan_stamp: Dict[Tuple[int, torch.dtype], tuple] = {}
+        self._plans: Dict[tuple, Plan] = {}
+        self._plan_stamp: Dict[tuple, tuple] = {}
         rng = np.random.RandomState(seed)
         for name, shape, kind in specs:
             self._register(name, _init_tensor(shape, kind, rng), is_buffer=kind.startswith('buffer'))
@@ -108,6 +108,14 @@ class EngineModule(nn.Module):
     def build_plan(self, pb: PlanBuilder, w: Dict[str, torch.Tensor]) -> None:  # pragma: no cover - abstract
         raise NotImplementedError
 
+    def _plan_variant(self):
+        """Hashable tag of the plan flavour the next forward needs (None: the module has one plan per device and dtype).
+        Modules whose output geometry depends on a call argument (SpanPP's ``scale``) override this and ``_plan_io_for_variant``."""
+        return None
+
+    def _plan_io_for_variant(self) -> Tuple[int, int, int]:
+        return self._plan_io
+
     def invalidate(self) -> None:
         """Drop every cached native plan; the next forward re-merges, re-packs and re-uploads the weights.  Needed only after
         weight edits the fingerprint cannot see (writes through ``.data``; see ``_stamp``)."""
@@ -137,11 +145,12 @@ class EngineModule(nn.Module):
             )
         index = device.index if device.index is not None else torch.cuda.current_device()
         cdt = self.compute_dtype_for(x_dtype)
-        key = (index, cdt)
+        variant = self._plan_variant()
+        key = (index, cdt) if variant is None else (index, cdt, variant)
         stamp = self._stamp()
         plan = self._plans.get(key)
         if plan is None or self._plan_stamp.get(key) != stamp:
-            pb = PlanBuilder(cdt, *self._plan_io)
+            pb = PlanBuilder(cdt, *(self._plan_io if variant is None else self._plan_io_for_variant()))
             self.build_plan(pb, self._weights())
             plan = pb.finalize(torch.device('cuda', index))
             self._plans[key] = plan

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = (
     'rsb_plan_add_buffer', 'rsb_plan_add_conv', 'rsb_plan_add_groupnorm', 'rsb_plan_add_op', 'rsb_plan_finalize',
     'rsb_plan_num_ops', 'rsb_plan_launches_per_forward', 'rsb_plan_flops', 'rsb_plan_workspace_bytes',
     'rsb_plan_forward', 'rsb_plan_forward_ops', 'rsb_plan_read_buffer',
-    'rsb_plan_num_direct_convs', 'rsb_plan_op_info', 'rsb_kernel_name',
+    'rsb_plan_num_direct_convs', 'rsb_plan_op_info', 'rsb_kernel_name', 'rsb_plan_set_nvtx', 'rsb_abi_struct_size',
 )
 
 
@@ -132,7 +132,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             failed.append(src)
     if failed:
         raise RuntimeError(f'nvcc failed on {failed}:\n' + log)
-    link = subprocess.run([nvcc, '-shared', '-o', LIB_PATH + '.tmp', *[obj for _, obj, _ in jobs]], cwd=CSRC_DIR, capture_output=True, text=True)
+    link = subprocess.run([nvcc, '-shared', '-o', LIB_PATH + '.tmp', *[obj for _, obj, _ in jobs], '-ldl'], cwd=CSRC_DIR, capture_output=True, text=True)
     if link.returncode != 0:
         raise RuntimeError('link failed:\n' + link.stdout + link.stderr)
     os.replace(LIB_PATH + '.tmp', LIB_PATH)
@@ -183,11 +183,16 @@ def lib() -> C.CDLL:
         ]
         L.rsb_plan_read_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.rsb_plan_num_direct_convs.argtypes = [C.c_void_p]
+        L.rsb_plan_set_nvtx.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_abi_struct_size.argtypes = [C.c_int]
         L.rsb_plan_op_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(OpInfo)]
         L.rsb_kernel_name.argtypes = [C.c_int]
         L.rsb_kernel_name.restype = C.c_char_p
         for name in EXPORTED_SYMBOLS:
             getattr(L, name)  # AttributeError if the library does not export the declared ABI
+        for which, struct in enumerate((ConvDesc, GroupNormDesc, OpDesc, OpInfo)):
+            if L.rsb_abi_struct_size(which) != C.sizeof(struct):
+                raise RuntimeError(f'{struct.__name__}: ctypes layout is {C.sizeof(struct)} bytes, the library was built with {L.rsb_abi_struct_size(which)}')
         _lib = L
     return _lib
 

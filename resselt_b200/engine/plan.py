@@ -265,6 +265,10 @@ class Plan:
         """bf16 plans: convolutions that fell back to the CUDA-core kernel (0 for every supported configuration)."""
         return int(self._lib.rsb_plan_num_direct_convs(self._h))
 
+    def set_nvtx(self, enable: bool = True) -> None:
+        """One NVTX range per op ("rsb op <index> <kernel>") around its launches, for nsys / ncu --nvtx captures."""
+        N.check(self._lib.rsb_plan_set_nvtx(self._h, int(bool(enable))))
+
     def op_info(self, index: int) -> dict:
         """Kernel, launch count, algorithmic FLOPs / HBM bytes of op ``index`` at the shape of the last forward."""
         info = N.OpInfo()

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import resselt_b200
-from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR, internal_registry
+from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR, internal_registry
 from resselt_b200.factory import Architecture, KeyCondition
 from resselt_b200.factory.arch import ModelMetadata
 from resselt_b200.registry import ArchitectureNotFound, Registry
@@ -37,6 +37,8 @@ def test_metadata_field_order():
         (SPAN(feature_channels=48, upscale=2), ('SPAN', 3, 3, 2)),
         (SPAN(feature_channels=32, upscale=4, norm=False), ('SPAN', 3, 3, 4)),
         (SPAN(num_in_ch=1, num_out_ch=1, feature_channels=56, upscale=2, norm=False), ('SPAN', 1, 1, 2)),
+        (SpanPP(feature_channels=48, implicit_dim=64, latent_layers=2), ('SpanPP', 3, 3, [1, 2, 3, 4])),   # the reference puts the scale list there
+        (SpanPP(feature_channels=32, scale_list=[2, 4], implicit_dim=32, latent_layers=4), ('SpanPP', 3, 3, [2, 4])),
         (SpanPlus(blocks=[4], upscale=2), ('SPANPlus', 3, 3, 2)),
         (SpanPlus(blocks=[2, 3], feature_channels=32, upscale=4), ('SPANPlus', 3, 3, 4)),
         (SpanPlus(blocks=[2], upscale=2, upsampler='dys'), ('SPANPlus', 3, 3, 2)),
@@ -65,6 +67,7 @@ def test_metadata_field_order():
         (SwinIR(embed_dim=60, depths=[2, 3], num_heads=[6, 6], upscale=2), ('SwinIR', 3, 3, 2)),
         (SwinIR(embed_dim=180, depths=[2], num_heads=[6], upscale=3, upsampler='pixelshuffledirect'), ('SwinIR', 3, 3, 3)),
         (SwinIR(embed_dim=180, depths=[2], num_heads=[6], upscale=3, upsampler='pixelshuffle'), ('SwinIR', 3, 3, 3)),
+        (DAT(embed_dim=60, split_size=[4, 8], depth=[3, 2], num_heads=[2, 2], upscale=3, img_size=32, upsampler='pixelshuffle'), ('DAT', 3, 3, 3)),
         (SwinIR(embed_dim=64, depths=[2, 2], num_heads=[4, 4], mlp_ratio=4.0, upscale=4, upsampler='nearest+conv', resi_connection='3conv', img_size=48),
          ('SwinIR', 3, 3, 4)),
         (SwinIR(in_chans=1, embed_dim=48, depths=[2], num_heads=[6], window_size=7, img_size=126, img_range=255.0, upsampler=''), ('SwinIR', 1, 1, 1)),
@@ -83,6 +86,8 @@ def test_detect_and_hyperparameter_inference(model, meta):
         assert loaded.blocks == model.blocks and loaded.upsampler_kind == model.upsampler_kind
     if isinstance(model, SPAN):
         assert loaded.norm == model.norm
+    if isinstance(model, SpanPP):
+        assert (loaded.feature_channels, loaded.scale_list, loaded.base_scale, loaded.ig_kernel_size) == (model.feature_channels, model.scale_list, 2, 3)
     if isinstance(model, RRDBNet):
         assert (loaded.num_blocks, loaded.plus, loaded.shuffle_factor, loaded._keys.style) == (
             model.num_blocks, model.plus, model.shuffle_factor, model._keys.style)

@@ -406,3 +406,25 @@ def test_full_depth_fp32_plan_against_oracle_at_256(name, make):
     with torch.inference_mode():
         y32 = _load(sd)(x.to(DEV)).cpu()
     assert norm_err(y32, ref) <= FP32_TOL, f'{name} 256^2 fp32 plan vs oracle: {norm_err(y32, ref):.3e}'
+
+
+@pytest.mark.parametrize('scale', [1, 2, 3, 4])
+def test_spanpp_every_scale_of_the_scale_list(scale):
+    """SpanPP.forward(x, scale): the IGConv kernel and the output geometry depend on the requested scale (spanpp/arch.py:289-297);
+    the engine keeps one native plan per scale."""
+    from resselt_b200.archs import SpanPP
+
+    sd = SpanPP(feature_channels=48, implicit_dim=64, latent_layers=2, seed=51).state_dict()
+    x = torch.rand(1, 3, 40, 56, generator=torch.Generator().manual_seed(scale))
+    ref = oracle.spanpp_forward({k: v.clone() for k, v in sd.items()}, x, torch.float32, scale=scale)
+    with torch.inference_mode():
+        m = _load(sd)
+        y32 = m(x.to(DEV), scale=scale).cpu()
+        y16 = _load(sd, torch.bfloat16)(x.to(DEV, torch.bfloat16), scale=scale).float().cpu()
+        if scale != 2:
+            assert m(x.to(DEV)).shape[-1] == 2 * 56  # the default stays eval_base_scale = 2
+    assert y32.shape == ref.shape == (1, 3, 40 * scale, 56 * scale)
+    assert norm_err(y32, ref) <= FP32_TOL
+    assert psnr(y16, ref) >= BF16_PSNR_DB
+    with pytest.raises(KeyError):
+        m(x.to(DEV), scale=5)

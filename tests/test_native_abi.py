@@ -83,3 +83,14 @@ def test_product_does_not_import_oracle():
     for path in glob.glob(os.path.join(ROOT, 'resselt_b200', '**', '*.py'), recursive=True):
         src = open(path).read()
         assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f'{path} imports the test oracle'
+
+
+def test_descriptor_struct_sizes_match_the_library():
+    import ctypes as C
+
+    from resselt_b200.engine import native as N
+
+    lib = N.lib()
+    for which, struct in enumerate((N.ConvDesc, N.GroupNormDesc, N.OpDesc, N.OpInfo)):
+        assert lib.rsb_abi_struct_size(which) == C.sizeof(struct), struct.__name__
+    assert lib.rsb_abi_struct_size(99) == -1

@@ -18,7 +18,9 @@ def test_oracle_matches_reference_fixture(name):
     # fp32 re-association noise only (the reference forward itself is fp32)
     assert norm_err(y32, y_ref) <= 2e-6
     assert norm_err(y64, y_ref) <= 2e-6
-    assert y_ref.shape[1] == meta['out_channels'] and y_ref.shape[2] == x.shape[2] * meta['upscale']
+    # SpanPP's loader hands its scale LIST to the metadata (spanpp/__init__.py:132); its forward defaults to eval_base_scale = 2
+    upscale = 2 if isinstance(meta['upscale'], list) else meta['upscale']
+    assert y_ref.shape[1] == meta['out_channels'] and y_ref.shape[2] == x.shape[2] * upscale
 
 
 def test_dead_eval_conv_tensors_do_not_matter():
