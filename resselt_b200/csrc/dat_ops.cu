@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(256) dwconv3_kernel(const __grid_constant__ To
 // weights live in registers for the whole run and the 3 x 3 window of 16-byte pixel chunks slides down, so an output costs
 // three loads (two of them L1 hits) instead of nine plus 72 weight loads; GELU uses the MUFU erf approximation of the
 // conv epilogues (|err| <= 1.5e-7).  First version: 170 us per launch on DAT 4x 512^2.
-constexpr int kDwRows = 8;
+constexpr int kDwRows = 8;  // rows per thread (48 rows, to amortise the 80 weight loads of the prologue, measured 151 instead of 104 us
+                            // per launch: the kernel lives on the number of independent row chains in flight, not on instruction count)
 __global__ void __launch_bounds__(128) dwconv3_bf16_kernel(const __grid_constant__ TokenOpParams p) {
   using T = __nv_bfloat16;
   const int C = p.channels, planes = (C + 7) >> 3;
@@ -358,14 +359,17 @@ __global__ void __launch_bounds__(128) dwconv3_bf16_kernel(const __grid_constant
     o[1] = r[0];
     o[2] = x + 1 < p.W ? r[1] : zero;
   };
-  uint4 win[3][3];
+  // ring of four rows: the load of row y + 2 is issued while row y is computed — two row loads in flight per thread (with one,
+  // 24 resident warps x 512 B per SM could not cover HBM latency: 1.4 TB/s)
+  uint4 win[4][3];
   ldrow(yb - 1, win[0]);
   ldrow(yb, win[1]);
+  ldrow(yb + 1, win[2]);
 #pragma unroll
   for (int r = 0; r < kDwRows; ++r) {
     const int y = yb + r;
     if (y < p.H) {
-      ldrow(y + 1, win[(r + 2) % 3]);
+      ldrow(y + 2, win[(r + 3) % 4]);
       float acc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = bias[k];
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(128) dwconv3_bf16_kernel(const __grid_constant
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           float v[8];
-          unpack8<T>(win[(r + ky) % 3][kx], v);
+          unpack8<T>(win[(r + ky) % 4][kx], v);
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc[k] = fmaf(v[k], w[ky * 3 + kx][k], acc[k]);
         }
@@ -886,14 +890,117 @@ __global__ void __launch_bounds__(256) chanattn_reduce_kernel(const __grid_const
   }
 }
 
+// bf16 plan: the same reduction on warp-level tensor-core MMAs.  G = Q^T K contracts over TOKENS, so both operands are needed
+// transposed relative to their natural [token][channel] staging: ldmatrix.trans delivers exactly those fragments.  A CTA stages
+// 128 tokens of the head's q and k channels (bf16, 80-byte rows, head dims d..31 zero) and its 8 warps each own one 16 x 8 tile
+// of the 32 x 32 Gram matrix — and of Q^T Q and K^T K, whose diagonals are the squared column norms — three MMAs per 16-token
+// step.  The CUDA-core kernel above spends ~1 700 thread instructions per token and head (211 us per launch on DAT 4x 512^2,
+// 0.15 of the HBM roofline); this one is bound by the staging loads.  Fixed summation order: run-to-run deterministic.
+constexpr int kCaTok = 128;          // tokens per staged tile
+constexpr int kCaRow = kHD + 8;      // bf16 elements per staged row (80 bytes: 16-byte aligned, conflict-free for ldmatrix)
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(ptx::smem_u32(smem_row)));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(ptx::smem_u32(smem_row)));
+}
+__global__ void __launch_bounds__(256) chanattn_reduce_mma_kernel(const __grid_constant__ ChanAttnParams p) {
+  using T = __nv_bfloat16;
+  __shared__ __align__(16) T qs[kCaTok][kCaRow], ks[kCaTok][kCaRow];
+  const int h = blockIdx.y, n = blockIdx.z, d = p.head_dim;
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t chunk = ((hw + gridDim.x - 1) / gridDim.x + kCaTok - 1) / kCaTok * kCaTok;
+  const size_t t0 = (size_t)blockIdx.x * chunk, t1 = min(hw, t0 + chunk);
+  const T* src = reinterpret_cast<const T*>(p.src);
+  const int cq = p.src_ch_off + h * d, ck = cq + p.qkv_stride;
+  const int pq0 = cq >> 3, npq = ((cq + d - 1) >> 3) - pq0 + 1;
+  const int pk0 = ck >> 3, npk = ((ck + d - 1) >> 3) - pk0 + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = warp >> 2, nt = warp & 3;  // this warp's tile: rows i in [16 mt, 16 mt + 16), columns j in [8 nt, 8 nt + 8)
+  float gqk[4] = {0, 0, 0, 0}, gqq[4] = {0, 0, 0, 0}, gkk[4] = {0, 0, 0, 0};
+  for (int e = threadIdx.x; e < kCaTok * kCaRow / 8; e += blockDim.x)
+    reinterpret_cast<uint4*>(&qs[0][0])[e] = make_uint4(0, 0, 0, 0), reinterpret_cast<uint4*>(&ks[0][0])[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // ldmatrix row addresses: lanes 0-7 / 8-15 / 16-23 / 24-31 give the rows of the four 8 x 8 matrices
+  //   A (x4): (tokens 0-7, i 0-7), (tokens 0-7, i 8-15), (tokens 8-15, i 0-7), (tokens 8-15, i 8-15)  = a0, a1, a2, a3
+  //   B (x2): (tokens 0-7, j 0-7), (tokens 8-15, j 0-7)                                              = b0, b1
+  const int a_tok = (lane & 7) + ((lane >> 4) << 3), a_col = mt * 16 + (((lane >> 3) & 1) << 3);
+  const int b_tok = lane & 15, b_col = nt * 8;
+  // Staging: thread = (token tt, plane phase); its items (pl = phase, phase + 2, ...) are the same for every tile.  All loads of
+  // a tile are issued back to back, and the NEXT tile's loads are in flight while this tile's MMAs run (one load per loop
+  // iteration, waited for before the scatter, made the first version latency-bound: 156 us per launch).
+  constexpr int kItems = 5;  // ceil(10 planes / 2 phases): a head of <= 32 channels straddles <= 5 planes per matrix
+  const int tt = threadIdx.x & (kCaTok - 1), phase = threadIdx.x >> 7;
+  const int nitems = npq + npk;
+  uint4 v[kItems];
+  auto fetch = [&](size_t base) {
+    const size_t tok = base + tt;
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      const int pl = phase + 2 * it;
+      v[it] = make_uint4(0, 0, 0, 0);  // tokens beyond the range contribute zeros
+      if (pl < nitems && tok < t1) {
+        const int plane = pl >= npq ? pk0 + (pl - npq) : pq0 + pl;
+        v[it] = *reinterpret_cast<const uint4*>(src + (((size_t)n * p.src_planes + plane) * hw + tok) * 8);
+      }
+    }
+  };
+  if (t0 < t1) fetch(t0);
+  for (size_t base = t0; base < t1; base += kCaTok) {
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      const int pl = phase + 2 * it;
+      if (pl < nitems) {
+        const bool isk = pl >= npq;
+        const int plane = isk ? pk0 + (pl - npq) : pq0 + pl;
+        const int cb = plane * 8 - (isk ? ck : cq);  // head dim of the plane's first channel
+        const T* ev = reinterpret_cast<const T*>(&v[it]);
+        T* row = isk ? ks[tt] : qs[tt];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if ((unsigned)(cb + k) < (unsigned)d) row[cb + k] = ev[k];
+      }
+    }
+    __syncthreads();
+    if (base + kCaTok < t1) fetch(base + kCaTok);
+#pragma unroll
+    for (int k16 = 0; k16 < kCaTok / 16; ++k16) {
+      uint32_t aq[4], ak[4], bq[2], bk[2];
+      ldsm_x4_trans(aq, &qs[k16 * 16 + a_tok][a_col]);
+      ldsm_x4_trans(ak, &ks[k16 * 16 + a_tok][a_col]);
+      ldsm_x2_trans(bk, &ks[k16 * 16 + b_tok][b_col]);
+      ldsm_x2_trans(bq, &qs[k16 * 16 + b_tok][b_col]);
+      mma_bf16_16816(gqk, aq, bk[0], bk[1]);
+      mma_bf16_16816(gqq, aq, bq[0], bq[1]);
+      mma_bf16_16816(gkk, ak, bk[0], bk[1]);
+    }
+    __syncthreads();
+  }
+  const int len = d * d + 2 * d;
+  float* out = p.partial + (((size_t)n * p.heads + h) * gridDim.x + blockIdx.x) * len;
+  const int g4 = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = mt * 16 + g4 + ((e >> 1) << 3), j = nt * 8 + 2 * t4 + (e & 1);
+    if (i < d && j < d) {
+      out[i * d + j] = gqk[e];
+      if (i == j) out[d * d + i] = gqq[e], out[d * d + d + i] = gkk[e];
+    }
+  }
+}
+
 // attn[n][head][i][j] = softmax_j( G[i][j] / (max(|q_i|, eps) max(|k_j|, eps)) * temperature[head] )
-__global__ void __launch_bounds__(256) chanattn_finalize_kernel(const __grid_constant__ ChanAttnParams p) {
+__global__ void __launch_bounds__(1024) chanattn_finalize_kernel(const __grid_constant__ ChanAttnParams p) {
   __shared__ float g[kHD * kHD + 2 * kHD];
   const int h = blockIdx.x, n = blockIdx.y, d = p.head_dim;
   const int len = d * d + 2 * d;
   const float* in = p.partial + ((size_t)n * p.heads + h) * p.blocks * len;
+  // one element per thread (the 6-CTA, 256-thread version walked four elements x 128 partials per thread: 94 us per launch);
+  // fixed order: run-to-run deterministic; 16 loads in flight
   for (int e = threadIdx.x; e < len; e += blockDim.x) {
-    double s = 0.0;  // fixed order: run-to-run deterministic; 16 loads in flight (the loop used to be one L2 round trip per block)
+    double s = 0.0;
     for (int b0 = 0; b0 < p.blocks; b0 += 16) {
       float t[16];
 #pragma unroll
@@ -1091,7 +1198,7 @@ __global__ void __launch_bounds__(256) aim_cmap_kernel(const __grid_constant__ A
 //   mode 1 (channel-attention block): Y = ATT * smap + CONVX * cmap[c]     (arch.py:602-607)
 template <typename T>
 __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant__ AimParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int C = p.channels, planes = (C + 7) >> 3, hidn = p.si_hidden;
   float* w1 = sm;                 // [hidn][cpad]
   float* cm = w1 + hidn * p.cpad; // [cpad]
@@ -1111,16 +1218,26 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
   float hid[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) hid[k] = k < hidn ? p.si_b1[k] : 0.0f;
-  for (int pl = 0; pl < planes; ++pl) {
-    float v[8];
-    load8<T>(ssrc + (size_t)pl * hw * 8, v);
+  // planes in batches of four: four independent 16-byte loads in flight per thread (one at a time left the kernel waiting on
+  // HBM latency: 2.4 TB/s)
+  for (int pl0 = 0; pl0 < planes; pl0 += 4) {
+    float v[4][8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      if (k < hidn) {
-        const float* wr = w1 + k * p.cpad + pl * 8;
+    for (int u = 0; u < 4; ++u)
+      if (pl0 + u < planes) load8<T>(ssrc + (size_t)(pl0 + u) * hw * 8, v[u]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) hid[k] = fmaf(wr[c], v[c], hid[k]);
-      }
+    for (int u = 0; u < 4; ++u) {
+      if (pl0 + u >= planes) break;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < hidn) {
+          // two 16-byte broadcast loads per 8 FMAs (one 4-byte shared-memory load per FMA made this kernel shared-memory bound)
+          const float4* wr = reinterpret_cast<const float4*>(w1 + k * p.cpad + (pl0 + u) * 8);
+          const float4 wa = wr[0], wb = wr[1];
+          hid[k] = fmaf(wa.x, v[u][0], fmaf(wa.y, v[u][1], fmaf(wa.z, v[u][2], fmaf(wa.w, v[u][3], hid[k]))));
+          hid[k] = fmaf(wb.x, v[u][4], fmaf(wb.y, v[u][5], fmaf(wb.z, v[u][6], fmaf(wb.w, v[u][7], hid[k]))));
+        }
+    }
   }
   float s = p.si_b2;
 #pragma unroll
@@ -1128,16 +1245,25 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
     if (k < hidn) s = fmaf(p.si_w2[k], gelu_f(hid[k]), s);
   const float smap = sigm_f(s);
   T* dst = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
-  for (int pl = 0; pl < planes; ++pl) {
-    float a[8], b[8], o[8];
-    load8<T>(att + (size_t)pl * hw * 8, a);
-    load8<T>(cvx + (size_t)pl * hw * 8, b);
+  for (int pl0 = 0; pl0 < planes; pl0 += 2) {
+    float a[2][8], b[2][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float cmv = cm[pl * 8 + c];
-      o[c] = p.mode == 0 ? fmaf(a[c], cmv, smap * b[c]) : fmaf(a[c], smap, b[c] * cmv);
+    for (int u = 0; u < 2; ++u)
+      if (pl0 + u < planes) {
+        load8<T>(att + (size_t)(pl0 + u) * hw * 8, a[u]);
+        load8<T>(cvx + (size_t)(pl0 + u) * hw * 8, b[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (pl0 + u >= planes) break;
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float cmv = cm[(pl0 + u) * 8 + c];
+        o[c] = p.mode == 0 ? fmaf(a[u][c], cmv, smap * b[u][c]) : fmaf(a[u][c], smap, b[u][c] * cmv);
+      }
+      store8<T>(dst + (size_t)(pl0 + u) * hw * 8, o);
     }
-    store8<T>(dst + (size_t)pl * hw * 8, o);
   }
 }
 
@@ -1419,14 +1545,22 @@ cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, cudaStream_t s) {
+cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, int num_sms, cudaStream_t s) {
   const size_t hw = (size_t)p.H * p.W;
   const dim3 g1(p.blocks, p.heads, p.n), g2(p.heads, p.n), g3((unsigned)((hw + 255) / 256), p.heads, p.n);
-  if (bf16)
-    chanattn_reduce_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>(p);
-  else
-    chanattn_reduce_kernel<float><<<g1, 256, 0, s>>>(p);
-  chanattn_finalize_kernel<<<g2, 256, 0, s>>>(p);
+  if (bf16 && p.head_dim <= kHD) {
+    // tensor-core reduction: two resident CTAs per SM stream disjoint token ranges; fewer partial blocks for the finalize step
+    ChanAttnParams q = p;
+    q.blocks = std::max(1, std::min(p.blocks, 2 * (num_sms > 0 ? num_sms : 148) / std::max(1, p.heads * p.n)));
+    chanattn_reduce_mma_kernel<<<dim3(q.blocks, p.heads, p.n), 256, 0, s>>>(q);
+    chanattn_finalize_kernel<<<g2, 1024, 0, s>>>(q);
+  } else {
+    if (bf16)
+      chanattn_reduce_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>(p);
+    else
+      chanattn_reduce_kernel<float><<<g1, 256, 0, s>>>(p);
+    chanattn_finalize_kernel<<<g2, 1024, 0, s>>>(p);
+  }
   const bool pairs_ok = p.head_dim % 2 == 0 && p.head_dim <= kHD && (p.src_ch_off + 2 * p.qkv_stride) % 2 == 0 && p.dst_ch_off % 2 == 0;
   if (bf16 && pairs_ok) {
     const unsigned gx = (unsigned)std::min<size_t>((hw + 127) / 128, 296);  // 8 warps x 16 tokens per block step
@@ -1438,9 +1572,13 @@ cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, cudaStream_t s) 
   return cudaGetLastError();
 }
 
-cudaError_t launch_aim(const AimParams& p, bool bf16, cudaStream_t s) {
-  const size_t hw = (size_t)p.H * p.W;
+cudaError_t launch_aim(const AimParams& p0, bool bf16, int num_sms, cudaStream_t s) {
+  // a few pooling CTAs per SM are enough to stream the map; fewer partial blocks make the single-CTA channel-map step (which adds
+  // them up) three times shorter
+  AimParams p = p0;
   const int planes = (p.channels + 7) / 8;
+  p.blocks = std::max(1, std::min(p0.blocks, std::max(8, 4 * (num_sms > 0 ? num_sms : 148) / std::max(1, planes * p.n))));
+  const size_t hw = (size_t)p.H * p.W;
   const dim3 g1(p.blocks, planes, p.n), g3((unsigned)((hw + 255) / 256), p.n);
   const size_t smem = ((size_t)p.si_hidden * p.cpad + p.cpad) * sizeof(float);
   if (bf16)

@@ -1259,14 +1259,14 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           case RSB_OP_LAYERNORM: e = rsb::launch_layernorm(a.tok, bf, p->num_sms, stream); break;
           case RSB_OP_DWCONV3: e = rsb::launch_dwconv3(a.tok, bf, stream); break;
           case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, stream); break;
-          case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, stream); break;
+          case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, p->num_sms, stream); break;
           case RSB_OP_DYSAMPLE: {
             rsb::DySampleParams q = a.dys;
             q.dst = y, q.dst_dtype = y_dtype;
             e = rsb::launch_dysample(q, bf, stream);
             break;
           }
-          default: e = rsb::launch_aim(a.aim, bf, stream); break;
+          default: e = rsb::launch_aim(a.aim, bf, p->num_sms, stream); break;
         }
       }
       if (e != cudaSuccess) {
