@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RSB_VERSION 200
+#define RSB_VERSION 201
 
 typedef struct rsb_plan rsb_plan;
 
@@ -119,6 +119,11 @@ typedef struct rsb_conv_desc {
   /* explicit top/left zero padding; -1 selects the 'same' default kh/2, kw/2.  With explicit pads the kernel
    * extents may be even (used for the 2x2 phase kernels of a nearest-upsample + 3x3 conv). Output size == input size. */
   int32_t pad_t, pad_l;
+  /* host, [16][cout] or NULL: extra bias for pixels on the border of the conv grid, indexed by the mask
+   * (y == 0) | (y == H-1) << 1 | (x == 0) << 2 | (x == W-1) << 3 (row 0 unused), added with the bias before the activation.
+   * This is what makes a 1x1 conv WITH BIAS followed by a zero-padded k x k conv collapse exactly into one k x k conv
+   * (the taps that fall outside the image must not see the 1x1 conv's bias): SPAN's conv_cat + upsampler, span/arch.py:247-248. */
+  const float* border_bias;
 } rsb_conv_desc;
 
 /* GroupNorm over (channels/groups, H, W) per sample, affine, followed by "+ skip". */

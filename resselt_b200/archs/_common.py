@@ -47,6 +47,36 @@ def merge_conv3xc(w: Dict[str, torch.Tensor], prefix: str):
     return merged, bias
 
 
+def merge_pointwise_into_conv(w1: torch.Tensor, b1, wk: torch.Tensor, bk):
+    """Collapse ``conv_kxk(conv_1x1(x))`` (no activation in between, zero padding on the k x k conv) into ONE k x k conv, fp64.
+
+    Returns (weight [O][C][k][k], bias [O], border_bias [16][O]).  W[o,c,ky,kx] = sum_m wk[o,m,ky,kx] w1[m,c]; the 1x1 conv's bias
+    reaches an output pixel through every tap that lies INSIDE the image (the k x k conv zero-pads the 1x1 conv's output, bias
+    included), so bias[o] = bk[o] + sum_{m,taps} wk[o,m,tap] b1[m] holds for interior pixels and border pixels get
+    border_bias[mask][o] = - sum_{m, taps outside under mask} wk[o,m,tap] b1[m], mask = top | bottom << 1 | left << 2 | right << 3
+    (rsb_conv_desc.border_bias).  Used for SPAN's / SPANPlus' / SpanPP's ``upsampler(conv_cat(cat))`` (span/arch.py:247-248):
+    one pass over the 192-channel concat instead of a 1x1 pass plus a 3x3 pass."""
+    f64 = torch.float64
+    w1, wk = w1.to(f64)[:, :, 0, 0], wk.to(f64)
+    b1 = torch.zeros(w1.shape[0], dtype=f64) if b1 is None else b1.to(f64)
+    bk = torch.zeros(wk.shape[0], dtype=f64) if bk is None else bk.to(f64)
+    k = wk.shape[-1]
+    r = k // 2
+    weight = torch.einsum('omyx,mc->ocyx', wk, w1)
+    per_tap = torch.einsum('omyx,m->oyx', wk, b1)  # what each tap contributes of the 1x1 conv's bias
+    bias = bk + per_tap.sum((1, 2))
+    border = torch.zeros(16, wk.shape[0], dtype=f64)
+    for mask in range(1, 16):
+        top, bottom, left, right = mask & 1, mask & 2, mask & 4, mask & 8
+        for ky in range(k):
+            for kx in range(k):
+                dy, dx = ky - r, kx - r
+                # a k x k conv with k > 3 would need distance-dependent classes; this table is exact for k == 3 (and k == 1)
+                if (dy < 0 and top) or (dy > 0 and bottom) or (dx < 0 and left) or (dx > 0 and right):
+                    border[mask] -= per_tap[:, ky, kx]
+    return weight, bias, border
+
+
 # ------------------------------------------------------------------------------------------------ DySample head
 def dysample_init_pos(scale: int, groups: int) -> torch.Tensor:
     """The ``init_pos`` buffer exactly as DySample._init_pos builds it (/root/reference/resselt/utilities/dysample.py:42-44)."""

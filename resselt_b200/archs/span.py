@@ -13,7 +13,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import pixelshuffle_scale
-from ._common import conv3xc_specs, conv_specs, merge_conv3xc
+from ._common import conv3xc_specs, conv_specs, merge_conv3xc, merge_pointwise_into_conv
 
 
 def emit_spab(pb: PlanBuilder, w, prefix: str, src, dst, t1, t2, act: int) -> None:
@@ -79,8 +79,11 @@ class SPAN(EngineModule):
         emit_spab(pb, w, 'block_5', p0, p1, t1, t2, N.ACT_SILU)
         emit_spab(pb, w, 'block_6', p1, p0, o1_end, t2, N.ACT_SILU)
         pb.conv(p0, tail, *merge_conv3xc(w, 'conv_2'))
-        pb.conv(cat, t1, w['conv_cat.weight'], w['conv_cat.bias'])
-        pb.conv(t1, OUTPUT, w['upsampler.0.weight'], w['upsampler.0.bias'], ps=self.upscale)
+        # conv_cat (1x1, 192 -> 48) and the upsampler conv (3x3, 48 -> 3 r^2) have nothing between them (span/arch.py:247-248):
+        # merged on the host into one 3x3 conv over the 192-channel concat (exact, border pixels included: border_bias) — one pass
+        # over the concat instead of a 1 GB 1x1 pass plus a 3x3 pass (148 + 51 us -> one launch at 1080p)
+        wm, bm, border = merge_pointwise_into_conv(w['conv_cat.weight'], w['conv_cat.bias'], w['upsampler.0.weight'], w['upsampler.0.bias'])
+        pb.conv(cat, OUTPUT, wm, bm, ps=self.upscale, border_bias=border)
 
 
 class SPANArch(Architecture[SPAN]):

@@ -13,7 +13,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import dysample_scale, get_seq_len, pixelshuffle_scale
-from ._common import conv3xc_specs, conv_specs, dysample_specs, emit_dysample, merge_conv3xc
+from ._common import merge_pointwise_into_conv, conv3xc_specs, conv_specs, dysample_specs, emit_dysample, merge_conv3xc
 from .span import emit_spab
 
 
@@ -81,7 +81,14 @@ class SpanPlus(EngineModule):
             end_out = pong[n_blocks % 2]
             emit_spab(pb, w, f'{pre}.block_end', cur, end_out, o1_end, t2, N.ACT_MISH)
             pb.conv(end_out, tail, *merge_conv3xc(w, f'{pre}.conv_2'))  # Dropout2d is the identity in eval
-            dst = cats[g].slice(0, f) if g < len(self.blocks) else t1
+            last = g == len(self.blocks)
+            if last and self.upsampler_kind == 'ps':
+                # the last group's conv_cat feeds the upsampler conv directly: one merged 3x3 conv over the concat (see span.py)
+                wm, bm, border = merge_pointwise_into_conv(w[f'{pre}.conv_cat.weight'], w[f'{pre}.conv_cat.bias'], w['upsampler.0.weight'],
+                                                           w['upsampler.0.bias'])
+                pb.conv(cat, OUTPUT, wm, bm, ps=self.upscale, border_bias=border)
+                return
+            dst = cats[g].slice(0, f) if not last else t1
             pb.conv(cat, dst, w[f'{pre}.conv_cat.weight'], w[f'{pre}.conv_cat.bias'])
         if self.upsampler_kind == 'ps':
             pb.conv(t1, OUTPUT, w['upsampler.0.weight'], w['upsampler.0.bias'], ps=self.upscale)

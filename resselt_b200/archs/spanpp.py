@@ -22,7 +22,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, ParamSpec, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import get_seq_len
-from ._common import conv3xc_specs, conv_specs, merge_conv3xc
+from ._common import conv3xc_specs, conv_specs, merge_conv3xc, merge_pointwise_into_conv
 
 
 def repconv_specs(prefix: str, cin: int, cout: int) -> List[ParamSpec]:
@@ -165,9 +165,15 @@ class SpanPP(EngineModule):
         spab('block_5', p0, p1, t1)
         spab('block_6', p1, p0, o1_end)
         pb.conv(p0, tail, *merge_repconv(w, 'conv_2'))
-        pb.conv(cat, t1, w['conv_cat.weight'], w['conv_cat.bias'])
         s = pb.upscale
-        pb.conv(t1, OUTPUT, igconv_kernel(w, 'upsampler', f, self.ig_kernel_size, s, self.max_scale), None, ps=s)
+        kernel = igconv_kernel(w, 'upsampler', f, self.ig_kernel_size, s, self.max_scale)
+        if self.ig_kernel_size == 3:
+            # conv_cat (1x1) merged into the IGConv kernel: one 3x3 conv over the concat (see span.py)
+            wm, bm, border = merge_pointwise_into_conv(w['conv_cat.weight'], w['conv_cat.bias'], kernel, None)
+            pb.conv(cat, OUTPUT, wm, bm, ps=s, border_bias=border)
+        else:
+            pb.conv(cat, t1, w['conv_cat.weight'], w['conv_cat.bias'])
+            pb.conv(t1, OUTPUT, kernel, None, ps=s)
 
 
 class SpanPPArch(Architecture[SpanPP]):

@@ -384,6 +384,9 @@ const RsVariant kRsVariants[] = {
     // upsampler convs storing PixelShuffle'd into the caller's tensor
     RSB_X(3, 1, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_X(4, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    // SPAN / SPANPlus / SpanPP: conv_cat (1x1 over the 4 x 48-channel concat) merged into the upsampler conv: 192 -> 12 / 48
+    RSB_X(12, 1, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_X(12, 3, RSB_ACT_NONE, RSB_COMB_NONE),
     // runtime geometry, specialised epilogue
     RSB_V(0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_V(0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),

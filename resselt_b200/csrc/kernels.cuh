@@ -24,6 +24,8 @@ constexpr int kTileW = 8;
 struct Epi {
   const float* bias;    // [cpad] (never null; zeros when the conv has no bias)
   const float* slopes;  // [cpad] PReLU slopes or null
+  const float* border_bias;  // [16][bb_stride] or null: extra bias of border pixels by (top | bottom << 1 | left << 2 | right << 3)
+  int bb_stride;
   int act;
   float act_param;
   int combine;
@@ -232,6 +234,14 @@ __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const
     const float4 b1 = reinterpret_cast<const float4*>(bias + c0)[1];
     v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w;
     v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+  }
+  if (e.border_bias != nullptr) {
+    const int mask = (y == 0 ? 1 : 0) | (y == e.H - 1 ? 2 : 0) | (x == 0 ? 4 : 0) | (x == e.W - 1 ? 8 : 0);
+    if (mask != 0) {
+      const float* bb = e.border_bias + (size_t)mask * e.bb_stride + c0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += bb[i];
+    }
   }
   const int plane = c0 >> 3;
   if (comb == RSB_COMB_SPAB_GATE) {

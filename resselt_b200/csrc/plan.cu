@@ -88,7 +88,8 @@ struct Buffer {
 
 struct ConvOp {
   rsb_conv_desc d;
-  std::vector<float> w, b, slopes;
+  std::vector<float> w, b, slopes, border;
+  float* d_border = nullptr;  // [16][max(npad, cpad32)]
   int scale = 1;  // grid of this conv relative to the input
   int cin_pad16 = 0, npad = 0, cpad32 = 0, cin_planes = 0;
   bool tc_ok = false;
@@ -302,7 +303,7 @@ void find_pairs(rsb_plan* p) {
     ConvOp& a = p->convs[p->ops[i].index];
     ConvOp& b = p->convs[p->ops[i + 1].index];
     const rsb_conv_desc &da = a.d, &db = b.d;
-    if (!a.rs_elig || !b.rs_elig || a.tc_cin > 64 || a.npad > 64) continue;
+    if (!a.rs_elig || !b.rs_elig || a.tc_cin > 64 || a.npad > 64 || !a.border.empty() || !b.border.empty()) continue;
     if ((a.pack_buf >= 0 && !a.pack_planar) || b.pack_buf >= 0 || a.scale != b.scale) continue;
     if ((da.combine != RSB_COMB_NONE && da.combine != RSB_COMB_SPAB_GATE) || da.res2_buf >= 0 || da.act == RSB_ACT_PRELU) continue;
     if (da.dst_buf < 0 || da.dst_ps > 1 || da.dst2_buf >= 0) continue;
@@ -333,6 +334,8 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
   memset(&e, 0, sizeof e);
   e.bias = c.d_bias;
   e.slopes = c.d_slopes;
+  e.border_bias = c.d_border;
+  e.bb_stride = std::max(c.npad, c.cpad32);
   e.act = d.act;
   e.act_param = d.act_param;
   e.combine = d.combine;
@@ -374,7 +377,7 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
       e.dst2_plane0 = d.dst2_ch_off / 8;
       e.split_ch = d.split_ch;
     }
-    e.simple = (e.dst_ps == 1 && e.dst2 == nullptr && e.res2 == nullptr) ? 1 : 0;
+    e.simple = (e.dst_ps == 1 && e.dst2 == nullptr && e.res2 == nullptr && e.border_bias == nullptr) ? 1 : 0;
   }
 }
 
@@ -709,7 +712,7 @@ int rsb_plan_destroy(rsb_plan* p) {
     // also after a finalize that failed half-way: whatever was allocated up to that point is released (null pointers are fine)
     DeviceGuard guard(p->device);
     for (ConvOp& c : p->convs) {
-      cudaFree(c.d_wtc), cudaFree(c.d_wrs), cudaFree(c.d_wlk), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes);
+      cudaFree(c.d_wtc), cudaFree(c.d_wrs), cudaFree(c.d_wlk), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes), cudaFree(c.d_border);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
     for (AuxOp& a : p->auxs)
@@ -798,7 +801,8 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
   c.w.assign(d.weight, d.weight + wn);
   if (d.bias) c.b.assign(d.bias, d.bias + d.cout);
   if (d.act == RSB_ACT_PRELU) c.slopes.assign(d.act_slopes, d.act_slopes + d.cout);
-  c.d.weight = nullptr, c.d.bias = nullptr, c.d.act_slopes = nullptr;
+  if (d.border_bias) c.border.assign(d.border_bias, d.border_bias + (size_t)16 * d.cout);
+  c.d.weight = nullptr, c.d.bias = nullptr, c.d.act_slopes = nullptr, c.d.border_bias = nullptr;
   c.cin_pad16 = ceil_div(d.cin, 16) * 16;
   c.npad = ceil_div(d.cout, 16) * 16;
   c.cpad32 = ceil_div(d.cout, 32) * 32;
@@ -971,6 +975,13 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
     }
     RSB_CUDA(cudaMalloc(&c.d_bias, cmax * sizeof(float)));
     RSB_CUDA(cudaMemcpy(c.d_bias, bias.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));
+    if (!c.border.empty()) {
+      std::vector<float> bb((size_t)16 * cmax, 0.0f);
+      for (int m = 0; m < 16; ++m)
+        for (int o = 0; o < d.cout; ++o) bb[(size_t)m * cmax + o] = c.border[(size_t)m * d.cout + o];
+      RSB_CUDA(cudaMalloc(&c.d_border, bb.size() * sizeof(float)));
+      RSB_CUDA(cudaMemcpy(c.d_border, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     if (d.act == RSB_ACT_PRELU) {
       RSB_CUDA(cudaMalloc(&c.d_slopes, cmax * sizeof(float)));
       RSB_CUDA(cudaMemcpy(c.d_slopes, slopes.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));

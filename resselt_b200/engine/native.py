@@ -58,6 +58,7 @@ class ConvDesc(C.Structure):
         ('src_upsample2', C.c_int32),
         ('dst_ps', C.c_int32), ('dst2_buf', C.c_int32), ('dst2_ch_off', C.c_int32), ('split_ch', C.c_int32),
         ('dst_phase', C.c_int32), ('pad_t', C.c_int32), ('pad_l', C.c_int32),
+        ('border_bias', C.POINTER(C.c_float)),
     ]
 
 

@@ -74,7 +74,7 @@ class PlanBuilder:
         cin16 = (cin + 15) // 16 * 16
         budget = 150 * 1024
         splittable = (self.compute_dtype == torch.bfloat16 and src.buf >= 0 and dst.buf >= 0 and kw.get('dst_ps', 1) == 1
-                      and kw.get('dst2') is None and not kw.get('src_upsample2', False))
+                      and kw.get('dst2') is None and not kw.get('src_upsample2', False) and kw.get('border_bias') is None)
         npad = (cout + 15) // 16 * 16
         if not splittable or (kh * kw_ * cin16 * npad * 2 <= budget and npad <= 256):
             return self._conv_one(src, dst, w, bias, **kw)
@@ -118,6 +118,7 @@ class PlanBuilder:
         dst_phase: int = -1,
         dst2: Optional[Ref] = None,
         pad: Optional[tuple] = None,
+        border_bias=None,
     ) -> None:
         w = _f32(weight)
         assert w.ndim == 4, 'conv weight must be [cout][cin][kh][kw]'
@@ -149,6 +150,10 @@ class PlanBuilder:
         d.dst_ps = int(dst_ps)
         d.dst_phase = int(dst_phase)
         d.pad_t, d.pad_l = (int(pad[0]), int(pad[1])) if pad is not None else (-1, -1)
+        bb = _f32(border_bias) if border_bias is not None else None
+        if bb is not None:
+            assert bb.shape == (16, cout), 'border_bias must be [16][cout]'
+        d.border_bias = _fptr(bb)
         d.dst2_buf, d.dst2_ch_off = (dst2.buf, dst2.ch_off) if dst2 is not None else (N.NO_BUFFER, 0)
         d.split_ch = main_ch if dst2 is not None else 0
         N.check(self._lib.rsb_plan_add_conv(self._h, C.byref(d)))

@@ -85,3 +85,22 @@ def test_plksr_large_kernel_layers_merge_into_one_dense_kernel(lk_type, kw):
         ref = cw('mn_conv', padding=(mm // 2, nn_ // 2)) + cw('nm_conv', padding=(nn_ // 2, mm // 2)) + cw('nn_conv', padding=nn_ // 2)
     ref = ref + x  # with_idt
     assert (F.conv2d(x, k, b, padding=m.kmax // 2) - ref).abs().max() < 1e-12
+
+
+def test_pointwise_conv_merged_into_3x3_is_exact_including_borders():
+    """merge_pointwise_into_conv (SPAN's upsampler(conv_cat(cat)), span/arch.py:247-248): one 3x3 conv + border bias table equals
+    conv3x3(zero-padded conv1x1 output) at every pixel — corners, edges, 1-pixel-high and 1-pixel-wide images included."""
+    from resselt_b200.archs._common import merge_pointwise_into_conv
+
+    g = torch.Generator().manual_seed(4)
+    w1, b1 = torch.randn(6, 10, 1, 1, generator=g).double(), torch.randn(6, generator=g).double()
+    wk, bk = torch.randn(5, 6, 3, 3, generator=g).double(), torch.randn(5, generator=g).double()
+    wm, bm, border = merge_pointwise_into_conv(w1, b1, wk, bk)
+    for H, W in ((7, 9), (1, 6), (5, 1), (1, 1), (2, 2)):
+        x = torch.randn(2, 10, H, W, generator=g).double()
+        ref = F.conv2d(F.conv2d(x, w1, b1), wk, bk, padding=1)
+        got = F.conv2d(x, wm, bm, padding=1)
+        ys, xs = torch.arange(H).view(-1, 1), torch.arange(W).view(1, -1)
+        mask = (ys == 0).long() + 2 * (ys == H - 1).long() + 4 * (xs == 0).long() + 8 * (xs == W - 1).long()
+        got = got + border[mask].permute(2, 0, 1).unsqueeze(0)
+        assert (got - ref).abs().max() < 1e-12, (H, W)
