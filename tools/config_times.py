@@ -1,5 +1,6 @@
 """Device-resident forward time of every BASELINE.json configuration on one B200 (bf16), one JSON line per config.
-    python tools/config_times.py [iters]
+Untiled forwards are replayed from a CUDA graph (no host launch cost: DAT is 675 launches); the tiled case runs eagerly.
+    python tools/config_times.py [iters] [case,case,...]
 Tensor-core ceilings: algorithmic FLOP per output pixel x out-MP/s against the sustained bf16 peak."""
 import json
 import os
@@ -8,7 +9,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
+from resselt_b200.engine.profiling import time_forward
 from resselt_b200.runner import tiled_forward
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 5
@@ -27,24 +29,30 @@ CASES = [
     ('config5 RealPLKSR 4x 512^2', lambda: RealPLKSR(n_blocks=28, upscaling_factor=4, seed=7), 1, 512, 512, 14753152, None),
     ('config5 DAT 4x 512^2', lambda: DAT(upscale=4, seed=8), 1, 512, 512, 26242128, None),
     ('8a-a19 SwinIR 4x (180ch 6x6 w8) 512^2', lambda: SwinIR(upscale=4, seed=9), 1, 512, 512, None, None),
+    ('8f-2 SpanPP 2x 1080p', lambda: SpanPP(feature_channels=48, seed=10), 1, 1080, 1920, None, None),
+    ('8f-4 SPANPlus 2x dys head 1080p', lambda: SpanPlus(blocks=[4], feature_channels=48, upscale=2, upsampler='dys', seed=4), 1, 1080, 1920, None, None),
 ]
 for idx, (label, make, b, h, w, flop_px, tile) in enumerate(CASES):
     if only is not None and idx not in only:
         continue
     m = make().eval().to(dev).bfloat16()
     x = torch.rand(b, 3, h, w, device=dev).bfloat16()
-    run = (lambda: tiled_forward(m, x, m.upscale, tile, m.receptive_radius)) if tile else (lambda: m(x))
     with torch.inference_mode():
-        for _ in range(2):
-            run()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            run()
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+        if tile:
+            run = lambda: tiled_forward(m, x, m.upscale, tile, m.receptive_radius)
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+        else:
+            out = torch.empty((b, m.out_channels, h * m.upscale, w * m.upscale), dtype=torch.bfloat16, device=dev)
+            ms = time_forward(m.plan_for(dev, torch.bfloat16), x, out, reps=iters)
     out_mp = b * h * w * m.upscale ** 2 / 1e6
     rec = dict(config=label, ms=round(ms, 3), out_mp_per_s=round(out_mp / ms * 1e3, 1))
     if flop_px:
