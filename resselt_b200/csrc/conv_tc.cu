@@ -269,6 +269,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             }
           }
         } else {
+          // wide / runtime N: the residual chunks of a gate / AXPY / MUL tail are loaded inside epilogue8, right where they are
+          // needed (no registers to hold 12 of them): ncu showed 44 % of this kernel's stall samples on the first use of that load
+          // (profiles/r2_conv_tc_axpy.md) — 12 serial HBM round trips per tile, 85 us for a 180 -> 180 linear with a residual
+          // against 39 us without.  So the lines of the NEXT tile this warpgroup will drain are pulled into L2 now, one tile
+          // (~5 us) ahead: the later loads then pay an L2 hit.
+          constexpr bool kMayRes = COMB == kRuntime || COMB == RSB_COMB_SPAB_GATE || COMB == RSB_COMB_MUL || COMB == RSB_COMB_AXPY;
+          if constexpr (kMayRes) {
+            const int comb_rt = COMB == kRuntime ? p.epi.combine : COMB;
+            if (comb_rt != RSB_COMB_NONE && !p.epi.dst_external && p.epi.dst_ps <= 1) {
+              const size_t plane_stride = (size_t)p.H * p.W * 8;
+              auto prefetch_tile = [&](int t) {
+                if (t >= p.num_tiles) return;
+                const int n2 = t / tiles_per_img, rem2 = t - n2 * tiles_per_img;
+                const int ty2 = rem2 / p.tiles_x, tx2 = rem2 - ty2 * p.tiles_x;
+                const int y2 = ty2 * kTileH + ry, x2 = tx2 * kTileW + rx;
+                if (y2 >= p.H || x2 >= p.W) return;
+                const T* rp = reinterpret_cast<const T*>(p.epi.res1) + planar_index(n2, p.epi.res1_planes, p.epi.res1_plane0, p.H, p.W, y2, x2);
+                for (int c = part * 16; c < cstore; c += 16 * parts) {
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)(c >> 3) * plane_stride));
+                  if (c + 8 < cstore) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)((c >> 3) + 1) * plane_stride));
+                }
+              };
+              if (tile == blockIdx.x + g * (int)gridDim.x) prefetch_tile(tile);  // first tile of this warpgroup
+              prefetch_tile(tile + A * (int)gridDim.x);
+            }
+          }
           mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
           for (int c = part * 16; c < p.npad; c += 16 * parts) {
