@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RSB_VERSION 201
+#define RSB_VERSION 202
 
 typedef struct rsb_plan rsb_plan;
 
@@ -146,7 +146,8 @@ typedef struct rsb_groupnorm_desc {
  * relative_position_index, cyclic shift and mask, window reverse). */
 enum rsb_op_kind {
   RSB_OP_LAYERNORM = 1, /* dst = LN_channels(src) * w[0] + w[1];  f[0] = eps                                         */
-  RSB_OP_DWCONV3 = 2,   /* dst = act(dwconv3x3(src; w[0] = [C][9], w[1] = bias[C])) [* src2];  i[0] = rsb_act          */
+  RSB_OP_DWCONV3 = 2,   /* dst = act(dwconv3x3(src; w[0] = [C][9], w[1] = bias[C])) [* src2];  i[0] = rsb_act;
+                           i[1] = K in {0, 3, 5, 7}: depthwise K x K instead (w[0] = [C][K*K]; K > 3: no act / gate)          */
   RSB_OP_WINATTN = 3,   /* src = [q | k | v]; i[0] heads, i[1] split_h, i[2] split_w, i[3] shifted, i[4] channel stride
                            between q, k and v (0: channels);
                            f[0] = qk scale; w[0] / w[1] = position-bias tables of the two branches
@@ -171,6 +172,16 @@ enum rsb_op_kind {
                            w[0] = init_pos [2 * groups * s^2], w[1] = end_conv weight [out][C], w[2] = end_conv bias [out].
                            Sampling position of output pixel (h*s+i, w*s+j), group g: (w + off_x, h + off_y) in input pixels,
                            clamped to the image (grid_sample bilinear, align_corners=False, padding_mode='border')            */
+  ,
+  /* ops of the gated-CNN SPAN descendants (RTMoSR: /root/reference/resselt/archs/rtmosr/arch.py) */
+  RSB_OP_RMSNORM = 7,        /* dst = src / (|src|_2 / sqrt(C) + f[0]) * w[0] + w[1] per pixel (channels-first RMSNorm, arch.py:25-38) */
+  RSB_OP_UNSHUFFLE_POOL = 8, /* src: C channels (C % 8 == 0) on a grid twice as fine as dst's; dst: [PixelUnshuffle(2)(src) (4C channels,
+                                channel c*4 + i*2 + j) | MaxPool2d(2)(src) (C channels)] = 5C channels: the two inputs of
+                                ParPixelUnshuffle (arch.py:284-292) in one pass; `channels` = C                              */
+  RSB_OP_SE_SHUFFLE = 9      /* src: C channels (C % 32 == 0); dst: C/4 channels on the twice finer grid =
+                                PixelShuffle(2)(src * gate), gate = Hardsigmoid(W2 . ReLU(W1 . mean_hw(src) + b1) + b2) per channel
+                                (CSELayer, arch.py:7-21) when i[0] = hidden width > 0 (w[0..3] = W1 [hidden][C], b1, W2 [C][hidden],
+                                b2), plain PixelShuffle(2) when i[0] == 0; `channels` = C                                       */
 };
 
 typedef struct rsb_op_desc {
@@ -198,6 +209,10 @@ int rsb_device_count(void);
 /* compute_dtype: RSB_BF16 (tcgen05 tensor-core path, bf16 storage, fp32 accumulate)
  *                RSB_F32  (CUDA-core FFMA path, fp32 storage) */
 int rsb_plan_create(int compute_dtype, int in_channels, int out_channels, int upscale, rsb_plan** out);
+/* Buffer grids are (H / divisor * scale) x (W / divisor * scale) from then on (call before the first rsb_plan_add_*): lets a plan
+ * hold buffers COARSER than its input (RTMoSR's half-resolution branch: divisor 2, full-resolution buffers get scale 2).  The
+ * caller's H and W must be multiples of the divisor.  Default 1. */
+int rsb_plan_set_base_divisor(rsb_plan* plan, int divisor);
 int rsb_plan_destroy(rsb_plan* plan);
 
 /* Activation buffer on the grid (H*scale) x (W*scale); returns its id in *buf_id. */
@@ -227,7 +242,10 @@ enum rsb_kernel_id {
   RSB_K_WINATTN = 8,
   RSB_K_CHANATTN = 9,
   RSB_K_AIM = 10,
-  RSB_K_DYSAMPLE = 11
+  RSB_K_DYSAMPLE = 11,
+  RSB_K_RMSNORM = 12,
+  RSB_K_UNSHUFFLE_POOL = 13,
+  RSB_K_SE_SHUFFLE = 14
 };
 typedef struct rsb_op_info {
   int32_t kind;       /* 0 convolution, 1 GroupNorm, 2 token / attention op                                        */

@@ -21,6 +21,7 @@ from .sr_forward import (  # noqa: F401
     forward_by_name,
     plksr_forward,
     realplksr_forward,
+    rtmosr_forward,
     span_forward,
     spanplus_forward,
     spanpp_forward,

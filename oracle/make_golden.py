@@ -68,6 +68,9 @@ def cases():
                                   upscale=3, upsampler='pixelshuffle', resi_connection='1conv'), 36, (1, 3, 20, 26), 126),
         'spanpp_f48': ('SpanPP', dict(num_in_ch=3, feature_channels=48, scale_list=[1, 2, 3, 4], implicit_dim=64, latent_layers=2), 37, (1, 3, 20, 28), 127),
         'spanpp_f32_s4': ('SpanPP', dict(num_in_ch=3, feature_channels=32, scale_list=[2, 4], implicit_dim=32, latent_layers=4), 38, (2, 3, 14, 18), 128),
+        'rtmosr_x2_d32': ('RTMoSR', dict(scale=2, dim=32, ffn_expansion=2, n_blocks=2, unshuffle_mod=False, dccm=True, se=True), 39, (1, 3, 21, 27), 129),
+        'rtmosr_x4_d48_nose_1x1': ('RTMoSR', dict(scale=4, dim=48, ffn_expansion=1.5, n_blocks=1, unshuffle_mod=False, dccm=False, se=False), 40, (2, 3, 16, 18), 130),
+        'rtmosr_x2_unshuffle': ('RTMoSR', dict(scale=2, dim=32, ffn_expansion=2, n_blocks=1, unshuffle_mod=True, dccm=True, se=True), 41, (1, 3, 22, 30), 131),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
     }
@@ -78,7 +81,7 @@ def engine_model(kind: str, kwargs: dict, seed: int):
 
     cls = {'SPAN': archs.SPAN, 'SPANPlus': archs.SpanPlus, 'Compact': archs.SRVGGNetCompact}
     extra = {k: getattr(archs, k) for k in ('RRDBNet', 'RealPLKSR') if hasattr(archs, k)}
-    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None), 'SpanPP': getattr(archs, 'SpanPP', None)})
+    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None), 'SpanPP': getattr(archs, 'SpanPP', None), 'RTMoSR': getattr(archs, 'RTMoSR', None)})
     return cls[kind](seed=seed, **kwargs)
 
 

@@ -133,6 +133,55 @@ def spanpp_forward(sd: SD, x: torch.Tensor, dtype=torch.float32, scale: int = 2)
     return F.pixel_shuffle(F.conv2d(out, kernel, None, padding=1), scale)
 
 
+def rtmosr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """RTMoSR.forward in eval mode (/root/reference/resselt/archs/rtmosr/arch.py:375-387; GatedCNNBlock :321-326, ParPixelUnshuffle :284-292,
+    OmniShift.reparam_5x5 :249-269, CSELayer :18-21, RMSNorm :32-38, RepConv.fuse :171-180)."""
+    x = x.to(dtype)
+    g = lambda k: sd[k].to(dtype)
+    unshuffle = 0
+    if 'to_feat.1.alpha' in sd:
+        unshuffle = math.isqrt(sd['to_feat.1.conv_3x3_rep.weight'].shape[1] // 3)
+        scale, inner, feat = 4 // unshuffle, 4, 'to_feat.1'
+    else:
+        scale = inner = math.isqrt(sd['to_img.0.conv_3x3_rep.weight'].shape[0] // 3)
+        feat = 'to_feat'
+    pad = 2 * max(unshuffle, 1)
+    b, _, h, w = x.shape
+
+    def rep(prefix, t):
+        k, bias = repconv_merged(sd, prefix, dtype)
+        return F.conv2d(t, k, bias, padding=1)
+
+    out = F.pad(x, (0, (pad - w % pad) % pad, 0, (pad - h % pad) % pad), 'reflect')
+    out = rep(feat, F.pixel_unshuffle(out, unshuffle) if unshuffle else out)
+    dim = out.shape[1]
+    for i in range(_seq_len(sd, 'body')):
+        p = f'body.{i}'
+        short = out
+        rms = out.norm(2, dim=1, keepdim=True) * dim ** -0.5
+        t = g(f'{p}.norm.scale')[:, None, None] * (out / (rms + 1e-6)) + g(f'{p}.norm.offset')[:, None, None]
+        t = rep(f'{p}.fc1', t)
+        hidden = t.shape[1] // 2
+        gate, ident, c = torch.split(t, [hidden, hidden - dim, dim], dim=1)
+        c = F.pixel_unshuffle(c, 2) + rep(f'{p}.conv.0.poll.1', F.max_pool2d(c, 2, 2))
+        q = f'{p}.conv.1'
+        a = [g(f'{q}.alpha{k}').reshape(-1, 1, 1, 1) for k in (1, 2, 3, 4)]
+        k5 = (a[0] * F.pad(torch.ones_like(g(f'{q}.conv1x1.weight')), (2, 2, 2, 2)) + a[1] * F.pad(g(f'{q}.conv1x1.weight'), (2, 2, 2, 2))
+              + a[2] * F.pad(g(f'{q}.conv3x3.weight'), (1, 1, 1, 1)) + a[3] * g(f'{q}.conv5x5.weight'))
+        b5 = a[1].flatten() * g(f'{q}.conv1x1.bias') + a[2].flatten() * g(f'{q}.conv3x3.bias') + a[3].flatten() * g(f'{q}.conv5x5.bias')
+        c = F.conv2d(c, k5, b5, padding=2, groups=c.shape[1])
+        if f'{p}.conv.2.squeezing.0.weight' in sd:
+            sq = c.mean(dim=(2, 3), keepdim=True)
+            sq = F.hardsigmoid(_conv(sd, f'{p}.conv.2.squeezing.2', F.relu(_conv(sd, f'{p}.conv.2.squeezing.0', sq, 0)), 0))
+            c = c * sq
+        c = F.pixel_shuffle(c, 2)
+        t = F.mish(gate) * torch.cat((ident, c), dim=1)
+        t = rep(f'{p}.fc2', t) if f'{p}.fc2.alpha' in sd else _conv(sd, f'{p}.fc2', t, 0)
+        out = F.mish(t) + short
+    out = F.pixel_shuffle(rep('to_img.0', out), inner)
+    return out[:, :, : h * scale, : w * scale] + F.interpolate(x, scale_factor=scale)
+
+
 def _dysample(sd: SD, p: str, x: torch.Tensor, groups: int) -> torch.Tensor:
     """DySample.forward (/root/reference/resselt/utilities/dysample.py:46-83), restated with the same ATen calls: offsets
     ``offset(x) * sigmoid(scope(x)) * 0.5 + init_pos``, a coordinate grid in normalised [-1, 1] units, pixel_shuffle of the
@@ -595,6 +644,7 @@ _FORWARDS: Dict[str, Callable] = {
     'SPANPlus': spanplus_forward,
     'Compact': compact_forward,
     'SpanPP': spanpp_forward,
+    'RTMoSR': rtmosr_forward,
 }
 
 

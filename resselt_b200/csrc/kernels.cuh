@@ -590,6 +590,19 @@ struct AimParams {
   float* cmap;     // [n][cpad]
 };
 
+struct SeParams {  // squeeze-excitation gate + PixelShuffle(2) (rt_ops.cu)
+  int n, H, W;     // source grid (the destination is 2H x 2W)
+  int channels;    // source channels (multiple of 32); destination has channels / 4
+  int hidden, blocks;
+  const void* src;
+  int src_planes, src_plane0;
+  void* dst;
+  int dst_planes, dst_plane0;
+  const float *w1, *b1, *w2, *b2;  // [hidden][C], [hidden], [C][hidden], [C]
+  float* partial;  // [n][blocks][C]
+  float* gate;     // [n][C]; null: plain PixelShuffle
+};
+
 struct DySampleParams {
   int n, H, W, channels, groups, s, out_ch;  // H x W: the low-res grid; output is (H*s) x (W*s)
   int projected;    // 1: src holds the per-group end_conv projections (4 channels per group), see dysample_proj_kernel
@@ -606,6 +619,10 @@ struct DySampleParams {
 };
 
 cudaError_t launch_dysample(const DySampleParams& p, bool bf16, cudaStream_t s);
+cudaError_t launch_rmsnorm(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s);
+cudaError_t launch_unshuffle_pool(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s);
+cudaError_t launch_dwconv_k(const TokenOpParams& p, int K, bool bf16, int num_sms, cudaStream_t s);
+cudaError_t launch_se_shuffle(const SeParams& p, bool bf16, int num_sms, cudaStream_t s);
 cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s);
 cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s);
 size_t winattn_smem_bytes(int split_h, int split_w);

@@ -151,6 +151,7 @@ struct AuxOp {
   rsb::ChanAttnParams chan;
   rsb::AimParams aim;
   rsb::DySampleParams dys;
+  rsb::SeParams se;
 };
 
 struct Op {
@@ -196,6 +197,7 @@ struct rsb_plan {
   int num_direct = 0;  // bf16 plans: convs that fell back to the CUDA-core kernel
   int info_mode = 0;   // force_direct of the last forward: what rsb_plan_op_info describes
   bool nvtx = false;   // rsb_plan_set_nvtx: one NVTX range per op
+  int base_div = 1;    // rsb_plan_set_base_divisor: buffer grids are (H / base_div * scale) x (W / base_div * scale)
   std::mutex mu;
   // binding
   int bn = 0, bh = 0, bw = 0;
@@ -230,6 +232,7 @@ size_t aux_scratch_bytes(const AuxOp& a, int n) {
     const int cpad = ceil_div(d.channels, 8) * 8;
     return ((size_t)n * kAuxBlocks * cpad + (size_t)n * cpad) * sizeof(float);
   }
+  if (d.kind == RSB_OP_SE_SHUFFLE && d.i[0] > 0) return ((size_t)n * kAuxBlocks * d.channels + (size_t)n * d.channels) * sizeof(float);
   return 0;
 }
 
@@ -597,7 +600,9 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
   }
   for (AuxOp& a : p->auxs) {
     const rsb_op_desc& d = a.d;
-    const int H = h * a.scale, W = w * a.scale;
+    // a.scale is the source buffer's grid; the pixel-unshuffle op iterates over its (half as fine) destination grid
+    const int gs = d.kind == RSB_OP_UNSHUFFLE_POOL ? a.scale / 2 : a.scale;
+    const int H = h * gs, W = w * gs;
     const Buffer& sb = p->bufs[d.src_buf];
     if (d.kind == RSB_OP_DYSAMPLE) {
       rsb::DySampleParams& t = a.dys;
@@ -613,7 +618,21 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     }
     const Buffer& db = p->bufs[d.dst_buf];
     uint8_t* scratch = ws + aux_off;
-    if (d.kind == RSB_OP_LAYERNORM || d.kind == RSB_OP_DWCONV3) {
+    if (d.kind == RSB_OP_SE_SHUFFLE) {
+      rsb::SeParams& t = a.se;
+      memset(&t, 0, sizeof t);
+      t.n = n, t.H = H, t.W = W, t.channels = d.channels, t.hidden = d.i[0];
+      t.blocks = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)H * W + 4095) / 4096));
+      t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_plane0 = d.src_ch_off / 8;
+      t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_plane0 = d.dst_ch_off / 8;
+      if (t.hidden > 0) {
+        t.w1 = a.dw[0], t.b1 = a.dw[1], t.w2 = a.dw[2], t.b2 = a.dw[3];
+        t.partial = reinterpret_cast<float*>(scratch);
+        t.gate = t.partial + (size_t)n * kAuxBlocks * d.channels;
+      }
+      continue;
+    }
+    if (d.kind == RSB_OP_LAYERNORM || d.kind == RSB_OP_DWCONV3 || d.kind == RSB_OP_RMSNORM || d.kind == RSB_OP_UNSHUFFLE_POOL) {
       rsb::TokenOpParams& t = a.tok;
       memset(&t, 0, sizeof t);
       t.n = n, t.H = H, t.W = W, t.channels = d.channels;
@@ -723,6 +742,14 @@ int rsb_plan_destroy(rsb_plan* p) {
   return 0;
 }
 
+int rsb_plan_set_base_divisor(rsb_plan* p, int divisor) {
+  if (!p) return fail(RSB_ERR_INVALID, "rsb_plan_set_base_divisor: NULL plan");
+  if (p->finalized || !p->bufs.empty() || !p->ops.empty()) return fail(RSB_ERR_STATE, "rsb_plan_set_base_divisor: call before adding buffers / ops");
+  if (divisor < 1 || divisor > 8) return fail(RSB_ERR_INVALID, "rsb_plan_set_base_divisor: divisor must be in [1, 8]");
+  p->base_div = divisor;
+  return 0;
+}
+
 int rsb_plan_add_buffer(rsb_plan* p, int channels, int scale, int* buf_id) {
   if (!p || !buf_id) return fail(RSB_ERR_INVALID, "rsb_plan_add_buffer: NULL argument");
   if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_buffer: plan already finalized");
@@ -751,7 +778,7 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
   ConvOp c;
   c.d = d;
   if (default_pad) c.d.pad_t = d.kh / 2, c.d.pad_l = d.kw / 2;
-  int scale = 1;
+  int scale = p->base_div;  // the caller's input lives on the full grid = base_div x the plan's base grid
   if (d.src_buf == RSB_EXTERNAL_INPUT) {
     if (d.cin != p->in_ch) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: external input has %d channels, conv wants %d", p->in_ch, d.cin);
     if (d.src_upsample2) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: upsampled external input");
@@ -760,10 +787,10 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
     scale = p->bufs[d.src_buf].scale * (d.src_upsample2 ? 2 : 1);
   }
   if (d.dst_buf == RSB_EXTERNAL_OUTPUT) {
-    if (d.ps < 1 || d.cout % (d.ps * d.ps) != 0 || d.cout / (d.ps * d.ps) != p->out_ch || scale * d.ps != p->upscale)
+    if (d.ps < 1 || d.cout % (d.ps * d.ps) != 0 || d.cout / (d.ps * d.ps) != p->out_ch || scale * d.ps != p->upscale * p->base_div)
       return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: external output shape mismatch (cout %d, ps %d, scale %d)", d.cout, d.ps, scale);
     if (d.add_base && p->in_ch != p->out_ch) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: add_base needs in_ch == out_ch");
-    if (d.add_base && scale != 1) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: add_base on an upsampled grid");
+    if (d.add_base && scale != p->base_div) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: add_base on an upsampled grid");
   } else {
     const int dps = d.dst_ps > 1 ? d.dst_ps : 1;
     int main_ch = d.cout;
@@ -812,7 +839,7 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
     Buffer hb;
     c.pack_planar = d.kh * d.kw > 1 && c.cin_pad16 <= 64;
     c.pack_k = c.pack_planar ? c.cin_pad16 : ceil_div(d.cin * d.kh * d.kw, 16) * 16;
-    hb.channels = c.pack_k, hb.planes = c.pack_k / 8, hb.scale = 1;
+    hb.channels = c.pack_k, hb.planes = c.pack_k / 8, hb.scale = p->base_div;
     p->bufs.push_back(hb);
     c.pack_buf = (int)p->bufs.size() - 1;
     c.tc_src_buf = c.pack_buf, c.tc_src_ch_off = 0, c.tc_cin = c.pack_k;
@@ -849,7 +876,7 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
   if (!p || !desc) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: NULL argument");
   if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_op: plan already finalized");
   const rsb_op_desc& d = *desc;
-  if (d.kind < RSB_OP_LAYERNORM || d.kind > RSB_OP_DYSAMPLE) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown kind %d", d.kind);
+  if (d.kind < RSB_OP_LAYERNORM || d.kind > RSB_OP_SE_SHUFFLE) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown kind %d", d.kind);
   if (d.channels < 1) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: bad channel count");
   if (d.kind == RSB_OP_DYSAMPLE) {
     const int g = d.i[0], s = d.i[1], oc = d.i[2];
@@ -861,7 +888,7 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
     if (int e = check_buf(p, d.src_buf, d.src_ch_off, d.channels, "rsb_plan_add_op(DySample src)")) return e;
     if (d.i[4] != 0 && d.i[4] < 2 * g * s * s) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: DySample gate offset overlaps the offsets");
     if (int e = check_buf(p, d.src2_buf, d.src2_ch_off, (d.i[4] > 0 ? d.i[4] : 0) + 2 * g * s * s, "rsb_plan_add_op(DySample offsets)")) return e;
-    if (p->bufs[d.src_buf].scale != p->bufs[d.src2_buf].scale || p->bufs[d.src_buf].scale * s != p->upscale)
+    if (p->bufs[d.src_buf].scale != p->bufs[d.src2_buf].scale || p->bufs[d.src_buf].scale * s != p->upscale * p->base_div)
       return fail(RSB_ERR_INVALID, "rsb_plan_add_op: DySample grid mismatch (buffer scale %d x %d != upscale %d)", p->bufs[d.src_buf].scale, s, p->upscale);
     if (!d.w[0] || d.wn[0] != 2 * g * s * s || !d.w[1] || (!proj && d.wn[1] != (int64_t)oc * d.channels) || !d.w[2] || d.wn[2] != oc)
       return fail(RSB_ERR_INVALID, "rsb_plan_add_op: DySample needs init_pos [2*groups*s^2], end_conv weight [out][C] and bias [out]");
@@ -874,6 +901,39 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
     p->ops.push_back({2, (int)p->auxs.size() - 1});
     return 0;
   }
+  if (d.kind == RSB_OP_UNSHUFFLE_POOL || d.kind == RSB_OP_SE_SHUFFLE) {
+    const bool un = d.kind == RSB_OP_UNSHUFFLE_POOL;
+    if (d.src_buf < 0 || d.src_buf >= (int)p->bufs.size() || d.dst_buf < 0 || d.dst_buf >= (int)p->bufs.size())
+      return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown buffer");
+    if (d.channels % (un ? 8 : 32) != 0) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: %s needs channels %% %d == 0", un ? "unshuffle" : "shuffle", un ? 8 : 32);
+    if (int e = check_buf(p, d.src_buf, d.src_ch_off, d.channels, "rsb_plan_add_op(src)")) return e;
+    if (int e = check_buf(p, d.dst_buf, d.dst_ch_off, un ? 5 * d.channels : d.channels / 4, "rsb_plan_add_op(dst)")) return e;
+    const int ss = p->bufs[d.src_buf].scale, ds = p->bufs[d.dst_buf].scale;
+    if (un ? (ss != 2 * ds) : (ds != 2 * ss)) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: %s changes the grid by a factor of two (src scale %d, dst scale %d)", un ? "unshuffle" : "shuffle", ss, ds);
+    if (!un && d.i[0] > 0) {
+      const int hd = d.i[0];
+      if (hd > 1024 || !d.w[0] || d.wn[0] != (int64_t)hd * d.channels || !d.w[1] || d.wn[1] != hd || !d.w[2] || d.wn[2] != (int64_t)hd * d.channels || !d.w[3] ||
+          d.wn[3] != d.channels)
+        return fail(RSB_ERR_INVALID, "rsb_plan_add_op: SE gate needs W1 [hidden][C], b1 [hidden], W2 [C][hidden], b2 [C]");
+    }
+    AuxOp a;
+    a.d = d;
+    for (int k = 0; k < 8; ++k) {
+      if (d.w[k] && d.wn[k] > 0) a.w[k].assign(d.w[k], d.w[k] + d.wn[k]);
+      a.d.w[k] = nullptr;
+    }
+    a.scale = ss;
+    p->auxs.push_back(std::move(a));
+    p->ops.push_back({2, (int)p->auxs.size() - 1});
+    return 0;
+  }
+  if (d.kind == RSB_OP_DWCONV3 && d.i[1] != 0 && d.i[1] != 3) {
+    const int K = d.i[1];
+    if ((K != 5 && K != 7) || d.i[0] != RSB_ACT_NONE || d.src2_buf >= 0 || !d.w[0] || d.wn[0] != (int64_t)d.channels * K * K || !d.w[1] || d.wn[1] != d.channels)
+      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: depthwise K x K needs K in {5, 7}, no activation / gate, weight [C][K*K], bias [C]");
+  }
+  if (d.kind == RSB_OP_RMSNORM && (!d.w[0] || d.wn[0] != d.channels || !d.w[1] || d.wn[1] != d.channels))
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_op: RMSNorm needs scale [C] and offset [C]");
   const bool qkv = d.kind == RSB_OP_WINATTN || d.kind == RSB_OP_CHANATTN;
   if (d.src_buf < 0 || d.src_buf >= (int)p->bufs.size() || d.dst_buf < 0 || d.dst_buf >= (int)p->bufs.size())
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown buffer");
@@ -1102,7 +1162,7 @@ int rsb_plan_set_nvtx(rsb_plan* p, int enable) {
 
 const char* rsb_kernel_name(int k) {
   static const char* const names[] = {"conv_direct", "conv_tc", "conv_rs", "conv_lk", "conv_pair", "groupnorm", "layernorm", "dwconv3",
-                                      "winattn", "chanattn", "aim", "dysample"};
+                                      "winattn", "chanattn", "aim", "dysample", "rmsnorm", "unshuffle_pool", "se_shuffle"};
   return (k >= 0 && k < (int)(sizeof(names) / sizeof(names[0]))) ? names[k] : "unknown";
 }
 
@@ -1155,6 +1215,9 @@ int rsb_plan_op_info(const rsb_plan* p, int op_index, rsb_op_info* out) {
       case RSB_OP_WINATTN: out->kernel = RSB_K_WINATTN; break;
       case RSB_OP_CHANATTN: out->kernel = RSB_K_CHANATTN, out->launches = 3; break;
       case RSB_OP_AIM: out->kernel = RSB_K_AIM, out->launches = 3; break;
+      case RSB_OP_RMSNORM: out->kernel = RSB_K_RMSNORM; break;
+      case RSB_OP_UNSHUFFLE_POOL: out->kernel = RSB_K_UNSHUFFLE_POOL; break;
+      case RSB_OP_SE_SHUFFLE: out->kernel = RSB_K_SE_SHUFFLE, out->launches = p->auxs[op.index].d.i[0] > 0 ? 3 : 1; break;
       default: out->kernel = RSB_K_DYSAMPLE; break;
     }
   }
@@ -1166,13 +1229,14 @@ int rsb_plan_launches_per_forward(const rsb_plan* p) {
   int packed = 0;
   for (const ConvOp& c : p->convs) packed += (c.pack_buf >= 0 && c.tc_ok) ? 1 : 0;
   int aux = 0;
-  for (const AuxOp& a : p->auxs) aux += (a.d.kind == RSB_OP_CHANATTN || a.d.kind == RSB_OP_AIM) ? 3 : 1;
+  for (const AuxOp& a : p->auxs) aux += (a.d.kind == RSB_OP_CHANATTN || a.d.kind == RSB_OP_AIM || (a.d.kind == RSB_OP_SE_SHUFFLE && a.d.i[0] > 0)) ? 3 : 1;
   return (int)p->convs.size() + packed + 2 * (int)p->gns.size() + aux;  // mode 0; mode 4 saves one launch per fused pair
 }
 
 int rsb_plan_flops(const rsb_plan* p, int n, int h, int w, double* flops) {
   if (!p || !flops) return fail(RSB_ERR_INVALID, "rsb_plan_flops: NULL argument");
   double f = 0.0;
+  h /= p->base_div, w /= p->base_div;
   for (const ConvOp& c : p->convs)
     f += 2.0 * c.d.cout * c.d.cin * c.d.kh * c.d.kw * (double)n * (h * c.scale) * (double)(w * c.scale);
   *flops = f;
@@ -1182,7 +1246,8 @@ int rsb_plan_flops(const rsb_plan* p, int n, int h, int w, double* flops) {
 int rsb_plan_workspace_bytes(const rsb_plan* p, int n, int h, int w, size_t* bytes) {
   if (!p || !bytes) return fail(RSB_ERR_INVALID, "rsb_plan_workspace_bytes: NULL argument");
   if (n < 1 || h < 1 || w < 1) return fail(RSB_ERR_INVALID, "rsb_plan_workspace_bytes: bad shape");
-  return layout(p, n, h, w, nullptr, nullptr, bytes);
+  if (h % p->base_div || w % p->base_div) return fail(RSB_ERR_INVALID, "rsb_plan_workspace_bytes: %d x %d is not a multiple of the plan's base divisor %d", h, w, p->base_div);
+  return layout(p, n, h / p->base_div, w / p->base_div, nullptr, nullptr, bytes);
 }
 
 int rsb_plan_forward(rsb_plan* p, const void* x, int x_dtype, int n, int h, int w, void* y, int y_dtype, void* workspace,
@@ -1200,6 +1265,8 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
   if (n < 1 || h < 1 || w < 1) return fail(RSB_ERR_INVALID, "rsb_plan_forward: bad shape %dx%dx%d", n, h, w);
   if (x_dtype < RSB_F32 || x_dtype > RSB_F16 || y_dtype < RSB_F32 || y_dtype > RSB_F16)
     return fail(RSB_ERR_INVALID, "rsb_plan_forward: bad tensor dtype");
+  if (h % p->base_div || w % p->base_div) return fail(RSB_ERR_INVALID, "rsb_plan_forward: %d x %d is not a multiple of the plan's base divisor %d", h, w, p->base_div);
+  h /= p->base_div, w /= p->base_div;  // everything below works on the plan's base grid
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   std::lock_guard<std::mutex> lock(p->mu);
   DeviceGuard guard(p->device);
@@ -1268,7 +1335,12 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
         const bool bf = p->dtype == RSB_BF16;
         switch (a.d.kind) {
           case RSB_OP_LAYERNORM: e = rsb::launch_layernorm(a.tok, bf, p->num_sms, stream); break;
-          case RSB_OP_DWCONV3: e = rsb::launch_dwconv3(a.tok, bf, stream); break;
+          case RSB_OP_DWCONV3:
+            e = (a.d.i[1] > 3) ? rsb::launch_dwconv_k(a.tok, a.d.i[1], bf, p->num_sms, stream) : rsb::launch_dwconv3(a.tok, bf, stream);
+            break;
+          case RSB_OP_RMSNORM: e = rsb::launch_rmsnorm(a.tok, bf, p->num_sms, stream); break;
+          case RSB_OP_UNSHUFFLE_POOL: e = rsb::launch_unshuffle_pool(a.tok, bf, p->num_sms, stream); break;
+          case RSB_OP_SE_SHUFFLE: e = rsb::launch_se_shuffle(a.se, bf, p->num_sms, stream); break;
           case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, stream); break;
           case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, p->num_sms, stream); break;
           case RSB_OP_DYSAMPLE: {

@@ -1,0 +1,266 @@
+// Token-wise ops of the gated-CNN SPAN descendants (RTMoSR) on planar-8 activations.
+//
+//   rmsnorm_kernel          channels-first RMSNorm: x / (|x|_2 / sqrt(C) + eps) * scale + offset
+//                           (/root/reference/resselt/archs/rtmosr/arch.py:25-38)
+//   unshuffle_pool_kernel   ParPixelUnshuffle's two inputs in one pass over the map: PixelUnshuffle(2) (C -> 4C channels on
+//                           the half grid, channel c*4 + i*2 + j) and MaxPool2d(2) (C channels on the half grid) (arch.py:284-292)
+//   dwconv_k_kernel         depthwise K x K conv (OmniShift's re-parameterised 5 x 5, arch.py:215-281)
+//   se_*                    CSELayer (global mean -> 1x1 -> ReLU -> 1x1 -> Hardsigmoid -> channel scale, arch.py:7-21) fused with
+//                           the PixelShuffle(2) that follows it in GatedCNNBlock.conv (arch.py:314-319): deterministic two-stage
+//                           mean, tiny MLP, then scale + shuffle in one pass
+// All arithmetic is fp32 regardless of the storage type (bf16 or fp32): one set of kernels serves both plans.  These are
+// bandwidth-bound element-wise / stencil passes; they are written for correctness and coalescing (16-byte plane chunks per thread),
+// not yet tuned like the DAT token kernels.
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace rsb {
+namespace {
+
+inline int grid_for(size_t total, int threads, int cap) {
+  return (int)std::max<size_t>(1, std::min<size_t>((total + threads - 1) / threads, (size_t)cap));
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const __grid_constant__ TokenOpParams p) {
+  const size_t hw = (size_t)p.H * p.W;
+  const int C = p.channels, planes = (C + 7) >> 3;
+  const size_t total = (size_t)p.n * hw;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  const float inv_sqrt_c = rsqrtf((float)C);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw, pix = i - n * hw;
+    const T* s = src + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8 + pix * 8;
+    float ss = 0.0f;
+    for (int pl = 0; pl < planes; ++pl) {
+      float v[8];
+      load8<T>(s + (size_t)pl * hw * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (pl * 8 + k < C) ss = fmaf(v[k], v[k], ss);
+    }
+    // x.norm(2, dim=1) * C^-0.5, then x / (rms + eps)
+    const float inv = 1.0f / (sqrtf(ss) * inv_sqrt_c + p.f0);
+    T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
+    for (int pl = 0; pl < planes; ++pl) {
+      float v[8], o[8];
+      load8<T>(s + (size_t)pl * hw * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = pl * 8 + k;
+        o[k] = c < C ? fmaf(p.w0[c], v[k] * inv, p.w1[c]) : 0.0f;
+      }
+      store8<T>(d + (size_t)pl * hw * 8, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ PixelUnshuffle(2) + MaxPool2d(2)
+// src: C channels on the (2H x 2W) grid; dst: [4C unshuffled | C pooled] on the (H x W) grid.  C % 8 == 0.
+// One thread per (half-grid pixel, source plane): four 16-byte loads, four + one 16-byte stores.
+template <typename T>
+__global__ void __launch_bounds__(256) unshuffle_pool_kernel(const __grid_constant__ TokenOpParams p) {
+  const int H = p.H, W = p.W;  // the half (destination) grid
+  const size_t hw = (size_t)H * W, hw2 = hw * 4;
+  const int planes = p.channels >> 3;
+  const size_t total = (size_t)p.n * planes * hw;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int pl = (int)((i / hw) % planes);
+    const int n = (int)(i / (hw * planes));
+    const T* s = src + ((size_t)n * p.src_planes + p.src_plane0 + pl) * hw2 * 8;
+    float q[4][8];  // q[i*2 + j] = the source pixel (2y + i, 2x + j)
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) load8<T>(s + ((size_t)(2 * y + a) * (2 * W) + 2 * x + b) * 8, q[a * 2 + b]);
+    T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + ((size_t)y * W + x) * 8;
+    // unshuffled channel (pl*8 + cc)*4 + phase lives in destination plane pl*4 + cc/2 at position (cc % 2)*4 + phase
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = q[e & 3][2 * k + (e >> 2)];
+      store8<T>(d + (size_t)(pl * 4 + k) * hw * 8, o);
+    }
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = fmaxf(fmaxf(q[0][e], q[1][e]), fmaxf(q[2][e], q[3][e]));
+    store8<T>(d + (size_t)(4 * planes + pl) * hw * 8, m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise K x K
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ TokenOpParams p, int K) {
+  const size_t hw = (size_t)p.H * p.W;
+  const int C = p.channels, planes = (C + 7) >> 3, R = K / 2, KK = K * K;
+  const size_t total = (size_t)p.n * planes * hw;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.W);
+    const int y = (int)((i / p.W) % p.H);
+    const int pl = (int)((i / hw) % planes);
+    const int n = (int)(i / (hw * planes));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = pl * 8 + k < C ? p.w1[pl * 8 + k] : 0.0f;
+    for (int ky = 0; ky < K; ++ky) {
+      const int sy = y + ky - R;
+      if (sy < 0 || sy >= p.H) continue;
+      for (int kx = 0; kx < K; ++kx) {
+        const int sx = x + kx - R;
+        if (sx < 0 || sx >= p.W) continue;
+        float v[8];
+        load8<T>(src + planar_index(n, p.src_planes, p.src_plane0 + pl, p.H, p.W, sy, sx), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (pl * 8 + k < C) acc[k] = fmaf(v[k], p.w0[(pl * 8 + k) * KK + ky * K + kx], acc[k]);
+      }
+    }
+    store8<T>(dst + planar_index(n, p.dst_planes, p.dst_plane0 + pl, p.H, p.W, y, x), acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SE + PixelShuffle(2)
+// partial[n][block][c]: per-channel sums over this block's pixel range (fixed order: deterministic)
+template <typename T>
+__global__ void __launch_bounds__(256) se_pool_kernel(const __grid_constant__ SeParams p) {
+  __shared__ float red[256][8];
+  const int pl = blockIdx.y, n = blockIdx.z;
+  const size_t hw = (size_t)p.H * p.W;
+  const T* base = reinterpret_cast<const T*>(p.src) + ((size_t)n * p.src_planes + p.src_plane0 + pl) * hw * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8<T>(base + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[threadIdx.x][k] += red[threadIdx.x + o][k];
+    __syncthreads();
+  }
+  if (threadIdx.x < 8) p.partial[((size_t)n * gridDim.x + blockIdx.x) * p.channels + pl * 8 + threadIdx.x] = red[0][threadIdx.x];
+}
+
+// gate[n][c] = hardsigmoid(W2 . relu(W1 . mean + b1) + b2)
+__global__ void __launch_bounds__(256) se_gate_kernel(const __grid_constant__ SeParams p) {
+  extern __shared__ float sm[];
+  float* mean = sm;          // [C]
+  float* hid = sm + p.channels;  // [hidden]
+  const int n = blockIdx.x, C = p.channels;
+  const float inv = 1.0f / ((float)p.H * (float)p.W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < p.blocks; ++b) s += p.partial[((size_t)n * p.blocks + b) * C + c];
+    mean[c] = (float)s * inv;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < p.hidden; k += blockDim.x) {
+    float s = p.b1[k];
+    for (int c = 0; c < C; ++c) s = fmaf(p.w1[k * C + c], mean[c], s);
+    hid[k] = fmaxf(s, 0.0f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = p.b2[c];
+    for (int k = 0; k < p.hidden; ++k) s = fmaf(p.w2[c * p.hidden + k], hid[k], s);
+    p.gate[(size_t)n * C + c] = fminf(fmaxf(s + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);  // nn.Hardsigmoid
+  }
+}
+
+// dst (C/4 channels on the 2H x 2W grid): channel c at (2y + i, 2x + j) = src channel c*4 + i*2 + j at (y, x) [* gate]
+template <typename T>
+__global__ void __launch_bounds__(256) se_shuffle_kernel(const __grid_constant__ SeParams p) {
+  const int H = p.H, W = p.W;  // the source (half) grid
+  const size_t hw = (size_t)H * W, hw2 = hw * 4;
+  const int oplanes = p.channels >> 5;  // destination planes: C / 4 channels / 8
+  const size_t total = (size_t)p.n * oplanes * hw;
+  const T* src = reinterpret_cast<const T*>(p.src);
+  T* dst = reinterpret_cast<T*>(p.dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int pl = (int)((i / hw) % oplanes);
+    const int n = (int)(i / (hw * oplanes));
+    const T* s = src + ((size_t)n * p.src_planes + p.src_plane0) * hw * 8 + ((size_t)y * W + x) * 8;
+    float q[4][8];  // q[phase][cc]: destination channel pl*8 + cc, phase i*2 + j
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      load8<T>(s + (size_t)(pl * 4 + k) * hw * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int sc = (pl * 4 + k) * 8 + e;  // source channel = (pl*8 + cc)*4 + phase with cc = 2k + e/4, phase = e % 4
+        q[e & 3][2 * k + (e >> 2)] = p.gate != nullptr ? v[e] * p.gate[(size_t)n * p.channels + sc] : v[e];
+      }
+    }
+    T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0 + pl) * hw2 * 8;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) store8<T>(d + ((size_t)(2 * y + a) * (2 * W) + 2 * x + b) * 8, q[a * 2 + b]);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_rmsnorm(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s) {
+  const int g = grid_for((size_t)p.n * p.H * p.W, 256, (num_sms > 0 ? num_sms : 148) * 32);
+  if (bf16)
+    rmsnorm_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    rmsnorm_kernel<float><<<g, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unshuffle_pool(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s) {
+  const int g = grid_for((size_t)p.n * (p.channels >> 3) * p.H * p.W, 256, (num_sms > 0 ? num_sms : 148) * 32);
+  if (bf16)
+    unshuffle_pool_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    unshuffle_pool_kernel<float><<<g, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dwconv_k(const TokenOpParams& p, int K, bool bf16, int num_sms, cudaStream_t s) {
+  const int g = grid_for((size_t)p.n * ((p.channels + 7) >> 3) * p.H * p.W, 256, (num_sms > 0 ? num_sms : 148) * 32);
+  if (bf16)
+    dwconv_k_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p, K);
+  else
+    dwconv_k_kernel<float><<<g, 256, 0, s>>>(p, K);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_se_shuffle(const SeParams& p, bool bf16, int num_sms, cudaStream_t s) {
+  const int sms = num_sms > 0 ? num_sms : 148;
+  if (p.gate != nullptr) {
+    const dim3 g1(p.blocks, p.channels >> 3, p.n);
+    if (bf16)
+      se_pool_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>(p);
+    else
+      se_pool_kernel<float><<<g1, 256, 0, s>>>(p);
+    se_gate_kernel<<<p.n, 256, (size_t)(p.channels + p.hidden) * sizeof(float), s>>>(p);
+  }
+  const int g = grid_for((size_t)p.n * (p.channels >> 5) * p.H * p.W, 256, sms * 32);
+  if (bf16)
+    se_shuffle_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    se_shuffle_kernel<float><<<g, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace rsb

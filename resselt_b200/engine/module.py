@@ -150,7 +150,8 @@ class EngineModule(nn.Module):
         stamp = self._stamp()
         plan = self._plans.get(key)
         if plan is None or self._plan_stamp.get(key) != stamp:
-            pb = PlanBuilder(cdt, *(self._plan_io if variant is None else self._plan_io_for_variant()))
+            pb = PlanBuilder(cdt, *(self._plan_io if variant is None else self._plan_io_for_variant()),
+                             base_divisor=getattr(self, '_plan_base_divisor', 1))
             self.build_plan(pb, self._weights())
             plan = pb.finalize(torch.device('cuda', index))
             self._plans[key] = plan

@@ -15,7 +15,7 @@ import threading
 CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'csrc'))
 BRINGUP = bool(os.environ.get('RSB_BRINGUP'))  # bring-up flavour: separate library, never the one the product loads
 LIB_PATH = os.path.join(CSRC_DIR, 'libresselt_b200_bringup.so' if BRINGUP else 'libresselt_b200.so')
-SOURCES = ('conv_tc.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_lk.cu', 'conv_direct.cu', 'dat_ops.cu', 'plan.cu')
+SOURCES = ('conv_tc.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_lk.cu', 'conv_direct.cu', 'dat_ops.cu', 'rt_ops.cu', 'plan.cu')
 HEADERS = ('kernels.cuh', 'ptx.cuh', os.path.join('..', '..', 'include', 'resselt_b200.h'))
 NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC')
 OBJ_DIR = os.path.join(CSRC_DIR, 'build')  # git-ignored object files, one per source
@@ -25,14 +25,14 @@ F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_MISH, ACT_LRELU, ACT_PRELU, ACT_SIGMOID, ACT_GELU = range(7)
 COMB_NONE, COMB_SPAB_GATE, COMB_MUL, COMB_AXPY = range(4)
 EXTERNAL_INPUT, EXTERNAL_OUTPUT, NO_BUFFER = -1, -2, -3
-OP_LAYERNORM, OP_DWCONV3, OP_WINATTN, OP_CHANATTN, OP_AIM, OP_DYSAMPLE = 1, 2, 3, 4, 5, 6
+OP_LAYERNORM, OP_DWCONV3, OP_WINATTN, OP_CHANATTN, OP_AIM, OP_DYSAMPLE, OP_RMSNORM, OP_UNSHUFFLE_POOL, OP_SE_SHUFFLE = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 EXPORTED_SYMBOLS = (
     'rsb_version', 'rsb_last_error', 'rsb_device_count', 'rsb_plan_create', 'rsb_plan_destroy',
     'rsb_plan_add_buffer', 'rsb_plan_add_conv', 'rsb_plan_add_groupnorm', 'rsb_plan_add_op', 'rsb_plan_finalize',
     'rsb_plan_num_ops', 'rsb_plan_launches_per_forward', 'rsb_plan_flops', 'rsb_plan_workspace_bytes',
     'rsb_plan_forward', 'rsb_plan_forward_ops', 'rsb_plan_read_buffer',
-    'rsb_plan_num_direct_convs', 'rsb_plan_op_info', 'rsb_kernel_name', 'rsb_plan_set_nvtx', 'rsb_abi_struct_size',
+    'rsb_plan_num_direct_convs', 'rsb_plan_op_info', 'rsb_kernel_name', 'rsb_plan_set_nvtx', 'rsb_abi_struct_size', 'rsb_plan_set_base_divisor',
 )
 
 
@@ -186,6 +186,7 @@ def lib() -> C.CDLL:
         L.rsb_plan_num_direct_convs.argtypes = [C.c_void_p]
         L.rsb_plan_set_nvtx.argtypes = [C.c_void_p, C.c_int]
         L.rsb_abi_struct_size.argtypes = [C.c_int]
+        L.rsb_plan_set_base_divisor.argtypes = [C.c_void_p, C.c_int]
         L.rsb_plan_op_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(OpInfo)]
         L.rsb_kernel_name.argtypes = [C.c_int]
         L.rsb_kernel_name.restype = C.c_char_p

@@ -50,16 +50,23 @@ OUTPUT = Ref(N.EXTERNAL_OUTPUT, 0, 0)
 
 
 class PlanBuilder:
-    def __init__(self, compute_dtype: torch.dtype, in_channels: int, out_channels: int, upscale: int):
+    def __init__(self, compute_dtype: torch.dtype, in_channels: int, out_channels: int, upscale: int, base_divisor: int = 1):
         self._lib = N.lib()
         handle = C.c_void_p()
         N.check(self._lib.rsb_plan_create(_TORCH_TO_RSB[compute_dtype], in_channels, out_channels, upscale, C.byref(handle)))
         self._h = handle
+        # buffer grids are (H / base_divisor * scale): plans with a branch coarser than the input (RTMoSR) use 2, their full-resolution
+        # buffers then have scale 2
+        self.base_divisor = int(base_divisor)
+        if self.base_divisor != 1:
+            N.check(self._lib.rsb_plan_set_base_divisor(self._h, self.base_divisor))
         self.compute_dtype = compute_dtype
         self.in_channels, self.out_channels, self.upscale = in_channels, out_channels, upscale
         self.scales = {}
 
-    def buffer(self, channels: int, scale: int = 1) -> Ref:
+    def buffer(self, channels: int, scale: Optional[int] = None) -> Ref:
+        """Activation buffer; ``scale`` defaults to the input's own grid (= base_divisor)."""
+        scale = self.base_divisor if scale is None else scale
         bid = C.c_int()
         N.check(self._lib.rsb_plan_add_buffer(self._h, channels, scale, C.byref(bid)))
         self.scales[bid.value] = scale
@@ -194,6 +201,27 @@ class PlanBuilder:
 
     def dwconv3(self, src: Ref, dst: Ref, weight, bias, act: int = N.ACT_NONE, gate: Optional[Ref] = None) -> None:
         self.op(N.OP_DWCONV3, src, dst, src.channels, src2=gate, ints=(act,), weights=(weight, bias))
+
+    def dwconv(self, src: Ref, dst: Ref, weight, bias) -> None:
+        """Depthwise K x K conv (K = 3, 5, 7 from the weight's shape [C][1][K][K])."""
+        k = int(_f32(weight).shape[-1])
+        self.op(N.OP_DWCONV3, src, dst, src.channels, ints=(N.ACT_NONE, 0 if k == 3 else k), weights=(weight, bias))
+
+    def rmsnorm(self, src: Ref, dst: Ref, scale, offset, eps: float = 1e-6) -> None:
+        self.op(N.OP_RMSNORM, src, dst, src.channels, floats=(eps,), weights=(scale, offset))
+
+    def unshuffle_pool(self, src: Ref, dst: Ref) -> None:
+        """dst (5C channels on the half grid) = [PixelUnshuffle(2)(src) | MaxPool2d(2)(src)]."""
+        self.op(N.OP_UNSHUFFLE_POOL, src, dst, src.channels)
+
+    def se_shuffle(self, src: Ref, dst: Ref, se=None) -> None:
+        """dst (C/4 channels on the twice finer grid) = PixelShuffle(2)(src * gate); ``se`` = (W1, b1, W2, b2) of the squeeze-excitation
+        MLP (ReLU, Hardsigmoid) or None for a plain PixelShuffle."""
+        if se is None:
+            self.op(N.OP_SE_SHUFFLE, src, dst, src.channels, ints=(0,))
+        else:
+            w1 = _f32(se[0]).reshape(-1, src.channels)
+            self.op(N.OP_SE_SHUFFLE, src, dst, src.channels, ints=(w1.shape[0],), weights=(w1, se[1], _f32(se[2]).reshape(src.channels, -1), se[3]))
 
     def finalize(self, device: torch.device) -> 'Plan':
         index = device.index if device.index is not None else torch.cuda.current_device()

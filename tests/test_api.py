@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import resselt_b200
-from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR, internal_registry
+from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR, internal_registry
 from resselt_b200.factory import Architecture, KeyCondition
 from resselt_b200.factory.arch import ModelMetadata
 from resselt_b200.registry import ArchitectureNotFound, Registry
@@ -39,6 +39,9 @@ def test_metadata_field_order():
         (SPAN(num_in_ch=1, num_out_ch=1, feature_channels=56, upscale=2, norm=False), ('SPAN', 1, 1, 2)),
         (SpanPP(feature_channels=48, implicit_dim=64, latent_layers=2), ('SpanPP', 3, 3, [1, 2, 3, 4])),   # the reference puts the scale list there
         (SpanPP(feature_channels=32, scale_list=[2, 4], implicit_dim=32, latent_layers=4), ('SpanPP', 3, 3, [2, 4])),
+        (RTMoSR(), ('RTMoSR', 3, 3, 2)),
+        (RTMoSR(scale=4, dim=48, ffn_expansion=1.5, n_blocks=1, dccm=False, se=False), ('RTMoSR', 3, 3, 2)),   # the reference always reports 2
+        (RTMoSR(scale=2, n_blocks=1, unshuffle_mod=True), ('RTMoSR', 3, 3, 2)),
         (SpanPlus(blocks=[4], upscale=2), ('SPANPlus', 3, 3, 2)),
         (SpanPlus(blocks=[2, 3], feature_channels=32, upscale=4), ('SPANPlus', 3, 3, 4)),
         (SpanPlus(blocks=[2], upscale=2, upsampler='dys'), ('SPANPlus', 3, 3, 2)),
@@ -86,6 +89,9 @@ def test_detect_and_hyperparameter_inference(model, meta):
         assert loaded.blocks == model.blocks and loaded.upsampler_kind == model.upsampler_kind
     if isinstance(model, SPAN):
         assert loaded.norm == model.norm
+    if isinstance(model, RTMoSR):
+        assert (loaded.scale, loaded.dim, loaded.hidden, loaded.n_blocks, loaded.unshuffle, loaded.dccm, loaded.se) == (
+            model.scale, model.dim, model.hidden, model.n_blocks, model.unshuffle, model.dccm, model.se)
     if isinstance(model, SpanPP):
         assert (loaded.feature_channels, loaded.scale_list, loaded.base_scale, loaded.ig_kernel_size) == (model.feature_channels, model.scale_list, 2, 3)
     if isinstance(model, RRDBNet):

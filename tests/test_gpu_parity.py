@@ -10,7 +10,7 @@ import torch.nn.functional as F
 import oracle
 import resselt_b200
 from conftest import golden_case, golden_index, norm_err, psnr
-from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
 from resselt_b200.engine import INPUT, OUTPUT, PlanBuilder
 from resselt_b200.engine import native as N
 from resselt_b200.runner import FramePipeline, tiled_forward
@@ -57,6 +57,10 @@ def test_golden_fixtures_fp32_and_bf16(name):
         ('RealPLKSR', RealPLKSR(dim=32, n_blocks=2, upscaling_factor=3, kernel_size=13, dysample=True, seed=46), (2, 3, 21, 30)),  # odd factor: groups = 3
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=24), (3, 3, 45, 61)),
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=1, seed=25), (1, 3, 40, 40)),
+        ('SpanPP', SpanPP(feature_channels=48, implicit_dim=64, latent_layers=2, seed=52), (2, 3, 37, 50)),
+        ('RTMoSR', RTMoSR(scale=2, dim=32, n_blocks=2, seed=53), (1, 3, 45, 61)),                                  # odd size: reflect pad + crop
+        ('RTMoSR', RTMoSR(scale=4, dim=64, ffn_expansion=2, n_blocks=3, seed=54), (2, 3, 40, 36)),
+        ('RTMoSR', RTMoSR(scale=2, dim=32, n_blocks=1, unshuffle_mod=True, seed=55), (1, 3, 41, 54)),              # pixel-unshuffle front end
         ('ESRGAN', RRDBNet(num_blocks=23, scale=4, seed=26), (1, 3, 48, 40)),           # full depth: 69 dense blocks
         ('ESRGAN', RRDBNet(num_blocks=2, scale=8, seed=27), (1, 3, 19, 23)),
         ('ESRGAN', RRDBNet(num_blocks=2, scale=4, key_style='new', seed=28), (2, 3, 24, 17)),  # Real-ESRGAN key names

@@ -280,3 +280,58 @@ def test_dysample_op(C, out_ch, scale, groups, B, H, W, dtype):
     ref = F.conv2d(samp.view(B, -1, scale * H, scale * W), D('up.end_conv.weight'), D('up.end_conv.bias'))
     # bf16 plan: the offsets themselves are stored in bf16 before sampling (8 mantissa bits of a sub-pixel position)
     _check(got, ref, dtype, bf16_tol=3e-2, what='DySample')
+
+
+# ------------------------------------------------------------------------------------------------ RTMoSR ops (rsb_op_kind 7-9, depthwise 5x5)
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,B,H,W', [(32, 1, 40, 56), (48, 2, 17, 30), (64, 1, 128, 96)])
+def test_rmsnorm_op(C, B, H, W, dtype):
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3
+    scale, offset = 1.0 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    pb = PlanBuilder(dtype, C, C, 1)
+    a, b = pb.buffer(C), pb.buffer(C)
+    pb.conv(INPUT, a, torch.eye(C).view(C, C, 1, 1))
+    pb.rmsnorm(a, b, scale, offset, eps=1e-6)
+    pb.conv(b, OUTPUT, torch.eye(C).view(C, C, 1, 1))
+    got, _ = _run(pb, x, dtype)
+    xq = _q(x, dtype)
+    rms = xq.norm(2, dim=1, keepdim=True) * C ** -0.5
+    ref = scale.double().view(1, -1, 1, 1) * (xq / (rms + 1e-6)) + offset.double().view(1, -1, 1, 1)
+    _check(got, ref, dtype, what='RMSNorm')
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,se,B,H,W', [(32, True, 1, 40, 56), (48, False, 2, 18, 30), (32, True, 1, 128, 96)])
+def test_unshuffle_pool_dw5_se_shuffle_chain(C, se, B, H, W, dtype):
+    """GatedCNNBlock.conv of RTMoSR in isolation (rtmosr/arch.py:314-319) on a base-divisor-2 plan:
+    PixelUnshuffle(2) + RepConv(MaxPool2d(2)) -> depthwise 5x5 -> [CSELayer] -> PixelShuffle(2)."""
+    g = torch.Generator().manual_seed(C + W)
+    x = torch.randn(B, C, H, W, generator=g)
+    wp, bp = torch.randn(4 * C, C, 3, 3, generator=g) / (C * 9) ** 0.5, torch.randn(4 * C, generator=g) * 0.1
+    w5, b5 = torch.randn(4 * C, 1, 5, 5, generator=g) / 5.0, torch.randn(4 * C, generator=g) * 0.1
+    s1w, s1b = torch.randn(2 * C, 4 * C, 1, 1, generator=g) / (4 * C) ** 0.5 * 3, torch.randn(2 * C, generator=g) * 0.3
+    s2w, s2b = torch.randn(4 * C, 2 * C, 1, 1, generator=g) / (2 * C) ** 0.5 * 3, torch.randn(4 * C, generator=g) * 0.3
+    pb = PlanBuilder(dtype, C, C, 1, base_divisor=2)
+    a, out = pb.buffer(C), pb.buffer(C)
+    u5, v, o = pb.buffer(5 * C, scale=1), pb.buffer(4 * C, scale=1), pb.buffer(4 * C, scale=1)
+    pb.conv(INPUT, a, torch.eye(C).view(C, C, 1, 1))
+    pb.unshuffle_pool(a, u5)
+    pb.conv(u5.slice(4 * C, C), v, wp, bp, combine=N.COMB_AXPY, res1=u5.slice(0, 4 * C))
+    pb.dwconv(v, o, w5, b5)
+    pb.se_shuffle(o, out, se=(s1w, s1b, s2w, s2b) if se else None)
+    pb.conv(out, OUTPUT, torch.eye(C).view(C, C, 1, 1))
+    got, plan = _run(pb, x, dtype)
+    xq = _q(x, dtype)
+    D = lambda t: t.double()
+    q = lambda t: t.to(dtype).double()  # a buffer between two ops holds bf16 on the bf16 plan
+    pu, pool = F.pixel_unshuffle(xq, 2), F.max_pool2d(xq, 2, 2)
+    assert torch.equal(plan.read_buffer(u5.slice(0, 4 * C)).double().cpu(), pu), 'PixelUnshuffle(2) is pure data movement'
+    assert torch.equal(plan.read_buffer(u5.slice(4 * C, C)).double().cpu(), pool), 'MaxPool2d(2) is exact'
+    t = q(pu + F.conv2d(pool, q(wp) if dtype == torch.bfloat16 else D(wp), D(bp), padding=1))
+    t = q(F.conv2d(t, D(w5), D(b5), padding=2, groups=4 * C))
+    if se:
+        sq = t.mean(dim=(2, 3), keepdim=True)
+        t = t * F.hardsigmoid(F.conv2d(F.relu(F.conv2d(sq, D(s1w), D(s1b))), D(s2w), D(s2b)))
+    ref = F.pixel_shuffle(t, 2)
+    _check(got, ref, dtype, bf16_tol=2e-2, what='unshuffle/pool -> dw5x5 -> SE -> shuffle')
