@@ -387,6 +387,14 @@ const RsVariant kRsVariants[] = {
     // SPAN / SPANPlus / SpanPP: conv_cat (1x1 over the 4 x 48-channel concat) merged into the upsampler conv: 192 -> 12 / 48
     RSB_X(12, 1, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_X(12, 3, RSB_ACT_NONE, RSB_COMB_NONE),
+    // RTMoSR (dim 32, hidden 64): stem on the 16-channel planar copy, the three fc1 parts (the gate part ends in mish(g) * cat(i, c)),
+    // fc2 with mish(.) + shortcut, and the same for dim 64 / hidden 128
+    RSB_V(1, 2, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(2, 2, RSB_ACT_NONE, RSB_COMB_NONE),
+    RSB_V(2, 4, RSB_ACT_MISH, RSB_COMB_MUL),
+    RSB_V(4, 2, RSB_ACT_MISH, RSB_COMB_AXPY),
+    RSB_V(8, 4, RSB_ACT_MISH, RSB_COMB_AXPY),
+    RSB_X(2, 1, RSB_ACT_NONE, RSB_COMB_NONE),
     // runtime geometry, specialised epilogue
     RSB_V(0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_V(0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),

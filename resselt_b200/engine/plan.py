@@ -249,6 +249,7 @@ class Plan:
         self._ws_shape = None
         self.force_direct = False
         self._scale_of = dict(builder.scales)
+        self._base_divisor = builder.base_divisor
         # CUDA-graph replay of whole forwards into caller-owned tensors: key = every pointer / shape baked into the launches
         self._graphs = {}
         self._graphs_enabled = os.environ.get('RSB_NO_GRAPH') is None
@@ -396,7 +397,7 @@ class Plan:
         """Debug/test helper: fp32 NCHW copy of a buffer range after the last forward."""
         n, h, w = self._ws_shape
         scale = self._scale_of[ref.buf]
-        dst = torch.empty((n, ref.channels, h * scale, w * scale), dtype=torch.float32, device=self.device)
+        dst = torch.empty((n, ref.channels, h // self._base_divisor * scale, w // self._base_divisor * scale), dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         N.check(self._lib.rsb_plan_read_buffer(self._h, ref.buf, ref.ch_off, ref.channels, dst.data_ptr(), stream))
         return dst

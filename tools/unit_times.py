@@ -9,7 +9,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
 from resselt_b200.engine.profiling import summarize_units, time_forward, time_units
 
 MODELS = {
@@ -21,6 +21,8 @@ MODELS = {
     'plksr': (lambda: RealPLKSR(n_blocks=28, upscaling_factor=4, seed=7), 1, 512, 512),
     'dat': (lambda: DAT(upscale=4, seed=8), 1, 512, 512),
     'swinir': (lambda: SwinIR(upscale=4, seed=9), 1, 512, 512),
+    'spanpp': (lambda: SpanPP(feature_channels=48, seed=10), 1, 1080, 1920),
+    'rtmosr': (lambda: RTMoSR(scale=2, dim=32, n_blocks=2, seed=11), 1, 1080, 1920),
 }
 
 if __name__ == '__main__':
