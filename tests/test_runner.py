@@ -95,3 +95,34 @@ def test_plan_tiles_multiple_aligns_origins_and_rounds_the_halo():
     assert tiles[0][5] == 44 + 20 and tiles[0][7] == 60 + 20            # halo 19 -> 20
     with pytest.raises(ValueError):
         plan_tiles(64, 64, 33, 32, halo=4, multiple=2)
+
+
+def _nccl_gather_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    count = 5
+    # ragged bf16 "tiles": unit i has its own width; rank r owns units r, r + world, ...
+    units = [torch.full((1, 3, 16, 24 + 8 * i), float(i + 1), dtype=torch.bfloat16) for i in range(count)]
+    mine = [units[i].to(dev) for i in shard_indices(count, rank, world)]
+    got = gather_to_rank(mine, count, dst=0)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ok = got is not None and len(got) == count and all(g.is_cuda and torch.equal(g.cpu(), u) for g, u in zip(got, units))
+        open(os.path.join(tmpdir, 'ok'), 'w').write('1' if ok else '0')
+    else:
+        assert got is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_gather_world_size_2(tmp_path):
+    """The engine's only communication on real hardware: ragged tiles gathered to rank 0 with NCCL send/recv (needs two GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two CUDA devices')
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / 'ok').read() == '1'
