@@ -504,16 +504,44 @@ __global__ void __launch_bounds__(256) winattn_kernel(const __grid_constant__ Wi
 // ---- tensor-core version (bf16 storage): one CTA per (window, head), one warp per 16 queries, FlashAttention-2 style.
 // S = Q K^T and O = P V run on warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) over 64-key chunks with an online
 // softmax in registers; the score scale, position bias, shift mask and softmax are fp32, P is rounded to bf16 for the PV
-// product (as in every bf16 attention kernel).  Q / K rows and V^T rows sit in shared memory as bf16 with padded strides
-// (conflict-free fragment loads).  The CUDA-core version above issues ~95 instructions per (query, key) pair and took
-// 2.35 ms per launch on DAT 4x 512^2 (46 % of the forward); this one is bound by the 65 536 exponentials per window-head.
-// A tcgen05 formulation (S in TMEM) is the next step; at head_dim 30 and 256 keys the softmax, not the MMA, is the limit.
-constexpr int kWaQS = kHD + 8;  // Q / K row stride in bf16 elements (80 B: fragment loads hit 32 distinct banks)
+// product (as in every bf16 attention kernel).  Q, K and V rows sit in shared memory as bf16 [token][32 dims + 8] (80-byte rows:
+// 16-byte aligned and conflict-free for ldmatrix).
+//
+// The kernel is bound by instruction issue, not by the tensor pipe or memory (ncu, round 1: issue slots 61-70 % busy at 24 %
+// occupancy, tensor pipe ~20 %, DRAM ~10 %), so the work per score is what counts.  The first MMA version spent ~19 instructions
+// per (query, key) pair; this one ~8:
+//   * K and V fragments come from ldmatrix.x4 (V through .trans, so V is staged like K instead of transposed element by element):
+//     16 loads per 64-key chunk instead of 64;
+//   * the relative-position bias of the two adjacent keys a thread holds per accumulator tile (same window row when the window
+//     width is even, so their table entries are neighbours) is ONE 8-byte load: the table is kept three times at a stride that
+//     makes [base + (a + b) * D + 4 i] 8-byte aligned whatever the parities a, b of the query and key halves of the index i
+//     (copy 0 and 2 serve even i, copy 1 odd i), so the address is a single subtraction of a per-key word from a per-row word;
+//   * the shift mask is skipped for windows whose tokens all carry one label (all but the last row / column of windows).
+// A tcgen05 formulation (S in TMEM) does not change this bound: at head_dim 30 the MMAs are ~1/8 of the instructions, and the
+// softmax (max, subtract, ex2, convert: 4.5 instructions per score on 128 lanes) is the floor either way.
+constexpr int kWaQS = kHD + 8;  // Q / K / V row stride in bf16 elements
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row) { ldsm_x4_trans(r, ptx::smem_u32(smem_row)); }
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(ptx::smem_u32(smem_row)));
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t smem_addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_addr));
+  return v;
 }
 constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -526,9 +554,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
+// distance (in floats) between the copies of the bias table: odd, and at least the table's length
+__host__ __device__ inline int winattn_tab_stride(int tab_n) { return ((tab_n + 2) & ~1) - 1; }
+
 size_t winattn_mma_smem_bytes(int split_h, int split_w) {
   const int N = split_h * split_w, NK = (N + 63) / 64 * 64, NQ = (N + 15) / 16 * 16;
-  return (size_t)(NQ + NK) * kWaQS * 2 + (size_t)kHD * (NK + 8) * 2 + (size_t)(2 * split_h - 1) * (2 * split_w - 1) * 4 + (size_t)NK * 8;
+  const int tab_n = (2 * split_h - 1) * (2 * split_w - 1);
+  return (size_t)(NQ + 2 * NK) * kWaQS * 2 + (size_t)(2 * winattn_tab_stride(tab_n) + tab_n + 1) * 4 + (size_t)NK * 12;
 }
 
 // kThreads = 128 serves windows of <= 64 tokens (SwinIR's 8x8): a tighter register budget keeps 5 CTAs per SM resident
@@ -539,39 +571,48 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
   using T = __nv_bfloat16;
   const int br = blockIdx.z, h = blockIdx.y;
   const int Hs = br == 0 ? p.split_h : p.split_w, Ws = br == 0 ? p.split_w : p.split_h;
-  const int N = Hs * Ws, NK = (N + 63) / 64 * 64, NQ = (N + 15) / 16 * 16, VS = NK + 8;
+  const int N = Hs * Ws, NK = (N + 63) / 64 * 64, NQ = (N + 15) / 16 * 16;
   const int sh = p.shifted ? Hs / 2 : 0, sw = p.shifted ? Ws / 2 : 0;
   const int nWx = p.Wp / Ws, nWy = p.Hp / Hs;
   const int win = blockIdx.x % (nWx * nWy), n = blockIdx.x / (nWx * nWy);
   const int wy = win / nWx, wx = win - wy * nWx;
   const int d = p.head_dim;
   const int tab_w = 2 * Ws - 1, tab_n = (2 * Hs - 1) * tab_w;
+  const int R1 = winattn_tab_stride(tab_n);
   T* Qs = reinterpret_cast<T*>(smraw);            // [NQ][kWaQS]
   T* Ks = Qs + (size_t)NQ * kWaQS;                // [NK][kWaQS]
-  T* Vt = Ks + (size_t)NK * kWaQS;                // [kHD][VS]   (V transposed: keys contiguous)
-  float* tab = reinterpret_cast<float*>(Vt + (size_t)kHD * VS);  // [tab_n] bias of this head
-  int* kinfo = reinterpret_cast<int*>(tab + tab_n);              // [NK] (jy * tab_w + jx) | label << 20
-  int* tokoff = kinfo + NK;                                      // [NK] pixel index y * W + x of the token, -1: padding
+  T* Vs = Ks + (size_t)NK * kWaQS;                // [NK][kWaQS]
+  float* tab3 = reinterpret_cast<float*>(Vs + (size_t)NK * kWaQS);  // bias of this head (x log2 e), copies at 0, R1, 2 R1
+  int* kval = reinterpret_cast<int*>(tab3 + 2 * R1 + tab_n + 1);    // [NK] 4 * kpos - (kpos & 1) * 4 R1   (kpos = jy * tab_w + jx)
+  int* kmeta = kval + NK;                                           // [NK] 4 * kpos | label << 20 | (not a key) << 30
+  int* tokoff = kmeta + NK;                                         // [NK] pixel index y * W + x of the token, -1: padding
   const float* table = br == 0 ? p.table0 : p.table1;
   const int hpb = p.heads / 2;
-  for (int i = threadIdx.x; i < tab_n; i += blockDim.x) tab[i] = table[(size_t)i * hpb + h] * kLog2e;  // softmax in base 2
+  for (int i = threadIdx.x; i < tab_n; i += blockDim.x) {
+    const float v = table[(size_t)i * hpb + h] * kLog2e;  // softmax in base 2
+    tab3[i] = v, tab3[R1 + i] = v, tab3[2 * R1 + i] = v;
+  }
   const float scale2 = p.scale * kLog2e;
-  const bool ones_row = d < kHD;  // spare V^T row carries the softmax denominators (see below)
+  const bool ones_col = d < kHD;  // spare V column carries the softmax denominators (see below)
 
   const T* src = reinterpret_cast<const T*>(p.src);
   const int half = p.dim / 2;
   const int cq = p.src_ch_off + br * half + h * d;
-  // Staging.  Q / K / V^T tiles are zero-filled first (padded tokens, head dims d..31 and chunk padding must read as 0),
-  // then every (matrix, 8-channel plane, token) item is ONE 16-byte load — consecutive threads take consecutive tokens,
-  // i.e. consecutive 16-byte chunks of a plane row — whose channels inside [cq, cq + d) are scattered to shared memory.
-  // A head's 30 channels start at any channel offset, so it touches up to 5 planes per matrix.  (The first version
-  // issued one 2-byte load per (token, channel); on SwinIR's 8x8 windows this staging plus the per-token div/mod
-  // address arithmetic was half of the kernel's instructions: 442 -> 254 us per launch at 4x 512^2.)
+  // Staging.  The tiles are zero-filled first (padded tokens, head dims d..31 and chunk padding must read as 0), then every
+  // (matrix, 8-channel plane, token) item is ONE 16-byte load — consecutive threads take consecutive tokens, i.e. consecutive
+  // 16-byte chunks of a plane row — whose channels inside [cq, cq + d) go to the token's row.  A head's 30 channels start at
+  // any channel offset, so it touches up to 5 planes per matrix.
   {
     uint4* z = reinterpret_cast<uint4*>(smraw);
-    const int nz = ((NQ + NK) * kWaQS * 2 + kHD * VS * 2) / 16;
+    const int nz = (NQ + 2 * NK) * kWaQS * 2 / 16;
     for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
+  int lab0 = 0;  // label of the window's first token
+  if (p.shifted) {
+    const int yr = wy * Hs, xr = wx * Ws;
+    lab0 = 3 * (yr < p.Hp - Hs ? 0 : (yr < p.Hp - sh ? 1 : 2)) + (xr < p.Wp - Ws ? 0 : (xr < p.Wp - sw ? 1 : 2));
+  }
+  int differs = 0;
   for (int t = threadIdx.x; t < NK; t += blockDim.x) {
     const bool active = t < N;
     const int ty = active ? t / Ws : 0, tx = active ? t - ty * Ws : 0;
@@ -579,31 +620,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
     int yo = yr + sh, xo = xr + sw;                  // where that token lives in the un-rolled image
     if (yo >= p.Hp) yo -= p.Hp;
     if (xo >= p.Wp) xo -= p.Wp;
-    int lab = 0;
+    int lab = lab0;
     if (p.shifted && active) {
       const int ry = yr < p.Hp - Hs ? 0 : (yr < p.Hp - sh ? 1 : 2);
       const int rx = xr < p.Wp - Ws ? 0 : (xr < p.Wp - sw ? 1 : 2);
       lab = 3 * ry + rx;
     }
-    kinfo[t] = (ty * tab_w + tx) | (lab << 20) | (active ? 0 : 1 << 30);
+    differs |= lab != lab0;
+    const int kpos = ty * tab_w + tx;
+    kval[t] = 4 * kpos - (kpos & 1) * 4 * R1;
+    kmeta[t] = (4 * kpos) | (lab << 20) | (active ? 0 : 1 << 30);
     tokoff[t] = (active && yo < p.H && xo < p.W) ? yo * p.W + xo : -1;  // padded tokens have q = k = v = 0
   }
-  __syncthreads();
-  if (ones_row)
-    for (int t = threadIdx.x; t < NK; t += blockDim.x) Vt[(kHD - 1) * VS + t] = __float2bfloat16_rn(1.0f);
-  {
-    // thread = one token, walking the (matrix, plane) items with a stride of blockDim / N: no per-item index arithmetic
+  const bool mixed = __syncthreads_or(differs) != 0;  // the shift mask only exists in windows that straddle the roll seam
+  if (ones_col)
+    for (int t = threadIdx.x; t < NK; t += blockDim.x) Vs[t * kWaQS + kHD - 1] = __float2bfloat16_rn(1.0f);
+  if constexpr (!kLoop) {
+    // small windows (several threads per token): the items are walked with a run-time stride.  A/B on one box, SwinIR 8x8
+    // windows: 226 us per launch against 245 us with the unrolled walk below (which wins on 256-token windows: 371 against 384)
     constexpr int kPl = (kHD + 7 + 7) / 8;  // planes a head can straddle
     const size_t ps = (size_t)p.H * p.W * 8;
-    // blocks with at least N threads: `groups` threads share a token; smaller blocks: each thread walks several tokens
+    const bool even = ((cq | p.qkv_stride | d) & 1) == 0;
     const int groups = max(1, (int)blockDim.x / N), g = threadIdx.x / N;
     const int tstep = (int)blockDim.x >= N ? N : (int)blockDim.x;
     for (int t = threadIdx.x - g * N; t < N && g < groups; t += tstep) {
-    const int po = tokoff[t];
-    if (po >= 0) {
+      const int po = tokoff[t];
+      if (po < 0) continue;
       const T* tok = src + ((size_t)n * p.src_planes * p.H * p.W + po) * 8;
-      // all of a thread's loads are issued before the first value is used: one DRAM round trip per CTA, not one per item
-      constexpr int kItems = (3 * kPl + 1) / 2;  // loads per batch: one batch when the block has two threads per token, else two
+      constexpr int kItems = (3 * kPl + 1) / 2;
       for (int mp0 = g; mp0 < 3 * kPl; mp0 += groups * kItems) {
         uint4 v[kItems];
 #pragma unroll
@@ -619,17 +663,77 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
           const int mp = mp0 + it * groups;
           const int m = mp / kPl, pl = mp - m * kPl;
           const int cm = cq + m * p.qkv_stride;
-          const int cbase = ((cm >> 3) + pl) * 8 - cm;  // head dim of the plane's first channel (negative: previous head's)
+          const int cbase = ((cm >> 3) + pl) * 8 - cm;
           if (mp >= 3 * kPl || cbase >= d) continue;
-          const T* e = reinterpret_cast<const T*>(&v[it]);
-          T* out = m == 0 ? Qs + t * kWaQS : (m == 1 ? Ks + t * kWaQS : Vt + t);
-          const int stride = m == 2 ? VS : 1;
+          T* out = (m == 0 ? Qs : (m == 1 ? Ks : Vs)) + t * kWaQS;
+          if (even) {
+            const uint32_t* e = reinterpret_cast<const uint32_t*>(&v[it]);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if ((unsigned)(cbase + k) < (unsigned)d) out[(cbase + k) * stride] = e[k];
+            for (int k = 0; k < 4; ++k)
+              if ((unsigned)(cbase + 2 * k) < (unsigned)d) *reinterpret_cast<uint32_t*>(out + cbase + 2 * k) = e[k];
+          } else {
+            const T* e = reinterpret_cast<const T*>(&v[it]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if ((unsigned)(cbase + k) < (unsigned)d) out[cbase + k] = e[k];
+          }
         }
       }
     }
+  } else {
+    // thread = (token, share g of the items).  The (matrix m, plane pl) items are walked by fully unrolled loops, so everything
+    // that does not depend on the token — which plane, which of its 8 channels belong to the head, where they go — is uniform
+    // arithmetic done once; an item costs its thread one 16-byte load and up to four 4-byte stores.  (Walking the items with a
+    // run-time stride cost ~35 instructions per item, a third of the kernel's instructions on 8x32 windows and two thirds on 8x8.)
+    constexpr int kPl = (kHD + 7 + 7) / 8;  // planes a head can straddle
+    const size_t ps = (size_t)p.H * p.W * 8;
+    const bool even = ((cq | p.qkv_stride | d) & 1) == 0;  // channel pairs never straddle the head: 4-byte stores
+    // blocks with at least 2N / 4N threads: 2 / 4 threads share a token (items split by index mod 2 / 4); smaller blocks: each
+    // thread walks several tokens
+    const int gbits = (int)blockDim.x >= 4 * N ? 2 : ((int)blockDim.x >= 2 * N ? 1 : 0);
+    const int g = threadIdx.x / N;
+    const int tstep = (int)blockDim.x >= N ? N : (int)blockDim.x;
+    int r8[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) r8[m] = (cq + m * p.qkv_stride) & 7;  // first channel of the head inside its first plane
+    for (int t = threadIdx.x - g * N; t < N && g < (1 << gbits); t += tstep) {
+      const int po = tokoff[t];
+      if (po < 0) continue;
+      const T* tok = src + ((size_t)n * p.src_planes * p.H * p.W + po) * 8;
+      const T* tokm[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) tokm[m] = tok + (size_t)((cq + m * p.qkv_stride) >> 3) * ps;
+      // all of a thread's loads are issued before the first value is used: ONE DRAM round trip per CTA (two batches measured
+      // 248 instead of 226 us per launch on SwinIR's 8x8 windows: the kernel's phases are latency chains)
+      constexpr int kBatch = 3 * kPl;
+#pragma unroll
+      for (int b0 = 0; b0 < 3 * kPl; b0 += kBatch) {
+        uint4 v[kBatch];
+#pragma unroll
+        for (int it = 0; it < kBatch; ++it) {
+          const int mp = b0 + it, m = mp / kPl, pl = mp - m * kPl;
+          if (mp < 3 * kPl && (mp & ((1 << gbits) - 1)) == g && pl * 8 - r8[m] < d) v[it] = *reinterpret_cast<const uint4*>(tokm[m] + (size_t)pl * ps);
+        }
+#pragma unroll
+        for (int it = 0; it < kBatch; ++it) {
+          const int mp = b0 + it, m = mp / kPl, pl = mp - m * kPl;
+          if (mp >= 3 * kPl) continue;
+          const int cbase = pl * 8 - r8[m];  // head dim of the plane's first channel (negative: the previous head's)
+          if ((mp & ((1 << gbits) - 1)) != g || cbase >= d) continue;
+          T* out = (m == 0 ? Qs : (m == 1 ? Ks : Vs)) + t * kWaQS;
+          if (even) {
+            const uint32_t* e = reinterpret_cast<const uint32_t*>(&v[it]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if ((unsigned)(cbase + 2 * k) < (unsigned)d) *reinterpret_cast<uint32_t*>(out + cbase + 2 * k) = e[k];
+          } else {
+            const T* e = reinterpret_cast<const T*>(&v[it]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if ((unsigned)(cbase + k) < (unsigned)d) out[cbase + k] = e[k];
+          }
+        }
+      }
     }  // tokens of this thread
   }
   __syncthreads();
@@ -638,6 +742,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
   const int g4 = lane >> 2, t4 = lane & 3;
   T* dst = reinterpret_cast<T*>(p.dst);
   const int co = p.dst_ch_off + br * half + h * d;
+  const bool pairs = (Ws & 1) == 0;  // keys 2k, 2k+1 share a window row: their bias entries are neighbours
+  const uint32_t tab_s = ptx::smem_u32(tab3);
+  // ldmatrix row addresses of this lane: K tile rows (lane & 7), 8-dim block (lane >> 3); V: key (lane & 15), dim block (lane >> 4)
+  const uint32_t k_ld = ptx::smem_u32(Ks) + (uint32_t)(((lane & 7) * kWaQS + (lane >> 3) * 8) * 2);
+  const uint32_t v_ld = ptx::smem_u32(Vs) + (uint32_t)(((lane & 15) * kWaQS + (lane >> 4) * 8) * 2);
   // a warp takes 16 queries at a time; with 256-token windows a 256-thread CTA walks two query tiles per warp, so that two
   // CTAs fit an SM and one window's staging overlaps the other's attention (one 512-thread CTA per SM left the SM idle
   // during every staging phase)
@@ -645,17 +754,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
   if (r0 >= NQ) return;
   do {  // (single pass, known at compile time, for the 128-thread variant)
   const int qa = r0 + g4, qb = qa + 8;  // the two query rows this thread holds fragments of
-  // query-side halves of the bias index and the shift-mask labels
-  int qpos[2], qlab[2];
-  bool qact[2];
+  // query-side halves of the bias address and the shift-mask labels
+  uint32_t qaddr[2];
+  int qlab[2];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const int t = e == 0 ? qa : qb;
-    qact[e] = t < N;
-    const int tt = qact[e] ? t : 0;
+    const int tt = t < N ? t : 0;
     const int ty = tt / Ws, tx = tt - ty * Ws;
-    qpos[e] = (ty + Hs - 1) * tab_w + tx + Ws - 1;
-    qlab[e] = (kinfo[tt] >> 20) & 0xF;
+    const int qpos = (ty + Hs - 1) * tab_w + tx + Ws - 1;
+    // pairs: entries (qpos - kpos - 1, qpos - kpos) of the copy that makes the pair 8-byte aligned; else entry qpos - kpos of copy 0
+    qaddr[e] = pairs ? tab_s + (uint32_t)(((qpos - 1) & 1) * 4 * R1 + 4 * (qpos - 1)) : tab_s + (uint32_t)(4 * qpos);
+    qlab[e] = (kmeta[tt] >> 20) & 0xF;
   }
   uint32_t qf[2][4];
 #pragma unroll
@@ -679,26 +789,41 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) sc[nt][e] = 0.0f;
-      const T* kr = Ks + (size_t)(kc + nt * 8 + g4) * kWaQS + t4 * 2;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        mma_bf16_16816(sc[nt], qf[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16), *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+      uint32_t kf[4];
+      ldsm_x4(kf, k_ld + (uint32_t)((kc + nt * 8) * kWaQS * 2));
+      mma_bf16_16816(sc[nt], qf[0], kf[0], kf[1]);
+      mma_bf16_16816(sc[nt], qf[1], kf[2], kf[3]);
     }
     // scale + position bias (both pre-multiplied by log2 e: the softmax runs on ex2), then — only where they exist — the
     // shift mask and the chunk padding, as warp-uniform branches around their own loops; chunk maxima last
+    if (pairs) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt) {
+        const int kv = kval[kc + nt * 8 + t4 * 2];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ki = kinfo[kc + nt * 8 + t4 * 2 + (e & 1)];
-        sc[nt][e] = fmaf(sc[nt][e], scale2, tab[qpos[e >> 1] - (ki & 0xFFFFF)]);
+        for (int r = 0; r < 2; ++r) {
+          const float2 b = lds_f32x2(qaddr[r] - (uint32_t)kv);  // .y: this key, .x: the next one
+          sc[nt][2 * r] = fmaf(sc[nt][2 * r], scale2, b.y);
+          sc[nt][2 * r + 1] = fmaf(sc[nt][2 * r + 1], scale2, b.x);
+        }
       }
-    if (p.shifted) {
+    } else {
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int ki = kinfo[kc + nt * 8 + t4 * 2 + (e & 1)];
+          const int ki = kmeta[kc + nt * 8 + t4 * 2 + (e & 1)];
+          float b;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(qaddr[e >> 1] - (uint32_t)(ki & 0xFFFFF)));
+          sc[nt][e] = fmaf(sc[nt][e], scale2, b);
+        }
+    }
+    if (mixed) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ki = kmeta[kc + nt * 8 + t4 * 2 + (e & 1)];
           if (((ki >> 20) & 0xF) != qlab[e >> 1]) sc[nt][e] += -100.0f * kLog2e;
         }
     }
@@ -707,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          if (kinfo[kc + nt * 8 + t4 * 2 + (e & 1)] >> 30) sc[nt][e] = -INFINITY;
+          if (kmeta[kc + nt * 8 + t4 * 2 + (e & 1)] >> 30) sc[nt][e] = -INFINITY;
     }
     float cm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
@@ -731,7 +856,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
       o[dt][2] *= corr[1], o[dt][3] *= corr[1];
     }
     // P = 2^(S - m) as bf16 A fragments.  O / l must be a true weighted mean of the ROUNDED probabilities: with head_dim < 32 the
-    // row sums come for free from the PV product itself (row kHD-1 of V^T is all ones, so column kHD-1 of O accumulates
+    // row sums come for free from the PV product itself (column kHD-1 of V is all ones, so column kHD-1 of O accumulates
     // sum_j P_ij); only head_dim == 32 adds the rounded values up by hand.
     uint32_t pf[4][4];
 #pragma unroll
@@ -739,7 +864,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
       const float p0 = ex2_approx(sc[nt][0] - m[0]), p1 = ex2_approx(sc[nt][1] - m[0]);
       const float p2 = ex2_approx(sc[nt][2] - m[1]), p3 = ex2_approx(sc[nt][3] - m[1]);
       const uint32_t lo = pack_bf16x2(p0, p1), hi = pack_bf16x2(p2, p3);
-      if (!ones_row) {
+      if (!ones_col) {
         l[0] += __uint_as_float(lo << 16) + __uint_as_float(lo & 0xFFFF0000u);
         l[1] += __uint_as_float(hi << 16) + __uint_as_float(hi & 0xFFFF0000u);
       }
@@ -749,14 +874,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) winattn_mma_kernel(const
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt)
 #pragma unroll
-      for (int dt = 0; dt < 4; ++dt) {
-        const T* vr = Vt + (size_t)(dt * 8 + g4) * VS + kc + kt * 16 + t4 * 2;
-        mma_bf16_16816(o[dt], pf[kt], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+      for (int dp = 0; dp < 2; ++dp) {
+        // matrices of one ldmatrix.x4.trans: keys [0, 8) and [8, 16) of the 16-key step for dim block 2 dp, then for 2 dp + 1
+        uint32_t vf[4];
+        ldsm_x4_trans(vf, v_ld + (uint32_t)(((kc + kt * 16) * kWaQS + dp * 16) * 2));
+        mma_bf16_16816(o[2 * dp], pf[kt], vf[0], vf[1]);
+        mma_bf16_16816(o[2 * dp + 1], pf[kt], vf[2], vf[3]);
       }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    if (ones_row) {
+    if (ones_col) {
       l[r] = __shfl_sync(0xffffffffu, o[3][2 * r + 1], lane | 3);  // column kHD-1 = 31 lives in the t4 == 3 lane of each row group
     } else {
       l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
@@ -898,14 +1026,6 @@ __global__ void __launch_bounds__(256) chanattn_reduce_kernel(const __grid_const
 // 0.15 of the HBM roofline); this one is bound by the staging loads.  Fixed summation order: run-to-run deterministic.
 constexpr int kCaTok = 128;          // tokens per staged tile
 constexpr int kCaRow = kHD + 8;      // bf16 elements per staged row (80 bytes: 16-byte aligned, conflict-free for ldmatrix)
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(ptx::smem_u32(smem_row)));
-}
-__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* smem_row) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(ptx::smem_u32(smem_row)));
-}
 __global__ void __launch_bounds__(256) chanattn_reduce_mma_kernel(const __grid_constant__ ChanAttnParams p) {
   using T = __nv_bfloat16;
   __shared__ __align__(16) T qs[kCaTok][kCaRow], ks[kCaTok][kCaRow];
