@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RSB_VERSION 202
+#define RSB_VERSION 203
 
 typedef struct rsb_plan rsb_plan;
 
@@ -124,6 +124,14 @@ typedef struct rsb_conv_desc {
    * This is what makes a 1x1 conv WITH BIAS followed by a zero-padded k x k conv collapse exactly into one k x k conv
    * (the taps that fall outside the image must not see the 1x1 conv's bias): SPAN's conv_cat + upsampler, span/arch.py:247-248. */
   const float* border_bias;
+  /* LayerNorm folded into this conv (1 x 1, buffer source).  ln_fold != 0: ln_stats_buf names an 8-channel buffer written by
+   * RSB_OP_LAYERNORM in statistics mode (i[0] = 1) over this conv's source; the caller passes weight' = weight * gamma and
+   * bias' = bias + weight . beta, and the conv computes  rstd * (weight' . x) - mean * rstd * rowsum(weight') + bias'
+   * == weight . LN(x) + bias, with rowsum taken over the weights as rounded to the plan's dtype, so the mean term cancels
+   * exactly.  One read of x instead of LayerNorm's read + write + the conv's read (swinir/arch.py:268-332 norm1 -> qkv,
+   * norm2 -> fc1; dat/arch.py:565-612).  A zero-initialised descriptor has no fold. */
+  int32_t ln_fold;
+  int32_t ln_stats_buf;
 } rsb_conv_desc;
 
 /* GroupNorm over (channels/groups, H, W) per sample, affine, followed by "+ skip". */
@@ -145,7 +153,8 @@ typedef struct rsb_groupnorm_desc {
  * (LayerNorm), :133-170 + :268-332 (W-MSA / SW-MSA: window partition, relative-position bias gathered through
  * relative_position_index, cyclic shift and mask, window reverse). */
 enum rsb_op_kind {
-  RSB_OP_LAYERNORM = 1, /* dst = LN_channels(src) * w[0] + w[1];  f[0] = eps                                         */
+  RSB_OP_LAYERNORM = 1, /* dst = LN_channels(src) * w[0] + w[1];  f[0] = eps.  i[0] = 1: statistics only — dst is an 8-channel
+                           buffer whose pixel chunks receive {rstd, -mean * rstd} as two floats (rsb_conv_desc.ln_stats_buf)  */
   RSB_OP_DWCONV3 = 2,   /* dst = act(dwconv3x3(src; w[0] = [C][9], w[1] = bias[C])) [* src2];  i[0] = rsb_act;
                            i[1] = K in {0, 3, 5, 7}: depthwise K x K instead (w[0] = [C][K*K]; K > 3: no act / gate)          */
   RSB_OP_WINATTN = 3,   /* src = [q | k | v]; i[0] heads, i[1] split_h, i[2] split_w, i[3] shifted, i[4] channel stride

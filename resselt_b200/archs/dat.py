@@ -182,6 +182,7 @@ class DAT(EngineModule):
         hpad = (half + 15) // 16 * 16
         hid, gate_n, gated = pb.buffer(2 * hpad), pb.buffer(half), pb.buffer(half)
         rg_res, img = pb.buffer(dim), pb.buffer(dim)
+        stats = pb.buffer(8)  # LayerNorm statistics of norm1 / norm2, folded into the linears that consume them
         tmp_a = tmp_b = None
         if self.resi_connection == '3conv':
             tmp_a, tmp_b = pb.buffer(dim // 4), pb.buffer(dim // 4)
@@ -195,11 +196,14 @@ class DAT(EngineModule):
             for b in range(nblk):
                 p = f'layers.{rg}.blocks.{b}'
                 a = f'{p}.attn'
-                pb.layernorm(x, xn, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
+                # norm1 -> qkv and norm2 -> fc1: the normalised map is never written (one statistics pass, LayerNorm applied in the
+                # linears' epilogues)
+                pb.layernorm_stats(x, stats)
+                ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
                 wq, bq = lin_w(f'{a}.qkv'), lin_b(f'{a}.qkv')
                 for part in range(3):  # one conv per q / k / v (UMMA N <= 256)
                     rows = slice(part * dim, (part + 1) * dim)
-                    pb.conv(xn, qkv.slice(part * pad, dim), wq[rows], None if bq is None else bq[rows])
+                    pb.conv(x, qkv.slice(part * pad, dim), wq[rows], None if bq is None else bq[rows], ln=ln1)
                 if b % 2 == 0:
                     t0, t1 = self._pos_table(w, f'{a}.attns.0'), self._pos_table(w, f'{a}.attns.1')
                     pb.op(N.OP_WINATTN, qkv, att, dim, ints=(heads, self.split[0], self.split[1], int(_is_shifted(rg, b)), pad),
@@ -215,11 +219,12 @@ class DAT(EngineModule):
                                si_w1, si_b1, w[f'{a}.spatial_interaction.3.weight'], w[f'{a}.spatial_interaction.3.bias']))
                 pb.conv(y, x, lin_w(f'{a}.proj'), lin_b(f'{a}.proj'), combine=N.COMB_AXPY, res1=x)        # x += proj(...)
                 f = f'{p}.ffn'
-                pb.layernorm(x, xn, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
+                pb.layernorm_stats(x, stats)
+                ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
                 w1, b1 = lin_w(f'{f}.fc1'), lin_b(f'{f}.fc1')
                 for part in range(2):  # x1 | x2 = chunk(2) of the hidden activations, each on its own plane range
                     rows = slice(part * half, (part + 1) * half)
-                    pb.conv(xn, hid.slice(part * hpad, half), w1[rows], b1[rows], act=N.ACT_GELU)
+                    pb.conv(x, hid.slice(part * hpad, half), w1[rows], b1[rows], act=N.ACT_GELU, ln=ln2)
                 pb.layernorm(hid.slice(hpad, half), gate_n, w[f'{f}.sg.norm.weight'], w[f'{f}.sg.norm.bias'])
                 pb.dwconv3(gate_n, gated, w[f'{f}.sg.conv.weight'], w[f'{f}.sg.conv.bias'], gate=hid.slice(0, half))
                 pb.conv(gated, x, lin_w(f'{f}.fc2'), lin_b(f'{f}.fc2'), combine=N.COMB_AXPY, res1=x)      # x += fc2(...)

@@ -139,6 +139,7 @@ class SwinIR(EngineModule):
         # wide MLPs: hidden width padded with zero weights to a multiple of 64 so fc2 stages whole 64-channel K chunks
         hpad = hidden if hidden <= 128 else (hidden + 63) // 64 * 64
         qkv, hid = pb.buffer(3 * pad), pb.buffer(hpad)
+        stats = pb.buffer(8)  # LayerNorm statistics of norm1 / norm2, folded into the linears that consume them
         tmp_a = tmp_b = None
         if self.resi_connection == '3conv':
             tmp_a, tmp_b = pb.buffer(dim // 4), pb.buffer(dim // 4)
@@ -149,22 +150,24 @@ class SwinIR(EngineModule):
             cur = a
             for blk in range(nblk):
                 p = f'layers.{i}.residual_group.blocks.{blk}'
-                pb.layernorm(cur, xn, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
+                pb.layernorm_stats(cur, stats)  # norm1 -> qkv: LayerNorm applied in the linears' epilogues, its output never written
+                ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
                 wq, bq = lin_w(f'{p}.attn.qkv'), lin_b(f'{p}.attn.qkv')
                 for part in range(3):  # one conv per q / k / v (UMMA N <= 256)
                     rows = slice(part * dim, (part + 1) * dim)
-                    pb.conv(xn, qkv.slice(part * pad, dim), wq[rows], None if bq is None else bq[rows])
+                    pb.conv(cur, qkv.slice(part * pad, dim), wq[rows], None if bq is None else bq[rows], ln=ln1)
                 table = w[f'{p}.attn.relative_position_bias_table']  # [(2w-1)^2][heads]; the kernel wants one table per head half
                 pb.op(N.OP_WINATTN, qkv, att, dim, ints=(heads, ws, ws, blk % 2, pad), floats=((dim // heads) ** -0.5,),
                       weights=(table[:, : heads // 2].contiguous(), table[:, heads // 2:].contiguous()))
                 pb.conv(att, b, lin_w(f'{p}.attn.proj'), lin_b(f'{p}.attn.proj'), combine=N.COMB_AXPY, res1=cur)  # shortcut + attn
                 cur = b
-                pb.layernorm(cur, xn, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
+                pb.layernorm_stats(cur, stats)  # norm2 -> fc1
+                ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
                 w1, b1, w2 = lin_w(f'{p}.mlp.fc1'), lin_b(f'{p}.mlp.fc1'), lin_w(f'{p}.mlp.fc2')
                 if hpad != hidden:  # gelu(0 * x + 0) = 0 feeds zero fc2 columns
                     w1, b1 = F.pad(w1, (0, 0, 0, 0, 0, 0, 0, hpad - hidden)), F.pad(b1, (0, hpad - hidden))
                     w2 = F.pad(w2, (0, 0, 0, 0, 0, hpad - hidden))
-                pb.conv(xn, hid, w1, b1, act=N.ACT_GELU)
+                pb.conv(cur, hid, w1, b1, act=N.ACT_GELU, ln=ln2)
                 pb.conv(hid, cur, w2, lin_b(f'{p}.mlp.fc2'), combine=N.COMB_AXPY, res1=cur)      # x + mlp(norm2(x))
             self._resi_conv(pb, w, f'layers.{i}.conv', cur, c, a, tmp_a, tmp_b)  # RSTB: conv(blocks(x)) + x
             a, c = c, a

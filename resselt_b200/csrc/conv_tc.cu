@@ -87,7 +87,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   }
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
     bias_sm[i] = p.epi.bias[i];
-    slope_sm[i] = p.epi.slopes != nullptr ? p.epi.slopes[i] : 0.0f;
+    // (a conv with a folded LayerNorm has no PReLU: the slot holds the weights' row sums instead)
+    slope_sm[i] = p.epi.ln_stats != nullptr ? p.epi.ln_rowsum[i] : (p.epi.slopes != nullptr ? p.epi.slopes[i] : 0.0f);
   }
   const int HT = kTileH + p.kh - 1;
   const int WT = kTileW + p.kw - 1;
@@ -242,6 +243,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 if (j * 8 < cstore) pre[j] = *reinterpret_cast<const uint4*>(rp + j * plane_stride);
             }
           }
+          const bool ln = p.epi.ln_stats != nullptr;
+          float2 lnst = make_float2(1.0f, 0.0f);
+          if (ln && valid) lnst = ln_stats_of(p.epi, n, y, x);  // folded LayerNorm: {rstd, -mean * rstd} of this pixel
           mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
           // software-pipelined accumulator reads: chunk ci+1 is in flight while chunk ci goes through the epilogue
@@ -261,11 +265,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ci & 1][j]);
-              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr);
+              if (ln) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], lnst.x, lnst.y * slope_sm[c + j]);
+              }
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr, true);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ci & 1][8 + j]);
+              if (ln) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], lnst.x, lnst.y * slope_sm[c + 8 + j]);
+              }
               if (c + 8 < cstore)
-                epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr);
+                epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr, true);
             }
           }
         } else {
@@ -295,6 +307,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               prefetch_tile(tile + A * (int)gridDim.x);
             }
           }
+          const bool ln = p.epi.ln_stats != nullptr;
+          float2 lnst = make_float2(1.0f, 0.0f);
+          if (ln && valid) lnst = ln_stats_of(p.epi, n, y, x);  // folded LayerNorm: {rstd, -mean * rstd} of this pixel
           mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
           for (int c = part * 16; c < p.npad; c += 16 * parts) {
@@ -305,10 +320,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x);
+              if (ln) {
+                const float4 s0 = *reinterpret_cast<const float4*>(slope_sm + c), s1 = *reinterpret_cast<const float4*>(slope_sm + c + 4);
+                v[0] = fmaf(v[0], lnst.x, lnst.y * s0.x), v[1] = fmaf(v[1], lnst.x, lnst.y * s0.y), v[2] = fmaf(v[2], lnst.x, lnst.y * s0.z), v[3] = fmaf(v[3], lnst.x, lnst.y * s0.w);
+                v[4] = fmaf(v[4], lnst.x, lnst.y * s1.x), v[5] = fmaf(v[5], lnst.x, lnst.y * s1.y), v[6] = fmaf(v[6], lnst.x, lnst.y * s1.z), v[7] = fmaf(v[7], lnst.x, lnst.y * s1.w);
+              }
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x, nullptr, true);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
-              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x);
+              if (ln) {
+                const float4 s0 = *reinterpret_cast<const float4*>(slope_sm + c + 8), s1 = *reinterpret_cast<const float4*>(slope_sm + c + 12);
+                v[0] = fmaf(v[0], lnst.x, lnst.y * s0.x), v[1] = fmaf(v[1], lnst.x, lnst.y * s0.y), v[2] = fmaf(v[2], lnst.x, lnst.y * s0.z), v[3] = fmaf(v[3], lnst.x, lnst.y * s0.w);
+                v[4] = fmaf(v[4], lnst.x, lnst.y * s1.x), v[5] = fmaf(v[5], lnst.x, lnst.y * s1.y), v[6] = fmaf(v[6], lnst.x, lnst.y * s1.z), v[7] = fmaf(v[7], lnst.x, lnst.y * s1.w);
+              }
+              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, nullptr, true);
             }
           }
         }

@@ -61,6 +61,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ 
     }
     const float rstd = rsqrtf(sq / C + p.f0);
     T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
+    if (p.i0 == 1) {  // statistics only (the normalisation is folded into the consuming conv: Epi::ln_stats)
+      *reinterpret_cast<float2*>(d) = make_float2(rstd, -mean * rstd);
+      continue;
+    }
     for (int pl = 0; pl < planes; ++pl) {
       float v[8];
       load8<T>(s + (size_t)pl * hw * 8, v);
@@ -145,6 +149,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_con
     const float rstd = rsqrtf(fmaxf(sq, 0.0f) * inv_c + p.f0);
     const float shift = -mean * rstd;
     T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
+    if (p.i0 == 1) {
+      if (live && sub == 0) *reinterpret_cast<float2*>(d) = make_float2(rstd, shift);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < kPP; ++j) {
       const int pl = 4 * j + sub;
@@ -258,7 +266,10 @@ __global__ void __launch_bounds__(kLnConsumers + 32, 1) layernorm_stream_kernel(
     sq += __shfl_xor_sync(0xffffffffu, sq, 16);
     const float rstd = rsqrtf(sq * inv_c + p.f0);
     const float shift = -mean * rstd;
-    if (live) {
+    if (p.i0 == 1) {
+      if (live && half == 0)
+        *reinterpret_cast<float2*>(reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8) = make_float2(rstd, shift);
+    } else if (live) {
       T* d = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8;
       for (int pl = half; pl < planes; pl += 2) {
         float v[8], o[8];

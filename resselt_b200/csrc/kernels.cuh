@@ -26,6 +26,13 @@ struct Epi {
   const float* slopes;  // [cpad] PReLU slopes or null
   const float* border_bias;  // [16][bb_stride] or null: extra bias of border pixels by (top | bottom << 1 | left << 2 | right << 3)
   int bb_stride;
+  // LayerNorm folded into this (1x1) conv: acc' = acc * rstd(pixel) - mean(pixel) * rstd(pixel) * rowsum[c], where the weights
+  // already carry gamma and the bias W beta.  ln_stats: per pixel {rstd, -mean * rstd} (two floats every ln_stride bytes, the
+  // pixel chunks of an 8-channel buffer written by the LayerNorm op in statistics mode); ln_rowsum[c] = sum_k W'[c][k] of the
+  // weights as the MMA sees them (rounded to the plan's dtype), so the mean term cancels exactly.
+  const void* ln_stats;
+  int ln_stride, ln_planes;  // bytes per pixel chunk, planes of the statistics buffer (its batch stride)
+  const float* ln_rowsum;
   int act;
   float act_param;
   int combine;
@@ -223,12 +230,25 @@ __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& q, float (&o
   }
 }
 
+// per-pixel LayerNorm statistics {rstd, -mean * rstd} of a folded LayerNorm (Epi::ln_stats)
+__device__ __forceinline__ float2 ln_stats_of(const Epi& e, int n, int y, int x) {
+  return __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const char*>(e.ln_stats) +
+                                               (((size_t)n * e.ln_planes * e.H + y) * e.W + x) * (size_t)e.ln_stride));
+}
+
 // EXT = 0: destination is known to be a planar buffer (the NCHW scatter code is compiled out); kRuntime: check e.dst_external.
+// ln_done: the caller has already applied the LayerNorm fold to v (conv_tc loads the statistics once per pixel, not per 8 channels)
 template <typename T, bool kFast, int ACT = kRuntime, int COMB = kRuntime, int EXT = kRuntime>
 __device__ __forceinline__ void epilogue8(const Epi& e, const float* bias, const float* slopes, float (&v)[8], int c0, int n,
-                                          int y, int x, const uint4* res1_pre = nullptr) {
+                                          int y, int x, const uint4* res1_pre = nullptr, bool ln_done = false) {
   const int act = ACT == kRuntime ? e.act : ACT;
   const int comb = COMB == kRuntime ? e.combine : COMB;
+  if (e.ln_stats != nullptr && !ln_done) {
+    const float2 st = ln_stats_of(e, n, y, x);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(e.ln_rowsum + c0)), s1 = __ldg(reinterpret_cast<const float4*>(e.ln_rowsum + c0) + 1);
+    v[0] = fmaf(v[0], st.x, st.y * s0.x), v[1] = fmaf(v[1], st.x, st.y * s0.y), v[2] = fmaf(v[2], st.x, st.y * s0.z), v[3] = fmaf(v[3], st.x, st.y * s0.w);
+    v[4] = fmaf(v[4], st.x, st.y * s1.x), v[5] = fmaf(v[5], st.x, st.y * s1.y), v[6] = fmaf(v[6], st.x, st.y * s1.z), v[7] = fmaf(v[7], st.x, st.y * s1.w);
+  }
   {
     const float4 b0 = reinterpret_cast<const float4*>(bias + c0)[0];
     const float4 b1 = reinterpret_cast<const float4*>(bias + c0)[1];
@@ -547,7 +567,7 @@ struct TokenOpParams {  // LayerNorm and depthwise 3x3
   const float* w0;  // LayerNorm gamma | dwconv weight [C][9]
   const float* w1;  // LayerNorm beta  | dwconv bias [C]
   float f0;         // LayerNorm eps
-  int i0;           // dwconv activation (RSB_ACT_NONE / RSB_ACT_GELU)
+  int i0;           // dwconv activation (RSB_ACT_NONE / RSB_ACT_GELU) | LayerNorm: 1 = statistics only (dst pixel chunk = {rstd, -mean * rstd})
 };
 
 struct WinAttnParams {

@@ -90,6 +90,7 @@ struct ConvOp {
   rsb_conv_desc d;
   std::vector<float> w, b, slopes, border;
   float* d_border = nullptr;  // [16][max(npad, cpad32)]
+  float* d_lnsum = nullptr;   // [max(npad, cpad32)] row sums of the rounded weights (LayerNorm fold)
   int scale = 1;  // grid of this conv relative to the input
   int cin_pad16 = 0, npad = 0, cpad32 = 0, cin_planes = 0;
   bool tc_ok = false;
@@ -275,6 +276,7 @@ bool region_dead_after(const rsb_plan* p, const Region& r, size_t last_reader) {
       const ConvOp& c = p->convs[op.index];
       const rsb_conv_desc& d = c.d;
       if (overlaps(conv_src(c), r)) return false;
+      if (d.ln_fold && d.ln_stats_buf == r.buf) return false;
       if (d.combine != RSB_COMB_NONE) {
         const int ch = ceil_div(d.cout, 8) * 8;
         if (overlaps({d.res1_buf, d.res1_ch_off, d.res1_ch_off + ch}, r)) return false;
@@ -339,6 +341,12 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
   e.slopes = c.d_slopes;
   e.border_bias = c.d_border;
   e.bb_stride = std::max(c.npad, c.cpad32);
+  if (d.ln_fold) {
+    e.ln_stats = ws + p->bufs[d.ln_stats_buf].offset;
+    e.ln_stride = p->dtype == RSB_BF16 ? 16 : 32;  // one 8-channel pixel chunk
+    e.ln_planes = p->bufs[d.ln_stats_buf].planes;
+    e.ln_rowsum = c.d_lnsum;
+  }
   e.act = d.act;
   e.act_param = d.act_param;
   e.combine = d.combine;
@@ -380,7 +388,7 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
       e.dst2_plane0 = d.dst2_ch_off / 8;
       e.split_ch = d.split_ch;
     }
-    e.simple = (e.dst_ps == 1 && e.dst2 == nullptr && e.res2 == nullptr && e.border_bias == nullptr) ? 1 : 0;
+    e.simple = (e.dst_ps == 1 && e.dst2 == nullptr && e.res2 == nullptr && e.border_bias == nullptr && e.ln_stats == nullptr) ? 1 : 0;
   }
 }
 
@@ -732,6 +740,7 @@ int rsb_plan_destroy(rsb_plan* p) {
     DeviceGuard guard(p->device);
     for (ConvOp& c : p->convs) {
       cudaFree(c.d_wtc), cudaFree(c.d_wrs), cudaFree(c.d_wlk), cudaFree(c.d_wdirect), cudaFree(c.d_bias), cudaFree(c.d_slopes), cudaFree(c.d_border);
+      cudaFree(c.d_lnsum);
     }
     for (GnOp& g : p->gns) cudaFree(g.d_gamma), cudaFree(g.d_beta);
     for (AuxOp& a : p->auxs)
@@ -822,6 +831,12 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
       if (int e = check_buf(p, d.res2_buf, d.res2_ch_off, d.cout, "rsb_plan_add_conv(res2)")) return e;
       if (p->bufs[d.res2_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: res2 grid mismatch");
     }
+  }
+  if (d.ln_fold) {
+    if (d.kh != 1 || d.kw != 1 || d.src_buf < 0 || d.act == RSB_ACT_PRELU || d.dst_buf < 0)
+      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: a LayerNorm fold needs a 1x1 conv from a buffer to a buffer, without PReLU");
+    if (int e = check_buf(p, d.ln_stats_buf, 0, 8, "rsb_plan_add_conv(ln_stats)")) return e;
+    if (p->bufs[d.ln_stats_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: ln_stats grid mismatch");
   }
   c.scale = scale;
   const size_t wn = (size_t)d.cout * d.cin * d.kh * d.kw;
@@ -939,7 +954,8 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown buffer");
   const int stride = d.kind == RSB_OP_WINATTN ? d.i[4] : (d.kind == RSB_OP_CHANATTN ? d.i[1] : 0);
   const int src_need = d.src_ch_off + (qkv ? 2 * (stride > 0 ? stride : d.channels) : 0) + d.channels;
-  if (src_need > p->bufs[d.src_buf].planes * 8 || d.dst_ch_off + d.channels > p->bufs[d.dst_buf].planes * 8)
+  const int dst_need = (d.kind == RSB_OP_LAYERNORM && d.i[0] == 1) ? 8 : d.channels;  // statistics mode writes one pixel chunk
+  if (src_need > p->bufs[d.src_buf].planes * 8 || d.dst_ch_off + dst_need > p->bufs[d.dst_buf].planes * 8)
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel range exceeds buffer");
   if (!qkv && (d.src_ch_off % 8 != 0 || d.dst_ch_off % 8 != 0))
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel offsets must be multiples of 8");
@@ -1041,6 +1057,24 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
         for (int o = 0; o < d.cout; ++o) bb[(size_t)m * cmax + o] = c.border[(size_t)m * d.cout + o];
       RSB_CUDA(cudaMalloc(&c.d_border, bb.size() * sizeof(float)));
       RSB_CUDA(cudaMemcpy(c.d_border, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (d.ln_fold) {
+      // row sums of the weights exactly as the kernels multiply them (bf16 plans round the weights)
+      std::vector<float> rs(cmax, 0.0f);
+      for (int o = 0; o < d.cout; ++o) {
+        double acc = 0.0;
+        for (int k = 0; k < d.cin; ++k) {
+          float w = c.w[(size_t)o * d.cin + k];
+          if (p->dtype == RSB_BF16) {
+            const uint32_t u = (uint32_t)f32_to_bf16(w) << 16;
+            memcpy(&w, &u, 4);
+          }
+          acc += (double)w;
+        }
+        rs[o] = (float)acc;
+      }
+      RSB_CUDA(cudaMalloc(&c.d_lnsum, cmax * sizeof(float)));
+      RSB_CUDA(cudaMemcpy(c.d_lnsum, rs.data(), cmax * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (d.act == RSB_ACT_PRELU) {
       RSB_CUDA(cudaMalloc(&c.d_slopes, cmax * sizeof(float)));

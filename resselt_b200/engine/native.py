@@ -59,6 +59,7 @@ class ConvDesc(C.Structure):
         ('dst_ps', C.c_int32), ('dst2_buf', C.c_int32), ('dst2_ch_off', C.c_int32), ('split_ch', C.c_int32),
         ('dst_phase', C.c_int32), ('pad_t', C.c_int32), ('pad_l', C.c_int32),
         ('border_bias', C.POINTER(C.c_float)),
+        ('ln_fold', C.c_int32), ('ln_stats_buf', C.c_int32),
     ]
 
 

@@ -72,10 +72,24 @@ class PlanBuilder:
         self.scales[bid.value] = scale
         return Ref(bid.value, 0, channels)
 
-    def conv(self, src: Ref, dst: Ref, weight, bias=None, **kw) -> None:
+    def conv(self, src: Ref, dst: Ref, weight, bias=None, ln=None, **kw) -> None:
         """Add a conv op.  On the bf16 (tensor-core) plan a conv whose packed kernel would not fit shared memory next
         to the activation stages is split over its output channels into several ops (each re-reads the input; every
-        op keeps its slice of bias / PReLU slopes / residual / destination)."""
+        op keeps its slice of bias / PReLU slopes / residual / destination).
+
+        ``ln = (stats, gamma, beta)``: the conv (1 x 1) consumes LayerNorm(src) without that map ever being written —
+        ``stats`` is the 8-channel buffer ``layernorm_stats(src, stats)`` filled; gamma goes into the weights and beta into the bias
+        here (fp64), the per-pixel mean / rstd are applied in the conv's epilogue (rsb_conv_desc.ln_fold)."""
+        if ln is not None:
+            stats, gamma, beta = ln
+            w64 = (weight.detach().to('cpu', torch.float64).numpy() if isinstance(weight, torch.Tensor) else np.asarray(weight, dtype=np.float64))
+            g64 = (gamma.detach().to('cpu', torch.float64).numpy() if isinstance(gamma, torch.Tensor) else np.asarray(gamma, dtype=np.float64))
+            b64 = (beta.detach().to('cpu', torch.float64).numpy() if isinstance(beta, torch.Tensor) else np.asarray(beta, dtype=np.float64))
+            assert w64.ndim == 4 and w64.shape[2:] == (1, 1), 'a LayerNorm fold needs a 1x1 conv'
+            extra = w64[:, :, 0, 0] @ b64
+            bias = extra if bias is None else (bias.detach().to('cpu', torch.float64).numpy() if isinstance(bias, torch.Tensor) else np.asarray(bias, dtype=np.float64)) + extra
+            weight = w64 * g64.reshape(1, -1, 1, 1)
+            kw['ln_stats'] = stats
         w = _f32(weight)
         cout, cin, kh, kw_ = w.shape
         cin16 = (cin + 15) // 16 * 16
@@ -126,6 +140,7 @@ class PlanBuilder:
         dst2: Optional[Ref] = None,
         pad: Optional[tuple] = None,
         border_bias=None,
+        ln_stats: Optional[Ref] = None,
     ) -> None:
         w = _f32(weight)
         assert w.ndim == 4, 'conv weight must be [cout][cin][kh][kw]'
@@ -163,6 +178,7 @@ class PlanBuilder:
         d.border_bias = _fptr(bb)
         d.dst2_buf, d.dst2_ch_off = (dst2.buf, dst2.ch_off) if dst2 is not None else (N.NO_BUFFER, 0)
         d.split_ch = main_ch if dst2 is not None else 0
+        d.ln_fold, d.ln_stats_buf = (1, ln_stats.buf) if ln_stats is not None else (0, N.NO_BUFFER)
         N.check(self._lib.rsb_plan_add_conv(self._h, C.byref(d)))
 
     def groupnorm(self, src: Ref, dst: Ref, groups: int, gamma, beta, eps: float = 1e-5, skip: Optional[Ref] = None) -> None:
@@ -198,6 +214,12 @@ class PlanBuilder:
 
     def layernorm(self, src: Ref, dst: Ref, gamma, beta, eps: float = 1e-5) -> None:
         self.op(N.OP_LAYERNORM, src, dst, src.channels, floats=(eps,), weights=(gamma, beta))
+
+    def layernorm_stats(self, src: Ref, dst: Ref, eps: float = 1e-5) -> None:
+        """Per-pixel LayerNorm statistics of ``src`` into the 8-channel buffer ``dst`` (consumed by ``conv(..., ln=(dst, gamma, beta))``)."""
+        assert dst.channels == 8 and dst.ch_off == 0, 'the statistics buffer is a whole 8-channel buffer'
+        c = src.channels
+        self.op(N.OP_LAYERNORM, src, dst, c, ints=(1,), floats=(eps,), weights=(np.ones(c, np.float32), np.zeros(c, np.float32)))
 
     def dwconv3(self, src: Ref, dst: Ref, weight, bias, act: int = N.ACT_NONE, gate: Optional[Ref] = None) -> None:
         self.op(N.OP_DWCONV3, src, dst, src.channels, src2=gate, ints=(act,), weights=(weight, bias))

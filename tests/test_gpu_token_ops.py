@@ -335,3 +335,36 @@ def test_unshuffle_pool_dw5_se_shuffle_chain(C, se, B, H, W, dtype):
         t = t * F.hardsigmoid(F.conv2d(F.relu(F.conv2d(sq, D(s1w), D(s1b))), D(s2w), D(s2b)))
     ref = F.pixel_shuffle(t, 2)
     _check(got, ref, dtype, bf16_tol=2e-2, what='unshuffle/pool -> dw5x5 -> SE -> shuffle')
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm folded into a linear
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,cout,act,residual,mean,B,H,W', [
+    (180, 180, N.ACT_NONE, False, 0.3, 1, 40, 56),    # norm1 -> q / k / v (swinir/arch.py:268-293)
+    (180, 360, N.ACT_GELU, False, 4.0, 2, 33, 47),    # norm2 -> fc1 + GELU; token mean ten times the spread (the term that must cancel)
+    (60, 60, N.ACT_NONE, True, -1.0, 1, 64, 64),      # light models; AXPY tail on top of the fold
+    (180, 600, N.ACT_NONE, False, 0.5, 1, 24, 40),    # wider than one UMMA N tile: the builder splits the conv, every part carries its row sums
+    (180, 180, N.ACT_NONE, False, 0.2, 1, 256, 256),  # many tiles
+])
+def test_layernorm_folded_into_linear(C, cout, act, residual, mean, B, H, W, dtype):
+    """conv(x, ln=(stats, gamma, beta)) == Linear(LayerNorm(x)): statistics pass + epilogue fold (rsb_conv_desc.ln_fold) against fp64."""
+    g = torch.Generator().manual_seed(C + cout + H)
+    x = torch.randn(B, C, H, W, generator=g) * 0.4 + mean + 0.5 * torch.randn(B, 1, H, W, generator=g)
+    gamma, beta = 1.0 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    wl, bl = torch.randn(cout, C, 1, 1, generator=g) / C ** 0.5, 0.1 * torch.randn(cout, generator=g)
+    pb = PlanBuilder(dtype, C, cout, 1)
+    a, stats, y = pb.buffer(C), pb.buffer(8), pb.buffer(cout)
+    pb.conv(INPUT, a, torch.eye(C).view(C, C, 1, 1))
+    pb.layernorm_stats(a, stats, eps=1e-5)
+    kw = dict(combine=N.COMB_AXPY, res1=a) if residual else {}
+    pb.conv(a, y, wl, bl, act=act, ln=(stats, gamma, beta), **kw)
+    pb.conv(y, OUTPUT, torch.eye(cout).view(cout, cout, 1, 1))
+    got, _ = _run(pb, x, dtype)
+    xq = _q(x, dtype)
+    ln = F.layer_norm(xq.permute(0, 2, 3, 1), (C,), gamma.double(), beta.double(), 1e-5).permute(0, 3, 1, 2)
+    ref = F.conv2d(ln, wl.double(), bl.double())
+    if act == N.ACT_GELU:
+        ref = F.gelu(ref)
+    if residual:
+        ref = ref + xq
+    _check(got, ref, dtype, what='LayerNorm fold')

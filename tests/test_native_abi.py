@@ -29,12 +29,12 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(N.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/ but not exported'
-    assert lib.rsb_version() == 202
+    assert lib.rsb_version() == 203
 
 
 def test_desc_struct_sizes_match_header_layout():
     # 4-byte fields + 8-byte pointers, natural alignment (what a C compiler produces for the header's structs)
-    assert C.sizeof(N.ConvDesc) == 184
+    assert C.sizeof(N.ConvDesc) == 192
     assert C.sizeof(N.GroupNormDesc) == 56
 
 
