@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_con
 // compute.  Consumer thread = (pixel, half): the two half-warps split the planes, statistics meet through one shuffle.
 constexpr int kLnTile = 128;  // pixels per tile
 constexpr int kLnConsumers = 256;
+constexpr int kLnSplit = 2;  // consumer threads per pixel (lane groups of 32 / kLnSplit pixels, each taking every kLnSplit-th plane).  Four
+                             // (16 consumer warps) measured slower: 32.9 vs 29.1 us per launch averaged over DAT's LayerNorms
 __global__ void __launch_bounds__(kLnConsumers + 32, 1) layernorm_stream_kernel(const __grid_constant__ TokenOpParams p, int stages) {
   using T = __nv_bfloat16;
   extern __shared__ __align__(128) uint8_t ln_smem[];
@@ -225,8 +227,9 @@ __global__ void __launch_bounds__(kLnConsumers + 32, 1) layernorm_stream_kernel(
     }
     return;
   }
-  // ---- consumers: warp w takes pixels [16 w, 16 w + 16) of the tile; lanes 0..15 the even planes, lanes 16..31 the odd ones
-  const int half = lane >> 4, px = warp * 16 + (lane & 15);
+  // ---- consumers: warp w takes 32 / kLnSplit pixels of the tile; lane group `half` takes planes half, half + kLnSplit, ...
+  constexpr int kPxW = 32 / kLnSplit;
+  const int half = lane / kPxW, px = warp * kPxW + (lane % kPxW);
   const int full_planes = C >> 3, tail = C & 7;
   const float inv_c = 1.0f / (float)C;
   auto unpack = [](const uint4& r, float (&v)[8]) {
@@ -243,35 +246,63 @@ __global__ void __launch_bounds__(kLnConsumers + 32, 1) layernorm_stream_kernel(
     ptx::mbar_wait(&full[s], ph);
     const uint4* mine = reinterpret_cast<const uint4*>(ring + (size_t)s * stage_bytes) + px;
     const bool live = px < npix;
-    float sum = 0.0f;
-    if (live)
-      for (int pl = half; pl < planes; pl += 2) {
+    // One pass over the tile for the statistics: sums of (x - k) and (x - k)^2 with k = the first channel this thread sees
+    // (a shift inside the data keeps the one-pass variance as accurate as the two-pass form), the lane groups of a pixel are merged with
+    // the pairwise update of Chan et al.  The kernel is bound by instruction issue, not by HBM (ncu: 64 % issue-active on 9
+    // warps per SM at 2.7 TB/s), so passes and per-element selects are what it pays for: the channel bound check is only made
+    // on the one plane that can be partial.
+    float k0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+    if (live) {
+      if (half < planes) {
+        float v[8];
+        unpack(mine[half * kLnTile], v);
+        k0 = v[0];
+      }
+      for (int pl = half; pl < full_planes; pl += kLnSplit) {
         float v[8];
         unpack(mine[pl * kLnTile], v);
-        const int lim = pl < full_planes ? 8 : tail;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum += k < lim ? v[k] : 0.0f;
+        for (int k = 0; k < 8; ++k) {
+          const float dlt = v[k] - k0;
+          s1 += dlt;
+          s2 = fmaf(dlt, dlt, s2);
+        }
       }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-    const float mean = sum * inv_c;
-    float sq = 0.0f;
-    if (live)
-      for (int pl = half; pl < planes; pl += 2) {
+      if (tail != 0 && (full_planes % kLnSplit) == half) {
         float v[8];
-        unpack(mine[pl * kLnTile], v);
-        const int lim = pl < full_planes ? 8 : tail;
+        unpack(mine[full_planes * kLnTile], v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sq += k < lim ? (v[k] - mean) * (v[k] - mean) : 0.0f;
+        for (int k = 0; k < 8; ++k) {
+          const float dlt = k < tail ? v[k] - k0 : 0.0f;
+          s1 += dlt;
+          s2 = fmaf(dlt, dlt, s2);
+        }
       }
-    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
-    const float rstd = rsqrtf(sq * inv_c + p.f0);
+    }
+    // channels held by this lane group; the (count, mean, M2) partials of a pixel are merged pairwise
+    const int mine_planes = (full_planes + kLnSplit - 1 - half) / kLnSplit;
+    float cnt = (float)(mine_planes * 8 + ((tail != 0 && (full_planes % kLnSplit) == half) ? tail : 0));
+    float mean = cnt > 0.0f ? k0 + s1 / cnt : 0.0f;
+    float m2 = cnt > 0.0f ? s2 - s1 * s1 / cnt : 0.0f;
+#pragma unroll
+    for (int sh = kPxW; sh <= 16; sh <<= 1) {
+      const float cnt_o = __shfl_xor_sync(0xffffffffu, cnt, sh), mean_o = __shfl_xor_sync(0xffffffffu, mean, sh);
+      const float m2_o = __shfl_xor_sync(0xffffffffu, m2, sh);
+      const float tot = cnt + cnt_o, dm = mean_o - mean;
+      const float inv = tot > 0.0f ? 1.0f / tot : 0.0f;
+      // symmetric form: both partners must end up with bit-identical results
+      mean = (cnt * mean + cnt_o * mean_o) * inv;
+      m2 = m2 + m2_o + dm * dm * cnt * cnt_o * inv;
+      cnt = tot;
+    }
+    const float rstd = rsqrtf(fmaxf(m2, 0.0f) * inv_c + p.f0);
     const float shift = -mean * rstd;
     if (p.i0 == 1) {
       if (live && half == 0)
         *reinterpret_cast<float2*>(reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8) = make_float2(rstd, shift);
     } else if (live) {
       T* d = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8;
-      for (int pl = half; pl < planes; pl += 2) {
+      for (int pl = half; pl < planes; pl += kLnSplit) {
         float v[8], o[8];
         unpack(mine[pl * kLnTile], v);
         const float4 g0 = *reinterpret_cast<const float4*>(gam + pl * 8), g1 = *reinterpret_cast<const float4*>(gam + pl * 8 + 4);
@@ -1597,12 +1628,15 @@ cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, int num_sms, cud
   static const bool no_stream = rsb_env("RSB_LN_REG") != nullptr;  // bring-up: the register-resident kernel instead
   if (bf16 && !no_stream && planes <= 64) {
     const size_t stage = (size_t)planes * kLnTile * 16;
-    int stages = (int)std::min<size_t>(8, (200 * 1024 - (size_t)planes * 64 - 256) / stage);
+    // two resident CTAs per SM with a two-stage ring each when that fits: the kernel is bound by instruction issue / latency, and 18
+    // warps hide more of it than 9 (A/B on one box, DAT 4x 512^2: 29.2 -> 24.8 us per LayerNorm launch)
+    const int ctas = 2 * stage + 1024 <= 100 * 1024 ? 2 : 1;
+    int stages = (int)std::min<size_t>(8, ((ctas == 2 ? 104 : 200) * 1024 - (size_t)planes * 64 - 256) / stage);
     const size_t hw = (size_t)p.H * p.W;
     const size_t tiles = (size_t)p.n * ((hw + kLnTile - 1) / kLnTile);
     if (stages >= 2 && tiles >= 1) {
       const size_t smem = (size_t)stages * stage + (size_t)planes * 64 + (size_t)stages * 16 + 16;
-      const int grid = (int)std::min<size_t>(tiles, (size_t)sms);  // persistent: one CTA per SM
+      const int grid = (int)std::min<size_t>(tiles, (size_t)sms * ctas);  // persistent
       layernorm_stream_kernel<<<grid, kLnConsumers + 32, smem, s>>>(p, stages);
       return cudaGetLastError();
     }
