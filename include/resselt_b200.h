@@ -168,7 +168,10 @@ enum rsb_op_kind {
   RSB_OP_AIM = 5        /* src = attention output, src2 = conv branch, dst = gated sum; i[0] mode (0 window block,
                            1 channel block), i[1] / i[2] hidden widths of the channel / spatial MLPs;
                            w[0..3] = channel MLP (W1 [h1][C], b1, W2 [C][h1], b2), w[4..7] = spatial MLP
-                           (W1 [h2][C], b1, w2 [h2], b2 [1]); BatchNorm folded by the caller                           */
+                           (W1 [h2][C], b1, w2 [h2], b2 [1]); BatchNorm folded by the caller.
+                           i[3] = 1 + id of a buffer (>= 16 channels) that already holds gelu(W1 . s + b1), written by a 1x1 conv
+                           op over the spatial-map source (src in mode 0, src2 in mode 1): the op then only applies w2 / b2 and
+                           the gated sum — the 180 -> 11 matrix product per pixel runs on the tensor cores; 0: computed here   */
   ,
   RSB_OP_DYSAMPLE = 6   /* DySample head (resselt/utilities/dysample.py:46-83) with its 1x1 end_conv fused, written to the caller's
                            NCHW output: src = features [C] on the low-res grid, src2 = 0.5 * offset(x) * sigmoid(scope(x))

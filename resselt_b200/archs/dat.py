@@ -183,6 +183,8 @@ class DAT(EngineModule):
         hid, gate_n, gated = pb.buffer(2 * hpad), pb.buffer(half), pb.buffer(half)
         rg_res, img = pb.buffer(dim), pb.buffer(dim)
         stats = pb.buffer(8)  # LayerNorm statistics of norm1 / norm2, folded into the linears that consume them
+        # hidden layer of AIM's spatial-interaction MLP (dim -> dim/16, GELU): a 1x1 conv on the tensor cores when the plan has them
+        si_hid = pb.buffer(16) if pb.compute_dtype == torch.bfloat16 and dim // 16 <= 16 else None
         tmp_a = tmp_b = None
         if self.resi_connection == '3conv':
             tmp_a, tmp_b = pb.buffer(dim // 4), pb.buffer(dim // 4)
@@ -214,7 +216,11 @@ class DAT(EngineModule):
                 pb.dwconv3(qkv.slice(2 * pad, dim), convx, dw_w, dw_b, act=N.ACT_GELU)
                 ci_w1, ci_b1 = self._fold_bn(w, f'{a}.channel_interaction.1', f'{a}.channel_interaction.2')
                 si_w1, si_b1 = self._fold_bn(w, f'{a}.spatial_interaction.0', f'{a}.spatial_interaction.1')
-                pb.op(N.OP_AIM, att, y, dim, src2=convx, ints=(b % 2, dim // 8, dim // 16),
+                hid_id = 0
+                if si_hid is not None:  # spatial map source: the attention output in window blocks, the conv branch in channel blocks
+                    pb.conv(att if b % 2 == 0 else convx, si_hid.slice(0, dim // 16), si_w1.reshape(dim // 16, dim, 1, 1), si_b1, act=N.ACT_GELU)
+                    hid_id = si_hid.buf + 1
+                pb.op(N.OP_AIM, att, y, dim, src2=convx, ints=(b % 2, dim // 8, dim // 16, hid_id),
                       weights=(ci_w1, ci_b1, w[f'{a}.channel_interaction.4.weight'], w[f'{a}.channel_interaction.4.bias'],
                                si_w1, si_b1, w[f'{a}.spatial_interaction.3.weight'], w[f'{a}.spatial_interaction.3.bias']))
                 pb.conv(y, x, lin_w(f'{a}.proj'), lin_b(f'{a}.proj'), combine=N.COMB_AXPY, res1=x)        # x += proj(...)

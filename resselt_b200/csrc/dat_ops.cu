@@ -1365,10 +1365,11 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
   float* w1 = sm;                 // [hidn][cpad]
   float* cm = w1 + hidn * p.cpad; // [cpad]
   const int n = blockIdx.y;
-  for (int e = threadIdx.x; e < hidn * p.cpad; e += blockDim.x) {
-    const int k = e / p.cpad, c = e - k * p.cpad;
-    w1[e] = c < C ? p.si_w1[k * C + c] : 0.0f;
-  }
+  if (p.hid == nullptr)
+    for (int e = threadIdx.x; e < hidn * p.cpad; e += blockDim.x) {
+      const int k = e / p.cpad, c = e - k * p.cpad;
+      w1[e] = c < C ? p.si_w1[k * C + c] : 0.0f;
+    }
   for (int c = threadIdx.x; c < p.cpad; c += blockDim.x) cm[c] = c < C ? p.cmap[(size_t)n * p.cpad + c] : 0.0f;
   __syncthreads();
   const size_t hw = (size_t)p.H * p.W;
@@ -1378,6 +1379,19 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
   const T* cvx = reinterpret_cast<const T*>(p.convx) + ((size_t)n * p.convx_planes + p.convx_plane0) * hw * 8 + pix * 8;
   const T* ssrc = p.mode == 0 ? att : cvx;
   float hid[16];
+  float s = p.si_b2;
+  if (p.hid != nullptr) {
+    // the hidden layer gelu(W1 . s + b1) was computed by a 1x1 conv on the tensor cores (1 980 FMAs per pixel here otherwise:
+    // the kernel is issue-bound, 51.6 M instructions for 293 MB)
+    if constexpr (sizeof(T) == 2) {
+      const T* hp = reinterpret_cast<const T*>(p.hid) + ((size_t)n * p.hid_planes * hw + pix) * 8;
+      load8<T>(hp, *reinterpret_cast<float(*)[8]>(&hid[0]));
+      load8<T>(hp + hw * 8, *reinterpret_cast<float(*)[8]>(&hid[8]));
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < hidn) s = fmaf(p.si_w2[k], hid[k], s);
+  } else {
 #pragma unroll
   for (int k = 0; k < 16; ++k) hid[k] = k < hidn ? p.si_b1[k] : 0.0f;
   // planes in batches of four: four independent 16-byte loads in flight per thread (one at a time left the kernel waiting on
@@ -1401,10 +1415,10 @@ __global__ void __launch_bounds__(256) aim_combine_kernel(const __grid_constant_
         }
     }
   }
-  float s = p.si_b2;
 #pragma unroll
   for (int k = 0; k < 16; ++k)
     if (k < hidn) s = fmaf(p.si_w2[k], gelu_f(hid[k]), s);
+  }
   const float smap = sigm_f(s);
   T* dst = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
   for (int pl0 = 0; pl0 < planes; pl0 += 2) {

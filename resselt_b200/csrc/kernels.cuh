@@ -608,6 +608,8 @@ struct AimParams {
   float si_b2;
   float* partial;  // [n][blocks][cpad]
   float* cmap;     // [n][cpad]
+  const void* hid; // optional: gelu(W1 . s + b1) of the spatial MLP, 16 channels per pixel, written by a 1x1 conv op
+  int hid_planes;
 };
 
 struct SeParams {  // squeeze-excitation gate + PixelShuffle(2) (rt_ops.cu)

@@ -291,6 +291,7 @@ bool region_dead_after(const rsb_plan* p, const Region& r, size_t last_reader) {
     } else {
       const rsb_op_desc& d = p->auxs[op.index].d;
       if (d.src_buf == r.buf || d.src2_buf == r.buf || d.dst_buf == r.buf) return false;
+      if (d.kind == RSB_OP_AIM && d.i[3] - 1 == r.buf) return false;
     }
   }
   return true;  // the next forward rewrites it before anything reads it
@@ -691,6 +692,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.si_w1 = a.dw[4], t.si_b1 = a.dw[5], t.si_w2 = a.dw[6], t.si_b2 = a.w[7].empty() ? 0.0f : a.w[7][0];
       t.partial = reinterpret_cast<float*>(scratch);
       t.cmap = t.partial + (size_t)n * kAuxBlocks * t.cpad;
+      if (d.i[3] > 0) t.hid = ws + p->bufs[d.i[3] - 1].offset, t.hid_planes = p->bufs[d.i[3] - 1].planes;
     }
   }
   p->bn = n, p->bh = h, p->bw = w, p->bws = workspace;
@@ -979,6 +981,11 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
   }
   if (d.kind == RSB_OP_AIM && (d.i[1] < 1 || d.i[1] > 64 || d.i[2] < 1 || d.i[2] > 16 || d.channels > 512))
     return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: AIM hidden widths out of range");
+  if (d.kind == RSB_OP_AIM && d.i[3] != 0) {
+    if (p->dtype != RSB_BF16) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: AIM with a precomputed hidden map is a bf16-plan feature");
+    if (int e = check_buf(p, d.i[3] - 1, 0, 16, "rsb_plan_add_op(AIM hidden)")) return e;
+    if (p->bufs[d.i[3] - 1].scale != p->bufs[d.src_buf].scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: AIM hidden map grid mismatch");
+  }
   AuxOp a;
   a.d = d;
   for (int k = 0; k < 8; ++k) {

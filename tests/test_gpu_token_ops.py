@@ -190,8 +190,12 @@ def test_depthwise3x3_op(C, act, gated, B, H, W, dtype):
 
 # ------------------------------------------------------------------------------------------------ AIM (adaptive interaction module)
 @pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('hid_conv', [False, True])
 @pytest.mark.parametrize('mode,C,B,H,W', [(0, 180, 1, 48, 56), (1, 180, 1, 48, 56), (0, 64, 2, 31, 20), (1, 96, 1, 128, 128)])
-def test_aim_op(mode, C, B, H, W, dtype):
+def test_aim_op(mode, C, B, H, W, hid_conv, dtype):
+    """hid_conv: the spatial MLP's hidden layer comes from a 1x1 conv op (tensor cores) instead of the AIM kernel itself (i[3], bf16 plans)."""
+    if hid_conv and dtype != torch.bfloat16:
+        pytest.skip('bf16-plan feature')
     g = torch.Generator().manual_seed(C + mode)
     h1, h2 = C // 8, C // 16
     x = torch.randn(B, 2 * C, H, W, generator=g)  # [attention output | conv branch]
@@ -203,7 +207,12 @@ def test_aim_op(mode, C, B, H, W, dtype):
     pb.conv(INPUT, raw, torch.eye(2 * C).view(2 * C, 2 * C, 1, 1))
     pb.conv(raw, att, _select(C, 2 * C, 0))
     pb.conv(raw, convx, _select(C, 2 * C, C))
-    pb.op(N.OP_AIM, att, y, C, src2=convx, ints=(mode, h1, h2), weights=(ci_w1, ci_b1, ci_w2, ci_b2, si_w1, si_b1, si_w2, si_b2))
+    hid_id = 0
+    if hid_conv:
+        hid = pb.buffer(16)
+        pb.conv(att if mode == 0 else convx, hid.slice(0, h2), si_w1.view(h2, C, 1, 1), si_b1, act=N.ACT_GELU)
+        hid_id = hid.buf + 1
+    pb.op(N.OP_AIM, att, y, C, src2=convx, ints=(mode, h1, h2, hid_id), weights=(ci_w1, ci_b1, ci_w2, ci_b2, si_w1, si_b1, si_w2, si_b2))
     pb.conv(y, OUTPUT, torch.eye(C).view(C, C, 1, 1))
     got, _ = _run(pb, x, dtype)
     xq = _q(x, dtype)
