@@ -262,7 +262,8 @@ enum rsb_kernel_id {
 typedef struct rsb_op_info {
   int32_t kind;       /* 0 convolution, 1 GroupNorm, 2 token / attention op                                        */
   int32_t kernel;     /* rsb_kernel_id of the (main) kernel                                                        */
-  int32_t fused_next; /* 1: this conv and the next op run as ONE fused launch; the totals below cover both ops      */
+  int32_t fused_next; /* k > 0: this conv and the next k ops run as ONE launch (a fused pair; an N-split group of convs over
+                         the same source); the totals below cover all of them and the followers report launches == 0 */
   int32_t launches;   /* kernels launched for this op (0 for the second op of a fused pair)                         */
   double flops;       /* 2 * MACs at the bound shape (convolutions; 0 otherwise)                                    */
   double bytes;       /* algorithmic HBM bytes at the bound shape: inputs + residuals read, outputs written (convs) */

@@ -18,6 +18,7 @@
 //              PixelShuffle (kernels.cuh::epilogue8) -> 16-byte stores, 8 neighbouring pixels filling a 128-byte line.
 // The packed weights of the layer ([tap][cin/8][npad][8] bf16, also canonical K-major), its bias and PReLU slopes
 // stay resident in shared memory for the CTA's lifetime.
+#include <algorithm>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -48,6 +49,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   const int S = p.stages;
   const int A = p.num_acc;
   pdl_launch_dependents();
+  // N-split group (ConvTcParams::nsplit): this CTA's slice, and its position among the CTAs of that slice
+  const bool split = p.nsplit > 1;
+  const int sl = split ? (int)blockIdx.x % p.nsplit : 0;
+  const int bid = split ? (int)blockIdx.x / p.nsplit : (int)blockIdx.x;
+  const int nblk = split ? (int)gridDim.x / p.nsplit : (int)gridDim.x;
+  const void* const wpack_g = split ? p.slice[sl].wpack : p.wpack;
+  const float* const bias_g = split ? p.slice[sl].bias : p.epi.bias;
+  const float* const aux_g = split ? p.slice[sl].aux : (p.epi.ln_stats != nullptr ? p.epi.ln_rowsum : p.epi.slopes);
+  const int coff = split ? p.slice[sl].dst_plane_off * 8 : 0;  // channel offset of the slice inside the destination range
+  const int cout_s = split ? p.slice[sl].cout : p.epi.cout;
 
   const uint32_t w_al = align_up(p.wbytes, kAlign);
   const uint32_t st_al = align_up(p.stage_bytes, kAlign);
@@ -86,9 +97,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
-    bias_sm[i] = p.epi.bias[i];
+    bias_sm[i] = bias_g[i];
     // (a conv with a folded LayerNorm has no PReLU: the slot holds the weights' row sums instead)
-    slope_sm[i] = p.epi.ln_stats != nullptr ? p.epi.ln_rowsum[i] : (p.epi.slopes != nullptr ? p.epi.slopes[i] : 0.0f);
+    slope_sm[i] = aux_g != nullptr ? aux_g[i] : 0.0f;
   }
   const int HT = kTileH + p.kh - 1;
   const int WT = kTileW + p.kw - 1;
@@ -110,12 +121,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       mbar_expect_tx(wbar, p.wbytes);
       for (uint32_t off = 0; off < p.wbytes; off += 32768u) {
         const uint32_t len = min(32768u, p.wbytes - off);
-        bulk_load_1d(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, len, wbar);
+        bulk_load_1d(wsm + off, reinterpret_cast<const uint8_t*>(wpack_g) + off, len, wbar);
       }
       int s = 0;
       uint32_t ph = 0;
       const int cp8 = p.kchunk >> 3;  // planes per K chunk (one shared-memory stage holds one chunk of one tile)
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = bid; tile < p.num_tiles; tile += nblk) {
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -148,7 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const uint32_t a_kstep = 2u * (a_lbo >> 4);  // descriptor address units (16 B) per 16-channel K step
     const uint32_t b_kstep = 2u * (b_lbo >> 4);
     int i = first;
-    for (int tile = blockIdx.x + first * gridDim.x; tile < p.num_tiles && !(solo && warp == 3); tile += tstep * gridDim.x, i += tstep) {
+    for (int tile = bid + first * nblk; tile < p.num_tiles && !(solo && warp == 3); tile += tstep * nblk, i += tstep) {
       const int acc = i % A;
       const uint32_t aph = (uint32_t)(i / A) & 1u;
       mbar_wait(&tempty[acc], aph ^ 1);
@@ -221,10 +232,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       const int q = warp & 3;  // TMEM lane quarter this warp may read
       const int row = q * 32 + lane;
       const int ry = row >> 3, rx = row & 7;
-      const int cstore = (p.epi.cout + 7) & ~7;
+      const int cstore = (cout_s + 7) & ~7;
+      // a slice of an N-split group addresses bias / destination by its channel offset inside the group's destination range
+      const float* const bias_e = bias_sm - coff;
+      const float* const slope_e = slope_sm - coff;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * p.acc_stride;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x + g * gridDim.x; tile < p.num_tiles; tile += A * gridDim.x) {
+      for (int tile = bid + g * nblk; tile < p.num_tiles; tile += A * nblk) {
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -252,7 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           uint32_t r[2][16];
           tmem_ld16(taddr, r[0]);
           const bool lean = EXT == 0 && p.epi.simple;
-          T* const drow = reinterpret_cast<T*>(p.epi.dst) + planar_index(n, p.epi.dst_planes, p.epi.dst_plane0, p.H, p.W, y, x);
+          T* const drow = reinterpret_cast<T*>(p.epi.dst) + planar_index(n, p.epi.dst_planes, p.epi.dst_plane0 + (coff >> 3), p.H, p.W, y, x);
           const size_t dstride = (size_t)p.H * p.W * 8;
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
@@ -269,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], lnst.x, lnst.y * slope_sm[c + j]);
               }
-              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr, true);
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_e, slope_e, v, coff + c, n, y, x, kUsesRes ? &pre[2 * ci] : nullptr, true);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[ci & 1][8 + j]);
               if (ln) {
@@ -277,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], lnst.x, lnst.y * slope_sm[c + 8 + j]);
               }
               if (c + 8 < cstore)
-                epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr, true);
+                epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_e, slope_e, v, coff + c + 8, n, y, x, kUsesRes ? &pre[2 * ci + 1] : nullptr, true);
             }
           }
         } else {
@@ -303,20 +317,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                   if (c + 8 < cstore) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)((c >> 3) + 1) * plane_stride));
                 }
               };
-              if (tile == blockIdx.x + g * (int)gridDim.x) prefetch_tile(tile);  // first tile of this warpgroup
-              prefetch_tile(tile + A * (int)gridDim.x);
+              if (tile == bid + g * nblk) prefetch_tile(tile);  // first tile of this warpgroup
+              prefetch_tile(tile + A * nblk);
             }
           }
           const bool ln = p.epi.ln_stats != nullptr;
           float2 lnst = make_float2(1.0f, 0.0f);
           if (ln && valid) lnst = ln_stats_of(p.epi, n, y, x);  // folded LayerNorm: {rstd, -mean * rstd} of this pixel
+          // Lean form for planar destinations (no sub-pixel scatter / split / second residual / border bias): row pointers once per
+          // tile, per 8 channels one fused multiply-add per element (bias and the LayerNorm shift merged), the residual chunk, a
+          // 16-byte store.  The token linears (K = 192: twelve MMAs per tile) are bound by the ISSUE of this epilogue, not by HBM:
+          // the generic epilogue8 re-derives the planar address and re-tests the destination kind for every 8 channels.
+          const int comb_rt = COMB == kRuntime ? p.epi.combine : COMB;
+          const bool lean = (EXT == 0 || !p.epi.dst_external) && p.epi.dst_ps <= 1 && p.epi.dst2 == nullptr && p.epi.res2 == nullptr &&
+                            p.epi.border_bias == nullptr && comb_rt != RSB_COMB_SPAB_GATE;
+          const size_t pstride = (size_t)p.H * p.W * 8;
+          T* const drow = lean && valid ? reinterpret_cast<T*>(p.epi.dst) + planar_index(n, p.epi.dst_planes, p.epi.dst_plane0 + (coff >> 3), p.H, p.W, y, x) : nullptr;
+          const T* const rrow = lean && valid && comb_rt != RSB_COMB_NONE
+                                    ? reinterpret_cast<const T*>(p.epi.res1) + planar_index(n, p.epi.res1_planes, p.epi.res1_plane0 + (coff >> 3), p.H, p.W, y, x)
+                                    : nullptr;
           mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
           for (int c = part * 16; c < p.npad; c += 16 * parts) {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)c, r);
             tmem_ld_wait();
-            if (valid) {
+            if (!valid) continue;
+            if (lean) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int c0 = c + 8 * half;
+                if (c0 >= cstore) break;
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + c0), b1 = *reinterpret_cast<const float4*>(bias_sm + c0 + 4);
+                float t[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float v[8];
+                if (ln) {
+                  const float4 s0 = *reinterpret_cast<const float4*>(slope_sm + c0), s1 = *reinterpret_cast<const float4*>(slope_sm + c0 + 4);
+                  const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[8 * half + j]), lnst.x, fmaf(lnst.y, sv[j], t[j]));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * half + j]) + t[j];
+                }
+                const int act_rt = ACT == kRuntime ? p.epi.act : ACT;
+                if (act_rt != RSB_ACT_NONE) {
+                  float sl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                  if (act_rt == RSB_ACT_PRELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sl[j] = slope_sm[c0 + j];
+                  }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = activate<true, ACT>(p.epi.act, v[j], p.epi.act_param, sl[j]);
+                }
+                if (comb_rt != RSB_COMB_NONE) {
+                  float rr[8];
+                  unpack8<__nv_bfloat16>(*reinterpret_cast<const uint4*>(rrow + (size_t)(c0 >> 3) * pstride), rr);
+                  if (comb_rt == RSB_COMB_MUL) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] *= rr[j];
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(p.epi.alpha, v[j], p.epi.beta1 * rr[j]);
+                  }
+                }
+                store8<T>(drow + (size_t)(c0 >> 3) * pstride, v);
+              }
+              continue;
+            }
+            {
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
@@ -325,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 v[0] = fmaf(v[0], lnst.x, lnst.y * s0.x), v[1] = fmaf(v[1], lnst.x, lnst.y * s0.y), v[2] = fmaf(v[2], lnst.x, lnst.y * s0.z), v[3] = fmaf(v[3], lnst.x, lnst.y * s0.w);
                 v[4] = fmaf(v[4], lnst.x, lnst.y * s1.x), v[5] = fmaf(v[5], lnst.x, lnst.y * s1.y), v[6] = fmaf(v[6], lnst.x, lnst.y * s1.z), v[7] = fmaf(v[7], lnst.x, lnst.y * s1.w);
               }
-              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c, n, y, x, nullptr, true);
+              if (c < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_e, slope_e, v, coff + c, n, y, x, nullptr, true);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 + j]);
               if (ln) {
@@ -333,7 +402,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 v[0] = fmaf(v[0], lnst.x, lnst.y * s0.x), v[1] = fmaf(v[1], lnst.x, lnst.y * s0.y), v[2] = fmaf(v[2], lnst.x, lnst.y * s0.z), v[3] = fmaf(v[3], lnst.x, lnst.y * s0.w);
                 v[4] = fmaf(v[4], lnst.x, lnst.y * s1.x), v[5] = fmaf(v[5], lnst.x, lnst.y * s1.y), v[6] = fmaf(v[6], lnst.x, lnst.y * s1.z), v[7] = fmaf(v[7], lnst.x, lnst.y * s1.w);
               }
-              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_sm, slope_sm, v, c + 8, n, y, x, nullptr, true);
+              if (c + 8 < cstore) epilogue8<T, true, ACT, COMB, EXT>(p.epi, bias_e, slope_e, v, coff + c + 8, n, y, x, nullptr, true);
             }
           }
         }
@@ -443,7 +512,9 @@ cudaError_t conv_tc_configure(size_t max_smem) {
 
 cudaError_t launch_conv_tc(const CUtensorMap& src_map, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_tc_smem_bytes(p.cin, p.kchunk, p.npad, p.kh, p.kw, p.stages);
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const int ns = p.nsplit > 1 ? p.nsplit : 1;
+  const int per = std::max(1, num_sms / ns);  // CTAs per slice
+  const int grid = (p.num_tiles < per ? p.num_tiles : per) * ns;
   const int threads = kMaxThreads;
   KernelFn fn = pick(p);
   return launch_pdl(fn, dim3(grid), dim3(threads), smem, stream, src_map, p);

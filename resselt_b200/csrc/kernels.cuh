@@ -449,6 +449,19 @@ struct ConvTcParams {
   uint32_t acc_stride;   // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;    // allocation (power of two >= 32)
   Epi epi;
+  // N-split group: nsplit > 1 convs that read the SAME source with the same geometry (q / k / v, the halves of an MLP's first
+  // linear) run as one launch.  CTA b serves slice b % nsplit with the weights / bias of that conv and walks the tiles
+  // b / nsplit + k * gridDim / nsplit, so the nsplit CTAs that need a source tile ask for it at about the same time and all but
+  // one of them are served by L2: the source is read from HBM once instead of nsplit times.  Everything not listed in the slice
+  // (shape, activation, destination buffer) is the same for all of them.
+  int nsplit;
+  struct Slice {
+    const void* wpack;
+    const float* bias;
+    const float* aux;   // PReLU slopes, or the row sums of a folded LayerNorm, or null
+    int dst_plane_off;  // destination plane of this slice's channel 0, relative to epi.dst_plane0
+    int cout;
+  } slice[3];
 };
 
 // Row-streaming 3x3 kernel (conv_rs.cu): units are (image, 128-pixel column strip, row)

@@ -123,6 +123,11 @@ struct ConvOp {
   // fused pair kernel (conv_pair.cu): this conv is the head (A) of a pair with the next op; decided at finalize
   bool pair_head = false, pair_ready = false;
   bool pair_store = false;  // a later op reads this conv's output: the pair kernel writes it to its buffer as well
+  // N-split group (ConvTcParams::nsplit): this conv heads a run of group_n consecutive convs over the same source that go out as
+  // one launch (gtcp); `grouped` marks the others
+  int group_n = 1;
+  bool grouped = false;
+  rsb::ConvTcParams gtcp;
   // bound state
   CUtensorMap map, map_rs, map_res;  // map_res: the pair's second conv's residual rows (L2 prefetch)
   rsb::ConvTcParams tcp;
@@ -537,6 +542,56 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     }
     q.wpack = c.d_wdirect;
     fill_epi(p, c, n, H, W, ws, q.epi);
+  }
+  // ---- N-split groups: runs of up to three consecutive tile-kernel convs that read the same source with the same geometry and
+  // differ only in weights / bias / destination channel offset (q, k, v; the halves of an MLP's first linear)
+  for (ConvOp& c : p->convs) c.group_n = 1, c.grouped = false;
+  {
+    static const bool no_split = rsb::rsb_env("RSB_NO_NSPLIT") != nullptr;
+    auto tile_only = [&](const ConvOp& c) {
+      return c.tc_ok && c.pack_buf < 0 && !(c.rs_ready && c.rs_pref) && !(c.lk_ready && c.rs_pref) && !c.pair_head;
+    };
+    auto same = [&](const ConvOp& a, const ConvOp& b) {
+      const rsb_conv_desc &x = a.d, &y = b.d;
+      const rsb::ConvTcParams &s = a.tcp, &t = b.tcp;
+      return a.tc_src_buf == b.tc_src_buf && a.tc_src_ch_off == b.tc_src_ch_off && a.tc_cin == b.tc_cin && a.scale == b.scale &&
+             x.kh == y.kh && x.kw == y.kw && x.pad_t == y.pad_t && x.pad_l == y.pad_l && x.dst_buf == y.dst_buf && x.dst_buf >= 0 &&
+             x.dst_ps <= 1 && y.dst_ps <= 1 && x.dst2_buf < 0 && y.dst2_buf < 0 && x.act == y.act && x.act_param == y.act_param &&
+             x.combine == RSB_COMB_NONE && y.combine == RSB_COMB_NONE && a.border.empty() && b.border.empty() &&
+             x.ln_fold == y.ln_fold && (!x.ln_fold || x.ln_stats_buf == y.ln_stats_buf) && a.npad == b.npad && s.stages == t.stages &&
+             s.kchunk == t.kchunk && s.solo_issue == t.solo_issue && s.num_acc == t.num_acc && s.acc_stride == t.acc_stride &&
+             s.tmem_cols == t.tmem_cols && s.wbytes == t.wbytes && s.stage_bytes == t.stage_bytes && y.dst_ch_off >= x.dst_ch_off;
+    };
+    for (size_t i = 0; i + 1 < p->ops.size() && !no_split; ++i) {
+      if (p->ops[i].kind != 0) continue;
+      ConvOp& a = p->convs[p->ops[i].index];
+      if (!tile_only(a) || a.d.dst_buf == a.tc_src_buf) continue;
+      int k = 1;
+      while (k < 3 && i + k < p->ops.size() && p->ops[i + k].kind == 0 && p->num_sms / (k + 1) >= 1) {
+        const ConvOp& b = p->convs[p->ops[i + k].index];
+        if (!tile_only(b) || !same(a, b)) break;
+        // destinations must not overlap one another
+        bool clash = false;
+        for (int j = 0; j < k && !clash; ++j) clash = overlaps(conv_dst(p->convs[p->ops[i + j].index]), conv_dst(b));
+        if (clash) break;
+        ++k;
+      }
+      if (k < 2) continue;
+      a.group_n = k;
+      a.gtcp = a.tcp;
+      a.gtcp.nsplit = k;
+      for (int j = 0; j < k; ++j) {
+        ConvOp& b = p->convs[p->ops[i + j].index];
+        if (j > 0) b.grouped = true;
+        rsb::ConvTcParams::Slice& sl = a.gtcp.slice[j];
+        sl.wpack = b.d_wtc;
+        sl.bias = b.d_bias;
+        sl.aux = b.d.ln_fold ? b.d_lnsum : b.d_slopes;
+        sl.dst_plane_off = (b.d.dst_ch_off - a.d.dst_ch_off) / 8;
+        sl.cout = b.d.cout;
+      }
+      i += k - 1;
+    }
   }
   for (size_t i = 0; i + 1 < p->ops.size(); ++i) {
     if (p->ops[i].kind != 0) continue;
@@ -1241,6 +1296,18 @@ int rsb_plan_op_info(const rsb_plan* p, int op_index, rsb_op_info* out) {
     }
     out->flops = flops(c);
     out->bytes = in_bytes(c) + res_bytes(c) + out_bytes(c);
+    if (p->info_mode != 1 && c.grouped) {  // runs inside the launch of the group's head
+      out->kernel = RSB_K_CONV_TC, out->launches = 0, out->flops = 0.0, out->bytes = 0.0;
+      return 0;
+    }
+    if (p->info_mode != 1 && c.group_n > 1 && op_index + c.group_n <= (int)p->ops.size()) {
+      out->kernel = RSB_K_CONV_TC, out->fused_next = c.group_n - 1;
+      for (int j = 1; j < c.group_n; ++j) {
+        const ConvOp& b = p->convs[p->ops[op_index + j].index];
+        out->flops += flops(b), out->bytes += out_bytes(b);  // the source is read once
+      }
+      return 0;
+    }
     if (!c.tc_ok)
       out->kernel = RSB_K_CONV_DIRECT;
     else {
@@ -1360,6 +1427,9 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
             rsb::ConvRsParams q = c.rsp;
             q.epi = t.epi;
             e = rsb::launch_conv_rs(c.map_rs, q, p->num_sms, stream);
+          } else if (c.group_n > 1 && oi + c.group_n <= op_end) {
+            e = rsb::launch_conv_tc(c.map, c.gtcp, p->num_sms, stream);  // this conv and the next group_n - 1 as one launch
+            oi += c.group_n - 1;
           } else
             e = rsb::launch_conv_tc(c.map, t, p->num_sms, stream);
         } else {

@@ -329,20 +329,20 @@ class Plan:
         """Kernel, launch count, algorithmic FLOPs / HBM bytes of op ``index`` at the shape of the last forward."""
         info = N.OpInfo()
         N.check(self._lib.rsb_plan_op_info(self._h, index, C.byref(info)))
-        return dict(kind=info.kind, kernel=(self._lib.rsb_kernel_name(info.kernel) or b'').decode(), fused_next=bool(info.fused_next),
+        return dict(kind=info.kind, kernel=(self._lib.rsb_kernel_name(info.kernel) or b'').decode(), fused_next=int(info.fused_next),
                     launches=info.launches, flops=info.flops, bytes=info.bytes)
 
     @property
     def fused_pairs(self) -> int:
         """Fused conv-pair launches per forward at the shape of the last forward."""
-        return sum(1 for i in range(self.num_ops) if self.op_info(i)['fused_next'])
+        return sum(1 for i in range(self.num_ops) if self.op_info(i)['fused_next'] and self.op_info(i)['kernel'] == 'conv_pair')
 
     def launch_units(self):
         """[(op_begin, op_end, info)] — the op ranges that run as one kernel launch group (a fused pair is one unit)."""
         units, i = [], 0
         while i < self.num_ops:
             info = self.op_info(i)
-            j = i + (2 if info['fused_next'] else 1)
+            j = i + 1 + info['fused_next']
             units.append((i, j, info))
             i = j
         return units
