@@ -338,16 +338,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                                     : nullptr;
           mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
-          for (int c = part * 16; c < p.npad; c += 16 * parts) {
-            uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t)c, r);
-            tmem_ld_wait();
-            if (!valid) continue;
-            if (lean) {
+          if (lean) {
+            auto emit = [&](const uint32_t (&r)[16], int c) {
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
                 const int c0 = c + 8 * half;
                 if (c0 >= cstore) break;
+                const uint32_t* const r8 = &r[8 * half];
                 const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + c0), b1 = *reinterpret_cast<const float4*>(bias_sm + c0 + 4);
                 float t[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float v[8];
@@ -355,10 +352,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                   const float4 s0 = *reinterpret_cast<const float4*>(slope_sm + c0), s1 = *reinterpret_cast<const float4*>(slope_sm + c0 + 4);
                   const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[8 * half + j]), lnst.x, fmaf(lnst.y, sv[j], t[j]));
+                  for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r8[j]), lnst.x, fmaf(lnst.y, sv[j], t[j]));
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * half + j]) + t[j];
+                  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r8[j]) + t[j];
                 }
                 const int act_rt = ACT == kRuntime ? p.epi.act : ACT;
                 if (act_rt != RSB_ACT_NONE) {
@@ -383,8 +380,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 }
                 store8<T>(drow + (size_t)(c0 >> 3) * pstride, v);
               }
-              continue;
+            };
+            // software-pipelined accumulator reads, two chunks per round: the next chunk's tcgen05.ld is in flight while this one
+            // goes through the epilogue
+            const int cstep = 16 * parts;
+            uint32_t ra[16], rbb[16];
+            int c = part * 16;
+            if (c < p.npad) tmem_ld16(taddr + (uint32_t)c, ra);
+            for (; c < p.npad; c += 2 * cstep) {
+              tmem_ld_wait();
+              if (c + cstep < p.npad) tmem_ld16(taddr + (uint32_t)(c + cstep), rbb);
+              if (valid) emit(ra, c);
+              if (c + cstep < p.npad) {
+                tmem_ld_wait();
+                if (c + 2 * cstep < p.npad) tmem_ld16(taddr + (uint32_t)(c + 2 * cstep), ra);
+                if (valid) emit(rbb, c + cstep);
+              }
             }
+          } else
+          for (int c = part * 16; c < p.npad; c += 16 * parts) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)c, r);
+            tmem_ld_wait();
+            if (!valid) continue;
             {
               float v[8];
 #pragma unroll
