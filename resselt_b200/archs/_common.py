@@ -78,6 +78,40 @@ def merge_pointwise_into_conv(w1: torch.Tensor, b1, wk: torch.Tensor, bk):
 
 
 # ------------------------------------------------------------------------------------------------ DySample head
+HEAD_PAD = 32  # channel stride of a head in the head-padded q / k / v layout (csrc/winattn_tc.cu)
+
+
+def winattn_head_padded(compute_dtype, dim: int, heads: int, split) -> bool:
+    """True when window attention can run on the tcgen05 kernel (rsb_op_desc.i[5] = 32): bf16 plan, even heads, head_dim < 32,
+    windows of 64 / 128 / 256 tokens whose sides are multiples of 8 (mirrors ``winattn_tc_supported`` in csrc/winattn_tc.cu)."""
+    hs, ws = int(split[0]), int(split[1])
+    return (compute_dtype == torch.bfloat16 and heads % 2 == 0 and dim % heads == 0 and dim // heads < HEAD_PAD
+            and hs * ws in (64, 128, 256) and hs % 8 == 0 and ws % 8 == 0 and max(hs, ws) <= 32)
+
+
+def head_pad_index(dim: int, heads: int) -> torch.Tensor:
+    """Position of channel c (head c // d, dim c % d) in the head-padded layout: (c // d) * 32 + c % d."""
+    d = dim // heads
+    c = torch.arange(dim)
+    return (c // d) * HEAD_PAD + c % d
+
+
+def pad_head_rows(t, dim: int, heads: int):
+    """Scatter dim 0 of a [dim, ...] tensor (an output-channel axis: weight rows, bias) into [heads * 32, ...], zeros elsewhere."""
+    if t is None:
+        return None
+    out = t.new_zeros((heads * HEAD_PAD,) + tuple(t.shape[1:]))
+    out[head_pad_index(dim, heads)] = t
+    return out
+
+
+def pad_head_cols(t, dim: int, heads: int):
+    """Scatter dim 1 of a [out, dim, ...] tensor (an input-channel axis) into [out, heads * 32, ...], zeros elsewhere."""
+    out = t.new_zeros((t.shape[0], heads * HEAD_PAD) + tuple(t.shape[2:]))
+    out[:, head_pad_index(dim, heads)] = t
+    return out
+
+
 def dysample_init_pos(scale: int, groups: int) -> torch.Tensor:
     """The ``init_pos`` buffer exactly as DySample._init_pos builds it (/root/reference/resselt/utilities/dysample.py:42-44)."""
     h = torch.arange((-scale + 1) / 2, (scale - 1) / 2 + 1) / scale

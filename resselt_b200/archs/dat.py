@@ -24,7 +24,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import get_seq_len, pixelshuffle_scale
-from ._common import conv_specs, emit_resi_conv, resi_conv_specs
+from ._common import HEAD_PAD, conv_specs, emit_resi_conv, pad_head_cols, pad_head_rows, resi_conv_specs, winattn_head_padded
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)
 
@@ -175,9 +175,15 @@ class DAT(EngineModule):
         lin_w = lambda name: w[f'{name}.weight'].view(*w[f'{name}.weight'].shape, 1, 1)
         lin_b = lambda name: w.get(f'{name}.bias')
         feat, x, xn = pb.buffer(dim), pb.buffer(dim), pb.buffer(dim)
-        pad = (dim + 15) // 16 * 16            # q | k | v (and the two FFN halves) start on 16-channel boundaries
+        # window blocks on a bf16 plan with head_dim < 32 and 8-aligned windows of 64 / 128 / 256 tokens: every head of q, k, v on a
+        # 32-channel stride (zero rows of the qkv weights) -> the tcgen05 window-attention kernel (winattn_tc.cu).  Everything between
+        # qkv and proj of such a block (attention output, depthwise-conv branch, AIM) then lives in that head-padded channel space:
+        # the padding channels are zeros that meet zero weights, proj's padded input columns are zero
+        padded = {h: winattn_head_padded(pb.compute_dtype, dim, h, self.split) for h in set(self.heads)}
+        apad = max([dim] + [h * HEAD_PAD for h in padded if padded[h]])
+        pad = max((dim + 15) // 16 * 16, apad)  # q | k | v (and the two FFN halves) start on 16-channel boundaries
         qkv = pb.buffer(3 * pad)
-        att, convx, y = pb.buffer(dim), pb.buffer(dim), pb.buffer(dim)
+        att, convx, y = pb.buffer(apad), pb.buffer(apad), pb.buffer(apad)
         half = hidden // 2
         hpad = (half + 15) // 16 * 16
         hid, gate_n, gated = pb.buffer(2 * hpad), pb.buffer(half), pb.buffer(half)
@@ -203,27 +209,33 @@ class DAT(EngineModule):
                 pb.layernorm_stats(x, stats)
                 ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
                 wq, bq = lin_w(f'{a}.qkv'), lin_b(f'{a}.qkv')
+                hp = b % 2 == 0 and padded[heads]
+                width = heads * HEAD_PAD if hp else dim            # channels of this block's attention space
+                rows_p = (lambda t: pad_head_rows(t, dim, heads)) if hp else (lambda t: t)   # output-channel axis -> padded layout
+                cols_p = (lambda t: pad_head_cols(t, dim, heads)) if hp else (lambda t: t)   # input-channel axis
                 for part in range(3):  # one conv per q / k / v (UMMA N <= 256)
                     rows = slice(part * dim, (part + 1) * dim)
-                    pb.conv(x, qkv.slice(part * pad, dim), wq[rows], None if bq is None else bq[rows], ln=ln1)
+                    pb.conv(x, qkv.slice(part * pad, width), rows_p(wq[rows]), None if bq is None else rows_p(bq[rows]), ln=ln1)
+                att_b, convx_b, y_b = att.slice(0, width), convx.slice(0, width), y.slice(0, width)
                 if b % 2 == 0:
                     t0, t1 = self._pos_table(w, f'{a}.attns.0'), self._pos_table(w, f'{a}.attns.1')
-                    pb.op(N.OP_WINATTN, qkv, att, dim, ints=(heads, self.split[0], self.split[1], int(_is_shifted(rg, b)), pad),
+                    pb.op(N.OP_WINATTN, qkv, att_b, dim, ints=(heads, self.split[0], self.split[1], int(_is_shifted(rg, b)), pad, HEAD_PAD if hp else 0),
                           floats=((dim // heads) ** -0.5,), weights=(t0, t1))
                 else:
-                    pb.op(N.OP_CHANATTN, qkv, att, dim, ints=(heads, pad), weights=(w[f'{a}.temperature'],))
+                    pb.op(N.OP_CHANATTN, qkv, att_b, dim, ints=(heads, pad), weights=(w[f'{a}.temperature'],))
                 dw_w, dw_b = self._fold_bn(w, f'{a}.dwconv.0', f'{a}.dwconv.1')
-                pb.dwconv3(qkv.slice(2 * pad, dim), convx, dw_w, dw_b, act=N.ACT_GELU)
+                pb.dwconv3(qkv.slice(2 * pad, width), convx_b, rows_p(dw_w), rows_p(dw_b), act=N.ACT_GELU)
                 ci_w1, ci_b1 = self._fold_bn(w, f'{a}.channel_interaction.1', f'{a}.channel_interaction.2')
                 si_w1, si_b1 = self._fold_bn(w, f'{a}.spatial_interaction.0', f'{a}.spatial_interaction.1')
+                ci_w1, si_w1 = cols_p(ci_w1), cols_p(si_w1)
                 hid_id = 0
                 if si_hid is not None:  # spatial map source: the attention output in window blocks, the conv branch in channel blocks
-                    pb.conv(att if b % 2 == 0 else convx, si_hid.slice(0, dim // 16), si_w1.reshape(dim // 16, dim, 1, 1), si_b1, act=N.ACT_GELU)
+                    pb.conv(att_b if b % 2 == 0 else convx_b, si_hid.slice(0, dim // 16), si_w1.reshape(dim // 16, width, 1, 1), si_b1, act=N.ACT_GELU)
                     hid_id = si_hid.buf + 1
-                pb.op(N.OP_AIM, att, y, dim, src2=convx, ints=(b % 2, dim // 8, dim // 16, hid_id),
-                      weights=(ci_w1, ci_b1, w[f'{a}.channel_interaction.4.weight'], w[f'{a}.channel_interaction.4.bias'],
+                pb.op(N.OP_AIM, att_b, y_b, width, src2=convx_b, ints=(b % 2, dim // 8, dim // 16, hid_id),
+                      weights=(ci_w1, ci_b1, rows_p(w[f'{a}.channel_interaction.4.weight']), rows_p(w[f'{a}.channel_interaction.4.bias']),
                                si_w1, si_b1, w[f'{a}.spatial_interaction.3.weight'], w[f'{a}.spatial_interaction.3.bias']))
-                pb.conv(y, x, lin_w(f'{a}.proj'), lin_b(f'{a}.proj'), combine=N.COMB_AXPY, res1=x)        # x += proj(...)
+                pb.conv(y_b, x, cols_p(lin_w(f'{a}.proj')), lin_b(f'{a}.proj'), combine=N.COMB_AXPY, res1=x)        # x += proj(...)
                 f = f'{p}.ffn'
                 pb.layernorm_stats(x, stats)
                 ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
@@ -237,6 +249,7 @@ class DAT(EngineModule):
             emit_resi_conv(pb, w, f'layers.{rg}.conv', self.resi_connection, x, img, rg_res, tmp_a, tmp_b)
             x, img = img, x
         pb.layernorm(x, xn, w['norm.weight'], w['norm.bias'])
+        y = y.slice(0, dim)
         emit_resi_conv(pb, w, 'conv_after_body', self.resi_connection, xn, y, feat, tmp_a, tmp_b)
         omean = mean if self.in_channels == 3 else (0.0, 0.0, 0.0)
         if self.upsampler_kind == 'pixelshuffledirect':

@@ -28,7 +28,7 @@ from ..engine import INPUT, OUTPUT, EngineModule, PlanBuilder
 from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import get_pixelshuffle_params, get_seq_len
-from ._common import conv_specs, emit_resi_conv, resi_conv_specs
+from ._common import HEAD_PAD, conv_specs, emit_resi_conv, pad_head_cols, pad_head_rows, resi_conv_specs, winattn_head_padded
 from .dat import RGB_MEAN, _lin_specs, _ln_specs
 from .esrgan import upconv_phase_kernels
 
@@ -133,9 +133,13 @@ class SwinIR(EngineModule):
         dim, hidden, ws = self.dim, self.hidden, self.window_size
         lin_w = lambda name: w[f'{name}.weight'].view(*w[f'{name}.weight'].shape, 1, 1)
         lin_b = lambda name: w.get(f'{name}.bias')
-        feat, xn, att = pb.buffer(dim), pb.buffer(dim), pb.buffer(dim)
+        # bf16 plan, 8x8 windows, head_dim < 32: heads on 32-channel strides -> the tcgen05 window-attention kernel (winattn_tc.cu);
+        # the padding is zero rows of the qkv weights and zero columns of proj, so it costs no pass
+        padded = {h: winattn_head_padded(pb.compute_dtype, dim, h, (ws, ws)) for h in set(self.heads)}
+        apad = max([dim] + [h * HEAD_PAD for h in padded if padded[h]])
+        feat, xn, att = pb.buffer(dim), pb.buffer(dim), pb.buffer(apad)
         a, b, c = pb.buffer(dim), pb.buffer(dim), pb.buffer(dim)
-        pad = (dim + 15) // 16 * 16  # q | k | v start on 16-channel boundaries
+        pad = max((dim + 15) // 16 * 16, apad)  # q | k | v start on 16-channel boundaries
         # wide MLPs: hidden width padded with zero weights to a multiple of 64 so fc2 stages whole 64-channel K chunks
         hpad = hidden if hidden <= 128 else (hidden + 63) // 64 * 64
         qkv, hid = pb.buffer(3 * pad), pb.buffer(hpad)
@@ -153,13 +157,20 @@ class SwinIR(EngineModule):
                 pb.layernorm_stats(cur, stats)  # norm1 -> qkv: LayerNorm applied in the linears' epilogues, its output never written
                 ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
                 wq, bq = lin_w(f'{p}.attn.qkv'), lin_b(f'{p}.attn.qkv')
+                hp = padded[heads]
+                width = heads * HEAD_PAD if hp else dim
                 for part in range(3):  # one conv per q / k / v (UMMA N <= 256)
                     rows = slice(part * dim, (part + 1) * dim)
-                    pb.conv(cur, qkv.slice(part * pad, dim), wq[rows], None if bq is None else bq[rows], ln=ln1)
+                    wp, bp = wq[rows], None if bq is None else bq[rows]
+                    if hp:
+                        wp, bp = pad_head_rows(wp, dim, heads), pad_head_rows(bp, dim, heads)
+                    pb.conv(cur, qkv.slice(part * pad, width), wp, bp, ln=ln1)
                 table = w[f'{p}.attn.relative_position_bias_table']  # [(2w-1)^2][heads]; the kernel wants one table per head half
-                pb.op(N.OP_WINATTN, qkv, att, dim, ints=(heads, ws, ws, blk % 2, pad), floats=((dim // heads) ** -0.5,),
+                pb.op(N.OP_WINATTN, qkv, att, dim, ints=(heads, ws, ws, blk % 2, pad, HEAD_PAD if hp else 0), floats=((dim // heads) ** -0.5,),
                       weights=(table[:, : heads // 2].contiguous(), table[:, heads // 2:].contiguous()))
-                pb.conv(att, b, lin_w(f'{p}.attn.proj'), lin_b(f'{p}.attn.proj'), combine=N.COMB_AXPY, res1=cur)  # shortcut + attn
+                wproj = lin_w(f'{p}.attn.proj')
+                pb.conv(att.slice(0, width), b, pad_head_cols(wproj, dim, heads) if hp else wproj, lin_b(f'{p}.attn.proj'),
+                        combine=N.COMB_AXPY, res1=cur)  # shortcut + attn
                 cur = b
                 pb.layernorm_stats(cur, stats)  # norm2 -> fc1
                 ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
@@ -172,6 +183,7 @@ class SwinIR(EngineModule):
             self._resi_conv(pb, w, f'layers.{i}.conv', cur, c, a, tmp_a, tmp_b)  # RSTB: conv(blocks(x)) + x
             a, c = c, a
         pb.layernorm(a, xn, w['norm.weight'], w['norm.bias'])
+        att = att.slice(0, dim)
         self._resi_conv(pb, w, 'conv_after_body', xn, att, feat, tmp_a, tmp_b)
         out_kw = dict(out_scale=1.0 / self.img_range, out_mean=mean)
         if self.upsampler == 'pixelshuffledirect':

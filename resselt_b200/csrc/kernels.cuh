@@ -593,6 +593,8 @@ struct WinAttnParams {
   int dst_planes, dst_ch_off;
   const float* table0;  // [(2 split_h - 1)(2 split_w - 1)][heads / 2]
   const float* table1;  // [(2 split_w - 1)(2 split_h - 1)][heads / 2]
+  int head_pad;         // 0: heads packed (head h of branch br at channel br * dim / 2 + h * head_dim); 32: every head of q, k, v and
+                        // dst starts on a 32-channel boundary ((br * heads / 2 + h) * 32) -> the tcgen05 kernel (winattn_tc.cu)
 };
 
 struct ChanAttnParams {
@@ -663,6 +665,9 @@ cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s);
 size_t winattn_smem_bytes(int split_h, int split_w);
 cudaError_t winattn_configure();
 cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s);
+bool winattn_tc_supported(int heads, int head_dim, int split_h, int split_w);  // shapes the head-padded tcgen05 kernel takes
+cudaError_t winattn_tc_configure();
+cudaError_t launch_winattn_tc(const WinAttnParams& p, cudaStream_t s);
 cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, int num_sms, cudaStream_t s);
 cudaError_t launch_aim(const AimParams& p, bool bf16, int num_sms, cudaStream_t s);
 

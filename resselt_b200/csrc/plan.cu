@@ -718,6 +718,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       t.qkv_stride = d.i[4] > 0 ? d.i[4] : d.channels;
       t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_ch_off = d.dst_ch_off;
       t.table0 = a.dw[0], t.table1 = a.dw[1];
+      t.head_pad = d.i[5];
     } else if (d.kind == RSB_OP_CHANATTN) {
       rsb::ChanAttnParams& t = a.chan;
       memset(&t, 0, sizeof t);
@@ -1010,8 +1011,10 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
   if (d.src_buf < 0 || d.src_buf >= (int)p->bufs.size() || d.dst_buf < 0 || d.dst_buf >= (int)p->bufs.size())
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown buffer");
   const int stride = d.kind == RSB_OP_WINATTN ? d.i[4] : (d.kind == RSB_OP_CHANATTN ? d.i[1] : 0);
-  const int src_need = d.src_ch_off + (qkv ? 2 * (stride > 0 ? stride : d.channels) : 0) + d.channels;
-  const int dst_need = (d.kind == RSB_OP_LAYERNORM && d.i[0] == 1) ? 8 : d.channels;  // statistics mode writes one pixel chunk
+  const int head_pad = d.kind == RSB_OP_WINATTN ? d.i[5] : 0;  // heads on 32-channel boundaries (tcgen05 window attention)
+  const int qkv_span = head_pad ? d.i[0] * head_pad : d.channels;
+  const int src_need = d.src_ch_off + (qkv ? 2 * (stride > 0 ? stride : d.channels) : 0) + qkv_span;
+  const int dst_need = (d.kind == RSB_OP_LAYERNORM && d.i[0] == 1) ? 8 : qkv_span;  // statistics mode writes one pixel chunk
   if (src_need > p->bufs[d.src_buf].planes * 8 || d.dst_ch_off + dst_need > p->bufs[d.dst_buf].planes * 8)
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel range exceeds buffer");
   if (!qkv && (d.src_ch_off % 8 != 0 || d.dst_ch_off % 8 != 0))
@@ -1032,6 +1035,13 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
       const int64_t tab = (int64_t)(2 * d.i[1] - 1) * (2 * d.i[2] - 1) * (heads / 2);
       if (!d.w[0] || !d.w[1] || d.wn[0] != tab || d.wn[1] != tab)
         return fail(RSB_ERR_INVALID, "rsb_plan_add_op: position-bias tables must hold %lld entries", (long long)tab);
+      if (head_pad != 0) {
+        if (head_pad != 32 || p->dtype != RSB_BF16 || !rsb::winattn_tc_supported(heads, d.channels / heads, d.i[1], d.i[2]))
+          return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: head-padded window attention (i[5] = 32) needs a bf16 plan, head_dim < 32 and "
+                                           "8-aligned windows of 64 / 128 / 256 tokens");
+        if (d.src_ch_off % 8 != 0 || d.dst_ch_off % 8 != 0 || stride % 8 != 0 || stride < heads * head_pad)
+          return fail(RSB_ERR_INVALID, "rsb_plan_add_op: head-padded window attention needs 8-aligned channel offsets and a q/k/v stride >= heads * 32");
+      }
     }
   }
   if (d.kind == RSB_OP_AIM && (d.i[1] < 1 || d.i[1] > 64 || d.i[2] < 1 || d.i[2] > 16 || d.channels > 512))

@@ -15,7 +15,7 @@ import threading
 CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'csrc'))
 BRINGUP = bool(os.environ.get('RSB_BRINGUP'))  # bring-up flavour: separate library, never the one the product loads
 LIB_PATH = os.path.join(CSRC_DIR, 'libresselt_b200_bringup.so' if BRINGUP else 'libresselt_b200.so')
-SOURCES = ('conv_tc.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_lk.cu', 'conv_direct.cu', 'dat_ops.cu', 'rt_ops.cu', 'plan.cu')
+SOURCES = ('conv_tc.cu', 'conv_rs.cu', 'conv_pair.cu', 'conv_lk.cu', 'conv_direct.cu', 'dat_ops.cu', 'winattn_tc.cu', 'rt_ops.cu', 'plan.cu')
 HEADERS = ('kernels.cuh', 'ptx.cuh', os.path.join('..', '..', 'include', 'resselt_b200.h'))
 NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC')
 OBJ_DIR = os.path.join(CSRC_DIR, 'build')  # git-ignored object files, one per source

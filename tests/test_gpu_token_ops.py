@@ -140,6 +140,59 @@ def test_window_attention_op(dim, heads, split, shifted, B, H, W, dtype):
     _check(got, ref, dtype, bf16_tol=1.5e-2, what=f'window attention {split} shifted={shifted}')
 
 
+@pytest.mark.parametrize('dim,heads,split,shifted,B,H,W', [
+    (60, 2, (8, 32), 0, 1, 64, 64),      # DAT: 256-token windows = two 128-query tiles per window
+    (60, 2, (8, 32), 1, 1, 64, 96),      # shifted: roll + region mask in the seam windows
+    (180, 6, (8, 32), 1, 2, 40, 72),     # DAT's real head layout (3 heads per branch), H and W padded (zero tokens take part)
+    (120, 4, (32, 8), 1, 1, 50, 33),     # transposed split first
+    (60, 2, (8, 8), 0, 1, 48, 64),       # Swin: two 64-token windows per tile (block-diagonal P)
+    (180, 6, (8, 8), 1, 2, 40, 56),      # Swin shifted, odd number of windows (ragged last tile)
+    (48, 2, (8, 16), 1, 1, 32, 48),      # 128-token windows, head_dim 24
+    (32, 4, (16, 16), 0, 1, 32, 64),     # 16x16 windows, head_dim 8
+])
+def test_window_attention_tc_op(dim, heads, split, shifted, B, H, W):
+    """Head-padded layout -> tcgen05 kernel (csrc/winattn_tc.cu): heads on 32-channel strides in q / k / v and in the output."""
+    from resselt_b200.archs._common import HEAD_PAD, head_pad_index, winattn_head_padded
+    dtype = torch.bfloat16
+    assert winattn_head_padded(dtype, dim, heads, split)
+    g = torch.Generator().manual_seed(dim * 31 + H * 7 + W + shifted)
+    pad = heads * HEAD_PAD
+    x = torch.randn(B, 3 * dim, H, W, generator=g)
+    hb = heads // 2
+    tabs = [torch.randn((2 * split[br] - 1) * (2 * split[1 - br] - 1), hb, generator=g) * 0.5 for br in (0, 1)]
+    scale = (dim // heads) ** -0.5
+    pb = PlanBuilder(dtype, 3 * dim, dim, 1)
+    raw, qkv, att = pb.buffer(3 * dim), pb.buffer(3 * pad), pb.buffer(pad)
+    pb.conv(INPUT, raw, torch.eye(3 * dim).view(3 * dim, 3 * dim, 1, 1))
+    idx = head_pad_index(dim, heads)
+    for part in range(3):
+        sel = torch.zeros(pad, 3 * dim, 1, 1)
+        sel[idx, part * dim + torch.arange(dim)] = 1.0
+        pb.conv(raw, qkv.slice(part * pad, pad), sel)
+    pb.op(N.OP_WINATTN, qkv, att, dim, ints=(heads, split[0], split[1], shifted, pad, HEAD_PAD), floats=(scale,), weights=(tabs[0], tabs[1]))
+    back = torch.zeros(dim, pad, 1, 1)
+    back[torch.arange(dim), idx] = 1.0
+    pb.conv(att, OUTPUT, back)
+    got, _ = _run(pb, x, dtype)
+    xq = _q(x, dtype)
+    ref = ref_window_attention(xq[:, :dim], xq[:, dim:2 * dim], xq[:, 2 * dim:], heads, split, shifted, scale, tabs)
+    _check(got, ref, dtype, bf16_tol=1.5e-2, what=f'tcgen05 window attention {split} shifted={shifted}')
+    # the padded channels of the output are exact zeros (they feed zero weight columns, but must not be NaN / Inf)
+    pb2 = PlanBuilder(dtype, 3 * dim, pad, 1)
+    raw, qkv, att = pb2.buffer(3 * dim), pb2.buffer(3 * pad), pb2.buffer(pad)
+    pb2.conv(INPUT, raw, torch.eye(3 * dim).view(3 * dim, 3 * dim, 1, 1))
+    for part in range(3):
+        sel = torch.zeros(pad, 3 * dim, 1, 1)
+        sel[idx, part * dim + torch.arange(dim)] = 1.0
+        pb2.conv(raw, qkv.slice(part * pad, pad), sel)
+    pb2.op(N.OP_WINATTN, qkv, att, dim, ints=(heads, split[0], split[1], shifted, pad, HEAD_PAD), floats=(scale,), weights=(tabs[0], tabs[1]))
+    pb2.conv(att, OUTPUT, torch.eye(pad).view(pad, pad, 1, 1))
+    full, _ = _run(pb2, x, dtype)
+    keep = torch.zeros(pad, dtype=torch.bool)
+    keep[idx] = True
+    assert float(full[:, ~keep].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------------ channel attention
 @pytest.mark.parametrize('dtype', DTYPES)
 @pytest.mark.parametrize('dim,heads,B,H,W', [(60, 2, 1, 48, 40), (180, 6, 1, 64, 72), (64, 2, 2, 33, 17), (96, 4, 1, 128, 128)])
