@@ -1712,8 +1712,8 @@ cudaError_t winattn_configure() {
   return cudaFuncSetAttribute(winattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
-cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s) {
-  if (p.head_pad != 0) return bf16 ? launch_winattn_tc(p, s) : cudaErrorInvalidValue;  // validated in rsb_plan_add_op
+cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, int num_sms, cudaStream_t s) {
+  if (p.head_pad != 0) return bf16 ? launch_winattn_tc(p, num_sms, s) : cudaErrorInvalidValue;  // validated in rsb_plan_add_op
   const int windows = (p.Hp / p.split_h) * (p.Wp / p.split_w);
   const dim3 grid(windows * p.n, p.heads / 2, 2);
   const size_t smem = winattn_smem_bytes(p.split_h, p.split_w);

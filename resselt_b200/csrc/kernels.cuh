@@ -664,10 +664,10 @@ cudaError_t launch_layernorm(const TokenOpParams& p, bool bf16, int num_sms, cud
 cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s);
 size_t winattn_smem_bytes(int split_h, int split_w);
 cudaError_t winattn_configure();
-cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, cudaStream_t s);
+cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, int num_sms, cudaStream_t s);
 bool winattn_tc_supported(int heads, int head_dim, int split_h, int split_w);  // shapes the head-padded tcgen05 kernel takes
 cudaError_t winattn_tc_configure();
-cudaError_t launch_winattn_tc(const WinAttnParams& p, cudaStream_t s);
+cudaError_t launch_winattn_tc(const WinAttnParams& p, int num_sms, cudaStream_t s);
 cudaError_t launch_chanattn(const ChanAttnParams& p, bool bf16, int num_sms, cudaStream_t s);
 cudaError_t launch_aim(const AimParams& p, bool bf16, int num_sms, cudaStream_t s);
 

@@ -1462,7 +1462,7 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           case RSB_OP_RMSNORM: e = rsb::launch_rmsnorm(a.tok, bf, p->num_sms, stream); break;
           case RSB_OP_UNSHUFFLE_POOL: e = rsb::launch_unshuffle_pool(a.tok, bf, p->num_sms, stream); break;
           case RSB_OP_SE_SHUFFLE: e = rsb::launch_se_shuffle(a.se, bf, p->num_sms, stream); break;
-          case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, stream); break;
+          case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, p->num_sms, stream); break;
           case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, p->num_sms, stream); break;
           case RSB_OP_DYSAMPLE: {
             rsb::DySampleParams q = a.dys;
