@@ -194,6 +194,12 @@ enum rsb_op_kind {
                                 PixelShuffle(2)(src * gate), gate = Hardsigmoid(W2 . ReLU(W1 . mean_hw(src) + b1) + b2) per channel
                                 (CSELayer, arch.py:7-21) when i[0] = hidden width > 0 (w[0..3] = W1 [hidden][C], b1, W2 [C][hidden],
                                 b2), plain PixelShuffle(2) when i[0] == 0; `channels` = C                                       */
+  ,
+  /* ops of GateRV3's MetaGated block (/root/reference/resselt/archs/gaterv3/arch.py:640-667) */
+  RSB_OP_CHAN_GATE = 10,     /* dst = src * ((w[0] . mean_hw(src) + w[1]) * w[2])[c] + src2: simplified channel attention
+                                `x * sca(x)` (AdaptiveAvgPool2d(1) -> Conv1x1, w[0] = [C][C], w[1] = bias [C]) times gamma0 (w[2] = [C])
+                                plus the block's shortcut (src2, required); C % 8 == 0, C <= 1024                                */
+  RSB_OP_CHAN_AFFINE = 11    /* dst = src * w[0][c] (+ src2 when given): `glob(x) * gamma1 + x`; C % 8 == 0                      */
 };
 
 typedef struct rsb_op_desc {
@@ -257,7 +263,9 @@ enum rsb_kernel_id {
   RSB_K_DYSAMPLE = 11,
   RSB_K_RMSNORM = 12,
   RSB_K_UNSHUFFLE_POOL = 13,
-  RSB_K_SE_SHUFFLE = 14
+  RSB_K_SE_SHUFFLE = 14,
+  RSB_K_CHAN_GATE = 15,
+  RSB_K_CHAN_AFFINE = 16
 };
 typedef struct rsb_op_info {
   int32_t kind;       /* 0 convolution, 1 GroupNorm, 2 token / attention op                                        */

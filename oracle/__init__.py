@@ -22,6 +22,7 @@ from .sr_forward import (  # noqa: F401
     plksr_forward,
     realplksr_forward,
     rtmosr_forward,
+    gaterv3_forward,
     span_forward,
     spanplus_forward,
     spanpp_forward,

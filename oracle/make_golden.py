@@ -70,6 +70,11 @@ def cases():
         'spanpp_f32_s4': ('SpanPP', dict(num_in_ch=3, feature_channels=32, scale_list=[2, 4], implicit_dim=32, latent_layers=4), 38, (2, 3, 14, 18), 128),
         'rtmosr_x2_d32': ('RTMoSR', dict(scale=2, dim=32, ffn_expansion=2, n_blocks=2, unshuffle_mod=False, dccm=True, se=True), 39, (1, 3, 21, 27), 129),
         'rtmosr_x4_d48_nose_1x1': ('RTMoSR', dict(scale=4, dim=48, ffn_expansion=1.5, n_blocks=1, unshuffle_mod=False, dccm=False, se=False), 40, (2, 3, 16, 18), 130),
+        # GateRV3 (third SPAN descendant): small U-Nets through the reference's own loader
+        'gaterv3_x2_ps': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=2, scale=2, upsample='pixelshuffle', upsample_mid_dim=16, span_blocks=1), 45, (1, 3, 21, 27), 135),
+        'gaterv3_x1_conv': ('GateRV3', dict(in_ch=3, dim=32, enc_blocks=(1, 1, 1), dec_blocks=(1, 1, 1), num_latent=1, scale=1, span_blocks=1), 46, (2, 3, 24, 16), 136),
+        'gaterv3_x3_psd': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(2, 1), dec_blocks=(1, 2), num_latent=1, scale=3, upsample='pixelshuffledirect', upsample_mid_dim=16, span_blocks=2), 47, (1, 3, 17, 19), 137),
+        'gaterv3_x2_dys': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=2, upsample='dysample', upsample_mid_dim=16, span_blocks=1), 48, (1, 3, 20, 24), 138),
         'rtmosr_x2_unshuffle': ('RTMoSR', dict(scale=2, dim=32, ffn_expansion=2, n_blocks=1, unshuffle_mod=True, dccm=True, se=True), 41, (1, 3, 22, 30), 131),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),
@@ -81,7 +86,7 @@ def engine_model(kind: str, kwargs: dict, seed: int):
 
     cls = {'SPAN': archs.SPAN, 'SPANPlus': archs.SpanPlus, 'Compact': archs.SRVGGNetCompact}
     extra = {k: getattr(archs, k) for k in ('RRDBNet', 'RealPLKSR') if hasattr(archs, k)}
-    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None), 'SpanPP': getattr(archs, 'SpanPP', None), 'RTMoSR': getattr(archs, 'RTMoSR', None)})
+    cls.update({'ESRGAN': extra.get('RRDBNet'), 'RealPLKSR': extra.get('RealPLKSR'), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None), 'SpanPP': getattr(archs, 'SpanPP', None), 'RTMoSR': getattr(archs, 'RTMoSR', None), 'GateRV3': getattr(archs, 'GateRV3', None)})
     return cls[kind](seed=seed, **kwargs)
 
 

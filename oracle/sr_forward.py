@@ -182,6 +182,104 @@ def rtmosr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor
     return out[:, :, : h * scale, : w * scale] + F.interpolate(x, scale_factor=scale)
 
 
+def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """GateRV3.forward in eval mode (/root/reference/resselt/archs/gaterv3/arch.py:783-802; MetaGated :658-667, GatedCNNBlock :623-629,
+    InceptionDWConv2d :550-557, RMSNorm :518-524, SPAB :497-508, Conv3XC.update_params :432-463, Block :682-692, UniUpsampleV3 :241-373:
+    the 'pixelshuffle', 'pixelshuffledirect' and 'dysample' heads and the scale-1 conv)."""
+    x = x.to(dtype)
+    g = lambda k: sd[k].to(dtype)
+    inp = x
+    B, C, H, W = x.shape
+    L = _seq_len(sd, 'gater_encode')
+    pad = 2 ** L
+    x = F.pad(x, (0, (pad - W % pad) % pad, 0, (pad - H % pad) % pad), 'reflect')
+
+    def conv(name, t, padding=0, groups=1):
+        return F.conv2d(t, g(f'{name}.weight'), g(f'{name}.bias') if f'{name}.bias' in sd else None, padding=padding, groups=groups)
+
+    def c3xc(prefix, t):  # the merged eval-mode kernel: 1x1 -> 3x3 -> 1x1 plus the 1x1 skip (biases optional)
+        w1, w2, w3 = g(f'{prefix}.conv.0.weight'), g(f'{prefix}.conv.1.weight'), g(f'{prefix}.conv.2.weight')
+        k = F.conv2d(w1.flip(2, 3).permute(1, 0, 2, 3), w2, padding=2).flip(2, 3).permute(1, 0, 2, 3)
+        k = F.conv2d(k.flip(2, 3).permute(1, 0, 2, 3), w3).flip(2, 3).permute(1, 0, 2, 3) + F.pad(g(f'{prefix}.sk.weight'), [1, 1, 1, 1])
+        bias = None
+        if f'{prefix}.conv.0.bias' in sd:
+            b = (w2 * g(f'{prefix}.conv.0.bias').reshape(1, -1, 1, 1)).sum((1, 2, 3)) + g(f'{prefix}.conv.1.bias')
+            bias = (w3 * b.reshape(1, -1, 1, 1)).sum((1, 2, 3)) + g(f'{prefix}.conv.2.bias') + g(f'{prefix}.sk.bias')
+        return F.conv2d(t, k, bias, padding=1)
+
+    def spab(prefix, t):
+        o1 = F.silu(c3xc(f'{prefix}.c1_r', t))
+        o3 = c3xc(f'{prefix}.c3_r', F.silu(c3xc(f'{prefix}.c2_r', o1)))
+        return (o3 + t) * (torch.sigmoid(o3) - 0.5), o1
+
+    def rms(p, t):
+        r = t.norm(2, dim=1, keepdim=True) * t.shape[1] ** -0.5
+        return g(f'{p}.scale')[:, None, None] * (t / (r + 1e-6)) + g(f'{p}.offset')[:, None, None]
+
+    def gated_cnn(p, t):
+        d = t.shape[1]
+        hidden, gc = int(1.5 * d), int(d * 0.125)
+        gate, ident, c = torch.split(conv(f'{p}.fc1', rms(f'{p}.norm', t)), [hidden, hidden - d, d], dim=1)
+        c_id, c_hw, c_w, c_h = torch.split(c, (d - 3 * gc, gc, gc, gc), dim=1)
+        c = torch.cat((c_id, conv(f'{p}.token_mix.dwconv_hw', c_hw, 1, gc), conv(f'{p}.token_mix.dwconv_w', c_w, (0, 5), gc),
+                       conv(f'{p}.token_mix.dwconv_h', c_h, (5, 0), gc)), dim=1)
+        return F.mish(conv(f'{p}.fc2', F.mish(gate) * torch.cat((ident, c), dim=1)))
+
+    def meta_gated(p, t):
+        d = t.shape[1]
+        u = conv(f'{p}.local.2', conv(f'{p}.local.1', rms(f'{p}.local.0', t)), 1, d)
+        u1, u2 = u.chunk(2, dim=1)
+        u = u1 * u2
+        u = u * conv(f'{p}.sca.1', u.mean(dim=(2, 3), keepdim=True))
+        u = u * g(f'{p}.gamma0') + t
+        return gated_cnn(f'{p}.glob', u) * g(f'{p}.gamma1') + u
+
+    x = conv('in_to_dim', x, 1)
+    sisr, _ = spab('span_block0', x)
+    sisr_short = sisr
+    for k in range(_seq_len(sd, 'span_n_b')):
+        sisr, _ = spab(f'span_n_b.{k}', sisr)
+    sisr, sisr_out = spab('span_end', sisr)
+    sisr = conv('sisr_cat_conv', torch.cat([x, c3xc('sisr_end_conv', sisr), sisr_short, sisr_out], dim=1))
+    shorts = []
+    for i in range(L):
+        for j in range(_seq_len(sd, f'gater_encode.{i}.gated')):
+            x = meta_gated(f'gater_encode.{i}.gated.{j}', x)
+        shorts.append(x)
+        x = F.pixel_unshuffle(conv(f'gater_encode.{i}.scale.0', x, 1), 2)
+    for k in range(_seq_len(sd, 'latent')):
+        x = gated_cnn(f'latent.{k}', x)
+    for i in range(_seq_len(sd, 'decode')):
+        x = torch.cat([F.pixel_shuffle(conv(f'decode.{i}.scale.0', x, 1), 2), shorts[L - 1 - i]], dim=1)
+        x = conv(f'decode.{i}.shor', x)
+        for j in range(_seq_len(sd, f'decode.{i}.gated')):
+            x = meta_gated(f'decode.{i}.gated.{j}', x)
+    x = x + sisr
+    if 'dim_to_in.MetaUpsample' not in sd:
+        scale, x = 1, conv('dim_to_in', x, 1)
+    else:
+        _, index, scale, _, _, _, groups = [int(v) for v in sd['dim_to_in.MetaUpsample']]
+        mode = ('conv', 'pixelshuffledirect', 'pixelshuffle', 'nearest+conv', 'dysample', 'transpose+conv', 'lda', 'pa_up')[index]
+        if mode == 'pixelshuffledirect':
+            x = F.pixel_shuffle(conv('dim_to_in.0', x, 1), scale)
+        elif mode == 'pixelshuffle':
+            x = F.leaky_relu(conv('dim_to_in.0', x, 1), 0.01)
+            i = 2
+            for r in ([3] if scale == 3 else [2] * int(math.log2(scale))):
+                x = F.pixel_shuffle(conv(f'dim_to_in.{i}', x, 1), r)
+                i += 2
+            x = conv(f'dim_to_in.{i}', x, 1)
+        elif mode == 'dysample':
+            i = 0
+            if 'dim_to_in.0.weight' in sd:
+                x, i = F.leaky_relu(conv('dim_to_in.0', x, 1), 0.01), 2
+            x = _dysample(sd, f'dim_to_in.{i}', x, groups)
+        else:
+            raise NotImplementedError(mode)
+    up = F.interpolate(inp, scale_factor=scale) if scale != 1 else inp
+    return x[:, :, : H * scale, : W * scale] + g('gamma') * up
+
+
 def _dysample(sd: SD, p: str, x: torch.Tensor, groups: int) -> torch.Tensor:
     """DySample.forward (/root/reference/resselt/utilities/dysample.py:46-83), restated with the same ATen calls: offsets
     ``offset(x) * sigmoid(scope(x)) * 0.5 + init_pos``, a coordinate grid in normalised [-1, 1] units, pixel_shuffle of the
@@ -645,6 +743,7 @@ _FORWARDS: Dict[str, Callable] = {
     'Compact': compact_forward,
     'SpanPP': spanpp_forward,
     'RTMoSR': rtmosr_forward,
+    'GateRV3': gaterv3_forward,
 }
 
 

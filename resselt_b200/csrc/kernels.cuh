@@ -638,6 +638,8 @@ struct SeParams {  // squeeze-excitation gate + PixelShuffle(2) (rt_ops.cu)
   const float *w1, *b1, *w2, *b2;  // [hidden][C], [hidden], [C][hidden], [C]
   float* partial;  // [n][blocks][C]
   float* gate;     // [n][C]; null: plain PixelShuffle
+  const void* res; // channel-gate op (GateRV3 sca): dst = src * gate + res, gate = (w1 . mean + b1) * w2 (w1 [C][C], b1 [C], w2 = gamma [C])
+  int res_planes, res_plane0;
 };
 
 struct DySampleParams {
@@ -665,6 +667,8 @@ cudaError_t launch_dwconv3(const TokenOpParams& p, bool bf16, cudaStream_t s);
 size_t winattn_smem_bytes(int split_h, int split_w);
 cudaError_t winattn_configure();
 cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, int num_sms, cudaStream_t s);
+cudaError_t launch_chan_gate(const SeParams& p, bool bf16, int num_sms, cudaStream_t s);
+cudaError_t launch_chan_affine(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s);
 bool winattn_tc_supported(int heads, int head_dim, int split_h, int split_w);  // shapes the head-padded tcgen05 kernel takes
 cudaError_t winattn_tc_configure();
 cudaError_t launch_winattn_tc(const WinAttnParams& p, int num_sms, cudaStream_t s);

@@ -238,7 +238,7 @@ size_t aux_scratch_bytes(const AuxOp& a, int n) {
     const int cpad = ceil_div(d.channels, 8) * 8;
     return ((size_t)n * kAuxBlocks * cpad + (size_t)n * cpad) * sizeof(float);
   }
-  if (d.kind == RSB_OP_SE_SHUFFLE && d.i[0] > 0) return ((size_t)n * kAuxBlocks * d.channels + (size_t)n * d.channels) * sizeof(float);
+  if ((d.kind == RSB_OP_SE_SHUFFLE && d.i[0] > 0) || d.kind == RSB_OP_CHAN_GATE) return ((size_t)n * kAuxBlocks * d.channels + (size_t)n * d.channels) * sizeof(float);
   return 0;
 }
 
@@ -682,6 +682,20 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
     }
     const Buffer& db = p->bufs[d.dst_buf];
     uint8_t* scratch = ws + aux_off;
+    if (d.kind == RSB_OP_CHAN_GATE) {
+      rsb::SeParams& t = a.se;
+      memset(&t, 0, sizeof t);
+      const Buffer& rb = p->bufs[d.src2_buf];
+      t.n = n, t.H = H, t.W = W, t.channels = d.channels;
+      t.blocks = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)H * W + 4095) / 4096));
+      t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_plane0 = d.src_ch_off / 8;
+      t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_plane0 = d.dst_ch_off / 8;
+      t.res = ws + rb.offset, t.res_planes = rb.planes, t.res_plane0 = d.src2_ch_off / 8;
+      t.w1 = a.dw[0], t.b1 = a.dw[1], t.w2 = a.dw[2];
+      t.partial = reinterpret_cast<float*>(scratch);
+      t.gate = t.partial + (size_t)n * kAuxBlocks * d.channels;
+      continue;
+    }
     if (d.kind == RSB_OP_SE_SHUFFLE) {
       rsb::SeParams& t = a.se;
       memset(&t, 0, sizeof t);
@@ -696,7 +710,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       }
       continue;
     }
-    if (d.kind == RSB_OP_LAYERNORM || d.kind == RSB_OP_DWCONV3 || d.kind == RSB_OP_RMSNORM || d.kind == RSB_OP_UNSHUFFLE_POOL) {
+    if (d.kind == RSB_OP_LAYERNORM || d.kind == RSB_OP_DWCONV3 || d.kind == RSB_OP_RMSNORM || d.kind == RSB_OP_UNSHUFFLE_POOL || d.kind == RSB_OP_CHAN_AFFINE) {
       rsb::TokenOpParams& t = a.tok;
       memset(&t, 0, sizeof t);
       t.n = n, t.H = H, t.W = W, t.channels = d.channels;
@@ -812,7 +826,7 @@ int rsb_plan_destroy(rsb_plan* p) {
 int rsb_plan_set_base_divisor(rsb_plan* p, int divisor) {
   if (!p) return fail(RSB_ERR_INVALID, "rsb_plan_set_base_divisor: NULL plan");
   if (p->finalized || !p->bufs.empty() || !p->ops.empty()) return fail(RSB_ERR_STATE, "rsb_plan_set_base_divisor: call before adding buffers / ops");
-  if (divisor < 1 || divisor > 8) return fail(RSB_ERR_INVALID, "rsb_plan_set_base_divisor: divisor must be in [1, 8]");
+  if (divisor < 1 || divisor > 64) return fail(RSB_ERR_INVALID, "rsb_plan_set_base_divisor: divisor must be in [1, 64]");
   p->base_div = divisor;
   return 0;
 }
@@ -949,7 +963,7 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
   if (!p || !desc) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: NULL argument");
   if (p->finalized) return fail(RSB_ERR_STATE, "rsb_plan_add_op: plan already finalized");
   const rsb_op_desc& d = *desc;
-  if (d.kind < RSB_OP_LAYERNORM || d.kind > RSB_OP_SE_SHUFFLE) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown kind %d", d.kind);
+  if (d.kind < RSB_OP_LAYERNORM || d.kind > RSB_OP_CHAN_AFFINE) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: unknown kind %d", d.kind);
   if (d.channels < 1) return fail(RSB_ERR_INVALID, "rsb_plan_add_op: bad channel count");
   if (d.kind == RSB_OP_DYSAMPLE) {
     const int g = d.i[0], s = d.i[1], oc = d.i[2];
@@ -1002,9 +1016,14 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
   }
   if (d.kind == RSB_OP_DWCONV3 && d.i[1] != 0 && d.i[1] != 3) {
     const int K = d.i[1];
-    if ((K != 5 && K != 7) || d.i[0] != RSB_ACT_NONE || d.src2_buf >= 0 || !d.w[0] || d.wn[0] != (int64_t)d.channels * K * K || !d.w[1] || d.wn[1] != d.channels)
-      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: depthwise K x K needs K in {5, 7}, no activation / gate, weight [C][K*K], bias [C]");
+    if ((K != 5 && K != 7 && K != 9 && K != 11) || d.i[0] != RSB_ACT_NONE || d.src2_buf >= 0 || !d.w[0] || d.wn[0] != (int64_t)d.channels * K * K || !d.w[1] || d.wn[1] != d.channels)
+      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_op: depthwise K x K needs K in {5, 7, 9, 11}, no activation / gate, weight [C][K*K], bias [C]");
   }
+  if (d.kind == RSB_OP_CHAN_GATE && (d.channels % 8 != 0 || d.channels > 1024 || d.src2_buf < 0 || !d.w[0] || d.wn[0] != (int64_t)d.channels * d.channels || !d.w[1] ||
+                                     d.wn[1] != d.channels || !d.w[2] || d.wn[2] != d.channels))
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel gate needs C %% 8 == 0, C <= 1024, src2, W [C][C], bias [C] and gamma [C]");
+  if (d.kind == RSB_OP_CHAN_AFFINE && (d.channels % 8 != 0 || !d.w[0] || d.wn[0] != d.channels))
+    return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel affine needs C %% 8 == 0 and a scale [C]");
   if (d.kind == RSB_OP_RMSNORM && (!d.w[0] || d.wn[0] != d.channels || !d.w[1] || d.wn[1] != d.channels))
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: RMSNorm needs scale [C] and offset [C]");
   const bool qkv = d.kind == RSB_OP_WINATTN || d.kind == RSB_OP_CHANATTN;
@@ -1268,7 +1287,7 @@ int rsb_plan_set_nvtx(rsb_plan* p, int enable) {
 
 const char* rsb_kernel_name(int k) {
   static const char* const names[] = {"conv_direct", "conv_tc", "conv_rs", "conv_lk", "conv_pair", "groupnorm", "layernorm", "dwconv3",
-                                      "winattn", "chanattn", "aim", "dysample", "rmsnorm", "unshuffle_pool", "se_shuffle"};
+                                      "winattn", "chanattn", "aim", "dysample", "rmsnorm", "unshuffle_pool", "se_shuffle", "chan_gate", "chan_affine"};
   return (k >= 0 && k < (int)(sizeof(names) / sizeof(names[0]))) ? names[k] : "unknown";
 }
 
@@ -1336,6 +1355,8 @@ int rsb_plan_op_info(const rsb_plan* p, int op_index, rsb_op_info* out) {
       case RSB_OP_RMSNORM: out->kernel = RSB_K_RMSNORM; break;
       case RSB_OP_UNSHUFFLE_POOL: out->kernel = RSB_K_UNSHUFFLE_POOL; break;
       case RSB_OP_SE_SHUFFLE: out->kernel = RSB_K_SE_SHUFFLE, out->launches = p->auxs[op.index].d.i[0] > 0 ? 3 : 1; break;
+      case RSB_OP_CHAN_GATE: out->kernel = RSB_K_CHAN_GATE, out->launches = 3; break;
+      case RSB_OP_CHAN_AFFINE: out->kernel = RSB_K_CHAN_AFFINE; break;
       default: out->kernel = RSB_K_DYSAMPLE; break;
     }
   }
@@ -1347,7 +1368,7 @@ int rsb_plan_launches_per_forward(const rsb_plan* p) {
   int packed = 0;
   for (const ConvOp& c : p->convs) packed += (c.pack_buf >= 0 && c.tc_ok) ? 1 : 0;
   int aux = 0;
-  for (const AuxOp& a : p->auxs) aux += (a.d.kind == RSB_OP_CHANATTN || a.d.kind == RSB_OP_AIM || (a.d.kind == RSB_OP_SE_SHUFFLE && a.d.i[0] > 0)) ? 3 : 1;
+  for (const AuxOp& a : p->auxs) aux += (a.d.kind == RSB_OP_CHANATTN || a.d.kind == RSB_OP_AIM || a.d.kind == RSB_OP_CHAN_GATE || (a.d.kind == RSB_OP_SE_SHUFFLE && a.d.i[0] > 0)) ? 3 : 1;
   return (int)p->convs.size() + packed + 2 * (int)p->gns.size() + aux;  // mode 0; mode 4 saves one launch per fused pair
 }
 
@@ -1462,6 +1483,8 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           case RSB_OP_RMSNORM: e = rsb::launch_rmsnorm(a.tok, bf, p->num_sms, stream); break;
           case RSB_OP_UNSHUFFLE_POOL: e = rsb::launch_unshuffle_pool(a.tok, bf, p->num_sms, stream); break;
           case RSB_OP_SE_SHUFFLE: e = rsb::launch_se_shuffle(a.se, bf, p->num_sms, stream); break;
+          case RSB_OP_CHAN_GATE: e = rsb::launch_chan_gate(a.se, bf, p->num_sms, stream); break;
+          case RSB_OP_CHAN_AFFINE: e = rsb::launch_chan_affine(a.tok, bf, p->num_sms, stream); break;
           case RSB_OP_WINATTN: e = rsb::launch_winattn(a.win, bf, p->num_sms, stream); break;
           case RSB_OP_CHANATTN: e = rsb::launch_chanattn(a.chan, bf, p->num_sms, stream); break;
           case RSB_OP_DYSAMPLE: {

@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(256) unshuffle_pool_kernel(const __grid_consta
 // (First version read the weights from global memory per FMA group: 839 us for RTMoSR's 128-channel half-resolution map at 1080p.)
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ TokenOpParams p, int K) {
-  __shared__ __align__(16) float wsm[49 * 8 + 8];
+  __shared__ __align__(16) float wsm[121 * 8 + 8];
+  __shared__ uint8_t taps[121];  // taps with a non-zero weight on any of the plane's channels (GateRV3's inception conv is an 11 x 11
+  __shared__ int ntaps;          // kernel with 1 / 9 / 11 live taps per channel: arch.py:527-557)
   const size_t hw = (size_t)p.H * p.W;
   const int C = p.channels, R = K / 2, KK = K * K;
   const int pl = blockIdx.y, n = blockIdx.z;
@@ -111,6 +113,17 @@ __global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ T
     wsm[e] = c < C ? (t < KK ? p.w0[c * KK + t] : p.w1[c]) : 0.0f;
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int t = 0; t < KK; ++t) {
+      bool live = false;
+      for (int k = 0; k < 8; ++k) live |= wsm[t * 8 + k] != 0.0f;
+      if (live) taps[m++] = (uint8_t)t;
+    }
+    ntaps = m;
+  }
+  __syncthreads();
+  const int nt = ntaps;
   const T* src = reinterpret_cast<const T*>(p.src) + ((size_t)n * p.src_planes + p.src_plane0 + pl) * hw * 8;
   T* dst = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0 + pl) * hw * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
@@ -118,19 +131,16 @@ __global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ T
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = wsm[KK * 8 + k];
-    for (int ky = 0; ky < K; ++ky) {
-      const int sy = y + ky - R;
-      if (sy < 0 || sy >= p.H) continue;
-      for (int kx = 0; kx < K; ++kx) {
-        const int sx = x + kx - R;
-        if (sx < 0 || sx >= p.W) continue;
-        float v[8];
-        load8<T>(src + ((size_t)sy * p.W + sx) * 8, v);
-        const float4 wa = *reinterpret_cast<const float4*>(&wsm[(ky * K + kx) * 8]);
-        const float4 wb = *reinterpret_cast<const float4*>(&wsm[(ky * K + kx) * 8 + 4]);
-        acc[0] = fmaf(v[0], wa.x, acc[0]), acc[1] = fmaf(v[1], wa.y, acc[1]), acc[2] = fmaf(v[2], wa.z, acc[2]), acc[3] = fmaf(v[3], wa.w, acc[3]);
-        acc[4] = fmaf(v[4], wb.x, acc[4]), acc[5] = fmaf(v[5], wb.y, acc[5]), acc[6] = fmaf(v[6], wb.z, acc[6]), acc[7] = fmaf(v[7], wb.w, acc[7]);
-      }
+    for (int ti = 0; ti < nt; ++ti) {
+      const int t = taps[ti], ky = t / K, kx = t - ky * K;
+      const int sy = y + ky - R, sx = x + kx - R;
+      if (sy < 0 || sy >= p.H || sx < 0 || sx >= p.W) continue;
+      float v[8];
+      load8<T>(src + ((size_t)sy * p.W + sx) * 8, v);
+      const float4 wa = *reinterpret_cast<const float4*>(&wsm[t * 8]);
+      const float4 wb = *reinterpret_cast<const float4*>(&wsm[t * 8 + 4]);
+      acc[0] = fmaf(v[0], wa.x, acc[0]), acc[1] = fmaf(v[1], wa.y, acc[1]), acc[2] = fmaf(v[2], wa.z, acc[2]), acc[3] = fmaf(v[3], wa.w, acc[3]);
+      acc[4] = fmaf(v[4], wb.x, acc[4]), acc[5] = fmaf(v[5], wb.y, acc[5]), acc[6] = fmaf(v[6], wb.z, acc[6]), acc[7] = fmaf(v[7], wb.w, acc[7]);
     }
     store8<T>(dst + i * 8, acc);
   }
@@ -223,7 +233,91 @@ __global__ void __launch_bounds__(256) se_shuffle_kernel(const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ simplified channel attention
+// GateRV3 MetaGated (/root/reference/resselt/archs/gaterv3/arch.py:640-667): x * sca(x) * gamma0 + short with
+// sca = Conv1x1(AdaptiveAvgPool2d(1)(x)).  Pooling re-uses se_pool_kernel; gate[n][c] = (W . mean + b)[c] * gamma0[c].
+__global__ void __launch_bounds__(256) sca_gate_kernel(const __grid_constant__ SeParams p) {
+  extern __shared__ float sm[];
+  float* mean = sm;  // [C]
+  const int n = blockIdx.x, C = p.channels;
+  const float inv = 1.0f / ((float)p.H * (float)p.W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < p.blocks; ++b) s += p.partial[((size_t)n * p.blocks + b) * C + c];
+    mean[c] = (float)s * inv;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = p.b1[c];
+    for (int k = 0; k < C; ++k) s = fmaf(p.w1[c * C + k], mean[k], s);
+    p.gate[(size_t)n * C + c] = s * p.w2[c];
+  }
+}
+
+// dst = src * gate[n][c] + res
+template <typename T>
+__global__ void __launch_bounds__(256) sca_apply_kernel(const __grid_constant__ SeParams p) {
+  const size_t hw = (size_t)p.H * p.W;
+  const int planes = p.channels >> 3;
+  const size_t total = (size_t)p.n * planes * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i % hw;
+    const int pl = (int)((i / hw) % planes), n = (int)(i / (hw * planes));
+    float v[8], r[8];
+    load8<T>(reinterpret_cast<const T*>(p.src) + (((size_t)n * p.src_planes + p.src_plane0 + pl) * hw + px) * 8, v);
+    load8<T>(reinterpret_cast<const T*>(p.res) + (((size_t)n * p.res_planes + p.res_plane0 + pl) * hw + px) * 8, r);
+    const float* g = p.gate + (size_t)n * p.channels + pl * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], g[k], r[k]);
+    store8<T>(reinterpret_cast<T*>(p.dst) + (((size_t)n * p.dst_planes + p.dst_plane0 + pl) * hw + px) * 8, v);
+  }
+}
+
+// dst = src * w0[c] (+ src2): the per-channel gamma1 of MetaGated's `glob(x) * gamma1 + x` (arch.py:665)
+template <typename T>
+__global__ void __launch_bounds__(256) chan_affine_kernel(const __grid_constant__ TokenOpParams p) {
+  const size_t hw = (size_t)p.H * p.W;
+  const int planes = p.channels >> 3;
+  const size_t total = (size_t)p.n * planes * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i % hw;
+    const int pl = (int)((i / hw) % planes), n = (int)(i / (hw * planes));
+    float v[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    load8<T>(reinterpret_cast<const T*>(p.src) + (((size_t)n * p.src_planes + p.src_plane0 + pl) * hw + px) * 8, v);
+    if (p.src2 != nullptr) load8<T>(reinterpret_cast<const T*>(p.src2) + (((size_t)n * p.src2_planes + p.src2_plane0 + pl) * hw + px) * 8, r);
+    const float4 ga = *reinterpret_cast<const float4*>(p.w0 + pl * 8), gb = *reinterpret_cast<const float4*>(p.w0 + pl * 8 + 4);
+    v[0] = fmaf(v[0], ga.x, r[0]), v[1] = fmaf(v[1], ga.y, r[1]), v[2] = fmaf(v[2], ga.z, r[2]), v[3] = fmaf(v[3], ga.w, r[3]);
+    v[4] = fmaf(v[4], gb.x, r[4]), v[5] = fmaf(v[5], gb.y, r[5]), v[6] = fmaf(v[6], gb.z, r[6]), v[7] = fmaf(v[7], gb.w, r[7]);
+    store8<T>(reinterpret_cast<T*>(p.dst) + (((size_t)n * p.dst_planes + p.dst_plane0 + pl) * hw + px) * 8, v);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_chan_gate(const SeParams& p, bool bf16, int num_sms, cudaStream_t s) {
+  const int sms = num_sms > 0 ? num_sms : 148;
+  const dim3 g1(p.blocks, p.channels >> 3, p.n);
+  if (bf16)
+    se_pool_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>(p);
+  else
+    se_pool_kernel<float><<<g1, 256, 0, s>>>(p);
+  sca_gate_kernel<<<p.n, 256, (size_t)p.channels * sizeof(float), s>>>(p);
+  const int g = grid_for((size_t)p.n * (p.channels >> 3) * p.H * p.W, 256, sms * 32);
+  if (bf16)
+    sca_apply_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    sca_apply_kernel<float><<<g, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chan_affine(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s) {
+  const int g = grid_for((size_t)p.n * (p.channels >> 3) * p.H * p.W, 256, (num_sms > 0 ? num_sms : 148) * 32);
+  if (bf16)
+    chan_affine_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p);
+  else
+    chan_affine_kernel<float><<<g, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_rmsnorm(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s) {
   const int g = grid_for((size_t)p.n * p.H * p.W, 256, (num_sms > 0 ? num_sms : 148) * 32);

@@ -26,6 +26,7 @@ ACT_NONE, ACT_SILU, ACT_MISH, ACT_LRELU, ACT_PRELU, ACT_SIGMOID, ACT_GELU = rang
 COMB_NONE, COMB_SPAB_GATE, COMB_MUL, COMB_AXPY = range(4)
 EXTERNAL_INPUT, EXTERNAL_OUTPUT, NO_BUFFER = -1, -2, -3
 OP_LAYERNORM, OP_DWCONV3, OP_WINATTN, OP_CHANATTN, OP_AIM, OP_DYSAMPLE, OP_RMSNORM, OP_UNSHUFFLE_POOL, OP_SE_SHUFFLE = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OP_CHAN_GATE, OP_CHAN_AFFINE = 10, 11
 
 EXPORTED_SYMBOLS = (
     'rsb_version', 'rsb_last_error', 'rsb_device_count', 'rsb_plan_create', 'rsb_plan_destroy',

@@ -225,7 +225,7 @@ class PlanBuilder:
         self.op(N.OP_DWCONV3, src, dst, src.channels, src2=gate, ints=(act,), weights=(weight, bias))
 
     def dwconv(self, src: Ref, dst: Ref, weight, bias) -> None:
-        """Depthwise K x K conv (K = 3, 5, 7 from the weight's shape [C][1][K][K])."""
+        """Depthwise K x K conv (K = 3, 5, 7, 9, 11 from the weight's shape [C][1][K][K]; taps that are zero on a whole 8-channel plane are skipped)."""
         k = int(_f32(weight).shape[-1])
         self.op(N.OP_DWCONV3, src, dst, src.channels, ints=(N.ACT_NONE, 0 if k == 3 else k), weights=(weight, bias))
 
@@ -244,6 +244,15 @@ class PlanBuilder:
         else:
             w1 = _f32(se[0]).reshape(-1, src.channels)
             self.op(N.OP_SE_SHUFFLE, src, dst, src.channels, ints=(w1.shape[0],), weights=(w1, se[1], _f32(se[2]).reshape(src.channels, -1), se[3]))
+
+    def chan_gate(self, src: Ref, dst: Ref, res: Ref, weight, bias, gamma) -> None:
+        """dst = src * ((weight . mean_hw(src) + bias) * gamma)[c] + res (GateRV3's simplified channel attention + shortcut)."""
+        c = src.channels
+        self.op(N.OP_CHAN_GATE, src, dst, c, src2=res, weights=(_f32(weight).reshape(c, c), bias, _f32(gamma).reshape(-1)))
+
+    def chan_affine(self, src: Ref, dst: Ref, scale, res: Optional[Ref] = None) -> None:
+        """dst = src * scale[c] (+ res)."""
+        self.op(N.OP_CHAN_AFFINE, src, dst, src.channels, src2=res, weights=(_f32(scale).reshape(-1),))
 
     def finalize(self, device: torch.device) -> 'Plan':
         index = device.index if device.index is not None else torch.cuda.current_device()

@@ -37,7 +37,7 @@ def golden_case(name):
 
     info = golden_index()[name]
     cls = {'SPAN': archs.SPAN, 'SPANPlus': archs.SpanPlus, 'Compact': archs.SRVGGNetCompact,
-           'ESRGAN': getattr(archs, 'RRDBNet', None), 'RealPLKSR': getattr(archs, 'RealPLKSR', None), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None), 'SpanPP': getattr(archs, 'SpanPP', None), 'RTMoSR': getattr(archs, 'RTMoSR', None)}[info['kind']]
+           'ESRGAN': getattr(archs, 'RRDBNet', None), 'RealPLKSR': getattr(archs, 'RealPLKSR', None), 'DAT': getattr(archs, 'DAT', None), 'SwinIR': getattr(archs, 'SwinIR', None), 'PLKSR': getattr(archs, 'PLKSR', None), 'SpanPP': getattr(archs, 'SpanPP', None), 'RTMoSR': getattr(archs, 'RTMoSR', None), 'GateRV3': getattr(archs, 'GateRV3', None)}[info['kind']]
     model = cls(seed=info['weight_seed'], **info['kwargs'])
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     data = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 import oracle
 import resselt_b200
 from conftest import golden_case, golden_index, norm_err, psnr
-from resselt_b200.archs import DAT, PLKSR, SPAN, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, PLKSR, SPAN, GateRV3, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
 from resselt_b200.engine import INPUT, OUTPUT, PlanBuilder
 from resselt_b200.engine import native as N
 from resselt_b200.runner import FramePipeline, tiled_forward
@@ -58,6 +58,8 @@ def test_golden_fixtures_fp32_and_bf16(name):
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=24), (3, 3, 45, 61)),
         ('Compact', SRVGGNetCompact(num_feat=64, num_conv=16, upscale=1, seed=25), (1, 3, 40, 40)),
         ('SpanPP', SpanPP(feature_channels=48, implicit_dim=64, latent_layers=2, seed=52), (2, 3, 37, 50)),
+        ('GateRV3', GateRV3(scale=2, span_blocks=2, num_latent=3, seed=56), (1, 3, 70, 90)),                              # full depth (2, 2, 4, 8) U-Net, dim 32, reflect pad to 16
+        ('GateRV3', GateRV3(dim=48, enc_blocks=(1, 1, 1), dec_blocks=(1, 1, 1), num_latent=2, scale=4, upsample='pixelshuffle', upsample_mid_dim=32, seed=57), (2, 3, 32, 40)),
         ('RTMoSR', RTMoSR(scale=2, dim=32, n_blocks=2, seed=53), (1, 3, 45, 61)),                                  # odd size: reflect pad + crop
         ('RTMoSR', RTMoSR(scale=4, dim=64, ffn_expansion=2, n_blocks=3, seed=54), (2, 3, 40, 36)),
         ('RTMoSR', RTMoSR(scale=2, dim=32, n_blocks=1, unshuffle_mod=True, seed=55), (1, 3, 41, 54)),              # pixel-unshuffle front end
