@@ -479,6 +479,9 @@ const Variant kVariants[] = {
     RSB_V(0, 0, 0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_V(0, 0, 0, 0, RSB_ACT_NONE, RSB_COMB_AXPY),
     RSB_V(0, 0, 0, 0, RSB_ACT_GELU, RSB_COMB_NONE),
+    RSB_V(0, 0, 0, 0, RSB_ACT_MISH, RSB_COMB_NONE),  // gated-CNN blocks of RTMoSR / GateRV3: mish(fc2(.)), mish(g) * cat(i, c), mish(fc2(.)) + x
+    RSB_V(0, 0, 0, 0, RSB_ACT_MISH, RSB_COMB_MUL),
+    RSB_V(0, 0, 0, 0, RSB_ACT_MISH, RSB_COMB_AXPY),
     RSB_V(1, 1, 12, 0, RSB_ACT_NONE, RSB_COMB_NONE),  // DAT token linears: 192 -> 180
     RSB_V(1, 1, 12, 0, RSB_ACT_GELU, RSB_COMB_NONE),
     RSB_V(1, 1, 12, 0, RSB_ACT_NONE, RSB_COMB_AXPY),

@@ -687,7 +687,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
       memset(&t, 0, sizeof t);
       const Buffer& rb = p->bufs[d.src2_buf];
       t.n = n, t.H = H, t.W = W, t.channels = d.channels;
-      t.blocks = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)H * W + 4095) / 4096));
+      t.blocks = (int)std::min<size_t>(kAuxBlocks, std::max<size_t>(1, ((size_t)H * W + 2047) / 2048));
       t.src = ws + sb.offset, t.src_planes = sb.planes, t.src_plane0 = d.src_ch_off / 8;
       t.dst = ws + db.offset, t.dst_planes = db.planes, t.dst_plane0 = d.dst_ch_off / 8;
       t.res = ws + rb.offset, t.res_planes = rb.planes, t.res_plane0 = d.src2_ch_off / 8;

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) unshuffle_pool_kernel(const __grid_consta
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ TokenOpParams p, int K) {
   __shared__ __align__(16) float wsm[121 * 8 + 8];
-  __shared__ uint8_t taps[121];  // taps with a non-zero weight on any of the plane's channels (GateRV3's inception conv is an 11 x 11
+  __shared__ uint32_t taps[121];  // (t | ky << 8 | kx << 16) of the taps with a non-zero weight on any of the plane's channels (GateRV3's inception conv is an 11 x 11
   __shared__ int ntaps;          // kernel with 1 / 9 / 11 live taps per channel: arch.py:527-557)
   const size_t hw = (size_t)p.H * p.W;
   const int C = p.channels, R = K / 2, KK = K * K;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ T
     for (int t = 0; t < KK; ++t) {
       bool live = false;
       for (int k = 0; k < 8; ++k) live |= wsm[t * 8 + k] != 0.0f;
-      if (live) taps[m++] = (uint8_t)t;
+      if (live) taps[m++] = (uint32_t)t | (uint32_t)(t / K) << 8 | (uint32_t)(t % K) << 16;
     }
     ntaps = m;
   }
@@ -131,8 +131,25 @@ __global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ T
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = wsm[KK * 8 + k];
+    if (nt == KK) {  // dense kernel (RTMoSR's OmniShift 5 x 5): plain loops, no tap list
+      for (int ky = 0; ky < K; ++ky) {
+        const int sy = y + ky - R;
+        if (sy < 0 || sy >= p.H) continue;
+        for (int kx = 0; kx < K; ++kx) {
+          const int sx = x + kx - R;
+          if (sx < 0 || sx >= p.W) continue;
+          float v[8];
+          load8<T>(src + ((size_t)sy * p.W + sx) * 8, v);
+          const float4 wa = *reinterpret_cast<const float4*>(&wsm[(ky * K + kx) * 8]);
+          const float4 wb = *reinterpret_cast<const float4*>(&wsm[(ky * K + kx) * 8 + 4]);
+          acc[0] = fmaf(v[0], wa.x, acc[0]), acc[1] = fmaf(v[1], wa.y, acc[1]), acc[2] = fmaf(v[2], wa.z, acc[2]), acc[3] = fmaf(v[3], wa.w, acc[3]);
+          acc[4] = fmaf(v[4], wb.x, acc[4]), acc[5] = fmaf(v[5], wb.y, acc[5]), acc[6] = fmaf(v[6], wb.z, acc[6]), acc[7] = fmaf(v[7], wb.w, acc[7]);
+        }
+      }
+    } else
     for (int ti = 0; ti < nt; ++ti) {
-      const int t = taps[ti], ky = t / K, kx = t - ky * K;
+      const uint32_t tp = taps[ti];
+      const int t = tp & 0xFF, ky = (tp >> 8) & 0xFF, kx = tp >> 16;
       const int sy = y + ky - R, sx = x + kx - R;
       if (sy < 0 || sy >= p.H || sx < 0 || sx >= p.W) continue;
       float v[8];

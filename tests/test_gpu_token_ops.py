@@ -399,6 +399,58 @@ def test_unshuffle_pool_dw5_se_shuffle_chain(C, se, B, H, W, dtype):
     _check(got, ref, dtype, bf16_tol=2e-2, what='unshuffle/pool -> dw5x5 -> SE -> shuffle')
 
 
+# ------------------------------------------------------------------------------------------------ GateRV3 ops (rsb_op_kind 10-11, sparse depthwise 11x11)
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,B,H,W', [(32, 1, 40, 56), (64, 2, 17, 30), (256, 1, 24, 40), (32, 1, 160, 192)])
+def test_channel_gate_and_affine_ops(C, B, H, W, dtype):
+    """MetaGated's tail (gaterv3/arch.py:661-665): x * sca(x) * gamma0 + short with sca = Conv1x1(mean_hw(x)), then y * gamma1 + x."""
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, 2 * C, H, W, generator=g) + 0.2
+    ws, bs = torch.randn(C, C, 1, 1, generator=g) / C ** 0.5, 0.3 * torch.randn(C, generator=g)
+    g0, g1 = 1.0 + 0.3 * torch.randn(1, C, 1, 1, generator=g), 1.0 + 0.3 * torch.randn(1, C, 1, 1, generator=g)
+    pb = PlanBuilder(dtype, 2 * C, C, 1)
+    a, u, v = pb.buffer(2 * C), pb.buffer(C), pb.buffer(C)
+    pb.conv(INPUT, a, torch.eye(2 * C).view(2 * C, 2 * C, 1, 1))
+    pb.chan_gate(a.slice(0, C), u, a.slice(C, C), ws, bs, g0)
+    pb.chan_affine(u, v, g1, res=a.slice(C, C))
+    pb.conv(v, OUTPUT, torch.eye(C).view(C, C, 1, 1))
+    got, _ = _run(pb, x, dtype)
+    xq = _q(x, dtype)
+    t, short = xq[:, :C], xq[:, C:]
+    sca = F.conv2d(t.mean(dim=(2, 3), keepdim=True), ws.double(), bs.double())
+    uu = (t * sca * g0.double() + short).to(dtype).double()
+    ref = uu * g1.double() + short
+    _check(got, ref, dtype, what='channel gate + affine')
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,B,H,W', [(32, 1, 40, 56), (48, 2, 9, 30), (512, 1, 12, 20)])
+def test_inception_depthwise_11x11(C, B, H, W, dtype):
+    """InceptionDWConv2d (gaterv3/arch.py:527-557) as one depthwise 11x11 kernel whose zero taps are skipped per 8-channel plane."""
+    from resselt_b200.archs.gaterv3 import merge_inception
+    g = torch.Generator().manual_seed(C + W)
+    gc = int(C * 0.125)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = {'t.dwconv_hw.weight': torch.randn(gc, 1, 3, 3, generator=g) / 3, 't.dwconv_hw.bias': 0.1 * torch.randn(gc, generator=g),
+         't.dwconv_w.weight': torch.randn(gc, 1, 1, 11, generator=g) / 3, 't.dwconv_w.bias': 0.1 * torch.randn(gc, generator=g),
+         't.dwconv_h.weight': torch.randn(gc, 1, 11, 1, generator=g) / 3, 't.dwconv_h.bias': 0.1 * torch.randn(gc, generator=g)}
+    pb = PlanBuilder(dtype, C, C, 1)
+    a, b = pb.buffer(C), pb.buffer(C)
+    pb.conv(INPUT, a, torch.eye(C).view(C, C, 1, 1))
+    pb.dwconv(a, b, *merge_inception(w, 't', C))
+    pb.conv(b, OUTPUT, torch.eye(C).view(C, C, 1, 1))
+    got, _ = _run(pb, x, dtype)
+    xq = _q(x, dtype)
+    D = lambda k: w[k].double()
+    c_id, c_hw, c_w, c_h = torch.split(xq, (C - 3 * gc, gc, gc, gc), dim=1)
+    ref = torch.cat((c_id, F.conv2d(c_hw, D('t.dwconv_hw.weight'), D('t.dwconv_hw.bias'), padding=1, groups=gc),
+                     F.conv2d(c_w, D('t.dwconv_w.weight'), D('t.dwconv_w.bias'), padding=(0, 5), groups=gc),
+                     F.conv2d(c_h, D('t.dwconv_h.weight'), D('t.dwconv_h.bias'), padding=(5, 0), groups=gc)), dim=1)
+    _check(got, ref, dtype, what='inception depthwise conv')
+    if dtype == torch.float32:
+        assert torch.equal(got[:, : C - 3 * gc], xq[:, : C - 3 * gc]), 'identity channels pass through bit for bit'
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm folded into a linear
 @pytest.mark.parametrize('dtype', DTYPES)
 @pytest.mark.parametrize('C,cout,act,residual,mean,B,H,W', [

@@ -9,7 +9,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, SPAN, GateRV3, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
 from resselt_b200.engine.profiling import time_forward
 from resselt_b200.runner import tiled_forward
 
@@ -31,6 +31,7 @@ CASES = [
     ('8a-a19 SwinIR 4x (180ch 6x6 w8) 512^2', lambda: SwinIR(upscale=4, seed=9), 1, 512, 512, None, None),
     ('8f-2 SpanPP 2x 1080p', lambda: SpanPP(feature_channels=48, seed=10), 1, 1080, 1920, None, None),
     ('8f-2 RTMoSR 2x (dim 32, 2 blocks) 1080p', lambda: RTMoSR(scale=2, dim=32, n_blocks=2, seed=11), 1, 1080, 1920, None, None),
+    ('8f-2 GateRV3 2x (dim 32, (2,2,4,8) U-Net, 12 latent blocks) 1088x1920 (1080p reflect-padded to 16)', lambda: GateRV3(scale=2, seed=12), 1, 1088, 1920, None, None),
     ('8f-4 SPANPlus 2x dys head 1080p', lambda: SpanPlus(blocks=[4], feature_channels=48, upscale=2, upsampler='dys', seed=4), 1, 1080, 1920, None, None),
 ]
 for idx, (label, make, b, h, w, flop_px, tile) in enumerate(CASES):

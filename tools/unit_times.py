@@ -9,7 +9,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, SPAN, GateRV3, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SpanPP, SRVGGNetCompact, SwinIR
 from resselt_b200.engine.profiling import summarize_units, time_forward, time_units
 
 MODELS = {
@@ -23,6 +23,7 @@ MODELS = {
     'swinir': (lambda: SwinIR(upscale=4, seed=9), 1, 512, 512),
     'spanpp': (lambda: SpanPP(feature_channels=48, seed=10), 1, 1080, 1920),
     'rtmosr': (lambda: RTMoSR(scale=2, dim=32, n_blocks=2, seed=11), 1, 1080, 1920),
+    'gaterv3': (lambda: GateRV3(scale=2, seed=12), 1, 1088, 1920),
 }
 
 if __name__ == '__main__':
