@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, 'baseline', '_ref'))
 import torch
 
 import resselt  # the unmodified reference
-from resselt_b200.archs import DAT, SPAN, RealPLKSR, RRDBNet, SpanPlus, SRVGGNetCompact, SwinIR
+from resselt_b200.archs import DAT, SPAN, GateRV3, RealPLKSR, RRDBNet, RTMoSR, SpanPlus, SRVGGNetCompact, SwinIR
 from resselt_b200.engine.profiling import time_forward
 
 dev = torch.device('cuda:0')
@@ -24,6 +24,8 @@ CASES = [
     ('RealPLKSR 4x 512^2', lambda: RealPLKSR(n_blocks=28, upscaling_factor=4, seed=7), 1, 512, 512),
     ('DAT 4x 512^2', lambda: DAT(upscale=4, seed=8), 1, 512, 512),
     ('SwinIR 4x 512^2', lambda: SwinIR(upscale=4, seed=9), 1, 512, 512),
+    ('RTMoSR 2x (dim 32, 2 blocks) 1080p', lambda: RTMoSR(scale=2, dim=32, n_blocks=2, seed=11), 1, 1080, 1920),
+    ('GateRV3 2x (dim 32) 1088x1920', lambda: GateRV3(scale=2, seed=12), 1, 1088, 1920),
 ]
 only = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else None
 torch.backends.cudnn.benchmark = True
