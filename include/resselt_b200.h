@@ -163,7 +163,11 @@ enum rsb_op_kind {
                            ([(2 sh - 1)(2 sw - 1)][heads / 2], offset index (dy + sh - 1)(2 sw - 1) + dx + sw - 1).
                            Branch 0 (first half of the channels / heads) uses split_h x split_w windows, branch 1 the
                            transposed shape; square windows (split_h == split_w) give plain Swin attention, the two
-                           tables then being the two head halves of the learned relative_position_bias_table           */
+                           tables then being the two head halves of the learned relative_position_bias_table.
+                           i[5] = 32 (bf16 plans, head_dim < 32, window sides multiples of 8 with 64 / 128 / 256 tokens): head g of
+                           q, k, v and of dst starts at channel 32 g (the caller pads its qkv weights with zero rows and its
+                           proj weights with zero columns); channels 32 g + head_dim .. 32 g + 31 of dst are written as zeros.
+                           This layout runs on the tcgen05 / TMEM kernel (winattn_tc.cu); i[5] = 0: heads packed             */
   RSB_OP_CHANATTN = 4,  /* src = [q | k | v]; i[0] heads, i[1] q/k/v channel stride (0: channels); w[0] = temperature[heads] */
   RSB_OP_AIM = 5        /* src = attention output, src2 = conv branch, dst = gated sum; i[0] mode (0 window block,
                            1 channel block), i[1] / i[2] hidden widths of the channel / spatial MLPs;
