@@ -44,6 +44,36 @@ __device__ __forceinline__ float lds_f32_off(uint32_t saddr) {
   asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(saddr), "n"(kOff));
   return v;
 }
+template <int kOff>
+__device__ __forceinline__ float2 lds_f32x2_off(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(saddr), "n"(kOff));
+  return v;
+}
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): two scores per issue slot
+__device__ __forceinline__ void fma2(float& x0, float& x1, float s, float b0, float b1) {  // x = x * s + b
+  asm("{\n\t"
+      ".reg .b64 ra, rs, rb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rs, {%2, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "fma.rn.f32x2 ra, ra, rs, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t"
+      "}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(s), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void add2(float& x0, float& x1, float c) {  // x = x + c
+  asm("{\n\t"
+      ".reg .b64 ra, rc;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rc, {%2, %2};\n\t"
+      "add.rn.f32x2 ra, ra, rc;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t"
+      "}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(c));
+}
 // 32 lanes x 32 consecutive 32-bit columns -> TMEM
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -102,22 +132,27 @@ constexpr uint32_t kIdescBMajorMN = 1u << 16;  // B operand MN-major (V is [key]
 // Softmax of this thread's query row (one row per thread, tcgen05.ld 32x32b: lane = row), two passes over the score columns with
 // the next chunk's tcgen05.ld in flight.  Pass 1: t = s * scale2 + bias (+ mask) goes back to TMEM in place, row maximum kept.
 // Pass 2: P = 2^(t - max) as bf16 pairs.  Key j of the row's window sits in column j; keys are row-major over the window, kWs keys
-// per window row, so the bias addresses of a 32-key chunk are compile-time offsets from one base: tab[qpos - ky * S - kx], with the
-// table's row stride S chosen so that the 32 / kWs window rows a warp's queries span fall into distinct banks.
-__host__ __device__ constexpr int tab_stride(int ws) { return ws == 8 ? 24 : (ws == 16 ? 48 : 63); }
+// per window row.  The bias table is stored REVERSED (ascending with the key: R[(ky - qy + Hs - 1) * S + kx - qx + Ws - 1]) on an even
+// row stride S, so the biases of keys (e, e + 1) are one 8-byte load at a compile-time offset from a per-thread base, and TWICE: copy A
+// serves the threads whose pair index is even, copy B (60 bytes past a 128-byte boundary: 8-byte aligned for odd indices, and the
+// other half of the bank window) the odd ones.  Scale + bias and the subtraction of the maximum run on packed fp32 pairs.
+__host__ __device__ constexpr int tab_stride(int ws) { return ws == 8 ? 24 : (ws == 16 ? 48 : 64); }
+__host__ __device__ constexpr int tab_copy_b_bytes(int hs, int ws) { return ((2 * hs - 1) * tab_stride(ws) * 4 + 127) / 128 * 128 + 60; }
 
 template <int kWs, bool kMask, int kE>
 struct ScoreStep {
   static __device__ __forceinline__ void run(uint32_t (&v)[32], uint32_t base, float scale2, const uint32_t (&labs)[8], int qlab, float& m0, float& m1) {
-    constexpr int kOff = -4 * ((kE / kWs) * tab_stride(kWs) + (kE % kWs));
-    float t = fmaf(__uint_as_float(v[kE]), scale2, lds_f32_off<kOff>(base));
+    constexpr int kOff = 4 * ((kE / kWs) * tab_stride(kWs) + (kE % kWs));
+    const float2 b = lds_f32x2_off<kOff>(base);
+    float t0 = __uint_as_float(v[kE]), t1 = __uint_as_float(v[kE + 1]);
+    fma2(t0, t1, scale2, b.x, b.y);
     if (kMask) {
-      const int lab = (labs[kE >> 2] >> (8 * (kE & 3))) & 0xFF;
-      if (lab != qlab) t += -100.0f * kLog2e;
+      if ((int)((labs[kE >> 2] >> (8 * (kE & 3))) & 0xFF) != qlab) t0 += -100.0f * kLog2e;
+      if ((int)((labs[kE >> 2] >> (8 * ((kE + 1) & 3))) & 0xFF) != qlab) t1 += -100.0f * kLog2e;
     }
-    if (kE & 1) m1 = fmaxf(m1, t); else m0 = fmaxf(m0, t);
-    v[kE] = __float_as_uint(t);
-    ScoreStep<kWs, kMask, kE + 1>::run(v, base, scale2, labs, qlab, m0, m1);
+    if (kE & 2) m1 = fmaxf(fmaxf(m1, t0), t1); else m0 = fmaxf(fmaxf(m0, t0), t1);
+    v[kE] = __float_as_uint(t0), v[kE + 1] = __float_as_uint(t1);
+    ScoreStep<kWs, kMask, kE + 2>::run(v, base, scale2, labs, qlab, m0, m1);
   }
 };
 template <int kWs, bool kMask>
@@ -127,7 +162,7 @@ struct ScoreStep<kWs, kMask, 32> {
 
 template <int kWs, bool kMask>
 __device__ __forceinline__ float score_chunk(uint32_t (&v)[32], int i, uint32_t qaddr, float scale2, const uint8_t* klab, int qlab) {
-  const uint32_t base = qaddr - 4u * (uint32_t)(i * (32 / kWs) * tab_stride(kWs));
+  const uint32_t base = qaddr + 4u * (uint32_t)(i * (32 / kWs) * tab_stride(kWs));
   uint32_t labs[8] = {};
   if (kMask) {
 #pragma unroll
@@ -162,20 +197,26 @@ __device__ __forceinline__ float softmax_max(uint32_t taddr, int ncols, uint32_t
 
 // Pass 2: P = 2^(t - max) as bf16 pairs to paddr (may alias the first half of the score columns: chunk i reads columns
 // [32 i, 32 i + 32) before it writes [16 i, 16 i + 16)); chunk 0 is already in flight into va.
+__device__ __forceinline__ uint32_t exp_pair(uint32_t a, uint32_t b, float nmx) {
+  float t0 = __uint_as_float(a), t1 = __uint_as_float(b);
+  add2(t0, t1, nmx);
+  return pack_bf16x2(ex2_approx(t0), ex2_approx(t1));
+}
 __device__ __forceinline__ void softmax_exp(uint32_t taddr, uint32_t paddr, int ncols, float mx, uint32_t (&va)[32]) {
   const int nch = ncols / 32;
+  const float nmx = -mx;
   uint32_t vb[32];
   for (int i = 0; i < nch; i += 2) {
     uint32_t pk[16];
     tmem_ld_wait();
     tmem_ld32(taddr + 32 * (i + 1), vb);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(ex2_approx(__uint_as_float(va[2 * e]) - mx), ex2_approx(__uint_as_float(va[2 * e + 1]) - mx));
+    for (int e = 0; e < 16; ++e) pk[e] = exp_pair(va[2 * e], va[2 * e + 1], nmx);
     tmem_ld_wait();
     tmem_st16(paddr + 16 * i, pk);
     if (i + 2 < nch) tmem_ld32(taddr + 32 * (i + 2), va);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(ex2_approx(__uint_as_float(vb[2 * e]) - mx), ex2_approx(__uint_as_float(vb[2 * e + 1]) - mx));
+    for (int e = 0; e < 16; ++e) pk[e] = exp_pair(vb[2 * e], vb[2 * e + 1], nmx);
     tmem_st16(paddr + 16 * (i + 1), pk);
   }
 }
@@ -197,8 +238,8 @@ __device__ __forceinline__ Item decode_item(const Geometry& g, int item) {
 
 // floats of the strided bias table: the larger of the two branches' (2 Hs - 1) rows x stride(Ws)
 __host__ __device__ inline int tab_floats(int sh, int sw) {
-  const int a = (2 * sh - 1) * tab_stride(sw), b = (2 * sw - 1) * tab_stride(sh);
-  return ((a > b ? a : b) + 3) & ~3;
+  const int a = tab_copy_b_bytes(sh, sw) + (2 * sh - 1) * tab_stride(sw) * 4, b = tab_copy_b_bytes(sw, sh) + (2 * sw - 1) * tab_stride(sh) * 4;
+  return ((a > b ? a : b) / 4 + 4) & ~3;
 }
 
 // per-buffer shared memory: Q [4 planes][128][8] | K [4][TK][8] | V [4][TK][8] | key labels [TK] | query info [128] (po, lab | ty << 8 | tx << 16)
@@ -329,9 +370,12 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) winattn_tc_kernel(co
     if (cur.br * g.hpb + cur.h != tab_bh) {  // (no thread is still in the previous item's softmax: that ended before its PV MMA)
       tab_bh = cur.br * g.hpb + cur.h;
       const float* table = cur.br == 0 ? p.table0 : p.table1;
-      for (int i = threadIdx.x; i < tab_n; i += kThreads) {  // rows of 2 Ws - 1 offsets, re-laid on the conflict-free stride
-        const int dy = i / tab_w;
-        tab[dy * tab_s + (i - dy * tab_w)] = table[(size_t)i * g.hpb + cur.h] * kLog2e;  // softmax in base 2
+      float* tab_b = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tab) + tab_copy_b_bytes(Hs, Ws));
+      for (int i = threadIdx.x; i < tab_n; i += kThreads) {  // reversed, on the even row stride, both copies
+        const int dy = i / tab_w, dx = i - dy * tab_w;
+        const int r = (2 * Hs - 2 - dy) * tab_s + (2 * Ws - 2 - dx);
+        const float v = table[(size_t)i * g.hpb + cur.h] * kLog2e;  // softmax in base 2
+        tab[r] = v, tab_b[r] = v;
       }
     }
     if (more) cp_async_wait_group1(); else cp_async_wait_all();
@@ -359,9 +403,10 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) winattn_tc_kernel(co
       umma_commit(&bars[0]);
     }
     // bias address of this row's first column (window row col0 / Ws of the keys): tab[qpos - ky * tab_w - kx]
-    const int qpos = (qty + Hs - 1) * tab_s + qtx + Ws - 1;
+    // index of the pair (key 0, key 1) of this row's first column: even for odd qtx (copy A), odd for even qtx (copy B)
     const int ky0 = kThreads == 256 ? (128 * half) >> (31 - __clz(Ws)) : 0;
-    const uint32_t qaddr = smem_u32(tab) + 4u * (uint32_t)(qpos - ky0 * tab_s);
+    const int j0 = (Hs - 1 - qty + ky0) * tab_s + (Ws - 1 - qtx);
+    const uint32_t qaddr = smem_u32(tab) + ((qtx & 1) ? 0u : (uint32_t)tab_copy_b_bytes(Hs, Ws)) + 4u * (uint32_t)j0;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t taddr = lane_base + (uint32_t)col0, paddr = lane_base + (uint32_t)pcol0;
     const uint8_t* klab_row = klab + col0;
@@ -445,9 +490,9 @@ bool winattn_tc_supported(int heads, int head_dim, int split_h, int split_w) {
 }
 
 cudaError_t winattn_tc_configure() {
-  cudaError_t e = cudaFuncSetAttribute(winattn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(winattn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(winattn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  return cudaFuncSetAttribute(winattn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 }
 
 cudaError_t launch_winattn_tc(const WinAttnParams& p, int num_sms, cudaStream_t s) {
