@@ -185,7 +185,7 @@ def rtmosr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor
 def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     """GateRV3.forward in eval mode (/root/reference/resselt/archs/gaterv3/arch.py:783-802; MetaGated :658-667, GatedCNNBlock :623-629,
     InceptionDWConv2d :550-557, RMSNorm :518-524, SPAB :497-508, Conv3XC.update_params :432-463, Block :682-692, UniUpsampleV3 :241-373:
-    the 'pixelshuffle', 'pixelshuffledirect' and 'dysample' heads and the scale-1 conv)."""
+    the 'pixelshuffle', 'pixelshuffledirect', 'nearest+conv', 'pa_up' and 'dysample' heads and the scale-1 conv; Attention :560-591)."""
     x = x.to(dtype)
     g = lambda k: sd[k].to(dtype)
     inp = x
@@ -220,9 +220,18 @@ def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tenso
         d = t.shape[1]
         hidden, gc = int(1.5 * d), int(d * 0.125)
         gate, ident, c = torch.split(conv(f'{p}.fc1', rms(f'{p}.norm', t)), [hidden, hidden - d, d], dim=1)
-        c_id, c_hw, c_w, c_h = torch.split(c, (d - 3 * gc, gc, gc, gc), dim=1)
-        c = torch.cat((c_id, conv(f'{p}.token_mix.dwconv_hw', c_hw, 1, gc), conv(f'{p}.token_mix.dwconv_w', c_w, (0, 5), gc),
-                       conv(f'{p}.token_mix.dwconv_h', c_h, (5, 0), gc)), dim=1)
+        if f'{p}.token_mix.qkv.weight' in sd:  # Attention (arch.py:572-591), 16 heads
+            tm = f'{p}.token_mix'
+            b_, c_, h_, w_ = c.shape
+            heads = sd[f'{tm}.temperature'].shape[0]
+            q, k, v = torch.chunk(conv(f'{tm}.qkv_dwconv', conv(f'{tm}.qkv', c), 1, 3 * c_), 3, dim=1)
+            q, k, v = (u.reshape(b_, heads, c_ // heads, h_ * w_) for u in (q, k, v))
+            attn = (F.normalize(q, dim=3) @ F.normalize(k, dim=3).transpose(2, 3)) * g(f'{tm}.temperature')
+            c = conv(f'{tm}.project_out', (attn.softmax(dim=3) @ v).reshape(b_, c_, h_, w_))
+        else:
+            c_id, c_hw, c_w, c_h = torch.split(c, (d - 3 * gc, gc, gc, gc), dim=1)
+            c = torch.cat((c_id, conv(f'{p}.token_mix.dwconv_hw', c_hw, 1, gc), conv(f'{p}.token_mix.dwconv_w', c_w, (0, 5), gc),
+                           conv(f'{p}.token_mix.dwconv_h', c_h, (5, 0), gc)), dim=1)
         return F.mish(conv(f'{p}.fc2', F.mish(gate) * torch.cat((ident, c), dim=1)))
 
     def meta_gated(p, t):
@@ -269,6 +278,18 @@ def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tenso
                 x = F.pixel_shuffle(conv(f'dim_to_in.{i}', x, 1), r)
                 i += 2
             x = conv(f'dim_to_in.{i}', x, 1)
+        elif mode == 'nearest+conv':
+            n = int(math.log2(scale))
+            for k in range(n):
+                x = F.leaky_relu(F.interpolate(conv(f'dim_to_in.{3 * k}', x, 1), scale_factor=2), 0.2)
+            x = conv(f'dim_to_in.{3 * n + 2}', F.leaky_relu(conv(f'dim_to_in.{3 * n}', x, 1), 0.2), 1)
+        elif mode == 'pa_up':
+            n = int(math.log2(scale))
+            for k in range(n):
+                x = conv(f'dim_to_in.{6 * k + 1}', F.interpolate(x, scale_factor=2), 1)
+                x = F.leaky_relu(x * torch.sigmoid(conv(f'dim_to_in.{6 * k + 2}.conv.0', x)), 0.2)
+                x = F.leaky_relu(conv(f'dim_to_in.{6 * k + 4}', x, 1), 0.2)
+            x = conv(f'dim_to_in.{6 * n}', x, 1)
         elif mode == 'dysample':
             i = 0
             if 'dim_to_in.0.weight' in sd:

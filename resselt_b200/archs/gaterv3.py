@@ -19,9 +19,10 @@ Lowering.  One plan with base divisor 16 holds all five grids (H, H/2, H/4, H/8,
     built on the host, whose zero taps the kernel skips per 8-channel plane; fc2's epilogue is the Mish.
   * Down = conv + PixelUnshuffle(2) (the unshuffle op of RTMoSR), Upsample = conv + PixelShuffle(2) (plain shuffle op); the
     encoder's level outputs are written straight into the second half of the decoder's concat buffers.
-  * Heads: ``pixelshuffle`` (default), ``pixelshuffledirect``, ``dysample`` with a 1x1 end conv, and the plain conv of scale 1.
-    ``nearest+conv``, ``transpose+conv``, ``lda`` (deformable LDA-AQU) and ``pa_up`` are refused at load, as is the latent
-    self-attention variant.
+  * Heads: ``pixelshuffle`` (default), ``pixelshuffledirect``, ``nearest+conv`` and ``pa_up`` (2^n; the nearest upsample folded into 2x2
+    phase convs), ``dysample`` with a 1x1 end conv, and the plain conv of scale 1.  ``transpose+conv`` and ``lda`` (deformable LDA-AQU)
+    are refused at load.  The latent self-attention variant (``attention=True``) maps onto DAT's channel-attention op behind a 1x1
+    conv and a depthwise 3x3.
 Reflect padding to a multiple of 16, the crop and ``+ gamma * nearest(inp)`` are host glue around the plan (arch.py:789-802).
 """
 from __future__ import annotations
@@ -37,9 +38,10 @@ from ..engine import native as N
 from ..factory import Architecture, KeyCondition
 from ..utilities.state_dict import get_seq_len
 from ._common import conv_specs, dysample_specs, emit_dysample
+from .esrgan import upconv_phase_kernels
 
 SAMPLE_MODS = ('conv', 'pixelshuffledirect', 'pixelshuffle', 'nearest+conv', 'dysample', 'transpose+conv', 'lda', 'pa_up')
-SUPPORTED_MODS = ('pixelshuffledirect', 'pixelshuffle', 'dysample')
+SUPPORTED_MODS = ('pixelshuffledirect', 'pixelshuffle', 'nearest+conv', 'dysample', 'pa_up')
 
 
 def _conv3xc_specs(prefix: str, cin: int, cout: int, gain: int, bias: bool) -> List[ParamSpec]:
@@ -67,10 +69,18 @@ def _spab_specs(prefix: str, dim: int) -> List[ParamSpec]:
     return sum((_conv3xc_specs(f'{prefix}.{c}', dim, dim, 2, False) for c in ('c1_r', 'c2_r', 'c3_r')), [])
 
 
-def _gated_cnn_specs(p: str, dim: int) -> List[ParamSpec]:
+ATT_HEADS = 16  # Attention(conv_channels, 16) in GatedCNNBlock (arch.py:616)
+
+
+def _gated_cnn_specs(p: str, dim: int, att: bool = False) -> List[ParamSpec]:
     hidden, gc = int(1.5 * dim), int(dim * 0.125)
     specs: List[ParamSpec] = [(f'{p}.norm.scale', (dim,), 'affine_w'), (f'{p}.norm.offset', (dim,), 'normal:0.1')]
     specs += conv_specs(f'{p}.fc1', dim, 2 * hidden, 1)
+    if att:  # Attention (arch.py:560-591): temperature, qkv 1x1 (no bias), depthwise 3x3 on 3 dim channels, project_out 1x1 (no bias)
+        specs += [(f'{p}.token_mix.temperature', (ATT_HEADS, 1, 1), 'affine_w'), (f'{p}.token_mix.qkv.weight', (3 * dim, dim, 1, 1), 'conv_w*2.0'),
+                  (f'{p}.token_mix.qkv_dwconv.weight', (3 * dim, 1, 3, 3), 'conv_w*2.0'), (f'{p}.token_mix.qkv_dwconv.bias', (3 * dim,), 'bias:9'),
+                  (f'{p}.token_mix.project_out.weight', (dim, dim, 1, 1), 'conv_w')]
+        return specs + conv_specs(f'{p}.fc2', hidden, dim, 1)
     specs += [(f'{p}.token_mix.dwconv_hw.weight', (gc, 1, 3, 3), 'conv_w*2.0'), (f'{p}.token_mix.dwconv_hw.bias', (gc,), 'bias:9'),
               (f'{p}.token_mix.dwconv_w.weight', (gc, 1, 1, 11), 'conv_w*2.0'), (f'{p}.token_mix.dwconv_w.bias', (gc,), 'bias:11'),
               (f'{p}.token_mix.dwconv_h.weight', (gc, 1, 11, 1), 'conv_w*2.0'), (f'{p}.token_mix.dwconv_h.bias', (gc,), 'bias:11')]
@@ -115,6 +125,18 @@ def _head_specs(upsample: str, scale: int, dim: int, out_ch: int, mid: int, end_
             specs += conv_specs(f'dim_to_in.{i}', mid, r * r * mid, 3)
             i += 2
         specs += conv_specs(f'dim_to_in.{i}', mid, out_ch, 3)
+    elif upsample == 'nearest+conv':  # [conv, Upsample(2), LeakyReLU] x n, conv, LeakyReLU, conv (arch.py:270-296)
+        n = int(math.log2(scale))
+        for k in range(n + 1):
+            specs += conv_specs(f'dim_to_in.{3 * k}', dim, dim, 3)
+        specs += conv_specs(f'dim_to_in.{3 * n + 2}', dim, out_ch, 3)
+    elif upsample == 'pa_up':  # [Upsample(2), conv, PA, LeakyReLU, conv, LeakyReLU] x n, conv (arch.py:325-352)
+        n, cin = int(math.log2(scale)), dim
+        for k in range(n):
+            specs += conv_specs(f'dim_to_in.{6 * k + 1}', cin, mid, 3) + conv_specs(f'dim_to_in.{6 * k + 2}.conv.0', mid, mid, 1) + conv_specs(f'dim_to_in.{6 * k + 4}', mid, mid, 3)
+            cin = mid
+        specs += conv_specs(f'dim_to_in.{6 * n}', mid, out_ch, 3)
+        meta[3] = mid  # the reference records in_dim after its loop has re-bound it (arch.py:338)
     else:  # dysample
         i = 0
         if mid != dim:
@@ -130,12 +152,16 @@ class GateRV3(EngineModule):
     def __init__(self, *, in_ch: int = 3, dim: int = 32, enc_blocks: Sequence[int] = (2, 2, 4, 8), dec_blocks: Sequence[int] = (2, 2, 2, 2),
                  num_latent: int = 12, scale: int = 1, upsample: str = 'pixelshuffle', upsample_mid_dim: int = 32, attention: bool = False,
                  span_blocks: int = 4, end_kernel: int = 1, seed: int = 0):
-        if attention:
-            raise NotImplementedError('GateRV3 with latent self-attention (attention=True) is not built')
+        if attention and (dim * 2 ** len(enc_blocks)) // ATT_HEADS > 32:
+            raise NotImplementedError('GateRV3 latent attention: head_dim <= 32 (the channel-attention kernels)')
         if scale != 1 and upsample not in SUPPORTED_MODS:
             raise NotImplementedError(f'GateRV3 upsampler {upsample!r} is not built (supported: {SUPPORTED_MODS})')
         if scale != 1 and upsample == 'pixelshuffle' and scale & (scale - 1) and scale != 3:
             raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
+        if scale != 1 and upsample in ('nearest+conv', 'pa_up') and scale & (scale - 1):
+            if scale != 3:
+                raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
+            raise NotImplementedError(f'GateRV3 {upsample!r} head: x3 (nearest x3 phase kernels) is not built')
         if len(enc_blocks) != len(dec_blocks) or dim % 16 or min(list(enc_blocks) + list(dec_blocks)) < 1:
             raise ValueError('GateRV3 needs as many decoder as encoder levels, >= 1 block per level and dim % 16 == 0 (planar-8 layout)')
         L = len(enc_blocks)
@@ -151,7 +177,7 @@ class GateRV3(EngineModule):
         specs += _spab_specs('span_end', dim)
         specs += _conv3xc_specs('sisr_end_conv', dim, dim, 1, True) + conv_specs('sisr_cat_conv', 4 * dim, dim, 1)
         for k in range(num_latent):
-            specs += _gated_cnn_specs(f'latent.{k}', dim * 2 ** L)
+            specs += _gated_cnn_specs(f'latent.{k}', dim * 2 ** L, attention)
         for i, nb in enumerate(dec_blocks):
             d = dim * 2 ** (L - i)
             specs += [(f'decode.{i}.scale.0.weight', (2 * d, d, 3, 3), 'conv_w')]
@@ -164,6 +190,7 @@ class GateRV3(EngineModule):
         self._plan_base_divisor = 2 ** L
         self.dim, self.enc_blocks, self.dec_blocks, self.num_latent = dim, list(enc_blocks), list(dec_blocks), num_latent
         self.scale, self.upsample, self.mid, self.span_blocks = int(scale), upsample, upsample_mid_dim, span_blocks
+        self.attention = bool(attention)
         self.pad = 2 ** L
 
     # ------------------------------------------------------------------ host glue (arch.py:783-802)
@@ -192,7 +219,16 @@ class GateRV3(EngineModule):
         g_rows, i_rows, c_rows = slice(0, hidden), slice(hidden, 2 * hidden - d), slice(2 * hidden - d, 2 * hidden)
         pb.conv(s['xn'], s['ic'].slice(0, hidden - d), w1[i_rows], b1[i_rows])
         pb.conv(s['xn'], s['c'], w1[c_rows], b1[c_rows])
-        pb.dwconv(s['c'], s['ic'].slice(hidden - d, d), *merge_inception(w, f'{p}.token_mix', d))
+        if f'{p}.token_mix.qkv.weight' in w:
+            # Attention (arch.py:572-591): q, k normalised over the pixels, (q k^T) * temperature, softmax over channels, attn @ v —
+            # the transposed attention of DAT's channel blocks (RSB_OP_CHANATTN) behind a 1x1 conv and a depthwise 3x3
+            t = f'{p}.token_mix'
+            pb.conv(s['c'], s['qkv'], w[f'{t}.qkv.weight'], None)
+            pb.dwconv3(s['qkv'], s['qkvd'], w[f'{t}.qkv_dwconv.weight'], w[f'{t}.qkv_dwconv.bias'])
+            pb.op(N.OP_CHANATTN, s['qkvd'], s['att'], d, ints=(ATT_HEADS, d), weights=(w[f'{t}.temperature'],))
+            pb.conv(s['att'], s['ic'].slice(hidden - d, d), w[f'{t}.project_out.weight'], None)
+        else:
+            pb.dwconv(s['c'], s['ic'].slice(hidden - d, d), *merge_inception(w, f'{p}.token_mix', d))
         pb.conv(s['xn'], s['gm'], w1[g_rows], b1[g_rows], act=N.ACT_MISH, combine=N.COMB_MUL, res1=s['ic'])
         pb.conv(s['gm'], out, w[f'{p}.fc2.weight'], w[f'{p}.fc2.bias'], act=N.ACT_MISH)
 
@@ -265,6 +301,8 @@ class GateRV3(EngineModule):
             cur = u5.slice(0, 2 * d)
         dl = dim * 2 ** L
         s = scratch(dl, grid(L), meta=False)
+        if self.attention:
+            s.update(qkv=pb.buffer(3 * dl, scale=grid(L)), qkvd=pb.buffer(3 * dl, scale=grid(L)), att=pb.buffer(dl, scale=grid(L)))
         for k in range(self.num_latent):
             dst = s['a'] if cur is not s['a'] else s['b']
             self._gated_cnn(pb, w, f'latent.{k}', cur, dst, s, dl)
@@ -306,6 +344,32 @@ class GateRV3(EngineModule):
                     pb.conv(cur, nxt, wk[sel], bk[sel], dst_ps=f, dst_phase=phase)
                 cur, grid, i = nxt, grid * f, i + 2
             pb.conv(cur, OUTPUT, w[f'dim_to_in.{i}.weight'], w[f'dim_to_in.{i}.bias'], ps=1)
+        elif self.upsample == 'nearest+conv':
+            # lrelu commutes with the nearest upsample: z0 = lrelu(conv0(x)) on the input grid, every later conv reads an upsampled map
+            # = four 2x2 phase convs on the source grid (esrgan.upconv_phase_kernels), stored pixel-interleaved
+            n, lrelu = int(math.log2(r)), dict(act=N.ACT_LRELU, act_param=0.2)
+            cur = pb.buffer(self.dim)
+            pb.conv(x, cur, w['dim_to_in.0.weight'], w['dim_to_in.0.bias'], **lrelu)
+            grid = 1
+            for k in range(1, n + 1):
+                nxt = pb.buffer(self.dim, scale=full * grid * 2)
+                for phase, wk, pad2 in upconv_phase_kernels(w[f'dim_to_in.{3 * k}.weight']):
+                    pb.conv(cur, nxt, wk, w[f'dim_to_in.{3 * k}.bias'], dst_ps=2, dst_phase=phase, pad=pad2, **lrelu)
+                cur, grid = nxt, grid * 2
+            pb.conv(cur, OUTPUT, w[f'dim_to_in.{3 * n + 2}.weight'], w[f'dim_to_in.{3 * n + 2}.bias'], ps=1)
+        elif self.upsample == 'pa_up':
+            n, mid, cur, grid = int(math.log2(r)), self.mid, x, 1
+            for k in range(n):
+                g2 = full * grid * 2
+                a, t, u, v = (pb.buffer(mid, scale=g2) for _ in range(4))
+                for phase, wk, pad2 in upconv_phase_kernels(w[f'dim_to_in.{6 * k + 1}.weight']):
+                    pb.conv(cur, a, wk, w[f'dim_to_in.{6 * k + 1}.bias'], dst_ps=2, dst_phase=phase, pad=pad2)
+                # PA: a * sigmoid(conv1x1(a)) as the 1x1 conv's epilogue; the LeakyReLU behind the product is one more 1x1 pass
+                pb.conv(a, t, w[f'dim_to_in.{6 * k + 2}.conv.0.weight'], w[f'dim_to_in.{6 * k + 2}.conv.0.bias'], act=N.ACT_SIGMOID, combine=N.COMB_MUL, res1=a)
+                pb.conv(t, u, torch.eye(mid).view(mid, mid, 1, 1), None, act=N.ACT_LRELU, act_param=0.2)
+                pb.conv(u, v, w[f'dim_to_in.{6 * k + 4}.weight'], w[f'dim_to_in.{6 * k + 4}.bias'], act=N.ACT_LRELU, act_param=0.2)
+                cur, grid = v, grid * 2
+            pb.conv(cur, OUTPUT, w[f'dim_to_in.{6 * n}.weight'], w[f'dim_to_in.{6 * n}.bias'], ps=1)
         else:  # dysample
             i = 0
             if self.mid != self.dim:

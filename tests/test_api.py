@@ -44,6 +44,8 @@ def test_metadata_field_order():
         (GateRV3(dim=16, enc_blocks=(1, 2), dec_blocks=(2, 1), num_latent=2, scale=1), ('GateRV3', 3, 3, 1)),
         (GateRV3(dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=4, upsample='dysample', upsample_mid_dim=16), ('GateRV3', 3, 3, 4)),
         (GateRV3(in_ch=1, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=3, upsample='pixelshuffledirect'), ('GateRV3', 1, 1, 3)),
+        (GateRV3(dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=2, scale=2, upsample='nearest+conv', attention=True), ('GateRV3', 3, 3, 2)),
+        (GateRV3(dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=4, upsample='pa_up', upsample_mid_dim=24), ('GateRV3', 3, 3, 4)),
         (RTMoSR(scale=4, dim=48, ffn_expansion=1.5, n_blocks=1, dccm=False, se=False), ('RTMoSR', 3, 3, 2)),   # the reference always reports 2
         (RTMoSR(scale=2, n_blocks=1, unshuffle_mod=True), ('RTMoSR', 3, 3, 2)),
         (SpanPlus(blocks=[4], upscale=2), ('SPANPlus', 3, 3, 2)),
@@ -97,6 +99,7 @@ def test_detect_and_hyperparameter_inference(model, meta):
         assert (loaded.dim, loaded.enc_blocks, loaded.dec_blocks, loaded.num_latent, loaded.scale, loaded.span_blocks) == (
             model.dim, model.enc_blocks, model.dec_blocks, model.num_latent, model.scale, model.span_blocks)
         assert model.scale == 1 or (loaded.upsample, loaded.mid) == (model.upsample, model.mid)
+        assert loaded.attention == model.attention
     if isinstance(model, RTMoSR):
         assert (loaded.scale, loaded.dim, loaded.hidden, loaded.n_blocks, loaded.unshuffle, loaded.dccm, loaded.se) == (
             model.scale, model.dim, model.hidden, model.n_blocks, model.unshuffle, model.dccm, model.se)
