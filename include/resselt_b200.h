@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RSB_VERSION 203
+#define RSB_VERSION 204
 
 typedef struct rsb_plan rsb_plan;
 
@@ -132,6 +132,16 @@ typedef struct rsb_conv_desc {
    * norm2 -> fc1; dat/arch.py:565-612).  A zero-initialised descriptor has no fold. */
   int32_t ln_fold;
   int32_t ln_stats_buf;
+  /* The statistics without their own pass.  ln_out != 0 (bf16 plans; 1 x 1 conv into a planar buffer, no sub-pixel / split / second
+   * residual / border bias / SPAB gate): this conv's epilogue also writes, per pixel, the partial sums {sum v, sum v^2} of the values
+   * it stores (all cout channels) into the pixel chunks of the 8-channel buffer ln_out_buf — two float pairs per chunk, one per
+   * epilogue warpgroup.  A consumer reads them with ln_fold == 2 (raw sums: mean and rstd are derived in its epilogue from the sums,
+   * its own cin and ln_eps) instead of ln_fold == 1 (the {rstd, -mean * rstd} the statistics-mode LayerNorm op writes).  Used for
+   * `x += proj(..)` -> norm2 -> fc1 and `x += fc2(..)` -> norm1 -> qkv (swinir/arch.py:296-335, dat/arch.py:636-683): one pass over
+   * x less per LayerNorm. */
+  int32_t ln_out;
+  int32_t ln_out_buf;
+  float ln_eps; /* epsilon of the LayerNorm whose raw sums are consumed (ln_fold == 2) */
 } rsb_conv_desc;
 
 /* GroupNorm over (channels/groups, H, W) per sample, affine, followed by "+ skip". */

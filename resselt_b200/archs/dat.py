@@ -201,13 +201,18 @@ class DAT(EngineModule):
             # res = x (ResidualGroup keeps its input, arch.py:768): copy through an identity-free path: LN output already in x,
             # so stash it with a 1x1 identity conv only when the group has blocks that overwrite x
             pb.conv(x, rg_res, torch.eye(dim).view(dim, dim, 1, 1), None)
+            # bf16 plan: `x += proj(..)` and `x += fc2(..)` also write the per-pixel {sum, sum of squares} of what they store
+            # (rsb_conv_desc.ln_out): norm2 and the next block's norm1 need no statistics pass of their own
+            fuse_stats = pb.ln_out_supported(dim)
+            raw = False  # `stats` holds raw sums (written by a conv) instead of the statistics op's {rstd, -mean * rstd}
             for b in range(nblk):
                 p = f'layers.{rg}.blocks.{b}'
                 a = f'{p}.attn'
                 # norm1 -> qkv and norm2 -> fc1: the normalised map is never written (one statistics pass, LayerNorm applied in the
                 # linears' epilogues)
-                pb.layernorm_stats(x, stats)
-                ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
+                if not raw:
+                    pb.layernorm_stats(x, stats)
+                ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias']) + ((1e-5,) if raw else ())
                 wq, bq = lin_w(f'{a}.qkv'), lin_b(f'{a}.qkv')
                 hp = b % 2 == 0 and padded[heads]
                 width = heads * HEAD_PAD if hp else dim            # channels of this block's attention space
@@ -235,17 +240,20 @@ class DAT(EngineModule):
                 pb.op(N.OP_AIM, att_b, y_b, width, src2=convx_b, ints=(b % 2, dim // 8, dim // 16, hid_id),
                       weights=(ci_w1, ci_b1, rows_p(w[f'{a}.channel_interaction.4.weight']), rows_p(w[f'{a}.channel_interaction.4.bias']),
                                si_w1, si_b1, w[f'{a}.spatial_interaction.3.weight'], w[f'{a}.spatial_interaction.3.bias']))
-                pb.conv(y_b, x, cols_p(lin_w(f'{a}.proj')), lin_b(f'{a}.proj'), combine=N.COMB_AXPY, res1=x)        # x += proj(...)
+                pb.conv(y_b, x, cols_p(lin_w(f'{a}.proj')), lin_b(f'{a}.proj'), combine=N.COMB_AXPY, res1=x,
+                        ln_out=stats if fuse_stats else None)                                                          # x += proj(...)
                 f = f'{p}.ffn'
-                pb.layernorm_stats(x, stats)
-                ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
+                if not fuse_stats:
+                    pb.layernorm_stats(x, stats)
+                ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias']) + ((1e-5,) if fuse_stats else ())
                 w1, b1 = lin_w(f'{f}.fc1'), lin_b(f'{f}.fc1')
                 for part in range(2):  # x1 | x2 = chunk(2) of the hidden activations, each on its own plane range
                     rows = slice(part * half, (part + 1) * half)
                     pb.conv(x, hid.slice(part * hpad, half), w1[rows], b1[rows], act=N.ACT_GELU, ln=ln2)
                 pb.layernorm(hid.slice(hpad, half), gate_n, w[f'{f}.sg.norm.weight'], w[f'{f}.sg.norm.bias'])
                 pb.dwconv3(gate_n, gated, w[f'{f}.sg.conv.weight'], w[f'{f}.sg.conv.bias'], gate=hid.slice(0, half))
-                pb.conv(gated, x, lin_w(f'{f}.fc2'), lin_b(f'{f}.fc2'), combine=N.COMB_AXPY, res1=x)      # x += fc2(...)
+                raw = fuse_stats and b + 1 < nblk  # the next block's norm1 statistics
+                pb.conv(gated, x, lin_w(f'{f}.fc2'), lin_b(f'{f}.fc2'), combine=N.COMB_AXPY, res1=x, ln_out=stats if raw else None)      # x += fc2(...)
             emit_resi_conv(pb, w, f'layers.{rg}.conv', self.resi_connection, x, img, rg_res, tmp_a, tmp_b)
             x, img = img, x
         pb.layernorm(x, xn, w['norm.weight'], w['norm.bias'])

@@ -152,10 +152,16 @@ class SwinIR(EngineModule):
         pb.layernorm(feat, a, w['patch_embed.norm.weight'], w['patch_embed.norm.bias'])
         for i, (nblk, heads) in enumerate(zip(self.depths, self.heads)):
             cur = a
+            # bf16 plan: the residual linears (`shortcut + proj(..)`, `x + fc2(..)`) also write the per-pixel {sum, sum of squares} of what
+            # they store (rsb_conv_desc.ln_out), so norm2 and the next block's norm1 need no statistics pass of their own
+            w2_bytes = ((hpad + 15) // 16 * 16) * ((dim + 15) // 16 * 16) * 2
+            fuse_stats = pb.ln_out_supported(dim) and w2_bytes <= 150 * 1024
+            raw = False  # does `stats` hold raw sums (written by a conv) or the statistics op's {rstd, -mean * rstd}?
             for blk in range(nblk):
                 p = f'layers.{i}.residual_group.blocks.{blk}'
-                pb.layernorm_stats(cur, stats)  # norm1 -> qkv: LayerNorm applied in the linears' epilogues, its output never written
-                ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias'])
+                if not raw:
+                    pb.layernorm_stats(cur, stats)  # norm1 -> qkv: LayerNorm applied in the linears' epilogues, its output never written
+                ln1 = (stats, w[f'{p}.norm1.weight'], w[f'{p}.norm1.bias']) + ((1e-5,) if raw else ())
                 wq, bq = lin_w(f'{p}.attn.qkv'), lin_b(f'{p}.attn.qkv')
                 hp = padded[heads]
                 width = heads * HEAD_PAD if hp else dim
@@ -170,16 +176,18 @@ class SwinIR(EngineModule):
                       weights=(table[:, : heads // 2].contiguous(), table[:, heads // 2:].contiguous()))
                 wproj = lin_w(f'{p}.attn.proj')
                 pb.conv(att.slice(0, width), b, pad_head_cols(wproj, dim, heads) if hp else wproj, lin_b(f'{p}.attn.proj'),
-                        combine=N.COMB_AXPY, res1=cur)  # shortcut + attn
+                        combine=N.COMB_AXPY, res1=cur, ln_out=stats if fuse_stats else None)  # shortcut + attn
                 cur = b
-                pb.layernorm_stats(cur, stats)  # norm2 -> fc1
-                ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias'])
+                if not fuse_stats:
+                    pb.layernorm_stats(cur, stats)  # norm2 -> fc1
+                ln2 = (stats, w[f'{p}.norm2.weight'], w[f'{p}.norm2.bias']) + ((1e-5,) if fuse_stats else ())
                 w1, b1, w2 = lin_w(f'{p}.mlp.fc1'), lin_b(f'{p}.mlp.fc1'), lin_w(f'{p}.mlp.fc2')
                 if hpad != hidden:  # gelu(0 * x + 0) = 0 feeds zero fc2 columns
                     w1, b1 = F.pad(w1, (0, 0, 0, 0, 0, 0, 0, hpad - hidden)), F.pad(b1, (0, hpad - hidden))
                     w2 = F.pad(w2, (0, 0, 0, 0, 0, hpad - hidden))
                 pb.conv(cur, hid, w1, b1, act=N.ACT_GELU, ln=ln2)
-                pb.conv(hid, cur, w2, lin_b(f'{p}.mlp.fc2'), combine=N.COMB_AXPY, res1=cur)      # x + mlp(norm2(x))
+                raw = fuse_stats and blk + 1 < nblk  # the next block's norm1 statistics
+                pb.conv(hid, cur, w2, lin_b(f'{p}.mlp.fc2'), combine=N.COMB_AXPY, res1=cur, ln_out=stats if raw else None)      # x + mlp(norm2(x))
             self._resi_conv(pb, w, f'layers.{i}.conv', cur, c, a, tmp_a, tmp_b)  # RSTB: conv(blocks(x)) + x
             a, c = c, a
         pb.layernorm(a, xn, w['norm.weight'], w['norm.bias'])

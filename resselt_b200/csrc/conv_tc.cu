@@ -338,6 +338,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                                     : nullptr;
           mbar_wait_parked(&tfull[g], aph);
           tc_fence_after();
+          const bool lnout = p.epi.ln_out != nullptr;  // partial LayerNorm sums of the stored values (Epi::ln_out)
+          float ls1 = 0.0f, ls2 = 0.0f;
           if (lean) {
             auto emit = [&](const uint32_t (&r)[16], int c) {
 #pragma unroll
@@ -378,6 +380,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                     for (int j = 0; j < 8; ++j) v[j] = fmaf(p.epi.alpha, v[j], p.epi.beta1 * rr[j]);
                   }
                 }
+                if (lnout) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) ls1 += v[j], ls2 = fmaf(v[j], v[j], ls2);
+                }
                 store8<T>(drow + (size_t)(c0 >> 3) * pstride, v);
               }
             };
@@ -396,6 +402,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 if (c + 2 * cstep < p.npad) tmem_ld16(taddr + (uint32_t)(c + 2 * cstep), ra);
                 if (valid) emit(rbb, c + cstep);
               }
+            }
+            if (lnout && valid) {  // this warpgroup's pair of the pixel's chunk (parts <= 2: conv_tc_num_acc)
+              float2* o = reinterpret_cast<float2*>(reinterpret_cast<char*>(p.epi.ln_out) +
+                                                    (((size_t)n * p.epi.ln_out_planes * p.H + y) * p.W + x) * (size_t)p.epi.ln_out_stride);
+              o[part] = make_float2(ls1, ls2);
+              if (parts == 1) o[1] = make_float2(0.0f, 0.0f);
             }
           } else
           for (int c = part * 16; c < p.npad; c += 16 * parts) {
@@ -504,6 +516,7 @@ KernelFn pick(const ConvTcParams& p) {
       const bool geo = pass == 0 ? (v.kh == p.kh && v.kw == p.kw && v.ksteps == ks && p.nchunks == 1) : v.kh == 0;
       const bool width = v.nch == 0 || v.nch * 16 == p.npad;
       const bool ext = p.epi.dst_external ? v.ext == kRuntime : v.ext == 0;
+      if (p.epi.ln_out != nullptr && v.nch != 0) continue;  // the partial LayerNorm sums live in the runtime-N lean epilogue
       if (geo && width && ext && v.act == act && v.comb == comb) return v.fn;
     }
   return kVariants[kNumVariants - 1].fn;

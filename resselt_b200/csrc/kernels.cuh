@@ -33,6 +33,12 @@ struct Epi {
   const void* ln_stats;
   int ln_stride, ln_planes;  // bytes per pixel chunk, planes of the statistics buffer (its batch stride)
   const float* ln_rowsum;
+  // ln_raw: the chunk holds two partial {sum, sum of squares} pairs written by the producing conv's epilogue (ln_out below) instead of
+  // {rstd, -mean * rstd}: statistics are derived here (ln_inv_n = 1 / channels, ln_eps)
+  int ln_raw;
+  float ln_inv_n, ln_eps;
+  void* ln_out;  // non-null: this conv writes the partial sums of the values it stores (conv_tc lean epilogue), chunk geometry below
+  int ln_out_stride, ln_out_planes;
   int act;
   float act_param;
   int combine;
@@ -232,8 +238,15 @@ __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& q, float (&o
 
 // per-pixel LayerNorm statistics {rstd, -mean * rstd} of a folded LayerNorm (Epi::ln_stats)
 __device__ __forceinline__ float2 ln_stats_of(const Epi& e, int n, int y, int x) {
-  return __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const char*>(e.ln_stats) +
-                                               (((size_t)n * e.ln_planes * e.H + y) * e.W + x) * (size_t)e.ln_stride));
+  const char* chunk = reinterpret_cast<const char*>(e.ln_stats) + (((size_t)n * e.ln_planes * e.H + y) * e.W + x) * (size_t)e.ln_stride;
+  if (e.ln_raw) {  // partial sums of the producing conv's two epilogue warpgroups
+    const float4 r = __ldg(reinterpret_cast<const float4*>(chunk));
+    const float mean = (r.x + r.z) * e.ln_inv_n;
+    const float var = fmaxf(fmaf(-mean, mean, (r.y + r.w) * e.ln_inv_n), 0.0f);
+    const float rstd = rsqrtf(var + e.ln_eps);
+    return make_float2(rstd, -mean * rstd);
+  }
+  return __ldg(reinterpret_cast<const float2*>(chunk));
 }
 
 // EXT = 0: destination is known to be a planar buffer (the NCHW scatter code is compiled out); kRuntime: check e.dst_external.
@@ -668,6 +681,8 @@ size_t winattn_smem_bytes(int split_h, int split_w);
 cudaError_t winattn_configure();
 cudaError_t launch_winattn(const WinAttnParams& p, bool bf16, int num_sms, cudaStream_t s);
 cudaError_t launch_chan_gate(const SeParams& p, bool bf16, int num_sms, cudaStream_t s);
+cudaError_t launch_ln_raw_sums(const void* src, int planes, int plane0, int nplanes, int n, int H, int W, void* out, int out_planes, int num_sms,
+                               cudaStream_t s);
 cudaError_t launch_chan_affine(const TokenOpParams& p, bool bf16, int num_sms, cudaStream_t s);
 bool winattn_tc_supported(int heads, int head_dim, int split_h, int split_w);  // shapes the head-padded tcgen05 kernel takes
 cudaError_t winattn_tc_configure();

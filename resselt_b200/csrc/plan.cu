@@ -352,6 +352,13 @@ void fill_epi(rsb_plan* p, ConvOp& c, int n, int H, int W, uint8_t* ws, rsb::Epi
     e.ln_stride = p->dtype == RSB_BF16 ? 16 : 32;  // one 8-channel pixel chunk
     e.ln_planes = p->bufs[d.ln_stats_buf].planes;
     e.ln_rowsum = c.d_lnsum;
+    e.ln_raw = d.ln_fold == 2 ? 1 : 0;
+    e.ln_inv_n = 1.0f / (float)d.cin, e.ln_eps = d.ln_eps;
+  }
+  if (d.ln_out) {
+    e.ln_out = ws + p->bufs[d.ln_out_buf].offset;
+    e.ln_out_stride = 16;  // bf16 plans only: one 8-channel pixel chunk
+    e.ln_out_planes = p->bufs[d.ln_out_buf].planes;
   }
   e.act = d.act;
   e.act_param = d.act_param;
@@ -558,7 +565,8 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
              x.kh == y.kh && x.kw == y.kw && x.pad_t == y.pad_t && x.pad_l == y.pad_l && x.dst_buf == y.dst_buf && x.dst_buf >= 0 &&
              x.dst_ps <= 1 && y.dst_ps <= 1 && x.dst2_buf < 0 && y.dst2_buf < 0 && x.act == y.act && x.act_param == y.act_param &&
              x.combine == RSB_COMB_NONE && y.combine == RSB_COMB_NONE && a.border.empty() && b.border.empty() &&
-             x.ln_fold == y.ln_fold && (!x.ln_fold || x.ln_stats_buf == y.ln_stats_buf) && a.npad == b.npad && s.stages == t.stages &&
+             x.ln_fold == y.ln_fold && (!x.ln_fold || (x.ln_stats_buf == y.ln_stats_buf && x.ln_eps == y.ln_eps)) && !x.ln_out && !y.ln_out &&
+             a.npad == b.npad && s.stages == t.stages &&
              s.kchunk == t.kchunk && s.solo_issue == t.solo_issue && s.num_acc == t.num_acc && s.acc_stride == t.acc_stride &&
              s.tmem_cols == t.tmem_cols && s.wbytes == t.wbytes && s.stage_bytes == t.stage_bytes && y.dst_ch_off >= x.dst_ch_off;
     };
@@ -909,6 +917,15 @@ int rsb_plan_add_conv(rsb_plan* p, const rsb_conv_desc* desc) {
       return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: a LayerNorm fold needs a 1x1 conv from a buffer to a buffer, without PReLU");
     if (int e = check_buf(p, d.ln_stats_buf, 0, 8, "rsb_plan_add_conv(ln_stats)")) return e;
     if (p->bufs[d.ln_stats_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: ln_stats grid mismatch");
+    if (d.ln_fold == 2 && (p->dtype != RSB_BF16 || !(d.ln_eps > 0.0f)))
+      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: raw LayerNorm sums (ln_fold = 2) need a bf16 plan and ln_eps > 0");
+  }
+  if (d.ln_out) {
+    if (p->dtype != RSB_BF16 || d.kh != 1 || d.kw != 1 || d.src_buf < 0 || d.dst_buf < 0 || d.dst_ps > 1 || d.dst2_buf >= 0 || d.res2_buf >= 0 ||
+        d.border_bias != nullptr || d.combine == RSB_COMB_SPAB_GATE || d.cout > 256)
+      return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_add_conv: ln_out needs a bf16 plan and a 1x1 conv between buffers with a plain planar destination (cout <= 256)");
+    if (int e = check_buf(p, d.ln_out_buf, 0, 8, "rsb_plan_add_conv(ln_out)")) return e;
+    if (p->bufs[d.ln_out_buf].scale != scale) return fail(RSB_ERR_INVALID, "rsb_plan_add_conv: ln_out grid mismatch");
   }
   c.scale = scale;
   const size_t wn = (size_t)d.cout * d.cin * d.kh * d.kw;
@@ -1133,6 +1150,7 @@ int rsb_plan_finalize(rsb_plan* p, int device) {
         c.stages = stages;
         c.kchunk = kchunk;
       }
+      if (d.ln_out && !c.tc_ok) return fail(RSB_ERR_UNSUPPORTED, "rsb_plan_finalize: a conv with ln_out does not fit the tensor-core tile kernel");
     }
     const int cmax = std::max(c.npad, c.cpad32);
     std::vector<float> bias(cmax, 0.0f), slopes(cmax, 0.0f);
@@ -1469,6 +1487,9 @@ int rsb_plan_forward_ops(rsb_plan* p, const void* x, int x_dtype, int n, int h, 
           if (q.epi.dst_external) q.epi.dst = y, q.epi.out_dtype = y_dtype;
           q.epi.base = x, q.epi.base_dtype = x_dtype;
           e = rsb::launch_conv_direct(q, p->dtype == RSB_BF16, stream);
+          if (e == cudaSuccess && c.d.ln_out)  // the CUDA-core kernel has no ln_out epilogue: the raw sums from the map it wrote
+            e = rsb::launch_ln_raw_sums(q.epi.dst, q.epi.dst_planes, q.epi.dst_plane0, ceil_div(c.d.cout, 8), c.tcp.n, q.epi.H, q.epi.W, c.tcp.epi.ln_out,
+                                        c.tcp.epi.ln_out_planes, p->num_sms, stream);
         }
       } else if (op.kind == 1) {
         e = rsb::launch_groupnorm(p->gns[op.index].gp, p->dtype == RSB_BF16, stream);

@@ -309,7 +309,33 @@ __global__ void __launch_bounds__(256) chan_affine_kernel(const __grid_constant_
   }
 }
 
+// Raw LayerNorm sums {sum, sum of squares, 0, 0} per pixel of a bf16 map: what conv_tc's epilogue writes with Epi::ln_out, for the
+// forwards that run a plan's convs on the CUDA-core kernel instead (the device-side cross-check mode)
+__global__ void __launch_bounds__(256) ln_raw_sums_kernel(const __nv_bfloat16* src, int planes, int plane0, int nplanes, int n, size_t hw, float4* out,
+                                                          int out_planes) {
+  const size_t total = (size_t)n * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / hw, px = i - b * hw;
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int pl = 0; pl < nplanes; ++pl) {
+      float v[8];
+      load8<__nv_bfloat16>(src + ((b * planes + plane0 + pl) * hw + px) * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s1 += v[k], s2 = fmaf(v[k], v[k], s2);
+    }
+    out[b * out_planes * hw + px] = make_float4(s1, s2, 0.0f, 0.0f);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_ln_raw_sums(const void* src, int planes, int plane0, int nplanes, int n, int H, int W, void* out, int out_planes, int num_sms,
+                               cudaStream_t s) {
+  const size_t hw = (size_t)H * W;
+  ln_raw_sums_kernel<<<grid_for((size_t)n * hw, 256, (num_sms > 0 ? num_sms : 148) * 16), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), planes, plane0, nplanes, n, hw, reinterpret_cast<float4*>(out), out_planes);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_chan_gate(const SeParams& p, bool bf16, int num_sms, cudaStream_t s) {
   const int sms = num_sms > 0 ? num_sms : 148;

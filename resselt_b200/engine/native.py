@@ -61,6 +61,7 @@ class ConvDesc(C.Structure):
         ('dst_phase', C.c_int32), ('pad_t', C.c_int32), ('pad_l', C.c_int32),
         ('border_bias', C.POINTER(C.c_float)),
         ('ln_fold', C.c_int32), ('ln_stats_buf', C.c_int32),
+        ('ln_out', C.c_int32), ('ln_out_buf', C.c_int32), ('ln_eps', C.c_float),
     ]
 
 

@@ -79,9 +79,17 @@ class PlanBuilder:
 
         ``ln = (stats, gamma, beta)``: the conv (1 x 1) consumes LayerNorm(src) without that map ever being written —
         ``stats`` is the 8-channel buffer ``layernorm_stats(src, stats)`` filled; gamma goes into the weights and beta into the bias
-        here (fp64), the per-pixel mean / rstd are applied in the conv's epilogue (rsb_conv_desc.ln_fold)."""
+        here (fp64), the per-pixel mean / rstd are applied in the conv's epilogue (rsb_conv_desc.ln_fold).  A fourth element
+        ``eps`` says that ``stats`` holds the raw partial sums a producing conv wrote with ``ln_out=stats`` (ln_fold = 2) instead of
+        the statistics op's {rstd, -mean * rstd}.
+
+        ``ln_out=stats`` (bf16 plans, 1 x 1 convs into a plain planar buffer, cout <= 256): the conv also writes the per-pixel
+        {sum, sum of squares} of the values it stores into ``stats`` — the LayerNorm statistics of its output without a pass of their
+        own (``ln_out_supported``)."""
         if ln is not None:
-            stats, gamma, beta = ln
+            stats, gamma, beta = ln[:3]
+            if len(ln) > 3:
+                kw['ln_raw_eps'] = float(ln[3])
             w64 = (weight.detach().to('cpu', torch.float64).numpy() if isinstance(weight, torch.Tensor) else np.asarray(weight, dtype=np.float64))
             g64 = (gamma.detach().to('cpu', torch.float64).numpy() if isinstance(gamma, torch.Tensor) else np.asarray(gamma, dtype=np.float64))
             b64 = (beta.detach().to('cpu', torch.float64).numpy() if isinstance(beta, torch.Tensor) else np.asarray(beta, dtype=np.float64))
@@ -99,6 +107,7 @@ class PlanBuilder:
         npad = (cout + 15) // 16 * 16
         if not splittable or (kh * kw_ * cin16 * npad * 2 <= budget and npad <= 256):
             return self._conv_one(src, dst, w, bias, **kw)
+        assert kw.get('ln_out') is None, 'a conv that writes LayerNorm sums (ln_out) cannot be split over its output channels'
         per = max(16, min(256, budget // (kh * kw_ * cin16 * 2) // 16 * 16))
         b = _f32(bias) if bias is not None else None
         slopes = _f32(kw['act_slopes']) if kw.get('act_slopes') is not None else None
@@ -141,6 +150,8 @@ class PlanBuilder:
         pad: Optional[tuple] = None,
         border_bias=None,
         ln_stats: Optional[Ref] = None,
+        ln_raw_eps: Optional[float] = None,
+        ln_out: Optional[Ref] = None,
     ) -> None:
         w = _f32(weight)
         assert w.ndim == 4, 'conv weight must be [cout][cin][kh][kw]'
@@ -178,7 +189,9 @@ class PlanBuilder:
         d.border_bias = _fptr(bb)
         d.dst2_buf, d.dst2_ch_off = (dst2.buf, dst2.ch_off) if dst2 is not None else (N.NO_BUFFER, 0)
         d.split_ch = main_ch if dst2 is not None else 0
-        d.ln_fold, d.ln_stats_buf = (1, ln_stats.buf) if ln_stats is not None else (0, N.NO_BUFFER)
+        d.ln_fold, d.ln_stats_buf = ((2 if ln_raw_eps is not None else 1), ln_stats.buf) if ln_stats is not None else (0, N.NO_BUFFER)
+        d.ln_eps = float(ln_raw_eps) if ln_raw_eps is not None else 0.0
+        d.ln_out, d.ln_out_buf = (1, ln_out.buf) if ln_out is not None else (0, N.NO_BUFFER)
         N.check(self._lib.rsb_plan_add_conv(self._h, C.byref(d)))
 
     def groupnorm(self, src: Ref, dst: Ref, groups: int, gamma, beta, eps: float = 1e-5, skip: Optional[Ref] = None) -> None:
@@ -214,6 +227,10 @@ class PlanBuilder:
 
     def layernorm(self, src: Ref, dst: Ref, gamma, beta, eps: float = 1e-5) -> None:
         self.op(N.OP_LAYERNORM, src, dst, src.channels, floats=(eps,), weights=(gamma, beta))
+
+    def ln_out_supported(self, channels: int) -> bool:
+        """Can a 1 x 1 conv producing ``channels`` channels also write their LayerNorm sums (``conv(..., ln_out=stats)``)?"""
+        return self.compute_dtype == torch.bfloat16 and channels <= 256
 
     def layernorm_stats(self, src: Ref, dst: Ref, eps: float = 1e-5) -> None:
         """Per-pixel LayerNorm statistics of ``src`` into the 8-channel buffer ``dst`` (consumed by ``conv(..., ln=(dst, gamma, beta))``)."""

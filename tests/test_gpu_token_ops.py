@@ -399,6 +399,44 @@ def test_unshuffle_pool_dw5_se_shuffle_chain(C, se, B, H, W, dtype):
     _check(got, ref, dtype, bf16_tol=2e-2, what='unshuffle/pool -> dw5x5 -> SE -> shuffle')
 
 
+@pytest.mark.parametrize('C,cin,cout,mean,B,H,W', [
+    (180, 192, 180, 0.3, 1, 40, 56),     # SwinIR / DAT: x += proj(att) writes the sums norm2 -> fc1 consumes (two epilogue warpgroups per pixel)
+    (180, 384, 360, 3.0, 2, 33, 47),     # x += fc2(hidden): K-chunked producer; token mean ten times the spread; image size not a multiple of 8
+    (60, 64, 120, -1.0, 1, 64, 64),      # light models: one epilogue warpgroup per pixel (second pair of the chunk written as zeros)
+    (180, 192, 180, 0.2, 1, 256, 256),   # many tiles
+])
+def test_layernorm_sums_from_the_producing_linear(C, cin, cout, mean, B, H, W):
+    """rsb_conv_desc.ln_out / ln_fold = 2: the residual linear writes {sum, sum of squares} of what it stores, the next linear derives
+    mean / rstd from them in its epilogue — Linear(LayerNorm(res + Linear(x))) against fp64, and against the statistics-op form."""
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(C + cin + H)
+    x = torch.randn(B, cin + C, H, W, generator=g) * 0.5
+    x[:, cin:] = x[:, cin:] * 0.8 + mean
+    w1, b1 = torch.randn(C, cin, 1, 1, generator=g) / cin ** 0.5, 0.1 * torch.randn(C, generator=g)
+    gamma, beta = 1.0 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    w2, b2 = torch.randn(cout, C, 1, 1, generator=g) / C ** 0.5, 0.1 * torch.randn(cout, generator=g)
+    outs = []
+    for fused in (True, False):
+        pb = PlanBuilder(dtype, cin + C, cout, 1)
+        a, res, mid, stats, y = pb.buffer(cin + C), pb.buffer(C), pb.buffer(C), pb.buffer(8), pb.buffer(cout)
+        pb.conv(INPUT, a, torch.eye(cin + C).view(cin + C, cin + C, 1, 1))
+        pb.conv(a.slice(cin, C), res, torch.eye(C).view(C, C, 1, 1))
+        assert pb.ln_out_supported(C)
+        pb.conv(a.slice(0, cin), mid, w1, b1, combine=N.COMB_AXPY, res1=res, ln_out=stats if fused else None)
+        if not fused:
+            pb.layernorm_stats(mid, stats, eps=1e-5)
+        pb.conv(mid, y, w2, b2, ln=(stats, gamma, beta) + ((1e-5,) if fused else ()))
+        pb.conv(y, OUTPUT, torch.eye(cout).view(cout, cout, 1, 1))
+        got, plan = _run(pb, x, dtype)
+        outs.append(got)
+        m = plan.read_buffer(mid).double().cpu()  # what the second linear actually read
+    ref = F.conv2d(F.layer_norm(m.permute(0, 2, 3, 1), (C,), gamma.double(), beta.double(), 1e-5).permute(0, 3, 1, 2), w2.to(dtype).double(), b2.double())
+    _check(outs[0], ref, dtype, what='linear(LayerNorm(.)) with sums from the producing linear')
+    _check(outs[1], ref, dtype, what='linear(LayerNorm(.)) with the statistics op')
+    span = float(ref.max() - ref.min())
+    assert float((outs[0] - outs[1]).abs().max()) <= 1.2e-2 * span
+
+
 # ------------------------------------------------------------------------------------------------ GateRV3 ops (rsb_op_kind 10-11, sparse depthwise 11x11)
 @pytest.mark.parametrize('dtype', DTYPES)
 @pytest.mark.parametrize('C,B,H,W', [(32, 1, 40, 56), (64, 2, 17, 30), (256, 1, 24, 40), (32, 1, 160, 192)])

@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(N.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/ but not exported'
-    assert lib.rsb_version() == 203
+    assert lib.rsb_version() == 204
 
 
 def test_desc_struct_sizes_match_header_layout():
