@@ -395,7 +395,15 @@ const RsVariant kRsVariants[] = {
     RSB_V(4, 2, RSB_ACT_MISH, RSB_COMB_AXPY),
     RSB_V(8, 4, RSB_ACT_MISH, RSB_COMB_AXPY),
     RSB_X(2, 1, RSB_ACT_NONE, RSB_COMB_NONE),
+    // GateRV3 (dim 32): SPABs at 32 channels, the grouped 3x3 conv as block-diagonal 32 / 64-channel convs whose first half ends in
+    // SimpleGate (x1 * x2)
+    RSB_V(2, 2, RSB_ACT_SILU, RSB_COMB_NONE),
+    RSB_V(2, 2, RSB_ACT_NONE, RSB_COMB_SPAB_GATE),
+    RSB_V(2, 2, RSB_ACT_NONE, RSB_COMB_MUL),
+    RSB_V(4, 4, RSB_ACT_NONE, RSB_COMB_MUL),
     // runtime geometry, specialised epilogue
+    RSB_V(0, 0, RSB_ACT_NONE, RSB_COMB_MUL),
+    RSB_V(0, 0, RSB_ACT_SILU, RSB_COMB_NONE),
     RSB_V(0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
     RSB_V(0, 0, RSB_ACT_LRELU, RSB_COMB_NONE),
     RSB_X(0, 0, RSB_ACT_NONE, RSB_COMB_NONE),
