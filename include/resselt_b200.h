@@ -164,7 +164,9 @@ typedef struct rsb_groupnorm_desc {
  * relative_position_index, cyclic shift and mask, window reverse). */
 enum rsb_op_kind {
   RSB_OP_LAYERNORM = 1, /* dst = LN_channels(src) * w[0] + w[1];  f[0] = eps.  i[0] = 1: statistics only — dst is an 8-channel
-                           buffer whose pixel chunks receive {rstd, -mean * rstd} as two floats (rsb_conv_desc.ln_stats_buf)  */
+                           buffer whose pixel chunks receive {rstd, -mean * rstd} as two floats (rsb_conv_desc.ln_stats_buf);
+                           i[0] = 2: the same for a channels-first RMSNorm x / (|x|_2 / sqrt(C) + eps): {1 / (rms + eps), 0}, so
+                           that a 1x1 conv with ln_fold = 1 computes conv(RMSNorm(x) * scale + offset) (gaterv3/arch.py:511-524)   */
   RSB_OP_DWCONV3 = 2,   /* dst = act(dwconv3x3(src; w[0] = [C][9], w[1] = bias[C])) [* src2];  i[0] = rsb_act;
                            i[1] = K in {0, 3, 5, 7}: depthwise K x K instead (w[0] = [C][K*K]; K > 3: no act / gate)          */
   RSB_OP_WINATTN = 3,   /* src = [q | k | v]; i[0] heads, i[1] split_h, i[2] split_w, i[3] shifted, i[4] channel stride

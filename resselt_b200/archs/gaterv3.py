@@ -214,11 +214,18 @@ class GateRV3(EngineModule):
     def _gated_cnn(self, pb: PlanBuilder, w, p: str, x, out, s, d: int) -> None:
         """out = mish(fc2(mish(g) * cat(i, token_mix(c)))) with g, i, c = split(fc1(RMSNorm(x))) (arch.py:623-629)."""
         hidden = int(1.5 * d)
-        pb.rmsnorm(x, s['xn'], w[f'{p}.norm.scale'], w[f'{p}.norm.offset'], eps=1e-6)
+        # bf16 plan: the RMSNorm is folded into the 1x1 convs that consume it (statistics pass + rsb_conv_desc.ln_fold with a zero mean
+        # term), the normalised map is never written
+        if pb.compute_dtype == torch.bfloat16:
+            pb.rmsnorm_stats(x, s['stats'], eps=1e-6)
+            xn, fold = x, dict(ln=(s['stats'], w[f'{p}.norm.scale'], w[f'{p}.norm.offset']))
+        else:
+            pb.rmsnorm(x, s['xn'], w[f'{p}.norm.scale'], w[f'{p}.norm.offset'], eps=1e-6)
+            xn, fold = s['xn'], {}
         w1, b1 = w[f'{p}.fc1.weight'], w[f'{p}.fc1.bias']
         g_rows, i_rows, c_rows = slice(0, hidden), slice(hidden, 2 * hidden - d), slice(2 * hidden - d, 2 * hidden)
-        pb.conv(s['xn'], s['ic'].slice(0, hidden - d), w1[i_rows], b1[i_rows])
-        pb.conv(s['xn'], s['c'], w1[c_rows], b1[c_rows])
+        pb.conv(xn, s['ic'].slice(0, hidden - d), w1[i_rows], b1[i_rows], **fold)
+        pb.conv(xn, s['c'], w1[c_rows], b1[c_rows], **fold)
         if f'{p}.token_mix.qkv.weight' in w:
             # Attention (arch.py:572-591): q, k normalised over the pixels, (q k^T) * temperature, softmax over channels, attn @ v —
             # the transposed attention of DAT's channel blocks (RSB_OP_CHANATTN) behind a 1x1 conv and a depthwise 3x3
@@ -229,12 +236,16 @@ class GateRV3(EngineModule):
             pb.conv(s['att'], s['ic'].slice(hidden - d, d), w[f'{t}.project_out.weight'], None)
         else:
             pb.dwconv(s['c'], s['ic'].slice(hidden - d, d), *merge_inception(w, f'{p}.token_mix', d))
-        pb.conv(s['xn'], s['gm'], w1[g_rows], b1[g_rows], act=N.ACT_MISH, combine=N.COMB_MUL, res1=s['ic'])
+        pb.conv(xn, s['gm'], w1[g_rows], b1[g_rows], act=N.ACT_MISH, combine=N.COMB_MUL, res1=s['ic'], **fold)
         pb.conv(s['gm'], out, w[f'{p}.fc2.weight'], w[f'{p}.fc2.bias'], act=N.ACT_MISH)
 
     def _meta_gated(self, pb: PlanBuilder, w, p: str, x, out, s, d: int) -> None:
-        pb.rmsnorm(x, s['xn'], w[f'{p}.local.0.scale'], w[f'{p}.local.0.offset'], eps=1e-6)
-        pb.conv(s['xn'], s['h'], w[f'{p}.local.1.weight'], w[f'{p}.local.1.bias'])
+        if pb.compute_dtype == torch.bfloat16:
+            pb.rmsnorm_stats(x, s['stats'], eps=1e-6)
+            pb.conv(x, s['h'], w[f'{p}.local.1.weight'], w[f'{p}.local.1.bias'], ln=(s['stats'], w[f'{p}.local.0.scale'], w[f'{p}.local.0.offset']))
+        else:
+            pb.rmsnorm(x, s['xn'], w[f'{p}.local.0.scale'], w[f'{p}.local.0.offset'], eps=1e-6)
+            pb.conv(s['xn'], s['h'], w[f'{p}.local.1.weight'], w[f'{p}.local.1.bias'])
         # nn.Conv2d(2d, 2d, 3, groups=d): output channel o reads input channels 2 (o // 2), 2 (o // 2) + 1 -> block-diagonal dense
         # convs per chunk of <= 64 channels; SimpleGate multiplies the two halves of the OUTPUT: second half first
         wg, bg = w[f'{p}.local.2.weight'].double(), w[f'{p}.local.2.bias']
@@ -278,7 +289,7 @@ class GateRV3(EngineModule):
         # per-level scratch (level l: width dim * 2^l on the H / 2^l grid), shared by the encoder and decoder blocks of the level
         def scratch(d, g, meta=True):
             hidden = int(1.5 * d)
-            s = dict(xn=pb.buffer(d, scale=g), ic=pb.buffer(hidden, scale=g), c=pb.buffer(d, scale=g), gm=pb.buffer(hidden, scale=g),
+            s = dict(xn=pb.buffer(d, scale=g), stats=pb.buffer(8, scale=g), ic=pb.buffer(hidden, scale=g), c=pb.buffer(d, scale=g), gm=pb.buffer(hidden, scale=g),
                      a=pb.buffer(d, scale=g), b=pb.buffer(d, scale=g))
             if meta:
                 s.update(h=pb.buffer(2 * d, scale=g), g2=pb.buffer(d, scale=g), gl=pb.buffer(d, scale=g), xl=pb.buffer(d, scale=g), m=pb.buffer(d, scale=g))

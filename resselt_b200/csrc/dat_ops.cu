@@ -61,8 +61,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ 
     }
     const float rstd = rsqrtf(sq / C + p.f0);
     T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
-    if (p.i0 == 1) {  // statistics only (the normalisation is folded into the consuming conv: Epi::ln_stats)
-      *reinterpret_cast<float2*>(d) = make_float2(rstd, -mean * rstd);
+    if (p.i0 >= 1) {  // statistics only (the normalisation is folded into the consuming conv: Epi::ln_stats)
+      // i0 == 2: RMSNorm statistics {1 / (|x|_2 / sqrt(C) + eps), 0} (x / (rms + eps) has no mean term)
+      *reinterpret_cast<float2*>(d) = p.i0 == 2 ? make_float2(1.0f / (sqrtf(sq / C + mean * mean) + p.f0), 0.0f) : make_float2(rstd, -mean * rstd);
       continue;
     }
     for (int pl = 0; pl < planes; ++pl) {
@@ -149,8 +150,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bf16_kernel(const __grid_con
     const float rstd = rsqrtf(fmaxf(sq, 0.0f) * inv_c + p.f0);
     const float shift = -mean * rstd;
     T* d = dst + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + pix * 8;
-    if (p.i0 == 1) {
-      if (live && sub == 0) *reinterpret_cast<float2*>(d) = make_float2(rstd, shift);
+    if (p.i0 >= 1) {
+      if (live && sub == 0)
+        *reinterpret_cast<float2*>(d) = p.i0 == 2 ? make_float2(1.0f / (sqrtf(fmaxf(sq, 0.0f) * inv_c + mean * mean) + p.f0), 0.0f) : make_float2(rstd, shift);
       continue;
     }
 #pragma unroll
@@ -297,9 +299,10 @@ __global__ void __launch_bounds__(kLnConsumers + 32, 1) layernorm_stream_kernel(
     }
     const float rstd = rsqrtf(fmaxf(m2, 0.0f) * inv_c + p.f0);
     const float shift = -mean * rstd;
-    if (p.i0 == 1) {
+    if (p.i0 >= 1) {
       if (live && half == 0)
-        *reinterpret_cast<float2*>(reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8) = make_float2(rstd, shift);
+        *reinterpret_cast<float2*>(reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8) =
+            p.i0 == 2 ? make_float2(1.0f / (sqrtf(fmaxf(m2, 0.0f) * inv_c + mean * mean) + p.f0), 0.0f) : make_float2(rstd, shift);
     } else if (live) {
       T* d = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0) * hw * 8 + (pix0 + px) * 8;
       for (int pl = half; pl < planes; pl += kLnSplit) {

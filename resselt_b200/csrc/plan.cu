@@ -1050,7 +1050,7 @@ int rsb_plan_add_op(rsb_plan* p, const rsb_op_desc* desc) {
   const int head_pad = d.kind == RSB_OP_WINATTN ? d.i[5] : 0;  // heads on 32-channel boundaries (tcgen05 window attention)
   const int qkv_span = head_pad ? d.i[0] * head_pad : d.channels;
   const int src_need = d.src_ch_off + (qkv ? 2 * (stride > 0 ? stride : d.channels) : 0) + qkv_span;
-  const int dst_need = (d.kind == RSB_OP_LAYERNORM && d.i[0] == 1) ? 8 : qkv_span;  // statistics mode writes one pixel chunk
+  const int dst_need = (d.kind == RSB_OP_LAYERNORM && d.i[0] >= 1) ? 8 : qkv_span;  // statistics mode writes one pixel chunk
   if (src_need > p->bufs[d.src_buf].planes * 8 || d.dst_ch_off + dst_need > p->bufs[d.dst_buf].planes * 8)
     return fail(RSB_ERR_INVALID, "rsb_plan_add_op: channel range exceeds buffer");
   if (!qkv && (d.src_ch_off % 8 != 0 || d.dst_ch_off % 8 != 0))

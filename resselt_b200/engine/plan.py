@@ -238,6 +238,13 @@ class PlanBuilder:
         c = src.channels
         self.op(N.OP_LAYERNORM, src, dst, c, ints=(1,), floats=(eps,), weights=(np.ones(c, np.float32), np.zeros(c, np.float32)))
 
+    def rmsnorm_stats(self, src: Ref, dst: Ref, eps: float = 1e-6) -> None:
+        """Per-pixel RMSNorm statistics {1 / (|x|_2 / sqrt(C) + eps), 0} of ``src`` into the 8-channel buffer ``dst``: a 1 x 1 conv with
+        ``ln=(dst, scale, offset)`` then computes conv(RMSNorm(src)) without the normalised map ever being written."""
+        assert dst.channels == 8 and dst.ch_off == 0, 'the statistics buffer is a whole 8-channel buffer'
+        c = src.channels
+        self.op(N.OP_LAYERNORM, src, dst, c, ints=(2,), floats=(eps,), weights=(np.ones(c, np.float32), np.zeros(c, np.float32)))
+
     def dwconv3(self, src: Ref, dst: Ref, weight, bias, act: int = N.ACT_NONE, gate: Optional[Ref] = None) -> None:
         self.op(N.OP_DWCONV3, src, dst, src.channels, src2=gate, ints=(act,), weights=(weight, bias))
 

@@ -364,6 +364,28 @@ def test_rmsnorm_op(C, B, H, W, dtype):
 
 
 @pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,cout,B,H,W', [(32, 64, 1, 40, 56), (256, 768, 1, 24, 40), (48, 72, 2, 17, 30)])
+def test_rmsnorm_folded_into_linear(C, cout, B, H, W, dtype):
+    """conv(x, ln=(rms stats, scale, offset)) == Conv1x1(RMSNorm(x)): statistics op in RMS mode (rsb_op_desc.i[0] = 2) + ln_fold."""
+    g = torch.Generator().manual_seed(C + cout)
+    x = torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3
+    scale, offset = 1.0 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    wl, bl = torch.randn(cout, C, 1, 1, generator=g) / C ** 0.5, 0.1 * torch.randn(cout, generator=g)
+    pb = PlanBuilder(dtype, C, cout, 1)
+    a, stats, y = pb.buffer(C), pb.buffer(8), pb.buffer(cout)
+    pb.conv(INPUT, a, torch.eye(C).view(C, C, 1, 1))
+    pb.rmsnorm_stats(a, stats, eps=1e-6)
+    pb.conv(a, y, wl, bl, ln=(stats, scale, offset), act=N.ACT_MISH)
+    pb.conv(y, OUTPUT, torch.eye(cout).view(cout, cout, 1, 1))
+    got, _ = _run(pb, x, dtype)
+    xq = _q(x, dtype)
+    rms = xq.norm(2, dim=1, keepdim=True) * C ** -0.5
+    t = scale.double().view(1, -1, 1, 1) * (xq / (rms + 1e-6)) + offset.double().view(1, -1, 1, 1)
+    ref = F.mish(F.conv2d(t, wl.double(), bl.double()))
+    _check(got, ref, dtype, what='linear(RMSNorm(.))')
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
 @pytest.mark.parametrize('C,se,B,H,W', [(32, True, 1, 40, 56), (48, False, 2, 18, 30), (32, True, 1, 128, 96)])
 def test_unshuffle_pool_dw5_se_shuffle_chain(C, se, B, H, W, dtype):
     """GatedCNNBlock.conv of RTMoSR in isolation (rtmosr/arch.py:314-319) on a base-divisor-2 plan:
