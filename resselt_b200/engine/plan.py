@@ -109,6 +109,9 @@ class PlanBuilder:
             return self._conv_one(src, dst, w, bias, **kw)
         assert kw.get('ln_out') is None, 'a conv that writes LayerNorm sums (ln_out) cannot be split over its output channels'
         per = max(16, min(256, budget // (kh * kw_ * cin16 * 2) // 16 * 16))
+        # equal parts (384 -> 192 + 192 rather than 256 + 128): parts of one width over the same source run as ONE N-split launch
+        parts = -(-cout // per)
+        per = min(per, -(-(-(-cout // parts)) // 16) * 16)
         b = _f32(bias) if bias is not None else None
         slopes = _f32(kw['act_slopes']) if kw.get('act_slopes') is not None else None
         for c0 in range(0, cout, per):
