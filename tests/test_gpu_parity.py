@@ -388,6 +388,8 @@ _SIZED = [
     ('Compact', lambda: SRVGGNetCompact(num_feat=64, num_conv=16, upscale=4, seed=5), (16, 3, 540, 960)),  # config 2
     ('ESRGAN', lambda: RRDBNet(num_blocks=23, scale=4, seed=6), (1, 3, 768, 768)),                 # config 4's tile unit
     ('SPANPlus', lambda: SpanPlus(blocks=[4], feature_channels=48, upscale=2, seed=4), (1, 3, 1080, 1920)),  # config 3
+    ('GateRV3', lambda: GateRV3(scale=2, seed=12), (1, 3, 1080, 1920)),                            # section 8f rank 2: global means over 2 M pixels, five grids
+    ('RTMoSR', lambda: RTMoSR(scale=2, dim=32, n_blocks=2, seed=11), (1, 3, 1080, 1920)),
 ]
 
 
@@ -404,7 +406,10 @@ def test_benchmarked_sizes_bf16_against_fp32_plan(name, make, shape):
     assert psnr(y16, y32) >= BF16_PSNR_DB, f'{name} at {shape}: bf16 vs fp32 plan PSNR {psnr(y16, y32):.2f} dB'
 
 
-@pytest.mark.parametrize('name,make', [(c[0], c[1]) for c in _SIZED[:3]], ids=[c[0] for c in _SIZED[:3]])
+_ORACLE_256 = _SIZED[:3] + [_SIZED[6]]
+
+
+@pytest.mark.parametrize('name,make', [(c[0], c[1]) for c in _ORACLE_256], ids=[c[0] for c in _ORACLE_256])
 def test_full_depth_fp32_plan_against_oracle_at_256(name, make):
     sd = make().state_dict()
     x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(13))
