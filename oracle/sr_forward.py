@@ -185,7 +185,7 @@ def rtmosr_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor
 def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     """GateRV3.forward in eval mode (/root/reference/resselt/archs/gaterv3/arch.py:783-802; MetaGated :658-667, GatedCNNBlock :623-629,
     InceptionDWConv2d :550-557, RMSNorm :518-524, SPAB :497-508, Conv3XC.update_params :432-463, Block :682-692, UniUpsampleV3 :241-373:
-    the 'pixelshuffle', 'pixelshuffledirect', 'nearest+conv', 'pa_up' and 'dysample' heads and the scale-1 conv; Attention :560-591)."""
+    the 'pixelshuffle', 'pixelshuffledirect', 'nearest+conv', 'transpose+conv', 'pa_up' and 'dysample' heads and the scale-1 conv; Attention :560-591)."""
     x = x.to(dtype)
     g = lambda k: sd[k].to(dtype)
     inp = x
@@ -283,6 +283,12 @@ def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tenso
             for k in range(n):
                 x = F.leaky_relu(F.interpolate(conv(f'dim_to_in.{3 * k}', x, 1), scale_factor=2), 0.2)
             x = conv(f'dim_to_in.{3 * n + 2}', F.leaky_relu(conv(f'dim_to_in.{3 * n}', x, 1), 0.2), 1)
+        elif mode == 'transpose+conv':
+            tconv = lambda name, t, s, pd: F.conv_transpose2d(t, g(f'{name}.weight'), g(f'{name}.bias'), stride=s, padding=pd)
+            if scale == 4:
+                x = conv('dim_to_in.3', tconv('dim_to_in.2', F.gelu(tconv('dim_to_in.0', x, 2, 1)), 2, 1), 1)
+            else:
+                x = conv('dim_to_in.1', tconv('dim_to_in.0', x, scale, 1 if scale == 2 else 0), 1)
         elif mode == 'pa_up':
             n = int(math.log2(scale))
             for k in range(n):

@@ -20,8 +20,8 @@ Lowering.  One plan with base divisor 16 holds all five grids (H, H/2, H/4, H/8,
   * Down = conv + PixelUnshuffle(2) (the unshuffle op of RTMoSR), Upsample = conv + PixelShuffle(2) (plain shuffle op); the
     encoder's level outputs are written straight into the second half of the decoder's concat buffers.
   * Heads: ``pixelshuffle`` (default), ``pixelshuffledirect``, ``nearest+conv`` and ``pa_up`` (2^n; the nearest upsample folded into 2x2
-    phase convs), ``dysample`` with a 1x1 end conv, and the plain conv of scale 1.  ``transpose+conv`` and ``lda`` (deformable LDA-AQU)
-    are refused at load.  The latent self-attention variant (``attention=True``) maps onto DAT's channel-attention op behind a 1x1
+    phase convs), ``transpose+conv`` (ConvTranspose2d as sub-pixel phase convs), ``dysample`` with a 1x1 end conv, and the plain conv of
+    scale 1.  ``lda`` (deformable LDA-AQU) is refused at load.  The latent self-attention variant (``attention=True``) maps onto DAT's channel-attention op behind a 1x1
     conv and a depthwise 3x3.
 Reflect padding to a multiple of 16, the crop and ``+ gamma * nearest(inp)`` are host glue around the plan (arch.py:789-802).
 """
@@ -41,7 +41,7 @@ from ._common import conv_specs, dysample_specs, emit_dysample
 from .esrgan import upconv_phase_kernels
 
 SAMPLE_MODS = ('conv', 'pixelshuffledirect', 'pixelshuffle', 'nearest+conv', 'dysample', 'transpose+conv', 'lda', 'pa_up')
-SUPPORTED_MODS = ('pixelshuffledirect', 'pixelshuffle', 'nearest+conv', 'dysample', 'pa_up')
+SUPPORTED_MODS = ('pixelshuffledirect', 'pixelshuffle', 'nearest+conv', 'dysample', 'transpose+conv', 'pa_up')
 
 
 def _conv3xc_specs(prefix: str, cin: int, cout: int, gain: int, bias: bool) -> List[ParamSpec]:
@@ -130,6 +130,12 @@ def _head_specs(upsample: str, scale: int, dim: int, out_ch: int, mid: int, end_
         for k in range(n + 1):
             specs += conv_specs(f'dim_to_in.{3 * k}', dim, dim, 3)
         specs += conv_specs(f'dim_to_in.{3 * n + 2}', dim, out_ch, 3)
+    elif upsample == 'transpose+conv':  # ConvTranspose2d(4, 2, 1) [GELU ConvTranspose2d(4, 2, 1)] | ConvTranspose2d(3, 3, 0), then a 3x3 conv (arch.py:303-318)
+        tw = lambda name, i, o, k: [(f'{name}.weight', (i, o, k, k), 'conv_w'), (f'{name}.bias', (o,), f'bias:{i * k * k}')]
+        if scale == 4:
+            specs += tw('dim_to_in.0', dim, dim, 4) + tw('dim_to_in.2', dim, out_ch, 4) + conv_specs('dim_to_in.3', out_ch, out_ch, 3)
+        else:
+            specs += tw('dim_to_in.0', dim, out_ch, 4 if scale == 2 else 3) + conv_specs('dim_to_in.1', out_ch, out_ch, 3)
     elif upsample == 'pa_up':  # [Upsample(2), conv, PA, LeakyReLU, conv, LeakyReLU] x n, conv (arch.py:325-352)
         n, cin = int(math.log2(scale)), dim
         for k in range(n):
@@ -158,6 +164,8 @@ class GateRV3(EngineModule):
             raise NotImplementedError(f'GateRV3 upsampler {upsample!r} is not built (supported: {SUPPORTED_MODS})')
         if scale != 1 and upsample == 'pixelshuffle' and scale & (scale - 1) and scale != 3:
             raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
+        if scale != 1 and upsample == 'transpose+conv' and scale not in (2, 3, 4):
+            raise ValueError(f'scale {scale} is not supported. Supported scales: 2, 3, 4')
         if scale != 1 and upsample in ('nearest+conv', 'pa_up') and scale & (scale - 1):
             if scale != 3:
                 raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
@@ -368,6 +376,40 @@ class GateRV3(EngineModule):
                     pb.conv(cur, nxt, wk, w[f'dim_to_in.{3 * k}.bias'], dst_ps=2, dst_phase=phase, pad=pad2, **lrelu)
                 cur, grid = nxt, grid * 2
             pb.conv(cur, OUTPUT, w[f'dim_to_in.{3 * n + 2}.weight'], w[f'dim_to_in.{3 * n + 2}.bias'], ps=1)
+        elif self.upsample == 'transpose+conv':
+            oc = self.out_channels
+
+            def transposed(src, dst, name, f, **kw):
+                """ConvTranspose2d as sub-pixel phase convs on the source grid.  k = 4, s = 2, p = 1: output row 2 y + a gets input rows
+                (y - 1, y) through kernel rows (3, 1) for a = 0 and rows (y, y + 1) through kernel rows (2, 0) for a = 1 (columns alike)
+                -> four 2x2 convs; k = 3, s = 3, p = 0: every output pixel has one source pixel -> nine 1x1 convs."""
+                wt, bt = w[f'{name}.weight'], w[f'{name}.bias']  # [in][out][k][k]
+                co = -(-wt.shape[1] // 8) * 8  # a sub-pixel phase writes whole 8-channel planes: zero output channels fill the last one
+                wt, bt = F.pad(wt, (0, 0, 0, 0, 0, co - wt.shape[1])), F.pad(bt, (0, co - bt.shape[0]))
+                dst = dst.slice(0, co) if dst.channels >= co else dst
+                if f == 3:
+                    for phase in range(9):
+                        pb.conv(src, dst, wt[:, :, phase // 3, phase % 3].t().reshape(wt.shape[1], wt.shape[0], 1, 1), bt, dst_ps=3, dst_phase=phase, **kw)
+                    return
+                taps = {0: ((3, 1), 1), 1: ((2, 0), 0)}  # parity -> (kernel indices of the two taps, zero padding in front)
+                for a in (0, 1):
+                    for b in (0, 1):
+                        (ky, pt), (kx, pl) = taps[a], taps[b]
+                        wk = wt[:, :, list(ky)][:, :, :, list(kx)].permute(1, 0, 2, 3).contiguous()
+                        pb.conv(src, dst, wk, bt, dst_ps=2, dst_phase=a * 2 + b, pad=(pt, pl), **kw)
+
+            hi = pb.buffer(16, scale=full * r)  # the head's out_ch-channel map on the output grid (16 channels: two whole planes for the conv)
+            if r == 4:
+                mid = pb.buffer(self.dim, scale=full * 2)
+                transposed(x, mid, 'dim_to_in.0', 2, act=N.ACT_GELU)
+                transposed(mid, hi, 'dim_to_in.2', 2)
+                last = 'dim_to_in.3'
+            else:
+                transposed(x, hi, 'dim_to_in.0', r)
+                last = 'dim_to_in.1'
+            wl = torch.zeros(oc, 16, 3, 3, dtype=w[f'{last}.weight'].dtype)
+            wl[:, :oc] = w[f'{last}.weight']
+            pb.conv(hi, OUTPUT, wl, w[f'{last}.bias'], ps=1)
         elif self.upsample == 'pa_up':
             n, mid, cur, grid = int(math.log2(r)), self.mid, x, 1
             for k in range(n):

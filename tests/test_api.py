@@ -46,6 +46,8 @@ def test_metadata_field_order():
         (GateRV3(in_ch=1, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=3, upsample='pixelshuffledirect'), ('GateRV3', 1, 1, 3)),
         (GateRV3(dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=2, scale=2, upsample='nearest+conv', attention=True), ('GateRV3', 3, 3, 2)),
         (GateRV3(dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=4, upsample='pa_up', upsample_mid_dim=24), ('GateRV3', 3, 3, 4)),
+        (GateRV3(dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=4, upsample='transpose+conv'), ('GateRV3', 3, 3, 4)),
+        (GateRV3(dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=3, upsample='transpose+conv'), ('GateRV3', 3, 3, 3)),
         (RTMoSR(scale=4, dim=48, ffn_expansion=1.5, n_blocks=1, dccm=False, se=False), ('RTMoSR', 3, 3, 2)),   # the reference always reports 2
         (RTMoSR(scale=2, n_blocks=1, unshuffle_mod=True), ('RTMoSR', 3, 3, 2)),
         (SpanPlus(blocks=[4], upscale=2), ('SPANPlus', 3, 3, 2)),
