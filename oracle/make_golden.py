@@ -80,6 +80,8 @@ def cases():
         'gaterv3_x2_transpose': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=2, upsample='transpose+conv', upsample_mid_dim=16, span_blocks=1), 51, (1, 3, 18, 22), 141),
         'gaterv3_x4_transpose': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=4, upsample='transpose+conv', upsample_mid_dim=16, span_blocks=1), 52, (1, 3, 16, 12), 142),
         'gaterv3_x3_transpose': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=3, upsample='transpose+conv', upsample_mid_dim=16, span_blocks=1), 53, (1, 3, 13, 17), 143),
+        'gaterv3_x3_nearest': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=3, upsample='nearest+conv', upsample_mid_dim=16, span_blocks=1), 54, (1, 3, 14, 18), 144),
+        'gaterv3_x3_paup': ('GateRV3', dict(in_ch=3, dim=16, enc_blocks=(1, 1), dec_blocks=(1, 1), num_latent=1, scale=3, upsample='pa_up', upsample_mid_dim=16, span_blocks=1), 55, (1, 3, 12, 15), 145),
         'rtmosr_x2_unshuffle': ('RTMoSR', dict(scale=2, dim=32, ffn_expansion=2, n_blocks=1, unshuffle_mod=True, dccm=True, se=True), 41, (1, 3, 22, 30), 131),
         'realplksr_x2_nb3_noea': ('RealPLKSR', dict(in_ch=3, dim=32, n_blocks=3, upscaling_factor=2, kernel_size=13, split_ratio=0.25,
                                                     use_ea=False, norm_groups=4, dysample=False), 21, (2, 3, 18, 18), 111),

@@ -279,9 +279,9 @@ def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tenso
                 i += 2
             x = conv(f'dim_to_in.{i}', x, 1)
         elif mode == 'nearest+conv':
-            n = int(math.log2(scale))
+            n, f = (1, 3) if scale == 3 else (int(math.log2(scale)), 2)
             for k in range(n):
-                x = F.leaky_relu(F.interpolate(conv(f'dim_to_in.{3 * k}', x, 1), scale_factor=2), 0.2)
+                x = F.leaky_relu(F.interpolate(conv(f'dim_to_in.{3 * k}', x, 1), scale_factor=f), 0.2)
             x = conv(f'dim_to_in.{3 * n + 2}', F.leaky_relu(conv(f'dim_to_in.{3 * n}', x, 1), 0.2), 1)
         elif mode == 'transpose+conv':
             tconv = lambda name, t, s, pd: F.conv_transpose2d(t, g(f'{name}.weight'), g(f'{name}.bias'), stride=s, padding=pd)
@@ -290,9 +290,9 @@ def gaterv3_forward(sd: SD, x: torch.Tensor, dtype=torch.float32) -> torch.Tenso
             else:
                 x = conv('dim_to_in.1', tconv('dim_to_in.0', x, scale, 1 if scale == 2 else 0), 1)
         elif mode == 'pa_up':
-            n = int(math.log2(scale))
+            n, f = (1, 3) if scale == 3 else (int(math.log2(scale)), 2)
             for k in range(n):
-                x = conv(f'dim_to_in.{6 * k + 1}', F.interpolate(x, scale_factor=2), 1)
+                x = conv(f'dim_to_in.{6 * k + 1}', F.interpolate(x, scale_factor=f), 1)
                 x = F.leaky_relu(x * torch.sigmoid(conv(f'dim_to_in.{6 * k + 2}.conv.0', x)), 0.2)
                 x = F.leaky_relu(conv(f'dim_to_in.{6 * k + 4}', x, 1), 0.2)
             x = conv(f'dim_to_in.{6 * n}', x, 1)

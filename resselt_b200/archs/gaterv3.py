@@ -19,7 +19,7 @@ Lowering.  One plan with base divisor 16 holds all five grids (H, H/2, H/4, H/8,
     built on the host, whose zero taps the kernel skips per 8-channel plane; fc2's epilogue is the Mish.
   * Down = conv + PixelUnshuffle(2) (the unshuffle op of RTMoSR), Upsample = conv + PixelShuffle(2) (plain shuffle op); the
     encoder's level outputs are written straight into the second half of the decoder's concat buffers.
-  * Heads: ``pixelshuffle`` (default), ``pixelshuffledirect``, ``nearest+conv`` and ``pa_up`` (2^n; the nearest upsample folded into 2x2
+  * Heads: ``pixelshuffle`` (default), ``pixelshuffledirect``, ``nearest+conv`` and ``pa_up`` (2^n and x3; the nearest upsample folded into 2x2
     phase convs), ``transpose+conv`` (ConvTranspose2d as sub-pixel phase convs), ``dysample`` with a 1x1 end conv, and the plain conv of
     scale 1.  ``lda`` (deformable LDA-AQU) is refused at load.  The latent self-attention variant (``attention=True``) maps onto DAT's channel-attention op behind a 1x1
     conv and a depthwise 3x3.
@@ -111,6 +111,31 @@ def merge_inception(w, p: str, dim: int):
     return k, b
 
 
+def nearest_phase_kernels(w: torch.Tensor, f: int):
+    """nearest-x f upsample followed by a 3x3 'same' conv == f^2 convs of 2x2 taps on the source grid (f = 2: esrgan.upconv_phase_kernels;
+    f = 3 here).  Output row 3 y + a reads upsampled rows 3 y + a - 1 .. 3 y + a + 1, i.e. source rows (y - 1, y, y) for a = 0, (y, y, y) for
+    a = 1 and (y, y, y + 1) for a = 2: taps folded onto two source rows [r0, r1] with `pad` zero rows in front.  Returns
+    [(phase index a * f + b, weight [cout][cin][2][2], (pad_top, pad_left))]."""
+    if f == 2:
+        return upconv_phase_kernels(w)
+    assert f == 3
+    zero = torch.zeros_like(w[:, :, 0])
+    rows = {0: ([w[:, :, 0], w[:, :, 1] + w[:, :, 2]], 1), 1: ([w[:, :, 0] + w[:, :, 1] + w[:, :, 2], zero], 0), 2: ([w[:, :, 0] + w[:, :, 1], w[:, :, 2]], 0)}
+    out = []
+    for a in range(3):
+        (r0, r1), pad_t = rows[a]
+        for b in range(3):
+            def fold(r):  # r: [cout][cin][3] over kx
+                if b == 0:
+                    return torch.stack([r[:, :, 0], r[:, :, 1] + r[:, :, 2]], -1), 1
+                if b == 1:
+                    return torch.stack([r[:, :, 0] + r[:, :, 1] + r[:, :, 2], torch.zeros_like(r[:, :, 0])], -1), 0
+                return torch.stack([r[:, :, 0] + r[:, :, 1], r[:, :, 2]], -1), 0
+            (c0, pad_l), (c1, _) = fold(r0), fold(r1)
+            out.append((a * 3 + b, torch.stack([c0, c1], 2).contiguous(), (pad_t, pad_l)))
+    return out
+
+
 def _head_specs(upsample: str, scale: int, dim: int, out_ch: int, mid: int, end_kernel: int) -> List[ParamSpec]:
     if scale == 1:
         return conv_specs('dim_to_in', dim, out_ch, 3)
@@ -125,8 +150,8 @@ def _head_specs(upsample: str, scale: int, dim: int, out_ch: int, mid: int, end_
             specs += conv_specs(f'dim_to_in.{i}', mid, r * r * mid, 3)
             i += 2
         specs += conv_specs(f'dim_to_in.{i}', mid, out_ch, 3)
-    elif upsample == 'nearest+conv':  # [conv, Upsample(2), LeakyReLU] x n, conv, LeakyReLU, conv (arch.py:270-296)
-        n = int(math.log2(scale))
+    elif upsample == 'nearest+conv':  # [conv, Upsample(2), LeakyReLU] x n, conv, LeakyReLU, conv (arch.py:270-296); x3: one Upsample(3) step
+        n = 1 if scale == 3 else int(math.log2(scale))
         for k in range(n + 1):
             specs += conv_specs(f'dim_to_in.{3 * k}', dim, dim, 3)
         specs += conv_specs(f'dim_to_in.{3 * n + 2}', dim, out_ch, 3)
@@ -136,8 +161,8 @@ def _head_specs(upsample: str, scale: int, dim: int, out_ch: int, mid: int, end_
             specs += tw('dim_to_in.0', dim, dim, 4) + tw('dim_to_in.2', dim, out_ch, 4) + conv_specs('dim_to_in.3', out_ch, out_ch, 3)
         else:
             specs += tw('dim_to_in.0', dim, out_ch, 4 if scale == 2 else 3) + conv_specs('dim_to_in.1', out_ch, out_ch, 3)
-    elif upsample == 'pa_up':  # [Upsample(2), conv, PA, LeakyReLU, conv, LeakyReLU] x n, conv (arch.py:325-352)
-        n, cin = int(math.log2(scale)), dim
+    elif upsample == 'pa_up':  # [Upsample(2), conv, PA, LeakyReLU, conv, LeakyReLU] x n, conv (arch.py:325-352); x3: one Upsample(3) step
+        n, cin = (1 if scale == 3 else int(math.log2(scale))), dim
         for k in range(n):
             specs += conv_specs(f'dim_to_in.{6 * k + 1}', cin, mid, 3) + conv_specs(f'dim_to_in.{6 * k + 2}.conv.0', mid, mid, 1) + conv_specs(f'dim_to_in.{6 * k + 4}', mid, mid, 3)
             cin = mid
@@ -166,10 +191,8 @@ class GateRV3(EngineModule):
             raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
         if scale != 1 and upsample == 'transpose+conv' and scale not in (2, 3, 4):
             raise ValueError(f'scale {scale} is not supported. Supported scales: 2, 3, 4')
-        if scale != 1 and upsample in ('nearest+conv', 'pa_up') and scale & (scale - 1):
-            if scale != 3:
-                raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
-            raise NotImplementedError(f'GateRV3 {upsample!r} head: x3 (nearest x3 phase kernels) is not built')
+        if scale != 1 and upsample in ('nearest+conv', 'pa_up') and scale & (scale - 1) and scale != 3:
+            raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
         if len(enc_blocks) != len(dec_blocks) or dim % 16 or min(list(enc_blocks) + list(dec_blocks)) < 1:
             raise ValueError('GateRV3 needs as many decoder as encoder levels, >= 1 block per level and dim % 16 == 0 (planar-8 layout)')
         L = len(enc_blocks)
@@ -366,15 +389,16 @@ class GateRV3(EngineModule):
         elif self.upsample == 'nearest+conv':
             # lrelu commutes with the nearest upsample: z0 = lrelu(conv0(x)) on the input grid, every later conv reads an upsampled map
             # = four 2x2 phase convs on the source grid (esrgan.upconv_phase_kernels), stored pixel-interleaved
-            n, lrelu = int(math.log2(r)), dict(act=N.ACT_LRELU, act_param=0.2)
+            f = 3 if r == 3 else 2
+            n, lrelu = (1 if r == 3 else int(math.log2(r))), dict(act=N.ACT_LRELU, act_param=0.2)
             cur = pb.buffer(self.dim)
             pb.conv(x, cur, w['dim_to_in.0.weight'], w['dim_to_in.0.bias'], **lrelu)
             grid = 1
             for k in range(1, n + 1):
-                nxt = pb.buffer(self.dim, scale=full * grid * 2)
-                for phase, wk, pad2 in upconv_phase_kernels(w[f'dim_to_in.{3 * k}.weight']):
-                    pb.conv(cur, nxt, wk, w[f'dim_to_in.{3 * k}.bias'], dst_ps=2, dst_phase=phase, pad=pad2, **lrelu)
-                cur, grid = nxt, grid * 2
+                nxt = pb.buffer(self.dim, scale=full * grid * f)
+                for phase, wk, pad2 in nearest_phase_kernels(w[f'dim_to_in.{3 * k}.weight'], f):
+                    pb.conv(cur, nxt, wk, w[f'dim_to_in.{3 * k}.bias'], dst_ps=f, dst_phase=phase, pad=pad2, **lrelu)
+                cur, grid = nxt, grid * f
             pb.conv(cur, OUTPUT, w[f'dim_to_in.{3 * n + 2}.weight'], w[f'dim_to_in.{3 * n + 2}.bias'], ps=1)
         elif self.upsample == 'transpose+conv':
             oc = self.out_channels
@@ -411,17 +435,18 @@ class GateRV3(EngineModule):
             wl[:, :oc] = w[f'{last}.weight']
             pb.conv(hi, OUTPUT, wl, w[f'{last}.bias'], ps=1)
         elif self.upsample == 'pa_up':
-            n, mid, cur, grid = int(math.log2(r)), self.mid, x, 1
+            f = 3 if r == 3 else 2
+            n, mid, cur, grid = (1 if r == 3 else int(math.log2(r))), self.mid, x, 1
             for k in range(n):
-                g2 = full * grid * 2
+                g2 = full * grid * f
                 a, t, u, v = (pb.buffer(mid, scale=g2) for _ in range(4))
-                for phase, wk, pad2 in upconv_phase_kernels(w[f'dim_to_in.{6 * k + 1}.weight']):
-                    pb.conv(cur, a, wk, w[f'dim_to_in.{6 * k + 1}.bias'], dst_ps=2, dst_phase=phase, pad=pad2)
+                for phase, wk, pad2 in nearest_phase_kernels(w[f'dim_to_in.{6 * k + 1}.weight'], f):
+                    pb.conv(cur, a, wk, w[f'dim_to_in.{6 * k + 1}.bias'], dst_ps=f, dst_phase=phase, pad=pad2)
                 # PA: a * sigmoid(conv1x1(a)) as the 1x1 conv's epilogue; the LeakyReLU behind the product is one more 1x1 pass
                 pb.conv(a, t, w[f'dim_to_in.{6 * k + 2}.conv.0.weight'], w[f'dim_to_in.{6 * k + 2}.conv.0.bias'], act=N.ACT_SIGMOID, combine=N.COMB_MUL, res1=a)
                 pb.conv(t, u, torch.eye(mid).view(mid, mid, 1, 1), None, act=N.ACT_LRELU, act_param=0.2)
                 pb.conv(u, v, w[f'dim_to_in.{6 * k + 4}.weight'], w[f'dim_to_in.{6 * k + 4}.bias'], act=N.ACT_LRELU, act_param=0.2)
-                cur, grid = v, grid * 2
+                cur, grid = v, grid * f
             pb.conv(cur, OUTPUT, w[f'dim_to_in.{6 * n}.weight'], w[f'dim_to_in.{6 * n}.bias'], ps=1)
         else:  # dysample
             i = 0
