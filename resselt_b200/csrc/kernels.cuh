@@ -594,6 +594,7 @@ struct TokenOpParams {  // LayerNorm and depthwise 3x3
   const float* w1;  // LayerNorm beta  | dwconv bias [C]
   float f0;         // LayerNorm eps
   int i0;           // dwconv activation (RSB_ACT_NONE / RSB_ACT_GELU) | LayerNorm: 1 = statistics only (dst pixel chunk = {rstd, -mean * rstd})
+  int dense5;       // depthwise 5 x 5: take the column-walking scatter kernel (rt_ops.cu)
 };
 
 struct WinAttnParams {

@@ -729,6 +729,7 @@ int bind(rsb_plan* p, int n, int h, int w, void* workspace, size_t ws_bytes, cud
         t.src2 = ws + s2.offset, t.src2_planes = s2.planes, t.src2_plane0 = d.src2_ch_off / 8;
       }
       t.w0 = a.dw[0], t.w1 = a.dw[1], t.f0 = d.f[0], t.i0 = d.i[0];
+      t.dense5 = (d.kind == RSB_OP_DWCONV3 && d.i[1] == 5) ? 1 : 0;
     } else if (d.kind == RSB_OP_WINATTN) {
       rsb::WinAttnParams& t = a.win;
       memset(&t, 0, sizeof t);

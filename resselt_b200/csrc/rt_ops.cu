@@ -163,6 +163,83 @@ __global__ void __launch_bounds__(256) dwconv_k_kernel(const __grid_constant__ T
   }
 }
 
+// Dense depthwise 5 x 5 (RTMoSR's re-parameterised OmniShift, 128 channels on the half grid: 25 % of the model's time in the generic
+// kernel above, which loads every input pixel 25 times and spends ~500 instructions per output).  Scatter form: a thread walks down
+// one pixel column; every input row (five 16-byte loads, unpacked once) is accumulated into the FIVE output rows it contributes to,
+// kept as a ring of accumulators whose slots are compile-time (the row loop is unrolled by five); the row whose last contribution
+// has arrived is stored.  5 loads, 100 packed FMAs and 50 shared-memory weight loads per output instead of 25 / 200 / 50.
+constexpr int kDw5Rows = 31;  // output rows per CTA: 31 + 4 input rows = 7 rounds of 5
+__device__ __forceinline__ void fma2_rt(float& a0, float& a1, float v0, float v1, float w0, float w1) {
+  asm("{\n\t"
+      ".reg .b64 rv, rw, ra;\n\t"
+      "mov.b64 rv, {%2, %3};\n\t"
+      "mov.b64 rw, {%4, %5};\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "fma.rn.f32x2 ra, rv, rw, ra;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t"
+      "}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(v0), "f"(v1), "f"(w0), "f"(w1));
+}
+template <typename T>
+__global__ void __launch_bounds__(128) dwconv5_rows_kernel(const __grid_constant__ TokenOpParams p) {
+  __shared__ __align__(16) float wsm[25 * 8 + 8];
+  const size_t hw = (size_t)p.H * p.W;
+  const int C = p.channels;
+  const int pl = blockIdx.z % ((C + 7) >> 3), n = blockIdx.z / ((C + 7) >> 3);
+  for (int e = threadIdx.x; e < 25 * 8 + 8; e += blockDim.x) {
+    const int t = e >> 3, k = e & 7, c = pl * 8 + k;
+    wsm[e] = c < C ? (t < 25 ? p.w0[c * 25 + t] : p.w1[c]) : 0.0f;
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= p.W) return;
+  const int yb = blockIdx.y * kDw5Rows;
+  const T* src = reinterpret_cast<const T*>(p.src) + ((size_t)n * p.src_planes + p.src_plane0 + pl) * hw * 8;
+  T* dst = reinterpret_cast<T*>(p.dst) + ((size_t)n * p.dst_planes + p.dst_plane0 + pl) * hw * 8;
+  float bias[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bias[k] = wsm[25 * 8 + k];
+  float acc[5][8];
+#pragma unroll
+  for (int s5 = 0; s5 < 5; ++s5)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[s5][k] = bias[k];
+  // input row sy = yb - 2 + 5 * round + u contributes through kernel row ky to output row sy + 2 - ky, ring slot (u + 2 - ky) mod 5
+  for (int round = 0; round < (kDw5Rows + 4) / 5; ++round) {
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int sy = yb - 2 + 5 * round + u;
+      if (sy >= 0 && sy < p.H) {
+        const T* row = src + (size_t)sy * p.W * 8;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const int sx = x + kx - 2;
+          if (sx < 0 || sx >= p.W) continue;
+          float v[8];
+          load8<T>(row + (size_t)sx * 8, v);
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) {
+            const float4 wa = *reinterpret_cast<const float4*>(&wsm[(ky * 5 + kx) * 8]);
+            const float4 wb = *reinterpret_cast<const float4*>(&wsm[(ky * 5 + kx) * 8 + 4]);
+            float(&a)[8] = acc[(u + 2 - ky + 5) % 5];
+            fma2_rt(a[0], a[1], v[0], v[1], wa.x, wa.y);
+            fma2_rt(a[2], a[3], v[2], v[3], wa.z, wa.w);
+            fma2_rt(a[4], a[5], v[4], v[5], wb.x, wb.y);
+            fma2_rt(a[6], a[7], v[6], v[7], wb.z, wb.w);
+          }
+        }
+      }
+      // output row sy - 2 has received its last contribution (ky = 4)
+      const int oy = sy - 2;
+      float(&done)[8] = acc[(u + 3) % 5];
+      if (oy >= yb && oy < yb + kDw5Rows && oy < p.H) store8<T>(dst + ((size_t)oy * p.W + x) * 8, done);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) done[k] = bias[k];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ SE + PixelShuffle(2)
 // partial[n][block][c]: per-channel sums over this block's pixel range (fixed order: deterministic)
 template <typename T>
@@ -384,6 +461,14 @@ cudaError_t launch_dwconv_k(const TokenOpParams& p, int K, bool bf16, int num_sm
   const int planes = (p.channels + 7) >> 3;
   const int gx = grid_for((size_t)p.H * p.W, 256, std::max(1, (num_sms > 0 ? num_sms : 148) * 16 / std::max(1, planes * p.n)));
   const dim3 g(gx, planes, p.n);
+  if (K == 5 && p.dense5 && (long long)planes * p.n <= 65535) {
+    const dim3 g5((p.W + 127) / 128, (p.H + kDw5Rows - 1) / kDw5Rows, planes * p.n);
+    if (bf16)
+      dwconv5_rows_kernel<__nv_bfloat16><<<g5, 128, 0, s>>>(p);
+    else
+      dwconv5_rows_kernel<float><<<g5, 128, 0, s>>>(p);
+    return cudaGetLastError();
+  }
   if (bf16)
     dwconv_k_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(p, K);
   else
